@@ -1,0 +1,455 @@
+"""CPU oracle for the rubix particle -> IFU datacube path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, not the product: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  Nothing under
+``rubix_b200/`` imports it.
+
+It is a plain-numpy restatement of the reference algorithm (AstroAI-Lab/rubix @ dbb4487, mounted
+at /root/reference while this was written; paths below are relative to it).  Every function keeps
+the reference's *dataflow* (materialised ``(P, L)`` and ``(P, W)`` intermediates) and, with
+``dtype=np.float32``, the reference's operation order, so that it can stand in for the JAX-CPU
+pipeline, which cannot be imported in this environment (no jax / interpax / equinox / h5py).
+With ``dtype=np.float64`` the same formulas are evaluated in double precision on the same float32
+inputs; that is the "truth" the float32 CUDA path and the float32 oracle are both compared with.
+
+PARITY PINS
+-----------
+* Checked against every known-answer test the reference holds for this path
+  (tests/test_oracle_golden.py lists them with file:line).
+* ``interp2d`` is NOT in the reference tree: it is ``interpax.interp2d`` (PyPI ``interpax``,
+  unpinned in the reference's pyproject.toml:38, no lock file).  Its published algorithm is restated
+  in :func:`interp2d` below.  The reference's tests pin it only at grid nodes and out-of-grid
+  (tests/test_core_ssp.py:95-181, tests/test_ssp_grid.py:653-698).  **Off-node interpolated values:
+  parity unpinned** (no golden vector exists in the reference and interpax cannot be run here).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+SPEED_OF_LIGHT = 299792.458  # rubix/config/rubix_config.yml:8  (km/s)
+
+
+# --------------------------------------------------------------------------------------
+# a0  spaxel assignment + aperture mask
+# --------------------------------------------------------------------------------------
+def square_spaxel_assignment(coords, spatial_bin_edges):
+    """rubix/telescope/utils.py:138-151.
+
+    ``jnp.digitize(x, edges)`` is ``searchsorted(edges, x, side='right')`` for increasing edges.
+    Returns int32 flat indices ``x + nbins * y``.
+    """
+    coords = np.asarray(coords)
+    edges = np.asarray(spatial_bin_edges)
+    xi = np.searchsorted(edges, coords[:, 0], side="right") - 1
+    yi = np.searchsorted(edges, coords[:, 1], side="right") - 1
+    nb = len(edges) - 1
+    xi = np.clip(xi, 0, nb - 1)
+    yi = np.clip(yi, 0, nb - 1)
+    return (xi + nb * yi).astype(np.int32)
+
+
+def mask_particles_outside_aperture(coords, spatial_bin_edges):
+    """rubix/telescope/utils.py:170-174 (inclusive on both boundaries)."""
+    coords = np.asarray(coords)
+    edges = np.asarray(spatial_bin_edges)
+    lo, hi = edges.min(), edges.max()
+    m = (coords[:, 0] >= lo) & (coords[:, 0] <= hi)
+    m &= (coords[:, 1] >= lo) & (coords[:, 1] <= hi)
+    return m
+
+
+def filter_particles(coords, mass, metallicity, age, spatial_bin_edges):
+    """rubix/core/telescope.py:155-174: masked particles get mass = metallicity = age = 0
+    (coords and velocity are left alone)."""
+    m = mask_particles_outside_aperture(coords, spatial_bin_edges)
+    z = lambda a: np.where(m, a, np.zeros((), dtype=np.asarray(a).dtype))
+    return z(mass), z(metallicity), z(age), m
+
+
+def reshape_array(arr, n_dev):
+    """rubix/core/data.py:461-487: pad with zeros to a multiple of n_dev, add leading device axis."""
+    arr = np.asarray(arr)
+    n = arr.shape[0]
+    per = (n + n_dev - 1) // n_dev
+    pad = per * n_dev - n
+    if pad:
+        arr = np.concatenate([arr, np.zeros((pad,) + arr.shape[1:], arr.dtype)], axis=0)
+    return arr.reshape((n_dev, per) + arr.shape[1:])
+
+
+# --------------------------------------------------------------------------------------
+# a1  SSP lookup: interpax.interp2d(xq=Z, yq=age, x=Zgrid, y=agegrid, f=flux, method, extrap=0)
+# --------------------------------------------------------------------------------------
+# Inverse of the bicubic-patch matrix (coefficients a_ij of sum a_ij x^i y^j from
+# [f, fx, fy, fxy] at the four corners, corner order (0,0),(1,0),(0,1),(1,1)); interpax A_BICUBIC.
+A_BICUBIC = np.array(
+    [
+        [1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [-3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0],
+        [0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0],
+        [-3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0],
+        [9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1],
+        [-6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1],
+        [2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0],
+        [0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0],
+        [-6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1],
+        [4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1],
+    ],
+    dtype=np.float64,
+)
+
+
+def approx_df(x, f, axis):
+    """interpax ``approx_df(x, f, method="cubic", axis)``: node derivatives for the C1 cubic
+    spline: one-sided secant at both ends, plain mean of the two adjacent secants inside."""
+    x = np.asarray(x)
+    f = np.asarray(f)
+    dx = np.diff(x)
+    df = np.diff(f, axis=axis)
+    with np.errstate(divide="ignore"):
+        dxi = np.where(dx == 0, 0, 1 / np.where(dx == 0, 1, dx)).astype(f.dtype)
+    shape = [1] * f.ndim
+    shape[axis] = -1
+    df = dxi.reshape(shape) * df
+    first = np.take(df, [0], axis=axis)
+    last = np.take(df, [-1], axis=axis)
+    n = df.shape[axis]
+    mid = f.dtype.type(0.5) * (
+        np.take(df, np.arange(0, n - 1), axis=axis) + np.take(df, np.arange(1, n), axis=axis)
+    )
+    return np.concatenate([first, mid, last], axis=axis)
+
+
+def interp2d(xq, yq, x, y, f, method="cubic", extrap=0, dtype=np.float32, hermite=False):
+    """Restatement of ``interpax.interp2d`` as bound by rubix/spectra/ssp/grid.py:113-120
+    (``x``=metallicity grid, ``y``=age grid, ``f``=flux ``(nx, ny, L)``, ``extrap=0``) and called at
+    rubix/core/ifu.py:107-110 with 1-D ``xq``, ``yq`` of equal length.  Returns ``(P, L)``.
+
+    ``hermite=True`` evaluates the same bicubic patch through the Hermite basis instead of the
+    16x16 coefficient matrix (mathematically identical; this is the form the CUDA kernel uses).
+    """
+    dt = np.dtype(dtype).type
+    xq = np.atleast_1d(np.asarray(xq)).astype(dtype)
+    yq = np.atleast_1d(np.asarray(yq)).astype(dtype)
+    x = np.asarray(x).astype(dtype)
+    y = np.asarray(y).astype(dtype)
+    f = np.asarray(f).astype(dtype)
+    i = np.clip(np.searchsorted(x, xq, side="right"), 1, len(x) - 1)
+    j = np.clip(np.searchsorted(y, yq, side="right"), 1, len(y) - 1)
+    x0, x1 = x[i - 1], x[i]
+    y0, y1 = y[j - 1], y[j]
+    dx = x1 - x0
+    dy = y1 - y0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dxi = np.where(dx == 0, dt(0), dt(1) / dx).astype(dtype)
+        dyi = np.where(dy == 0, dt(0), dt(1) / dy).astype(dtype)
+
+    if method == "linear":
+        f00 = f[i - 1, j - 1]
+        f01 = f[i - 1, j]
+        f10 = f[i, j - 1]
+        f11 = f[i, j]
+        tx = np.stack([x1 - xq, xq - x0])  # (2, P)
+        ty = np.stack([y1 - yq, yq - y0])
+        F = np.stack([np.stack([f00, f01]), np.stack([f10, f11])])  # (2,2,P,L)
+        acc = np.einsum("ijkl,ik,jk->kl", F, tx, ty).astype(dtype)
+        fq = ((dxi * dyi)[:, None] * acc).astype(dtype)
+    elif method == "cubic":
+        fx = approx_df(x, f, 0)
+        fy = approx_df(y, f, 1)
+        fxy = approx_df(y, fx, 1)
+        tx = (xq - x0) * dxi
+        ty = (yq - y0) * dyi
+        vals = []
+        for name, tab in (("f", f), ("fx", fx), ("fy", fy), ("fxy", fxy)):
+            for jj in (0, 1):
+                for ii in (0, 1):
+                    v = tab[i - 1 + ii, j - 1 + jj]  # (P, L)
+                    if "x" in name:
+                        v = dx[:, None] * v
+                    if "y" in name:
+                        v = dy[:, None] * v
+                    vals.append(v.astype(dtype))
+        F = np.stack(vals, axis=0)  # (16, P, L)
+        if hermite:
+            def hb(t):
+                t2 = t * t
+                t3 = t2 * t
+                return (
+                    (dt(2) * t3 - dt(3) * t2 + dt(1)),  # value at 0
+                    (dt(-2) * t3 + dt(3) * t2),  # value at 1
+                    (t3 - dt(2) * t2 + t),  # slope at 0
+                    (t3 - t2),  # slope at 1
+                )
+            hx = hb(tx)
+            hy = hb(ty)
+            fq = np.zeros(F.shape[1:], dtype=dtype)
+            k = 0
+            for (sx, sy) in ((0, 0), (2, 0), (0, 2), (2, 2)):  # f, fx, fy, fxy
+                for jj in (0, 1):
+                    for ii in (0, 1):
+                        w = hx[sx + ii] * hy[sy + jj]
+                        fq = fq + w[:, None] * F[k]
+                        k += 1
+            fq = fq.astype(dtype)
+        else:
+            coef = np.einsum("ab,bpl->apl", A_BICUBIC.astype(dtype), F).astype(dtype)  # (16,P,L)
+            coef = coef.reshape((4, 4) + coef.shape[1:], order="F")  # [i_pow_x, j_pow_y, P, L]
+            ttx = np.stack([np.ones_like(tx), tx, tx * tx, tx * tx * tx])  # (4, P)
+            tty = np.stack([np.ones_like(ty), ty, ty * ty, ty * ty * ty])
+            fq = np.einsum("jkil,ji,ki->il", coef, ttx, tty).astype(dtype)
+    else:
+        raise ValueError(f"unknown method {method}")
+
+    # extrap=0 (an int, not a bool): values outside [x0, x_last] are replaced by 0, boundaries
+    # inclusive (interpax _extrap: where(xq < x[0], lo, fq); where(xq > x[-1], hi, fq)).
+    lo = dt(extrap)
+    fq = np.where((xq < x[0])[:, None], lo, fq)
+    fq = np.where((xq > x[-1])[:, None], lo, fq)
+    fq = np.where((yq < y[0])[:, None], lo, fq)
+    fq = np.where((yq > y[-1])[:, None], lo, fq)
+    return fq.astype(dtype)
+
+
+def calculate_spectra(metallicity, age, ssp_metallicity, ssp_age, ssp_flux, method="cubic",
+                      dtype=np.float32, chunk_size=250000):
+    """rubix/core/ifu.py:95-118 (250k-particle chunks, concatenated).  1-D inputs (device shard 0)."""
+    out = []
+    n = len(metallicity)
+    for s in range(0, n, chunk_size):
+        e = min(s + chunk_size, n)
+        out.append(interp2d(metallicity[s:e], age[s:e], ssp_metallicity, ssp_age, ssp_flux,
+                            method=method, dtype=dtype))
+    if not out:
+        return np.zeros((0, np.asarray(ssp_flux).shape[-1]), dtype=dtype)
+    return np.concatenate(out, axis=0)
+
+
+# --------------------------------------------------------------------------------------
+# a2  mass scaling
+# --------------------------------------------------------------------------------------
+def scale_spectrum_by_mass(spectra, mass):
+    """rubix/core/ifu.py:152-154: ``spectra * mass[..., None]`` (a single multiply)."""
+    return spectra * np.asarray(mass, dtype=spectra.dtype)[..., None]
+
+
+# --------------------------------------------------------------------------------------
+# a3  Doppler shift
+# --------------------------------------------------------------------------------------
+def cosmological_doppler_shift(z, wavelength, dtype=np.float32):
+    """rubix/spectra/ifu.py:80: ``(1 + z) * wavelength`` (python float times f32 array -> f32)."""
+    return (np.dtype(dtype).type(1 + z) * np.asarray(wavelength, dtype=dtype)).astype(dtype)
+
+
+def doppler_factor(velocity_component, dtype=np.float32, c=SPEED_OF_LIGHT):
+    """rubix/spectra/ifu.py:190: ``exp(v / c)`` per particle."""
+    v = np.asarray(velocity_component, dtype=dtype)
+    return np.exp(v / np.dtype(dtype).type(c)).astype(dtype)
+
+
+def velocity_doppler_shift(wavelength, velocity, direction="z", dtype=np.float32):
+    """rubix/spectra/ifu.py:216-220: (P, L) shifted wavelengths."""
+    comp = {"x": 0, "y": 1, "z": 2}[direction]
+    d = doppler_factor(np.asarray(velocity)[:, comp], dtype=dtype)
+    return (np.asarray(wavelength, dtype=dtype)[None, :] * d[:, None]).astype(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# a4  flux-conserving resample
+# --------------------------------------------------------------------------------------
+def calculate_diff(vec):
+    """rubix/spectra/ifu.py:84-102: ``jnp.diff(vec, prepend=vec[0])`` -> [0, v1-v0, ...]."""
+    vec = np.asarray(vec)
+    return np.diff(vec, prepend=vec[..., :1], axis=-1)
+
+
+def jnp_interp(x, xp, fp):
+    """``jax.numpy.interp(x, xp, fp)`` (non-periodic, left/right = end values), 1-D ``xp``."""
+    x = np.asarray(x)
+    xp = np.asarray(xp)
+    fp = np.asarray(fp)
+    i = np.clip(np.searchsorted(xp, x, side="right"), 1, len(xp) - 1)
+    df = fp[i] - fp[i - 1]
+    dx = xp[i] - xp[i - 1]
+    delta = x - xp[i - 1]
+    eps = np.spacing(np.finfo(xp.dtype).eps)
+    dx0 = np.abs(dx) <= eps
+    with np.errstate(invalid="ignore", divide="ignore"):
+        f = np.where(dx0, fp[i - 1], fp[i - 1] + (delta / np.where(dx0, 1, dx)) * df)
+    f = np.where(x < xp[0], fp[0], f)
+    f = np.where(x > xp[-1], fp[-1], f)
+    return f.astype(fp.dtype)
+
+
+def resample_spectrum(initial_spectrum, initial_wavelength, target_wavelength):
+    """rubix/spectra/ifu.py:241-260 for one particle (dtype follows the inputs)."""
+    s = np.asarray(initial_spectrum)
+    lam = np.asarray(initial_wavelength)
+    t = np.asarray(target_wavelength)
+    dt = s.dtype.type
+    in_range = (lam >= t.min()) & (lam <= t.max())
+    wave_diff = calculate_diff(lam) * in_range
+    total_lum = np.sum(s * wave_diff, dtype=s.dtype)
+    p = jnp_interp(t, lam, s)
+    new_total = np.sum(p * calculate_diff(t), dtype=s.dtype)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        scale = total_lum / new_total
+    scale = np.nan_to_num(scale, nan=0.0)  # +-inf -> +-max finite, like jnp.nan_to_num
+    return (p * dt(scale)).astype(s.dtype)
+
+
+def resample_spectra(spectra, wavelengths, target_wavelength):
+    """vmapped :func:`resample_spectrum` (rubix/core/ifu.py:164-183)."""
+    spectra = np.asarray(spectra)
+    out = np.empty((spectra.shape[0], len(target_wavelength)), dtype=spectra.dtype)
+    for k in range(spectra.shape[0]):
+        out[k] = resample_spectrum(spectra[k], wavelengths[k], target_wavelength)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a5  cube
+# --------------------------------------------------------------------------------------
+def calculate_cube(spectra, spaxel_index, num_spaxels, acc_dtype=None):
+    """rubix/spectra/ifu.py:286-287: ``segment_sum`` (indices outside [0, S^2) are dropped, as XLA
+    scatter does) then C-order reshape to (S, S, W) => cube[y, x, w].  Adds run in particle order."""
+    spectra = np.asarray(spectra)
+    idx = np.asarray(spaxel_index)
+    acc_dtype = acc_dtype or spectra.dtype
+    cube = np.zeros((num_spaxels * num_spaxels, spectra.shape[-1]), dtype=acc_dtype)
+    ok = (idx >= 0) & (idx < num_spaxels * num_spaxels)
+    np.add.at(cube, idx[ok], spectra[ok].astype(acc_dtype))
+    return cube.reshape(num_spaxels, num_spaxels, spectra.shape[-1])
+
+
+# --------------------------------------------------------------------------------------
+# a6  PSF
+# --------------------------------------------------------------------------------------
+def gaussian_kernel_2d(m, n, sigma, dtype=np.float32):
+    """rubix/telescope/psf/kernels.py:26-31."""
+    x = np.arange(-((m - 1) / 2), ((m - 1) / 2) + 1).astype(dtype)
+    y = np.arange(-((n - 1) / 2), ((n - 1) / 2) + 1).astype(dtype)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    dt = np.dtype(dtype).type
+    values = np.exp(-(X**2 + Y**2) / dt(2 * sigma**2)).astype(dtype)
+    return (values / np.sum(values, dtype=dtype)).astype(dtype)
+
+
+def convolve2d_same(plane, kernel):
+    """``jax.scipy.signal.convolve2d(plane, kernel, mode="same")`` for plane >= kernel in both
+    dims: zero-padded true convolution, out[i,j] = sum_mn K[m,n] plane[i-m+(M-1)//2, j-n+(N-1)//2]."""
+    plane = np.asarray(plane)
+    kernel = np.asarray(kernel)
+    M, N = kernel.shape
+    H, Wd = plane.shape
+    cm, cn = (M - 1) // 2, (N - 1) // 2
+    pad = np.zeros((H + M - 1, Wd + N - 1), dtype=plane.dtype)
+    pad[M - 1 - cm:M - 1 - cm + H, N - 1 - cn:N - 1 - cn + Wd] = plane
+    out = np.zeros_like(plane)
+    for m in range(M):
+        for n in range(N):
+            # plane[i - m + cm] == pad[i - m + cm + (M-1-cm)] = pad[i + (M-1-m)]
+            out = out + kernel[m, n] * pad[M - 1 - m:M - 1 - m + H, N - 1 - n:N - 1 - n + Wd]
+    return out.astype(plane.dtype)
+
+
+def apply_psf(datacube, psf_kernel):
+    """rubix/telescope/psf/psf.py:56-57: convolve every wavelength slice."""
+    datacube = np.asarray(datacube)
+    kernel = np.asarray(psf_kernel).astype(datacube.dtype)
+    M, N = kernel.shape
+    H, Wd, L = datacube.shape
+    cm, cn = (M - 1) // 2, (N - 1) // 2
+    pad = np.zeros((H + M - 1, Wd + N - 1, L), dtype=datacube.dtype)
+    pad[M - 1 - cm:M - 1 - cm + H, N - 1 - cn:N - 1 - cn + Wd] = datacube
+    out = np.zeros_like(datacube)
+    for m in range(M):
+        for n in range(N):
+            out = out + kernel[m, n] * pad[M - 1 - m:M - 1 - m + H, N - 1 - n:N - 1 - n + Wd]
+    return out.astype(datacube.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# a7  LSF
+# --------------------------------------------------------------------------------------
+def lsf_kernel(sigma, wave_res, factor=12, dtype=np.float32):
+    """rubix/telescope/lsf/lsf.py:12-26."""
+    x = np.arange(-factor * wave_res, factor * wave_res + wave_res, wave_res).astype(dtype)
+    dt = np.dtype(dtype).type
+    res = np.exp(dt(-0.5) * (x**2) / dt(sigma**2)).astype(dtype)
+    return (res / np.sum(res, dtype=dtype)).astype(dtype)
+
+
+def apply_lsf(datacube, lsf_sigma, wave_resolution, extend_factor=12):
+    """rubix/telescope/lsf/lsf.py:59-65,96-105: full convolution along the last axis, then the
+    slice ``[extend_factor : W + K - 1 - extend_factor]``."""
+    datacube = np.asarray(datacube)
+    shape = datacube.shape
+    flat = datacube.reshape(-1, shape[-1])
+    k = lsf_kernel(lsf_sigma, wave_resolution, extend_factor, dtype=datacube.dtype)
+    K = len(k)
+    Wn = shape[-1]
+    full = np.zeros((flat.shape[0], Wn + K - 1), dtype=datacube.dtype)
+    for m in range(K):
+        full[:, m:m + Wn] += k[m] * flat
+    end = Wn + K - 1 - extend_factor
+    return full[:, extend_factor:end].reshape(shape[:-1] + (end - extend_factor,))
+
+
+# --------------------------------------------------------------------------------------
+# grids
+# --------------------------------------------------------------------------------------
+def calculate_wave_seq(wave_range, wave_res, dtype=np.float32):
+    """rubix/telescope/utils.py:53 (``jnp.arange`` in f32).  Pinned bit-exactly by the ``wave``
+    dataset of the reference's notebooks/data/dummy_datacube.h5 (tests/golden/muse_wave.npy)."""
+    return np.arange(wave_range[0], wave_range[1], wave_res, dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------
+# whole path
+# --------------------------------------------------------------------------------------
+def particles_to_cube(coords, velocity, mass, metallicity, age, spatial_bin_edges, num_spaxels,
+                      ssp_metallicity, ssp_age, ssp_wavelength, ssp_flux, target_wavelength,
+                      redshift, method="cubic", direction="z", dtype=np.float32,
+                      apply_filter=True, chunk=20000, acc_dtype=None):
+    """filter_particles -> spaxel_assignment -> calculate_spectra -> scale_spectrum_by_mass ->
+    doppler_shift_and_resampling -> calculate_datacube, in the reference's order
+    (rubix/config/pipeline_config.yml:1-45), chunked over particles only to bound memory.
+    All inputs are float32 arrays; ``dtype`` selects the arithmetic precision."""
+    coords = np.asarray(coords, dtype=np.float32)
+    edges = np.asarray(spatial_bin_edges, dtype=np.float32)
+    if apply_filter:
+        mass, metallicity, age, _ = filter_particles(coords, mass, metallicity, age, edges)
+    idx = square_spaxel_assignment(coords, edges)
+    t = np.asarray(target_wavelength, dtype=dtype)
+    lam_z = cosmological_doppler_shift(redshift, ssp_wavelength, dtype=dtype)
+    acc_dtype = acc_dtype or dtype
+    W = len(t)
+    cube = np.zeros((num_spaxels, num_spaxels, W), dtype=acc_dtype)
+    n = coords.shape[0]
+    for s in range(0, n, chunk):
+        e = min(s + chunk, n)
+        spec = calculate_spectra(metallicity[s:e], age[s:e], ssp_metallicity, ssp_age, ssp_flux,
+                                 method=method, dtype=dtype)
+        spec = scale_spectrum_by_mass(spec, np.asarray(mass[s:e], dtype=dtype))
+        lam = velocity_doppler_shift(lam_z, velocity[s:e], direction=direction, dtype=dtype)
+        res = resample_spectra(spec, lam, t)
+        cube += calculate_cube(res, idx[s:e], num_spaxels, acc_dtype=acc_dtype)
+    return cube, idx
+
+
+def full_pipeline(*args, psf_kernel=None, lsf_sigma=None, wave_res=None, **kw):
+    """particles_to_cube -> convolve_psf -> convolve_lsf (pipeline_config.yml:40-55)."""
+    cube, idx = particles_to_cube(*args, **kw)
+    if psf_kernel is not None:
+        cube = apply_psf(cube, np.asarray(psf_kernel).astype(cube.dtype))
+    if lsf_sigma is not None:
+        cube = apply_lsf(cube, lsf_sigma, wave_res)
+    return cube, idx

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def bc03():
+    """BC03lr SSP template as float32 (tests/golden/bc03lr_f32.npz, made by tools/make_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, "bc03lr_f32.npz"))
+    return {k: d[k] for k in d.files}
+
+
+@pytest.fixture(scope="session")
+def muse_wave():
+    return np.load(os.path.join(GOLDEN, "muse_wave.npy"))
+
+
+@pytest.fixture(scope="session")
+def tng_subset():
+    d = np.load(os.path.join(GOLDEN, "tng50_subset.npz"))
+    return {k: d[k] for k in d.files}
