@@ -1,0 +1,148 @@
+/*
+ * rubix_b200 -- C ABI of the B200-native particle -> IFU-datacube path.
+ *
+ * This is the drop-in boundary for the hot path of AstroAI-Lab/rubix (reference @ dbb4487; all
+ * file:line citations below are relative to the reference tree).  rubix itself is pure Python/JAX
+ * and has no FFI; the entry points below are what a `jax.ffi.ffi_call` (or ctypes / cffi) binding
+ * for this path binds -- see INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - Every function returns RBX_OK (0) or a negative rbx_status; rbx_last_error() gives the text
+ *     (thread-local).
+ *   - Pointers named d_* are DEVICE pointers owned by the caller (JAX / torch allocator); h_* are
+ *     HOST pointers.  Outputs are pre-allocated by the caller.  The only hidden allocations are
+ *     inside rbx_plan_create (per-config tables, a few MB) and the rbx_*_host convenience calls.
+ *   - All floating-point data is float32 and all indices are int32, like the reference (JAX x64 off:
+ *     rubix/spectra/ssp/grid.py:327, rubix/core/data.py:545, rubix/telescope/utils.py:151).
+ *   - Launches are asynchronous on the given stream; nothing here calls cudaDeviceSynchronize.
+ *     Functions are re-entrant per (plan, stream, workspace).
+ *   - `stream` is a cudaStream_t passed as void* so that this header needs no CUDA include.
+ */
+#ifndef RUBIX_B200_H
+#define RUBIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RBX_OK = 0,
+  RBX_ERR_INVALID_ARGUMENT = -1,
+  RBX_ERR_CUDA = -2,
+  RBX_ERR_WORKSPACE_TOO_SMALL = -3,
+  RBX_ERR_UNSUPPORTED = -4, /* configuration outside the fused kernel's limits: use the stage calls */
+  RBX_ERR_NO_DEVICE = -5
+} rbx_status;
+
+/* rubix/core/ssp.py:57-62: `ssp.method`; rubix's default when the key is absent is "cubic". */
+typedef enum { RBX_METHOD_LINEAR = 0, RBX_METHOD_CUBIC = 1 } rbx_method;
+
+typedef struct rbx_plan rbx_plan; /* opaque, device-resident per-configuration tables */
+
+const char *rbx_last_error(void);
+int rbx_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t rbx_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plan: everything that depends only on the configuration (SSP template, telescope wavelength
+ * grid, redshift, interpolation method, Doppler direction).
+ * Replaces the host-side setup in get_lookup_interpolation (rubix/core/ssp.py:38-65),
+ * SSPGrid.get_lookup_interpolation (rubix/spectra/ssp/grid.py:61-124: binds x=metallicity, y=age,
+ * f=flux, extrap=0) and get_doppler_shift_and_resampling's closure state
+ * (rubix/core/ifu.py:248-266: (1+z)*ssp.wavelength, telescope.wave_seq, velocity direction).
+ *   h_flux is (nz, na, L) C-order; h_target_wave is the telescope wave_seq (W,), increasing.
+ *   vel_component: 0/1/2 for rubix_config ifu.doppler.velocity_direction "x"/"y"/"z".
+ * ------------------------------------------------------------------------------------------- */
+int rbx_plan_create(rbx_plan **plan, const float *h_metallicity, int nz, const float *h_age, int na,
+                    const float *h_wavelength, int L, const float *h_flux,
+                    const float *h_target_wave, int W, double redshift, int method,
+                    int vel_component, void *stream);
+int rbx_plan_destroy(rbx_plan *plan);
+int rbx_plan_dims(const rbx_plan *plan, int *nz, int *na, int *L, int *W);
+
+/* ---------------------------------------------------------------------------------------------
+ * a0  square_spaxel_assignment (rubix/telescope/utils.py:138-151) and
+ *     mask_particles_outside_aperture (:170-174).  d_coords is (n, 3) row-major; d_edges (n_edges,).
+ *     d_pixel: int32 (n,), x + nbins*y, bit-exact with the reference.  d_mask: uint8 (n,) or NULL.
+ * ------------------------------------------------------------------------------------------- */
+int rbx_spaxel_assign(const float *d_coords, int64_t n, const float *d_edges, int n_edges,
+                      int32_t *d_pixel, uint8_t *d_mask, void *stream);
+/* get_filter_particles (rubix/core/telescope.py:155-174): where(mask, x, 0) on mass, metallicity,
+ * age in place (any may be NULL); coords and velocity are left alone, as in the reference. */
+int rbx_filter_particles(const float *d_coords, int64_t n, const float *d_edges, int n_edges,
+                         float *d_mass, float *d_metallicity, float *d_age, uint8_t *d_mask,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage calls: one per reference stage, materialising the same intermediates as the reference.
+ * Used by the stepwise (notebook) path and for stage-level parity.
+ * ------------------------------------------------------------------------------------------- */
+/* a1 calculate_spectra (rubix/core/ifu.py:95-118): d_spectra (n, L) = interp2d(Z, age). */
+int rbx_ssp_lookup(const rbx_plan *plan, const float *d_metallicity, const float *d_age, int64_t n,
+                   float *d_spectra, void *stream);
+/* a2 scale_spectrum_by_mass (rubix/core/ifu.py:152-154): d_out[p,l] = d_spectra[p,l] * d_mass[p]
+ * (d_out may alias d_spectra). */
+int rbx_scale_by_mass(const float *d_spectra, const float *d_mass, int64_t n, int L, float *d_out,
+                      void *stream);
+/* a3+a4 doppler_shift_and_resampling (rubix/core/ifu.py:269-293, rubix/spectra/ifu.py:190,241-260):
+ * d_velocity (n,3); d_spectra (n, L) -> d_out (n, W). */
+int rbx_doppler_resample(const rbx_plan *plan, const float *d_spectra, const float *d_velocity,
+                         int64_t n, float *d_out, void *stream);
+/* a5 calculate_cube (rubix/spectra/ifu.py:286-287): d_cube (num_segments, W) += segment_sum of
+ * d_spectra (n, W) by d_pixel; indices outside [0, num_segments) are dropped.  The caller zeroes
+ * d_cube (or passes zero_first = 1). */
+int rbx_segment_sum(const float *d_spectra, const int32_t *d_pixel, int64_t n, int W,
+                    int num_segments, float *d_cube, int zero_first, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused a1..a5: particles -> cube without materialising (n, L) or (n, W).
+ *   d_velocity (n,3), d_mass/d_metallicity/d_age (n,), d_pixel (n,) from rbx_spaxel_assign.
+ *   d_cube (num_spaxels^2, W) is overwritten.  Workspace: rbx_build_cube_workspace_bytes().
+ * Particles with mass == 0, (Z, age) outside the SSP grid or pixel outside [0, S^2) contribute
+ * exactly 0, as in the reference (extrap=0 -> zero spectrum -> nan_to_num(0/0) = 0; segment_sum
+ * drops out-of-range ids).
+ * ------------------------------------------------------------------------------------------- */
+size_t rbx_build_cube_workspace_bytes(const rbx_plan *plan, int64_t n, int num_spaxels);
+int rbx_build_cube(const rbx_plan *plan, const float *d_velocity, const float *d_mass,
+                   const float *d_metallicity, const float *d_age, const int32_t *d_pixel, int64_t n,
+                   int num_spaxels, float *d_cube, void *d_workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6 apply_psf (rubix/telescope/psf/psf.py:56-57): per wavelength slice
+ *    convolve2d(slice, kernel, mode="same"); d_kernel is (M, N) row-major on the device.
+ * a7 apply_lsf (rubix/telescope/lsf/lsf.py:59-65,96-105): convolve(full) along lambda then the
+ *    slice [ext : W+K-1-ext]; d_kernel (K,) on the device; ext = extend_factor (12).
+ * rbx_psf_lsf does both in one pass (d_out must not alias d_in).
+ * d_in / d_out are (ny, nx, W), lambda fastest.
+ * ------------------------------------------------------------------------------------------- */
+int rbx_convolve_psf(const float *d_in, float *d_out, int ny, int nx, int W, const float *d_kernel,
+                     int M, int N, void *stream);
+int rbx_convolve_lsf(const float *d_in, float *d_out, int64_t rows, int W, const float *d_kernel,
+                     int K, int ext, void *stream);
+int rbx_psf_lsf(const float *d_in, float *d_out, int ny, int nx, int W, const float *d_psf, int M,
+                int N, const float *d_lsf, int K, int ext, void *stream);
+/* gaussian_kernel_2d (rubix/telescope/psf/kernels.py:26-31) and _get_kernel
+ * (rubix/telescope/lsf/lsf.py:12-26) evaluated in float32 on the device. */
+int rbx_gaussian_psf_kernel(int m, int n, float sigma, float *d_kernel, void *stream);
+int rbx_gaussian_lsf_kernel(float sigma, float wave_res, int factor, float *d_kernel, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer convenience call: the whole path (filter -> spaxel -> fused cube -> PSF -> LSF) for
+ * callers that hold numpy / host arrays.  Copies inputs H2D, runs the kernels, copies the cube
+ * back; h_cube is (num_spaxels, num_spaxels, W).  h_psf (M,N) / h_lsf (K,) may be NULL to skip.
+ * ------------------------------------------------------------------------------------------- */
+int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity,
+                      const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                      const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
+                      const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                      float *h_cube, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUBIX_B200_H */

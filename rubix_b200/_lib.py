@@ -1,0 +1,100 @@
+"""ctypes binding of ``librubix_b200.so`` (the C ABI declared in include/rubix_b200.h).
+
+The library is the product: if it is missing or cannot be loaded this module raises, it never
+falls back to a CPU or PyTorch implementation.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "librubix_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+EXPORTED = [
+    "rbx_last_error", "rbx_version", "rbx_launch_count",
+    "rbx_plan_create", "rbx_plan_destroy", "rbx_plan_dims",
+    "rbx_spaxel_assign", "rbx_filter_particles",
+    "rbx_ssp_lookup", "rbx_scale_by_mass", "rbx_doppler_resample", "rbx_segment_sum",
+    "rbx_build_cube_workspace_bytes", "rbx_build_cube",
+    "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf",
+    "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
+    "rbx_pipeline_host",
+]
+
+RBX_OK = 0
+RBX_ERR_UNSUPPORTED = -4
+
+_lib = None
+
+
+class RubixB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rubix_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building librubix_b200.so failed")
+    return SO_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C rubix_b200/csrc`). There is no CPU fallback."
+        )
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+    L.rbx_last_error.restype = C.c_char_p
+    L.rbx_last_error.argtypes = []
+    L.rbx_version.restype = i32
+    L.rbx_launch_count.restype = i64
+    sigs = {
+        "rbx_plan_create": [C.POINTER(vp), vp, i32, vp, i32, vp, i32, vp, vp, i32, f64, i32, i32, vp],
+        "rbx_plan_destroy": [vp],
+        "rbx_plan_dims": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        "rbx_spaxel_assign": [vp, i64, vp, i32, vp, vp, vp],
+        "rbx_filter_particles": [vp, i64, vp, i32, vp, vp, vp, vp, vp],
+        "rbx_ssp_lookup": [vp, vp, vp, i64, vp, vp],
+        "rbx_scale_by_mass": [vp, vp, i64, i32, vp, vp],
+        "rbx_doppler_resample": [vp, vp, vp, i64, vp, vp],
+        "rbx_segment_sum": [vp, vp, i64, i32, i32, vp, i32, vp],
+        "rbx_build_cube": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp],
+        "rbx_convolve_psf": [vp, vp, i32, i32, i32, vp, i32, i32, vp],
+        "rbx_convolve_lsf": [vp, vp, i64, i32, vp, i32, i32, vp],
+        "rbx_psf_lsf": [vp, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp],
+        "rbx_gaussian_psf_kernel": [i32, i32, f32, vp, vp],
+        "rbx_gaussian_lsf_kernel": [f32, f32, i32, vp, vp],
+        "rbx_pipeline_host": [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = i32
+    L.rbx_build_cube_workspace_bytes.argtypes = [vp, i64, i32]
+    L.rbx_build_cube_workspace_bytes.restype = sz
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != RBX_OK:
+        raise RubixB200Error(code, lib().rbx_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    return int(lib().rbx_launch_count())

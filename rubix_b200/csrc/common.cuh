@@ -1,0 +1,158 @@
+// Shared declarations for the rubix_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "rubix_b200.h"
+
+namespace rbx {
+
+void set_error(const std::string &msg);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define RBX_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      rbx::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+      return RBX_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define RBX_REQUIRE(cond, msg)                                                              \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      rbx::set_error(msg);                                                                  \
+      return RBX_ERR_INVALID_ARGUMENT;                                                      \
+    }                                                                                       \
+  } while (0)
+
+#define RBX_LAUNCH_OK()                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      rbx::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));              \
+      return RBX_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+constexpr int kChunk = 16;           // targets per chunk in the fused kernel
+constexpr int kFusedThreads = 256;   // one thread per chunk -> W <= 4096
+constexpr int kMaxWindow = 512;      // SSP knots the fused kernel can hold per particle
+constexpr float kSpeedOfLight = 299792.458f;  // rubix/config/rubix_config.yml:8
+
+// Device view of a plan (passed by value to kernels).
+struct PlanView {
+  int nz, na, L, Lp, W, method, vel_comp, nchunks;
+  float tmin, tmax;
+  const float *zgrid, *agrid;  // SSP metallicity / age axes
+  const float *tab[4];         // f, fx, fy, fxy: (nz*na, Lp) float32, rows 16-byte aligned
+  const float *lamz;           // (L)  (1+z)*wavelength                       rubix/spectra/ifu.py:80
+  const float *rdl;            // (L)  1/(lamz[j+1]-lamz[j]); 0 for the last knot or zero width
+  const float *t;              // (W)  telescope wave_seq
+  const float *dt;             // (W)  diff0(t): [0, t1-t0, ...]                rubix/spectra/ifu.py:84-102
+  const float *tau;            // (W)  t[w] - tc[w / kChunk]   (exact in f32)
+  const float2 *suf;           // (W)  suffix sums inside the chunk: (sum dt, sum tau*dt) over k' >= k
+  const float *tc;             // (nchunks) chunk reference wavelength
+};
+
+}  // namespace rbx
+
+struct rbx_plan {
+  rbx::PlanView v;
+  std::vector<void *> allocs;
+  std::vector<float> h_lamz, h_t;
+  int device;
+};
+
+namespace rbx {
+
+// ---- small device helpers ---------------------------------------------------------------------
+// searchsorted(a, v, side='right') on a sorted array: number of elements <= v (NaN v -> n, like numpy/XLA
+// where NaN sorts last).
+__device__ __forceinline__ int ss_right(const float *__restrict__ a, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (!(a[mid] > v)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// nan_to_num(x, nan=0): NaN -> 0, +-inf -> +-FLT_MAX   (rubix/spectra/ifu.py:253-255)
+__device__ __forceinline__ float nan_to_num0(float x) {
+  if (x != x) return 0.f;
+  if (isinf(x)) return x > 0 ? 3.4028234664e38f : -3.4028234664e38f;
+  return x;
+}
+
+// Interpolation weights of one (Z, age) query: up to 16 (row offset, weight) pairs such that
+// spectrum[l] = sum_q w[q] * tab[tq[q]][row[q] * Lp + l].   Restates interpax.interp2d
+// (method linear / cubic, extrap=0) as bound at rubix/spectra/ssp/grid.py:113-120.
+// Returns the number of terms (0 when the query is outside the grid -> zero spectrum).
+struct SspTerms {
+  int n;
+  int row[16];   // row index iz*na+ia
+  int tabid[16]; // which table
+  float w[16];
+};
+
+__device__ __forceinline__ void ssp_cell(const PlanView &p, float zq, float aq, int &i, int &j, bool &inside) {
+  inside = (zq >= p.zgrid[0]) && (zq <= p.zgrid[p.nz - 1]) && (aq >= p.agrid[0]) && (aq <= p.agrid[p.na - 1]);
+  i = min(max(ss_right(p.zgrid, p.nz, zq), 1), p.nz - 1);
+  j = min(max(ss_right(p.agrid, p.na, aq), 1), p.na - 1);
+}
+
+__device__ inline void ssp_terms(const PlanView &p, float zq, float aq, float mass, SspTerms &o) {
+  int i, j;
+  bool inside;
+  ssp_cell(p, zq, aq, i, j, inside);
+  if (!inside) { o.n = 0; return; }
+  float x0 = p.zgrid[i - 1], x1 = p.zgrid[i], y0 = p.agrid[j - 1], y1 = p.agrid[j];
+  float dx = x1 - x0, dy = y1 - y0;
+  float dxi = dx == 0.f ? 0.f : 1.f / dx, dyi = dy == 0.f ? 0.f : 1.f / dy;
+  if (p.method == RBX_METHOD_LINEAR) {
+    float tx0 = x1 - zq, tx1 = zq - x0, ty0 = y1 - aq, ty1 = aq - y0, sc = dxi * dyi * mass;
+    o.n = 4;
+    o.row[0] = (i - 1) * p.na + (j - 1); o.w[0] = sc * (tx0 * ty0);
+    o.row[1] = (i - 1) * p.na + j;       o.w[1] = sc * (tx0 * ty1);
+    o.row[2] = i * p.na + (j - 1);       o.w[2] = sc * (tx1 * ty0);
+    o.row[3] = i * p.na + j;             o.w[3] = sc * (tx1 * ty1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.tabid[q] = 0;
+    return;
+  }
+  float tx = (zq - x0) * dxi, ty = (aq - y0) * dyi;
+  float tx2 = tx * tx, tx3 = tx2 * tx, ty2 = ty * ty, ty3 = ty2 * ty;
+  float hx[4] = {2.f * tx3 - 3.f * tx2 + 1.f, -2.f * tx3 + 3.f * tx2, tx3 - 2.f * tx2 + tx, tx3 - tx2};
+  float hy[4] = {2.f * ty3 - 3.f * ty2 + 1.f, -2.f * ty3 + 3.f * ty2, ty3 - 2.f * ty2 + ty, ty3 - ty2};
+  o.n = 16;
+  int k = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int sx = (t & 1) ? 2 : 0, sy = (t & 2) ? 2 : 0;
+    float scale = ((t & 1) ? dx : 1.f) * ((t & 2) ? dy : 1.f) * mass;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii) {
+        o.w[k] = hx[sx + ii] * hy[sy + jj] * scale;
+        o.row[k] = (i - 1 + ii) * p.na + (j - 1 + jj);
+        o.tabid[k] = t;
+        ++k;
+      }
+  }
+}
+
+}  // namespace rbx

@@ -1,0 +1,604 @@
+// Fused a1..a5: particles -> (S*S, W) cube without materialising (n, L) or (n, W).
+//
+// Pipeline (all on the caller's stream, no host synchronisation):
+//   prep_kernel      validity, template cell, sort key = spaxel * ncell + cell, per-spaxel histogram,
+//                    min/max Doppler factor
+//   cub radix sort   (key, particle index) pairs -- stable, so the summation order is deterministic
+//   segment_kernel   one block: segment starts, work items (segments split into <= psub particles),
+//                    SSP knot window for the observed Doppler range
+//   gather_kernel    sorted per-particle records {d, 1/d, template row, interpolation weights * mass}
+//   fused_cube_kernel persistent CTAs pull work items; per item the spaxel's spectrum is accumulated
+//                    in registers + shared memory (no global atomics) and written once
+//   reduce_partials_kernel  spaxels that were split over several items: fixed-order sum of partial rows
+//
+// Algorithm of fused_cube_kernel.  For one particle the reference evaluates, for every telescope
+// channel t_w,  p_w = jnp.interp(t_w, lam' = lam_z * d, s)  and then rescales by total/new
+// (rubix/spectra/ifu.py:241-260).  p is piecewise linear in t with break points at the Doppler-shifted
+// SSP knots, so instead of touching all W channels per particle we accumulate, per chunk of 16
+// channels, the line that is valid at the chunk's first channel (base: value at the chunk reference
+// wavelength + slope) and, for every SSP knot that falls inside the chunk, the change of line at the
+// first channel behind the knot (step).  Lines are continuous at knots, so the step is
+// (dA, dB) = (-(m_j - m_{j-1}) * tau_x, m_j - m_{j-1}) in chunk-local coordinates tau = t - tc.
+// The spaxel spectrum is recovered once per work item by a 16-long prefix sum of the steps.
+// Work per particle is O(#knots in band + W/16) instead of O(W * log L); every quantity that is
+// summed is bounded by the spectrum itself (chunk-local coordinates), so float32 accumulation is as
+// benign as the reference's.  sum_w p_w * dt_w (the "new total") comes from the same lines through
+// per-chunk suffix tables of dt and tau*dt.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace rbx {
+
+constexpr int NB = 4;  // particles per batch (between block barriers)
+constexpr int kStepPitch = kChunk + 1;
+constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
+
+struct Item { int start, count, spaxel, slot; };
+
+enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_COUNT };
+
+struct FusedWs {
+  uint32_t *keys_in, *keys_out, *idx_in, *idx_out;
+  float *rec;       // (n, rec_stride) sorted particle records
+  int *counts;      // (nseg + 1)
+  int *seg_start;   // (nseg + 1)
+  int *item_start;  // (nseg + 1)
+  int *ctrl;        // C_COUNT
+  Item *items;      // (max_items)
+  float *partials;  // (max_split, Wp)
+  void *cub_temp;
+  size_t cub_bytes;
+  int rec_stride, max_items, max_split, Wp, psub, end_bit, ncell;
+};
+
+__device__ __forceinline__ int rec_stride_for(int method) { return method == RBX_METHOD_LINEAR ? 8 : 20; }
+
+// ---- prep ---------------------------------------------------------------------------------------
+__global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const float *__restrict__ mass,
+                            const float *__restrict__ met, const float *__restrict__ age,
+                            const int32_t *__restrict__ pixel, int n, int nseg, int ncell,
+                            uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
+                            int *__restrict__ ctrl) {
+  float dmin = 3.0e38f, dmax = 0.f;
+  int nvalid = 0;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    int i, j;
+    bool inside;
+    ssp_cell(p, met[q], age[q], i, j, inside);
+    int px = pixel[q];
+    float d = expf(vel[3 * (size_t)q + p.vel_comp] / kSpeedOfLight);
+    bool valid = inside && (mass[q] != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
+    uint32_t key = (uint32_t)nseg * (uint32_t)ncell;  // invalid: sorts behind every valid key
+    if (valid) {
+      uint32_t cell = (uint32_t)((i - 1) * (p.na - 1) + (j - 1));
+      key = (uint32_t)px * (uint32_t)ncell + (ncell > 1 ? cell : 0u);
+      atomicAdd(counts + px, 1);
+      dmin = fminf(dmin, d);
+      dmax = fmaxf(dmax, d);
+      ++nvalid;
+    }
+    keys[q] = key;
+    idx[q] = (uint32_t)q;
+  }
+  // positive floats order like their bit patterns
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+  }
+  if ((threadIdx.x & 31) == 0 && nvalid > 0) {
+    atomicMin(ctrl + C_DMIN, __float_as_int(dmin));
+    atomicMax(ctrl + C_DMAX, __float_as_int(dmax));
+    atomicAdd(ctrl + C_NVALID, nvalid);
+  }
+}
+
+// ---- segments / items / knot window (one block) -----------------------------------------------
+__global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
+                               const int *__restrict__ counts, int *__restrict__ seg_start,
+                               int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl) {
+  __shared__ int s_a[1024], s_b[1024], s_c[1024];
+  const int T = blockDim.x, t = threadIdx.x;
+  const int per = (nseg + T - 1) / T;
+  const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
+  int ca = 0, cb = 0, cc = 0;  // particles, items, split rows
+  for (int s = lo; s < hi; ++s) {
+    int c = counts[s];
+    int ni = (c + psub - 1) / psub;
+    ca += c; cb += ni; cc += ni > 1 ? ni : 0;
+  }
+  s_a[t] = ca; s_b[t] = cb; s_c[t] = cc;
+  __syncthreads();
+  if (t == 0) {  // tiny serial exclusive scan over <= 1024 partials
+    int ra = 0, rb = 0, rc = 0;
+    for (int k = 0; k < T; ++k) {
+      int a = s_a[k], b = s_b[k], c = s_c[k];
+      s_a[k] = ra; s_b[k] = rb; s_c[k] = rc;
+      ra += a; rb += b; rc += c;
+    }
+    int err = 0;
+    if (rb > max_items || rc > max_split) err = 1;
+    // SSP knot window for the Doppler factors actually present
+    int ja = 0, jb = 0;
+    if (ra > 0) {
+      float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+      float lo_l = p.tmin / dmax, hi_l = p.tmax / dmin;
+      int a = 0;
+      while (a < p.L && p.lamz[a] < lo_l) ++a;  // first knot that can reach the band
+      int b = a;
+      while (b < p.L && p.lamz[b] <= hi_l) ++b;  // one past the last knot that can be in the band
+      ja = max(0, a - 3);
+      jb = min(p.L, b + 3);
+      if (jb - ja > kMaxWindow) err = 2;
+    }
+    ctrl[C_NITEMS] = err ? 0 : rb;
+    ctrl[C_JA] = ja;
+    ctrl[C_JB] = jb;
+    ctrl[C_ERROR] = err;
+    ctrl[C_WORK] = 0;
+    ctrl[C_NSPLIT] = rc;
+    seg_start[nseg] = ra;
+    item_start[nseg] = rb;
+  }
+  __syncthreads();
+  int ra = s_a[t], rb = s_b[t], rc = s_c[t];
+  const bool err = ctrl[C_ERROR] != 0;
+  for (int s = lo; s < hi; ++s) {
+    int c = counts[s];
+    int ni = (c + psub - 1) / psub;
+    seg_start[s] = ra;
+    item_start[s] = rb;
+    if (!err) {
+      for (int k = 0; k < ni; ++k) {
+        Item it;
+        it.start = ra + k * psub;
+        it.count = min(psub, c - k * psub);
+        it.spaxel = s;
+        it.slot = ni > 1 ? rc + k : -1;
+        items[rb + k] = it;
+      }
+    }
+    ra += c; rb += ni; rc += ni > 1 ? ni : 0;
+  }
+}
+
+// ---- gather sorted records ----------------------------------------------------------------------
+// record (floats): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=unused  [4..]=weights * mass
+__global__ void gather_kernel(PlanView p, const uint32_t *__restrict__ idx_sorted, const int *__restrict__ ctrl,
+                              const float *__restrict__ vel, const float *__restrict__ mass,
+                              const float *__restrict__ met, const float *__restrict__ age,
+                              float *__restrict__ rec, int stride) {
+  const int nvalid = ctrl[C_NVALID];
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nvalid; q += gridDim.x * blockDim.x) {
+    uint32_t src = idx_sorted[q];
+    SspTerms tm;
+    ssp_terms(p, met[src], age[src], mass[src], tm);
+    float d = expf(vel[3 * (size_t)src + p.vel_comp] / kSpeedOfLight);
+    float *r = rec + (size_t)q * stride;
+    r[0] = d;
+    r[1] = 1.f / d;
+    r[2] = __int_as_float(tm.n ? tm.row[0] : 0);
+    r[3] = 0.f;
+    const int nw = p.method == RBX_METHOD_LINEAR ? 4 : 16;
+    for (int k = 0; k < nw; ++k) r[4 + k] = tm.n ? tm.w[k] : 0.f;
+  }
+}
+
+// ---- the fused kernel -----------------------------------------------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
+                  float *__restrict__ cube, float *__restrict__ partials, int Wp) {
+  constexpr int NW = METHOD == RBX_METHOD_LINEAR ? 4 : 16;
+  constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;
+  constexpr int NWARP = kFusedThreads / 32;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int ja = ctrl[C_JA], jb = ctrl[C_JB];
+  const int KW = jb - ja;      // real knots in the window, u = j - ja + 1 in [1, KW]
+  const int KP = KW + 2;       // + one sentinel each side
+  float *s_lamz = reinterpret_cast<float *>(smraw);
+  float *s_rdl = s_lamz + KP;
+  float *s_S = s_rdl + KP;                         // [2][NB][KP]
+  float2 *s_step = reinterpret_cast<float2 *>(s_S + 2 * NB * KP + ((2 * NB * KP + 2 * KP) & 1));  // 8B aligned
+  float *s_rec = reinterpret_cast<float *>(s_step + kFusedThreads * kStepPitch);  // [2][NB][RS]
+  float *s_red = s_rec + 2 * NB * RS;              // [2][NWARP][NB]  (tot, new)
+  float *s_scale = s_red + 2 * NWARP * NB;         // [NB]
+  __shared__ int s_item;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_items = ctrl[C_NITEMS];
+
+  // window tables (+ sentinels: knots at -inf / +inf carrying the end values, slope 0 beyond)
+  for (int u = tid; u < KP; u += kFusedThreads) {
+    float lz, rd;
+    if (u == 0) { lz = -1.0e30f; rd = 0.f; }
+    else if (u == KP - 1) { lz = 1.0e30f; rd = 0.f; }
+    else { lz = p.lamz[ja + u - 1]; rd = (u == KP - 2) ? ((jb == p.L) ? 0.f : p.rdl[jb - 1]) : p.rdl[ja + u - 1]; }
+    s_lamz[u] = lz;
+    s_rdl[u] = rd;
+  }
+  for (int q = tid; q < kFusedThreads * kStepPitch; q += kFusedThreads) s_step[q] = make_float2(0.f, 0.f);
+
+  // per-thread chunk constants
+  const int c = tid;
+  const bool has_chunk = c < p.nchunks;
+  const int w0 = c * kChunk;
+  const int nk = has_chunk ? min(kChunk, p.W - w0) : 0;
+  float tcc = 0.f, tfirst = 0.f, tlast = 0.f, rdtc = 0.f, D0 = 0.f, T0 = 0.f;
+  if (has_chunk) {
+    tcc = p.tc[c];
+    tfirst = p.tau[w0];
+    tlast = p.tau[w0 + nk - 1];
+    rdtc = nk > 1 ? (float)(nk - 1) / (tlast - tfirst) : 0.f;
+    float2 s0 = p.suf[w0];
+    D0 = s0.x; T0 = s0.y;
+  }
+  int ug = 1;  // running guess of the knot at/below the chunk's first channel
+  float2 *my_step = s_step + (size_t)c * kStepPitch;
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(ctrl + C_WORK, 1);
+    __syncthreads();
+    const int item_id = s_item;
+    if (item_id >= n_items) break;
+    const Item it = items[item_id];
+    float baseA = 0.f, baseB = 0.f;
+    const int nbatch = (it.count + NB - 1) / NB;
+
+    // records of batch 0
+    for (int q = tid; q < NB * RS; q += kFusedThreads) {
+      int b = q / RS;
+      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q % RS)] : 0.f;
+    }
+    __syncthreads();
+
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const int buf = bt & 1;
+      const float *r_cur = s_rec + buf * NB * RS;
+      float *S_cur = s_S + buf * NB * KP;
+      // prefetch the next batch's records
+      if (bt + 1 < nbatch) {
+        for (int q = tid; q < NB * RS; q += kFusedThreads) {
+          int b = (bt + 1) * NB + q / RS;
+          s_rec[(buf ^ 1) * NB * RS + q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q % RS)] : 0.f;
+        }
+      }
+
+      // ---- phase K: mass-weighted SSP spectrum at the window knots; "total" partial sums -------
+      float tot[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tot[b] = 0.f;
+      for (int u = tid + 1; u <= KW; u += kFusedThreads) {
+        const int j = ja + u - 1;
+        const float lz = s_lamz[u], lzm = s_lamz[u - 1];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float *rb = r_cur + b * RS;
+          const int row = __float_as_int(rb[2]);
+          float S = 0.f;
+          if (METHOD == RBX_METHOD_LINEAR) {
+            const float *f = p.tab[0] + (size_t)row * p.Lp + j;
+            S = rb[4] * __ldg(f);
+            S = fmaf(rb[5], __ldg(f + p.Lp), S);
+            S = fmaf(rb[6], __ldg(f + (size_t)p.na * p.Lp), S);
+            S = fmaf(rb[7], __ldg(f + (size_t)(p.na + 1) * p.Lp), S);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float *f = p.tab[t] + (size_t)row * p.Lp + j;
+              // weight order (jj, ii) = (0,0),(0,1),(1,0),(1,1): rows +0, +na, +1, +na+1
+              S = fmaf(rb[4 + 4 * t + 0], __ldg(f), S);
+              S = fmaf(rb[4 + 4 * t + 1], __ldg(f + (size_t)p.na * p.Lp), S);
+              S = fmaf(rb[4 + 4 * t + 2], __ldg(f + p.Lp), S);
+              S = fmaf(rb[4 + 4 * t + 3], __ldg(f + (size_t)(p.na + 1) * p.Lp), S);
+            }
+          }
+          S_cur[b * KP + u] = S;
+          if (u == 1) S_cur[b * KP] = S;
+          if (u == KW) S_cur[b * KP + KW + 1] = S;
+          // total luminosity in band: sum s_j * (x_j - x_{j-1}) * [tmin <= x_j <= tmax]
+          const float d = rb[0];
+          const float x = __fmul_rn(lz, d);
+          if (j > 0 && x >= p.tmin && x <= p.tmax) tot[b] = fmaf(S, x - __fmul_rn(lzm, d), tot[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float v = warp_sum(tot[b]);
+        if (lane == 0) s_red[wid * NB + b] = v;
+      }
+      __syncthreads();  // (A) S_cur, tot partials visible
+
+      // ---- phase C1: lines of this particle on my chunk; "new total" partial sums -------------
+      float A0[NB], B0[NB], dA1[NB], dB1[NB];
+      int k1[NB], nbp[NB], u0[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float np = 0.f;
+        A0[b] = B0[b] = dA1[b] = dB1[b] = 0.f;
+        k1[b] = 0; nbp[b] = 0; u0[b] = 0;
+        if (has_chunk && bt * NB + b < it.count) {
+          const float *rb = r_cur + b * RS;
+          const float d = rb[0], rd = rb[1];
+          const float *S = S_cur + b * KP;
+          // knot at or below the first channel (chunk-local: tau_x = lam_z * d - tc, one rounding)
+          while (fmaf(s_lamz[ug + 1], d, -tcc) <= tfirst) ++ug;
+          while (fmaf(s_lamz[ug], d, -tcc) > tfirst) --ug;
+          u0[b] = ug;
+          const float Sa = S[ug];
+          const float m0 = (S[ug + 1] - Sa) * s_rdl[ug] * rd;
+          const float tx0 = fmaf(s_lamz[ug], d, -tcc);
+          A0[b] = fmaf(-m0, tx0, Sa);  // value of the line at tau = 0
+          B0[b] = m0;
+          np = fmaf(A0[b], D0, m0 * T0);
+          float mprev = m0;
+          for (int u = ug + 1;; ++u) {
+            const float tx = fmaf(s_lamz[u], d, -tcc);
+            if (!(tx <= tlast)) break;
+            int k = (int)ceilf((tx - tfirst) * rdtc);
+            k = min(max(k, 0), nk - 1);
+            while (k > 0 && p.tau[w0 + k - 1] >= tx) --k;
+            while (k < nk - 1 && p.tau[w0 + k] < tx) ++k;
+            const float m = (S[u + 1] - S[u]) * s_rdl[u] * rd;
+            const float dB = m - mprev;
+            const float dA = -dB * tx;
+            const float2 sf = p.suf[w0 + k];
+            np = fmaf(dA, sf.x, np);
+            np = fmaf(dB, sf.y, np);
+            if (nbp[b] == 0) { k1[b] = k; dA1[b] = dA; dB1[b] = dB; }
+            ++nbp[b];
+            mprev = m;
+          }
+        }
+        float v = warp_sum(np);
+        if (lane == 0) s_red[NWARP * NB + wid * NB + b] = v;
+      }
+      __syncthreads();  // (B) new partials visible
+      if (tid < NB) {
+        float a = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NWARP; ++k) { a += s_red[k * NB + tid]; bsum += s_red[NWARP * NB + k * NB + tid]; }
+        s_scale[tid] = nan_to_num0(a / bsum);  // rubix/spectra/ifu.py:252-255
+      }
+      __syncthreads();  // (C) scale visible
+
+      // ---- phase C2: accumulate the scaled lines ---------------------------------------------
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (has_chunk && bt * NB + b < it.count) {
+          const float sc = s_scale[b];
+          baseA = fmaf(sc, A0[b], baseA);
+          baseB = fmaf(sc, B0[b], baseB);
+          if (nbp[b] > 0) {
+            float2 st = my_step[k1[b]];
+            st.x = fmaf(sc, dA1[b], st.x);
+            st.y = fmaf(sc, dB1[b], st.y);
+            my_step[k1[b]] = st;
+          }
+          if (nbp[b] > 1) {  // fine SSP grids: more than one knot per chunk -> replay the rest
+            const float *rb = r_cur + b * RS;
+            const float d = rb[0], rd = rb[1];
+            const float *S = S_cur + b * KP;
+            int u = u0[b] + 1;
+            float mprev = (S[u + 1] - S[u]) * s_rdl[u] * rd;
+            for (++u;; ++u) {
+              const float tx = fmaf(s_lamz[u], d, -tcc);
+              if (!(tx <= tlast)) break;
+              int k = (int)ceilf((tx - tfirst) * rdtc);
+              k = min(max(k, 0), nk - 1);
+              while (k > 0 && p.tau[w0 + k - 1] >= tx) --k;
+              while (k < nk - 1 && p.tau[w0 + k] < tx) ++k;
+              const float m = (S[u + 1] - S[u]) * s_rdl[u] * rd;
+              const float dB = m - mprev;
+              float2 st = my_step[k];
+              st.x = fmaf(sc, -dB * tx, st.x);
+              st.y = fmaf(sc, dB, st.y);
+              my_step[k] = st;
+              mprev = m;
+            }
+          }
+        }
+      }
+    }  // batches
+
+    // ---- expand lines + steps into the spaxel spectrum and store it ------------------------------
+    if (has_chunk) {
+      float *row = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
+      float pa = baseA, pb = baseB;
+      for (int k = 0; k < nk; ++k) {
+        float2 st = my_step[k];
+        my_step[k] = make_float2(0.f, 0.f);
+        pa += st.x; pb += st.y;
+        row[w0 + k] = fmaf(pb, p.tau[w0 + k], pa);
+      }
+    }
+  }
+}
+
+// cube[s] = sum over the spaxel's items, in item order (deterministic two-level reduction)
+__global__ void reduce_partials_kernel(const int *__restrict__ item_start, const Item *__restrict__ items,
+                                       const float *__restrict__ partials, int Wp, int W, int nseg,
+                                       const int *__restrict__ ctrl, float *__restrict__ cube) {
+  if (ctrl[C_ERROR]) return;
+  for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+    const int i0 = item_start[s], i1 = item_start[s + 1];
+    if (i1 - i0 < 2) continue;
+    const int slot0 = items[i0].slot;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < i1 - i0; ++k) acc += partials[(size_t)(slot0 + k) * Wp + w];
+      cube[(size_t)s * W + w] = acc;
+    }
+  }
+}
+
+// a configuration the kernel cannot hold (knot window too large) poisons the cube with NaN rather
+// than returning a silently wrong result
+__global__ void poison_kernel(const int *__restrict__ ctrl, float *__restrict__ cube, size_t total) {
+  if (!ctrl[C_ERROR]) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    cube[i] = __int_as_float(0x7fc00000);
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int choose_psub(int64_t n) {
+  int64_t t = n / 4096;
+  int ps = 256;
+  while (ps < t && ps < 8192) ps <<= 1;
+  return ps;
+}
+
+static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *base, FusedWs &ws, size_t &total) {
+  const PlanView &v = plan->v;
+  ws.ncell = (v.nz - 1) * (v.na - 1);
+  if ((double)nseg * ws.ncell >= 2.0e9) ws.ncell = 1;  // key would overflow: sort by spaxel only
+  uint64_t maxkey = (uint64_t)nseg * ws.ncell;
+  ws.end_bit = 1;
+  while ((1ull << ws.end_bit) <= maxkey) ++ws.end_bit;
+  ws.rec_stride = v.method == RBX_METHOD_LINEAR ? 8 : 20;
+  ws.psub = choose_psub(n);
+  ws.max_split = (int)(2 * (n / ws.psub) + 2);
+  ws.max_items = nseg + (int)(n / ws.psub) + 2;
+  ws.Wp = (v.W + 3) & ~3;
+  ws.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, ws.cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, ws.end_bit);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return (char *)base + o; };
+  ws.keys_in = (uint32_t *)take(sizeof(uint32_t) * n);
+  ws.keys_out = (uint32_t *)take(sizeof(uint32_t) * n);
+  ws.idx_in = (uint32_t *)take(sizeof(uint32_t) * n);
+  ws.idx_out = (uint32_t *)take(sizeof(uint32_t) * n);
+  ws.rec = (float *)take(sizeof(float) * n * ws.rec_stride);
+  ws.counts = (int *)take(sizeof(int) * (nseg + 1));
+  ws.seg_start = (int *)take(sizeof(int) * (nseg + 1));
+  ws.item_start = (int *)take(sizeof(int) * (nseg + 1));
+  ws.ctrl = (int *)take(sizeof(int) * C_COUNT);
+  ws.items = (Item *)take(sizeof(Item) * ws.max_items);
+  ws.partials = (float *)take(sizeof(float) * (size_t)ws.max_split * ws.Wp);
+  ws.cub_temp = take(ws.cub_bytes);
+  total = off;
+  return RBX_OK;
+}
+
+}  // namespace rbx
+
+using namespace rbx;
+
+static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
+  const PlanView &v = plan->v;
+  if (v.nchunks > kFusedThreads) {
+    set_error("rbx_build_cube: more than 4096 telescope channels; use the stage calls");
+    return RBX_ERR_UNSUPPORTED;
+  }
+  // knots inside the band at rest (+25% head-room for Doppler spread) must fit the window
+  int inband = 0;
+  for (int l = 0; l < v.L; ++l) inband += (plan->h_lamz[l] >= v.tmin && plan->h_lamz[l] <= v.tmax);
+  if (inband + inband / 4 + 8 > kMaxWindow) {
+    set_error("rbx_build_cube: SSP grid too fine for the fused kernel's knot window; use the stage calls");
+    return RBX_ERR_UNSUPPORTED;
+  }
+  for (int w = 1; w < v.W; ++w)
+    if (!(plan->h_t[w] > plan->h_t[w - 1])) {
+      set_error("rbx_build_cube: telescope wavelength grid must be strictly increasing");
+      return RBX_ERR_UNSUPPORTED;
+    }
+  for (int l = 1; l < v.L; ++l)
+    if (!(plan->h_lamz[l] >= plan->h_lamz[l - 1])) {
+      set_error("rbx_build_cube: SSP wavelength grid must be non-decreasing");
+      return RBX_ERR_UNSUPPORTED;
+    }
+  if (num_spaxels < 1 || (int64_t)num_spaxels * num_spaxels > (1 << 24)) {
+    set_error("rbx_build_cube: num_spaxels out of range");
+    return RBX_ERR_INVALID_ARGUMENT;
+  }
+  return RBX_OK;
+}
+
+extern "C" size_t rbx_build_cube_workspace_bytes(const rbx_plan *plan, int64_t n, int num_spaxels) {
+  if (!plan || n < 0 || num_spaxels < 1) return 0;
+  FusedWs ws;
+  size_t total = 0;
+  layout_workspace(plan, n > 0 ? n : 1, num_spaxels * num_spaxels, nullptr, ws, total);
+  return total + 256;
+}
+
+extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
+                              const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels,
+                              float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBX_REQUIRE(plan && d_cube, "rbx_build_cube: null plan or cube");
+  RBX_REQUIRE(n >= 0 && n < (1ll << 31) - 1, "rbx_build_cube: n out of range");
+  int rc = check_fused_config(plan, num_spaxels);
+  if (rc != RBX_OK) return rc;
+  const PlanView &v = plan->v;
+  const int nseg = num_spaxels * num_spaxels;
+  RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)nseg * v.W, stream));
+  if (n == 0) return RBX_OK;
+  RBX_REQUIRE(d_vel && d_mass && d_met && d_age && d_pixel && d_ws, "rbx_build_cube: null pointer");
+  FusedWs ws;
+  size_t need = 0;
+  uintptr_t base = ((uintptr_t)d_ws + 255) & ~(uintptr_t)255;
+  layout_workspace(plan, n, nseg, (void *)base, ws, need);
+  if (need + (base - (uintptr_t)d_ws) > ws_bytes) {
+    set_error("rbx_build_cube: workspace too small (see rbx_build_cube_workspace_bytes)");
+    return RBX_ERR_WORKSPACE_TOO_SMALL;
+  }
+  RBX_CUDA_OK(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (nseg + 1), stream));
+  int h_ctrl[C_COUNT] = {0};
+  // ctrl init: dmin = +big, dmax = 0 -- via memset then a tiny kernel-free trick: 0x7f7fffff pattern
+  RBX_CUDA_OK(cudaMemsetAsync(ws.ctrl, 0, sizeof(int) * C_COUNT, stream));
+  RBX_CUDA_OK(cudaMemsetAsync(ws.ctrl + C_DMIN, 0x7f, sizeof(int), stream));  // 0x7f7f7f7f ~ 3.4e38
+  (void)h_ctrl;
+
+  const int threads = 256;
+  int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
+  prep_kernel<<<blocks, threads, 0, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n, nseg, ws.ncell,
+                                               ws.keys_in, ws.idx_in, ws.counts, ws.ctrl);
+  count_launch();
+  RBX_LAUNCH_OK();
+  size_t cb = ws.cub_bytes;
+  RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, cb, ws.keys_in, ws.keys_out, ws.idx_in, ws.idx_out,
+                                              (int)n, 0, ws.end_bit, stream));
+  count_launch(3);
+  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, ws.max_items, ws.max_split, ws.counts, ws.seg_start,
+                                          ws.item_start, ws.items, ws.ctrl);
+  count_launch();
+  RBX_LAUNCH_OK();
+  gather_kernel<<<blocks, threads, 0, stream>>>(v, ws.idx_out, ws.ctrl, d_vel, d_mass, d_met, d_age, ws.rec,
+                                                 ws.rec_stride);
+  count_launch();
+  RBX_LAUNCH_OK();
+
+  const int KPmax = kMaxWindow + 2;
+  const int RS = ws.rec_stride;
+  size_t smem = sizeof(float) * (2 * KPmax + 2 * NB * KPmax + 2) + sizeof(float2) * kFusedThreads * kStepPitch +
+                sizeof(float) * (2 * NB * RS + 2 * (kFusedThreads / 32) * NB + NB) + 64;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  int ctas_per_sm = 2;
+  if (v.method == RBX_METHOD_LINEAR) {
+    RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fused_cube_kernel<RBX_METHOD_LINEAR><<<nsm * ctas_per_sm, kFusedThreads, smem, stream>>>(
+        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp);
+  } else {
+    RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fused_cube_kernel<RBX_METHOD_CUBIC><<<nsm * ctas_per_sm, kFusedThreads, smem, stream>>>(
+        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp);
+  }
+  count_launch();
+  RBX_LAUNCH_OK();
+  dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
+  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.items, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube);
+  count_launch();
+  RBX_LAUNCH_OK();
+  poison_kernel<<<148, 256, 0, stream>>>(ws.ctrl, d_cube, (size_t)nseg * v.W);
+  count_launch();
+  RBX_LAUNCH_OK();
+  return RBX_OK;
+}

@@ -1,0 +1,97 @@
+// rbx_pipeline_host: the whole path for callers that hold host (numpy) arrays.
+// filter_particles -> spaxel_assignment -> fused cube -> PSF + LSF, with the H2D copies of the
+// particle arrays and the D2H copy of the cube inside the call.  Device scratch comes from the
+// stream-ordered allocator (cudaMallocAsync), so repeated calls reuse the pool without cudaMalloc.
+#include "common.cuh"
+
+using namespace rbx;
+
+namespace {
+struct Scratch {
+  std::vector<void *> ptrs;
+  cudaStream_t s;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  ~Scratch() {
+    for (void *p : ptrs) cudaFreeAsync(p, s);
+  }
+  template <typename T>
+  int get(T **out, size_t count) {
+    void *p = nullptr;
+    RBX_CUDA_OK(cudaMallocAsync(&p, count * sizeof(T) + 256, s));
+    ptrs.push_back(p);
+    *out = (T *)p;
+    return RBX_OK;
+  }
+};
+}  // namespace
+
+#define TRY(x) do { int _rc = (x); if (_rc != RBX_OK) return _rc; } while (0)
+
+extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity,
+                                 const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                                 const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
+                                 const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                                 float *h_cube, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBX_REQUIRE(plan && h_cube && h_edges, "rbx_pipeline_host: null argument");
+  RBX_REQUIRE(n >= 0 && n_edges >= 2 && num_spaxels >= 1, "rbx_pipeline_host: bad sizes");
+  RBX_REQUIRE(n == 0 || (h_coords && h_velocity && h_mass && h_metallicity && h_age), "rbx_pipeline_host: null particle array");
+  const int W = plan->v.W;
+  const size_t cube_elems = (size_t)num_spaxels * num_spaxels * W;
+  Scratch sc(stream);
+  float *d_coords, *d_vel, *d_mass, *d_met, *d_age, *d_edges, *d_cube, *d_cube2 = nullptr, *d_psf = nullptr, *d_lsf = nullptr;
+  int32_t *d_pixel;
+  void *d_ws;
+  const size_t np = n > 0 ? (size_t)n : 1;
+  TRY(sc.get(&d_coords, 3 * np));
+  TRY(sc.get(&d_vel, 3 * np));
+  TRY(sc.get(&d_mass, np));
+  TRY(sc.get(&d_met, np));
+  TRY(sc.get(&d_age, np));
+  TRY(sc.get(&d_pixel, np));
+  TRY(sc.get(&d_edges, (size_t)n_edges));
+  TRY(sc.get(&d_cube, cube_elems));
+  const size_t ws_bytes = rbx_build_cube_workspace_bytes(plan, n, num_spaxels);
+  TRY(sc.get((char **)&d_ws, ws_bytes));
+  RBX_CUDA_OK(cudaMemcpyAsync(d_edges, h_edges, sizeof(float) * n_edges, cudaMemcpyHostToDevice, stream));
+  if (n > 0) {
+    RBX_CUDA_OK(cudaMemcpyAsync(d_coords, h_coords, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, stream));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_vel, h_velocity, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, stream));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_mass, h_mass, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_met, h_metallicity, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_age, h_age, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+  }
+  if (apply_filter) TRY(rbx_filter_particles(d_coords, n, d_edges, n_edges, d_mass, d_met, d_age, nullptr, stream));
+  TRY(rbx_spaxel_assign(d_coords, n, d_edges, n_edges, d_pixel, nullptr, stream));
+  TRY(rbx_build_cube(plan, d_vel, d_mass, d_met, d_age, d_pixel, n, num_spaxels, d_cube, d_ws, ws_bytes, stream));
+  float *result = d_cube;
+  if (h_psf || h_lsf) TRY(sc.get(&d_cube2, cube_elems));
+  if (h_psf) {
+    TRY(sc.get(&d_psf, (size_t)M * N));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_psf, h_psf, sizeof(float) * M * N, cudaMemcpyHostToDevice, stream));
+  }
+  if (h_lsf) {
+    TRY(sc.get(&d_lsf, (size_t)K));
+    RBX_CUDA_OK(cudaMemcpyAsync(d_lsf, h_lsf, sizeof(float) * K, cudaMemcpyHostToDevice, stream));
+  }
+  if (h_psf && h_lsf) {
+    int rc = rbx_psf_lsf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, d_lsf, K, ext, stream);
+    if (rc == RBX_ERR_UNSUPPORTED) {  // taps too large for the fused tile: two passes
+      TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
+      TRY(rbx_convolve_lsf(d_cube2, d_cube, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
+      result = d_cube;
+    } else {
+      TRY(rc);
+      result = d_cube2;
+    }
+  } else if (h_psf) {
+    TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
+    result = d_cube2;
+  } else if (h_lsf) {
+    TRY(rbx_convolve_lsf(d_cube, d_cube2, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
+    result = d_cube2;
+  }
+  RBX_CUDA_OK(cudaMemcpyAsync(h_cube, result, sizeof(float) * cube_elems, cudaMemcpyDeviceToHost, stream));
+  RBX_CUDA_OK(cudaStreamSynchronize(stream));  // the caller reads h_cube right after this returns
+  return RBX_OK;
+}

@@ -1,0 +1,236 @@
+"""Device-level operators: thin Python wrappers over the C ABI (include/rubix_b200.h).
+
+PyTorch is used only for device memory and streams.  Every function takes/returns CUDA float32 /
+int32 tensors (numpy inputs are copied to the current device) and launches on the current stream.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METHODS = {"linear": 0, "cubic": 1}
+DIRECTIONS = {"x": 0, "y": 1, "z": 2}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("rubix_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def dev(x, dtype=torch.float32) -> torch.Tensor:
+    """Contiguous CUDA tensor of ``dtype`` from a tensor / numpy array / sequence."""
+    _require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    return t.to(device="cuda", dtype=dtype).contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Plan:
+    """Per-configuration device tables (``rbx_plan``): SSP template, telescope wavelength grid,
+    redshift, ``ssp.method`` and the Doppler velocity direction."""
+
+    def __init__(self, metallicity, age, wavelength, flux, target_wave, redshift: float,
+                 method: str = "cubic", direction: str = "z"):
+        _require_cuda()
+        if method not in METHODS:
+            raise ValueError(f"unknown ssp.method {method!r}: expected 'linear' or 'cubic'")
+        if direction not in DIRECTIONS:
+            raise ValueError(
+                f"{direction} is not a valid direction. Supported directions are 'x', 'y', or 'z'.")
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+        self.metallicity, self.age = f32(metallicity), f32(age)
+        self.wavelength, self.flux, self.target_wave = f32(wavelength), f32(flux), f32(target_wave)
+        nz, na, L = len(self.metallicity), len(self.age), len(self.wavelength)
+        if self.flux.shape != (nz, na, L):
+            raise ValueError(f"flux shape {self.flux.shape} != ({nz}, {na}, {L})")
+        self.method, self.direction, self.redshift = method, direction, float(redshift)
+        self.L, self.W = L, len(self.target_wave)
+        self._h = C.c_void_p()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().rbx_plan_create(
+            C.byref(self._h), vp(self.metallicity), nz, vp(self.age), na, vp(self.wavelength), L,
+            vp(self.flux), vp(self.target_wave), self.W, self.redshift, METHODS[method],
+            DIRECTIONS[direction], _stream()))
+        self.device = torch.cuda.current_device()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().rbx_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def spaxel_assign(coords, edges, with_mask: bool = False):
+    """rubix/telescope/utils.py:138-151 -> int32 pixel ids (and the inclusive aperture mask)."""
+    coords, edges = dev(coords), dev(edges)
+    if coords.ndim != 2 or coords.shape[1] != 3:
+        raise ValueError(f"coords must have shape (n, 3), got {tuple(coords.shape)}")
+    n = coords.shape[0]
+    pixel = torch.empty(n, dtype=torch.int32, device="cuda")
+    mask = torch.empty(n, dtype=torch.uint8, device="cuda") if with_mask else None
+    _lib.check(_lib.lib().rbx_spaxel_assign(_p(coords), n, _p(edges), edges.numel(), _p(pixel), _p(mask), _stream()))
+    return (pixel, mask.bool()) if with_mask else pixel
+
+
+def filter_particles(coords, edges, mass=None, metallicity=None, age=None):
+    """rubix/core/telescope.py:155-174: zero mass / metallicity / age (in place) outside the aperture;
+    returns the boolean mask."""
+    coords, edges = dev(coords), dev(edges)
+    n = coords.shape[0]
+    for t in (mass, metallicity, age):
+        if t is not None and not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
+                                  and t.is_contiguous() and t.numel() == n):
+            raise ValueError("filter_particles works in place on contiguous CUDA float32 tensors of length n")
+    mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().rbx_filter_particles(_p(coords), n, _p(edges), edges.numel(), _p(mass),
+                                               _p(metallicity), _p(age), _p(mask), _stream()))
+    return mask.bool()
+
+
+def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
+    metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    n = metallicity.numel()
+    if age.numel() != n:
+        raise ValueError("metallicity and age must have the same length")
+    out = torch.empty((n, plan.L), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().rbx_ssp_lookup(plan.handle, _p(metallicity), _p(age), n, _p(out), _stream()))
+    return out
+
+
+def scale_by_mass(spectra, mass) -> torch.Tensor:
+    spectra, mass = dev(spectra), dev(mass).reshape(-1)
+    L = spectra.shape[-1]
+    n = spectra.numel() // L if L else 0
+    if mass.numel() != n:
+        raise ValueError("mass must have one entry per spectrum")
+    out = torch.empty_like(spectra)
+    _lib.check(_lib.lib().rbx_scale_by_mass(_p(spectra), _p(mass), n, L, _p(out), _stream()))
+    return out
+
+
+def doppler_resample(plan: Plan, spectra, velocity) -> torch.Tensor:
+    spectra, velocity = dev(spectra), dev(velocity)
+    n = velocity.shape[0]
+    if spectra.shape != (n, plan.L) or velocity.shape != (n, 3):
+        raise ValueError(f"expected spectra (n, {plan.L}) and velocity (n, 3)")
+    out = torch.empty((n, plan.W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().rbx_doppler_resample(plan.handle, _p(spectra), _p(velocity), n, _p(out), _stream()))
+    return out
+
+
+def segment_sum(spectra, pixel, num_segments: int) -> torch.Tensor:
+    spectra, pixel = dev(spectra), dev(pixel, torch.int32).reshape(-1)
+    n, W = spectra.shape
+    if pixel.numel() != n:
+        raise ValueError("pixel must have one entry per spectrum")
+    cube = torch.empty((num_segments, W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().rbx_segment_sum(_p(spectra), _p(pixel), n, W, num_segments, _p(cube), 1, _stream()))
+    return cube
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int) -> torch.Tensor:
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device="cuda")
+        _ws_cache[key] = ws
+    return ws
+
+
+def build_cube(plan: Plan, velocity, mass, metallicity, age, pixel, num_spaxels: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused calculate_spectra -> scale_spectrum_by_mass -> doppler_shift_and_resampling ->
+    calculate_datacube.  Returns the (S, S, W) cube."""
+    velocity, mass = dev(velocity), dev(mass).reshape(-1)
+    metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    pixel = dev(pixel, torch.int32).reshape(-1)
+    n = mass.numel()
+    if velocity.shape != (n, 3) or metallicity.numel() != n or age.numel() != n or pixel.numel() != n:
+        raise ValueError("particle arrays disagree in length")
+    S = int(num_spaxels)
+    cube = out if out is not None else torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    nbytes = L.rbx_build_cube_workspace_bytes(plan.handle, n, S)
+    ws = _workspace(nbytes)
+    _lib.check(L.rbx_build_cube(plan.handle, _p(velocity), _p(mass), _p(metallicity), _p(age), _p(pixel),
+                                n, S, _p(cube), _p(ws), ws.numel(), _stream()))
+    return cube
+
+
+def convolve_psf(cube, kernel) -> torch.Tensor:
+    cube, kernel = dev(cube), dev(kernel)
+    ny, nx, W = cube.shape
+    out = torch.empty_like(cube)
+    _lib.check(_lib.lib().rbx_convolve_psf(_p(cube), _p(out), ny, nx, W, _p(kernel), kernel.shape[0],
+                                           kernel.shape[1], _stream()))
+    return out
+
+
+def convolve_lsf(cube, kernel, ext: int = 12) -> torch.Tensor:
+    cube, kernel = dev(cube), dev(kernel).reshape(-1)
+    W = cube.shape[-1]
+    rows = cube.numel() // W
+    out = torch.empty_like(cube)
+    _lib.check(_lib.lib().rbx_convolve_lsf(_p(cube), _p(out), rows, W, _p(kernel), kernel.numel(), ext, _stream()))
+    return out
+
+
+def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12) -> torch.Tensor:
+    cube, pk, lk = dev(cube), dev(psf_kernel), dev(lsf_kernel).reshape(-1)
+    ny, nx, W = cube.shape
+    out = torch.empty_like(cube)
+    rc = _lib.lib().rbx_psf_lsf(_p(cube), _p(out), ny, nx, W, _p(pk), pk.shape[0], pk.shape[1], _p(lk),
+                                lk.numel(), ext, _stream())
+    if rc == _lib.RBX_ERR_UNSUPPORTED:  # taps too large for the fused tile: two CUDA passes
+        return convolve_lsf(convolve_psf(cube, pk), lk, ext)
+    _lib.check(rc)
+    return out
+
+
+def pipeline_host(plan: Plan, coords, velocity, mass, metallicity, age, edges, num_spaxels: int,
+                  psf_kernel=None, lsf_kernel=None, ext: int = 12, apply_filter: bool = True,
+                  out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Host-buffer entry point (``rbx_pipeline_host``): numpy in, numpy cube out, copies included."""
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+    coords, velocity, mass = f32(coords), f32(velocity), f32(mass)
+    metallicity, age, edges = f32(metallicity), f32(age), f32(edges)
+    n = coords.shape[0]
+    S = int(num_spaxels)
+    cube = out if out is not None else np.empty((S, S, plan.W), dtype=np.float32)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    pk = None if psf_kernel is None else f32(psf_kernel)
+    lk = None if lsf_kernel is None else f32(lsf_kernel)
+    M, N = (pk.shape if pk is not None else (0, 0))
+    K = len(lk) if lk is not None else 0
+    _lib.check(_lib.lib().rbx_pipeline_host(
+        plan.handle, vp(coords), vp(velocity), vp(mass), vp(metallicity), vp(age), n, vp(edges), len(edges), S,
+        1 if apply_filter else 0, vp(pk), M, N, vp(lk), K, ext, vp(cube), _stream()))
+    return cube

@@ -1,0 +1,356 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Integer work (spaxel ids, masks) must be bit-exact.  Floating-point tolerances, all relative to
+the float64 evaluation of the reference formulas on the same float32 inputs:
+
+* per-stage arrays:  max |delta| <= 4e-6 * max |ref|      (a few float32 ulps of accumulated rounding)
+* cubes:             max |delta| <= 5e-6 * max |cube|      and the north-star bound
+                     max |delta| <= 1e-5 * sum |cube| / n_voxel_scale (see _cube_close)
+"""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle  # noqa: E402
+from oracle import rubix_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rubix_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def plans(ops, bc03, muse_wave):
+    out = {}
+    for m in ("linear", "cubic"):
+        out[m] = ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1,
+                          method=m, direction="z")
+    return out
+
+
+def _cube_close(out, ref, tag="", rtol_max=5e-6):
+    out = np.asarray(out, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert out.shape == ref.shape
+    assert np.isfinite(out).all(), f"{tag}: non-finite values in the cube"
+    err = np.abs(out - ref).max()
+    mx = np.abs(ref).max()
+    tot = np.abs(ref).sum()
+    print(f"[{tag}] max|d|={err:.3e} max|ref|={mx:.3e} rel_to_max={err / max(mx, 1e-300):.3e} "
+          f"rel_to_total={err / max(tot, 1e-300):.3e}")
+    # north star: rtol 1e-5 per voxel relative to the cube's total flux
+    assert err <= 1e-5 * tot, f"{tag}: north-star tolerance violated"
+    assert err <= rtol_max * mx, f"{tag}: max error {err:.3e} > {rtol_max} * {mx:.3e}"
+
+
+# ---- a0 -------------------------------------------------------------------------------------------
+def test_spaxel_assign_kat(ops):
+    # tests/test_telescope_utils.py:20-35 (z column added: our coords are (n,3))
+    coords = np.array([[0.5, 1.5, 0], [2.5, 3.5, 0]], dtype=np.float32)
+    out = ops.spaxel_assign(coords, np.array([0, 1, 2, 3, 4], dtype=np.float32))
+    assert out.dtype == torch.int32
+    assert out.cpu().tolist() == [4, 14]
+
+
+def test_spaxel_assign_bit_exact_random(ops):
+    from rubix_b200.synthetic import spatial_edges
+    rng = np.random.default_rng(0)
+    for S in (25, 150):
+        edges = spatial_edges(S)
+        coords = rng.normal(0, 3.0, (200000, 3)).astype(np.float32)
+        # put particles exactly on edges and just beside them
+        k = len(edges)
+        coords[:k, 0] = edges
+        coords[k:2 * k, 1] = edges
+        coords[2 * k:3 * k, 0] = np.nextafter(edges, np.float32(np.inf))
+        coords[3 * k:4 * k, 1] = np.nextafter(edges, np.float32(-np.inf))
+        pix, mask = ops.spaxel_assign(coords, edges, with_mask=True)
+        assert np.array_equal(pix.cpu().numpy(), orc.square_spaxel_assignment(coords, edges))
+        assert np.array_equal(mask.cpu().numpy(), orc.mask_particles_outside_aperture(coords, edges))
+    # reference quirk: len(edges) - 1 may differ from num_spaxels (S+2 edges); ids follow the edges
+    edges = np.linspace(-1, 1, 28).astype(np.float32)
+    pix = ops.spaxel_assign(coords, edges)
+    assert np.array_equal(pix.cpu().numpy(), orc.square_spaxel_assignment(coords, edges))
+
+
+def test_mask_boundaries_and_empty(ops):
+    # tests/test_telescope_utils.py:38-79
+    e = np.array([0, 1], dtype=np.float32)
+    cases = [([[0.5, 0.5, 0], [0.2, 0.2, 0]], 2), ([[1.5, 1.5, 0], [-0.1, -0.1, 0]], 0),
+             ([[0, 0, 0], [1, 1, 0], [0, 1, 0], [1, 0, 0]], 4),
+             ([[0.5, 0.5, 0], [1.5, 1.5, 0], [0, 0, 0], [-0.1, -0.1, 0]], 2)]
+    for coords, expected in cases:
+        _, m = ops.spaxel_assign(np.array(coords, dtype=np.float32), e, with_mask=True)
+        assert int(m.sum()) == expected
+    pix, m = ops.spaxel_assign(np.zeros((0, 3), dtype=np.float32), e, with_mask=True)
+    assert pix.numel() == 0 and m.numel() == 0
+
+
+def test_filter_particles(ops):
+    rng = np.random.default_rng(1)
+    coords = rng.uniform(-2, 2, (5000, 3)).astype(np.float32)
+    e = np.linspace(-1, 1, 11).astype(np.float32)
+    mass = ops.dev(rng.random(5000).astype(np.float32) + 1)
+    met = ops.dev(rng.random(5000).astype(np.float32) + 1)
+    age = ops.dev(rng.random(5000).astype(np.float32) + 1)
+    m0, z0, a0 = mass.cpu().numpy().copy(), met.cpu().numpy().copy(), age.cpu().numpy().copy()
+    mask = ops.filter_particles(coords, e, mass, met, age).cpu().numpy()
+    em, ez, ea, emask = orc.filter_particles(coords, m0, z0, a0, e)
+    assert np.array_equal(mask, emask)
+    assert np.array_equal(mass.cpu().numpy(), em) and np.array_equal(met.cpu().numpy(), ez)
+    assert np.array_equal(age.cpu().numpy(), ea)
+
+
+# ---- a1 -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_ssp_lookup_nodes_and_outside(ops, plans, bc03, method):
+    # tests/test_core_ssp.py:158-173 (grid-node identity, rtol 1e-5 / atol 1e-6) and :116-126,176-181
+    Z, A = np.meshgrid(bc03["metallicity"], bc03["age"], indexing="ij")
+    out = ops.ssp_lookup(plans[method], Z.ravel(), A.ravel()).cpu().numpy()
+    assert np.allclose(out, bc03["flux"].reshape(-1, 842), rtol=1e-5, atol=1e-6)
+    zq = np.array([0.1, 1e-5, 0.02, 0.02, 0.0], dtype=np.float32)
+    aq = np.array([5.0, 5.0, 11.0, -1.0, 0.0], dtype=np.float32)
+    out = ops.ssp_lookup(plans[method], zq, aq).cpu().numpy()
+    assert (out == 0).all()
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_ssp_lookup_off_node(ops, plans, bc03, method):
+    rng = np.random.default_rng(2)
+    zq = rng.uniform(1e-4, 0.05, 3000).astype(np.float32)
+    aq = rng.uniform(0.0, 10.3, 3000).astype(np.float32)
+    out = ops.ssp_lookup(plans[method], zq, aq).cpu().numpy().astype(np.float64)
+    ref = orc.interp2d(zq, aq, bc03["metallicity"], bc03["age"], bc03["flux"], method=method, dtype=np.float64)
+    err = np.abs(out - ref).max()
+    print(f"[lookup {method}] max|d|={err:.3e} max|ref|={np.abs(ref).max():.3e}")
+    assert err <= 4e-6 * np.abs(ref).max()
+
+
+# ---- a2 -------------------------------------------------------------------------------------------
+def test_scale_by_mass_exact(ops):
+    # tests/test_core_ifu.py:249-282 (array_equal)
+    rng = np.random.default_rng(3)
+    spec = rng.random((257, 842)).astype(np.float32)
+    mass = (rng.random(257) * 1e5).astype(np.float32)
+    out = ops.scale_by_mass(spec, mass).cpu().numpy()
+    assert np.array_equal(out, spec * mass[:, None])
+
+
+# ---- a3 + a4 --------------------------------------------------------------------------------------
+def test_resample_kat(ops):
+    # tests/test_spectra_ifu.py:175-228 through a 5-bin "template" plan
+    lam = np.array([4000.0, 5000.0, 6000.0, 7000.0, 8000.0], dtype=np.float32)
+    t = np.array([4500.0, 5500.0, 6500.0, 7500.0], dtype=np.float32)
+    flux = np.zeros((2, 2, 5), dtype=np.float32)
+    plan = ops.Plan([0.0, 1.0], [0.0, 1.0], lam, flux, t, 0.0, method="linear", direction="y")
+    s = np.array([[1.0, 2.0, 3.0, 4.0, 5.0], [0, 0, 0, 0, 0]], dtype=np.float32)
+    out = ops.doppler_resample(plan, s, np.zeros((2, 3), dtype=np.float32)).cpu().numpy()
+    assert np.allclose(out[0], [1.2857143, 2.142857, 3.0, 3.857143], rtol=1e-5)
+    assert (out[1] == 0).all() and not np.isnan(out).any()
+
+
+def test_doppler_resample_matches_oracle(ops, plans, bc03, muse_wave):
+    rng = np.random.default_rng(4)
+    n = 400
+    zq = rng.uniform(1e-4, 0.05, n).astype(np.float32)
+    aq = rng.uniform(5.1, 10.3, n).astype(np.float32)
+    vel = rng.normal(0, 200, (n, 3)).astype(np.float32)
+    spec = orc.interp2d(zq, aq, bc03["metallicity"], bc03["age"], bc03["flux"], method="linear")
+    out = ops.doppler_resample(plans["linear"], spec, vel).cpu().numpy().astype(np.float64)
+    lam = orc.velocity_doppler_shift(orc.cosmological_doppler_shift(0.1, bc03["wavelength"], np.float64), vel,
+                                     "z", dtype=np.float64)
+    ref = orc.resample_spectra(spec.astype(np.float64), lam, muse_wave.astype(np.float64))
+    err = np.abs(out - ref).max()
+    print(f"[resample] max|d|={err:.3e} max|ref|={np.abs(ref).max():.3e}")
+    assert err <= 4e-6 * np.abs(ref).max()
+
+
+# ---- a5 -------------------------------------------------------------------------------------------
+def test_segment_sum_kat(ops):
+    # tests/test_spectra_ifu.py:231-257, plus out-of-range ids are dropped like XLA's scatter
+    spectra = np.array([[100, 200, 300], [400, 500, 600], [700, 800, 900], [1, 2, 3], [9, 9, 9]], dtype=np.float32)
+    idx = np.array([0, 1, 1, 3, 7], dtype=np.int32)
+    cube = ops.segment_sum(spectra, idx, 4).cpu().numpy().reshape(2, 2, 3)
+    assert np.array_equal(cube, [[[100, 200, 300], [1100, 1300, 1500]], [[0, 0, 0], [1, 2, 3]]])
+
+
+# ---- fused a1..a5 -----------------------------------------------------------------------------------
+def _run_fused(ops, plan, data, edges, S, apply_filter=True):
+    coords = ops.dev(data["coords"])
+    mass, met, age = ops.dev(data["mass"]).clone(), ops.dev(data["metallicity"]).clone(), ops.dev(data["age"]).clone()
+    if apply_filter:
+        ops.filter_particles(coords, edges, mass, met, age)
+    pix = ops.spaxel_assign(coords, edges)
+    cube = ops.build_cube(plan, data["velocity"], mass, met, age, pix, S)
+    torch.cuda.synchronize()
+    return cube.cpu().numpy()
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_fused_cube_tng_subset(ops, plans, bc03, muse_wave, tng_subset, method):
+    from rubix_b200.synthetic import spatial_edges
+    edges = spatial_edges(25)
+    out = _run_fused(ops, plans[method], tng_subset, edges, 25)
+    ref = c_oracle.particles_to_cube(tng_subset["coords"], tng_subset["velocity"], tng_subset["mass"],
+                                     tng_subset["metallicity"], tng_subset["age"], edges, 25, bc03["metallicity"],
+                                     bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1, method=method,
+                                     dtype=np.float64, n_threads=8)
+    assert ref.max() > 0
+    _cube_close(out, ref, f"fused tng {method}")
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+@pytest.mark.parametrize("gen", ["bench_u", "bench_g"])
+def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(25)
+    data = getattr(synthetic, gen)(20000)
+    out = _run_fused(ops, plans[method], data, edges, 25)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], muse_wave, 0.1, method=method, dtype=np.float64, n_threads=8)
+    _cube_close(out, ref, f"fused {gen} {method}")
+
+
+def test_fused_equals_stage_path(ops, plans, tng_subset):
+    """The fused kernel and the materialising stage kernels are two CUDA implementations of the same
+    stages; they must agree to float32 rounding."""
+    from rubix_b200.synthetic import spatial_edges
+    edges = spatial_edges(25)
+    plan = plans["cubic"]
+    d = tng_subset
+    coords = ops.dev(d["coords"])
+    mass, met, age = ops.dev(d["mass"]).clone(), ops.dev(d["metallicity"]).clone(), ops.dev(d["age"]).clone()
+    ops.filter_particles(coords, edges, mass, met, age)
+    pix = ops.spaxel_assign(coords, edges)
+    spec = ops.scale_by_mass(ops.ssp_lookup(plan, met, age), mass)
+    res = ops.doppler_resample(plan, spec, d["velocity"])
+    staged = ops.segment_sum(res, pix, 625).cpu().numpy().reshape(25, 25, -1)
+    fused = ops.build_cube(plan, d["velocity"], mass, met, age, pix, 25).cpu().numpy()
+    _cube_close(fused, staged, "fused vs staged", rtol_max=1e-5)
+
+
+def test_fused_edge_cases(ops, plans):
+    from rubix_b200.synthetic import spatial_edges, bench_u
+    plan = plans["linear"]
+    # empty input -> zero cube
+    z = np.zeros((0,), dtype=np.float32)
+    cube = ops.build_cube(plan, np.zeros((0, 3), dtype=np.float32), z, z, z, np.zeros((0,), dtype=np.int32), 25)
+    assert cube.shape == (25, 25, 3721) and float(cube.abs().max()) == 0.0
+    # all particles invalid (mass 0 / Z out of grid / pixel out of range) -> exactly zero
+    d = bench_u(1000)
+    pix = np.full(1000, 3, dtype=np.int32)
+    assert float(ops.build_cube(plan, d["velocity"], np.zeros(1000, np.float32), d["metallicity"], d["age"], pix, 25).abs().max()) == 0.0
+    assert float(ops.build_cube(plan, d["velocity"], d["mass"], np.full(1000, 0.1, np.float32), d["age"], pix, 25).abs().max()) == 0.0
+    assert float(ops.build_cube(plan, d["velocity"], d["mass"], d["metallicity"], d["age"], np.full(1000, 625, np.int32), 25).abs().max()) == 0.0
+    # one particle
+    one = ops.build_cube(plan, d["velocity"][:1], d["mass"][:1], d["metallicity"][:1], d["age"][:1], pix[:1], 25)
+    assert float(one[0, 3].max()) > 0 and float(one.sum() - one[0, 3].sum()) == 0.0
+    # a single crowded spaxel (exercises segment splitting + the two-level reduction), run twice:
+    # deterministic bit-for-bit
+    d = bench_u(30000)
+    pix = np.full(30000, 7, dtype=np.int32)
+    a = ops.build_cube(plan, d["velocity"], d["mass"], d["metallicity"], d["age"], pix, 25).cpu().numpy()
+    b = ops.build_cube(plan, d["velocity"], d["mass"], d["metallicity"], d["age"], pix, 25).cpu().numpy()
+    assert np.array_equal(a, b)
+    assert a[0, 7].min() > 0 and a.sum() == a[0, 7].sum()
+
+
+def test_fused_linearity_and_sharding(ops, plans):
+    """Size-independent properties: the cube is a sum over particles (shards add up) and scales
+    linearly with mass."""
+    from rubix_b200.synthetic import spatial_edges, bench_g
+    plan = plans["linear"]
+    edges = spatial_edges(25)
+    d = bench_g(200000)
+    pix = ops.spaxel_assign(d["coords"], edges)
+    args = lambda sl: (d["velocity"][sl], d["mass"][sl], d["metallicity"][sl], d["age"][sl], pix[sl])
+    full = ops.build_cube(plan, *args(slice(None)), 25).double()
+    parts = sum(ops.build_cube(plan, *args(slice(k, None, 4)), 25).double() for k in range(4))
+    assert float((full - parts).abs().max()) <= 2e-6 * float(full.abs().max())
+    v, m, z, a, p = args(slice(None))
+    twice = ops.build_cube(plan, v, 2 * m, z, a, p, 25).double()
+    assert float((twice - 2 * full).abs().max()) <= 1e-6 * float(full.abs().max())
+
+
+# ---- a6 / a7 ----------------------------------------------------------------------------------------
+def test_psf_matches_oracle(ops):
+    rng = np.random.default_rng(6)
+    cube = rng.random((25, 25, 300)).astype(np.float32)
+    for shape in ((5, 5), (3, 3), (4, 4), (3, 5)):
+        k = rng.random(shape).astype(np.float32)
+        out = ops.convolve_psf(cube, k).cpu().numpy()
+        ref = orc.apply_psf(cube.astype(np.float64), k.astype(np.float64))
+        assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    # tests/test_telescope_psf.py:22-54
+    c = np.zeros((10, 10, 3), dtype=np.float32)
+    c[5, 5, :] = 1
+    out = ops.convolve_psf(c, np.ones((3, 3), dtype=np.float32)).cpu().numpy()
+    assert np.array_equal(out, orc.apply_psf(c, np.ones((3, 3), dtype=np.float32)))
+
+
+def test_lsf_matches_oracle(ops):
+    # tests/test_telescope_lsf.py:6-60 (delta -> normalised gaussian, atol 1e-5)
+    for pos in (20, 50, 75):
+        s = np.zeros((1, 1, 100), dtype=np.float32)
+        s[0, 0, pos] = 1
+        k = orc.lsf_kernel(2.0, 1.0)
+        out = ops.convolve_lsf(s, k).cpu().numpy()[0, 0]
+        x = np.arange(100)
+        g = np.exp(-0.5 * ((x - pos) ** 2) / 4.0)
+        assert np.allclose(out, g / g.sum(), atol=1e-5)
+    rng = np.random.default_rng(7)
+    cube = rng.random((7, 9, 500)).astype(np.float32)
+    k = orc.lsf_kernel(0.5, 1.25)
+    out = ops.convolve_lsf(cube, k).cpu().numpy()
+    ref = orc.apply_lsf(cube.astype(np.float64), 0.5, 1.25)
+    assert out.shape == cube.shape
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("S,W", [(25, 3721), (13, 517), (31, 130)])
+def test_fused_psf_lsf(ops, S, W):
+    rng = np.random.default_rng(8)
+    cube = rng.random((S, S, W)).astype(np.float32)
+    pk = orc.gaussian_kernel_2d(5, 5, 0.6)
+    lk = orc.lsf_kernel(0.5, 1.25)
+    out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+    ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
+    err = np.abs(out - ref).max()
+    print(f"[psf+lsf {S}x{W}] max|d|={err:.3e}")
+    assert err <= 2e-6 * np.abs(ref).max()
+    two = ops.convolve_lsf(ops.convolve_psf(cube, pk), lk).cpu().numpy()
+    assert np.abs(two - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_gaussian_kernels_on_device(ops):
+    from rubix_b200 import _lib
+    import ctypes as C
+    k = torch.empty(25, device="cuda")
+    _lib.check(_lib.lib().rbx_gaussian_psf_kernel(5, 5, 0.6, C.c_void_p(k.data_ptr()), None))
+    assert np.allclose(k.cpu().numpy().reshape(5, 5), orc.gaussian_kernel_2d(5, 5, 0.6), rtol=1e-6, atol=1e-9)
+    _lib.check(_lib.lib().rbx_gaussian_lsf_kernel(0.5, 1.25, 12, C.c_void_p(k.data_ptr()), None))
+    assert np.allclose(k.cpu().numpy(), orc.lsf_kernel(0.5, 1.25), rtol=1e-5, atol=1e-12)
+
+
+# ---- host-buffer entry point ----------------------------------------------------------------------
+def test_pipeline_host_end_to_end(ops, plans, bc03, muse_wave, tng_subset):
+    from rubix_b200.synthetic import spatial_edges
+    edges = spatial_edges(25)
+    pk = orc.gaussian_kernel_2d(5, 5, 0.6)
+    lk = orc.lsf_kernel(0.5, 1.25)
+    d = tng_subset
+    out = ops.pipeline_host(plans["cubic"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"],
+                            edges, 25, pk, lk)
+    ref = c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, 25,
+                                     bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave,
+                                     0.1, method="cubic", dtype=np.float64, n_threads=8)
+    ref = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
+    _cube_close(out, ref, "pipeline_host cubic + psf + lsf")

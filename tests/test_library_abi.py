@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/rubix_b200.h declares,
+and reports errors (not crashes) when no device is present.  No compute calls here."""
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from rubix_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "rubix_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rbx_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed from the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rubix_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED)
+
+
+def test_version_and_error_string(lib):
+    assert lib.rbx_version() >= 100
+    assert isinstance(lib.rbx_last_error(), bytes)
+
+
+def test_argument_validation_without_device(lib):
+    # null plan / bad shapes are rejected before any CUDA call
+    assert lib.rbx_ssp_lookup(None, None, None, 0, None, None) != 0
+    assert b"null plan" in lib.rbx_last_error()
+    assert lib.rbx_spaxel_assign(None, 5, None, 1, None, None, None) != 0
+    assert lib.rbx_convolve_lsf(None, None, 1, 1, None, 1, 0, None) != 0
+    assert lib.rbx_build_cube_workspace_bytes(None, 10, 25) == 0
+    h = C.c_void_p()
+    rc = lib.rbx_plan_create(C.byref(h), None, 2, None, 2, None, 2, None, None, 1, 0.1, 0, 2, None)
+    assert rc == -1  # RBX_ERR_INVALID_ARGUMENT
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
