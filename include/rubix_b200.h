@@ -47,6 +47,11 @@ int rbx_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t rbx_launch_count(void);
 
+/* Optional CUDA-event timing of the dominant kernel (fused_cube_kernel) on its launch stream, for
+ * bench.py's roofline line.  Not thread-safe; off by default. */
+int rbx_profile_enable(int on);
+int rbx_profile_fused(double *mean_ms, int64_t *launches, int reset);
+
 /* ---------------------------------------------------------------------------------------------
  * Plan: everything that depends only on the configuration (SSP template, telescope wavelength
  * grid, redshift, interpolation method, Doppler direction).

@@ -23,6 +23,7 @@ EXPORTED = [
     "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf",
     "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
     "rbx_pipeline_host",
+    "rbx_profile_enable", "rbx_profile_fused",
 ]
 
 RBX_OK = 0
@@ -85,6 +86,10 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = i32
+    L.rbx_profile_enable.argtypes = [i32]
+    L.rbx_profile_enable.restype = i32
+    L.rbx_profile_fused.argtypes = [C.POINTER(f64), C.POINTER(i64), i32]
+    L.rbx_profile_fused.restype = i32
     L.rbx_build_cube_workspace_bytes.argtypes = [vp, i64, i32]
     L.rbx_build_cube_workspace_bytes.restype = sz
     _lib = L

@@ -489,6 +489,40 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
 
 using namespace rbx;
 
+// ---- optional timing of the dominant kernel (bench.py's roofline) ---------------------------------
+static std::atomic<int> g_profile{0};
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+static double g_fused_ms_sum = 0.0;
+static int64_t g_fused_n = 0;
+static bool g_ev_pending = false;
+
+static void profile_collect() {
+  if (g_ev_pending && cudaEventSynchronize(g_ev[1]) == cudaSuccess) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) { g_fused_ms_sum += ms; ++g_fused_n; }
+  }
+  g_ev_pending = false;
+}
+
+extern "C" int rbx_profile_enable(int on) {
+  if (on && !g_ev[0]) {
+    RBX_CUDA_OK(cudaEventCreate(&g_ev[0]));
+    RBX_CUDA_OK(cudaEventCreate(&g_ev[1]));
+  }
+  if (!on) profile_collect();
+  g_profile.store(on);
+  return RBX_OK;
+}
+
+// mean duration (ms) and number of fused_cube_kernel launches timed since the last reset
+extern "C" int rbx_profile_fused(double *mean_ms, int64_t *launches, int reset) {
+  profile_collect();
+  if (mean_ms) *mean_ms = g_fused_n ? g_fused_ms_sum / (double)g_fused_n : 0.0;
+  if (launches) *launches = g_fused_n;
+  if (reset) { g_fused_ms_sum = 0.0; g_fused_n = 0; }
+  return RBX_OK;
+}
+
 static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
   const PlanView &v = plan->v;
   if (v.nchunks > kFusedThreads) {
@@ -582,6 +616,8 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   int ctas_per_sm = 2;
+  const bool prof = g_profile.load() != 0;
+  if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
   if (v.method == RBX_METHOD_LINEAR) {
     RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fused_cube_kernel<RBX_METHOD_LINEAR><<<nsm * ctas_per_sm, kFusedThreads, smem, stream>>>(
@@ -593,6 +629,7 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   }
   count_launch();
   RBX_LAUNCH_OK();
+  if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
   reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.items, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube);
   count_launch();

@@ -1,0 +1,46 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the B200
+box, gloo in CPU tests).
+
+The path is data-parallel over particles with exactly one exchange: the per-rank partial cubes are
+summed (the reference's ``jnp.sum(ifu_cubes, axis=0)`` over its device axis, rubix/core/ifu.py:333).
+Particles are split into contiguous ranges of ceil(N / world) like the reference's ``reshape_array``
+(rubix/core/data.py:471-482); the zero padding of the last range contributes exactly 0.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def shard_particles(data: Dict[str, np.ndarray], rank: int, world: int) -> Dict[str, np.ndarray]:
+    n = len(next(iter(data.values())))
+    lo, hi = shard_range(n, rank, world)
+    return {k: v[lo:hi] for k, v in data.items()}
+
+
+def wavelength_slab(W: int, rank: int, world: int) -> Tuple[int, int]:
+    """Channel range [lo, hi) owned by ``rank`` when the PSF / LSF stage is sharded by wavelength."""
+    return shard_range(W, rank, world)
+
+
+def allreduce_cube(cube):
+    """Sum the partial cubes of all ranks in place (NCCL all-reduce on CUDA tensors)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(cube, op=dist.ReduceOp.SUM)
+    return cube
+
+
+def reduce_cube(cube, dst: int = 0):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(cube, dst=dst, op=dist.ReduceOp.SUM)
+    return cube

@@ -35,6 +35,25 @@ def plans(ops, bc03, muse_wave):
     return out
 
 
+def _well_conditioned(data, lamz, wave, direction=2, tol=1e-2):
+    """Drop particles sitting on a knife edge of the reference's own formula.
+
+    rubix/spectra/ifu.py:241-244 masks the SSP knots with ``tmin <= lam' <= tmax``; a knot within a
+    float32 ulp (~5e-4 A) of either end flips in or out of ``total_lum`` depending on how lam_z * d
+    was rounded, which changes that particle's whole spectrum by ~0.5 % (one 22 A bin of 4650 A).
+    float32 and float64 evaluations of the reference disagree there (oracle f32 vs f64: 3.6e-5 of
+    the cube maximum for one such particle in bench_g(20000)), so those particles cannot pin
+    anything; they are removed from the parity inputs (about 1 in 10^4)."""
+    d = np.exp(data["velocity"][:, direction].astype(np.float64) / 299792.458)
+    lz = lamz.astype(np.float64)
+    lo = np.searchsorted(lz, wave[0] / d.max()) - 2
+    hi = np.searchsorted(lz, wave[-1] / d.min()) + 2
+    x = lz[None, max(lo, 0):hi] * d[:, None]
+    dist = np.minimum(np.abs(x - float(wave[0])).min(1), np.abs(x - float(wave[-1])).min(1))
+    keep = dist > tol
+    return {k: v[keep] for k, v in data.items()}
+
+
 def _cube_close(out, ref, tag="", rtol_max=5e-6):
     out = np.asarray(out, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
@@ -197,6 +216,7 @@ def _run_fused(ops, plan, data, edges, S, apply_filter=True):
 def test_fused_cube_tng_subset(ops, plans, bc03, muse_wave, tng_subset, method):
     from rubix_b200.synthetic import spatial_edges
     edges = spatial_edges(25)
+    tng_subset = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
     out = _run_fused(ops, plans[method], tng_subset, edges, 25)
     ref = c_oracle.particles_to_cube(tng_subset["coords"], tng_subset["velocity"], tng_subset["mass"],
                                      tng_subset["metallicity"], tng_subset["age"], edges, 25, bc03["metallicity"],
@@ -211,7 +231,7 @@ def test_fused_cube_tng_subset(ops, plans, bc03, muse_wave, tng_subset, method):
 def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
     from rubix_b200 import synthetic
     edges = synthetic.spatial_edges(25)
-    data = getattr(synthetic, gen)(20000)
+    data = _well_conditioned(getattr(synthetic, gen)(20000), np.float32(1.1) * bc03["wavelength"], muse_wave)
     out = _run_fused(ops, plans[method], data, edges, 25)
     ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
                                      data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
@@ -346,7 +366,7 @@ def test_pipeline_host_end_to_end(ops, plans, bc03, muse_wave, tng_subset):
     edges = spatial_edges(25)
     pk = orc.gaussian_kernel_2d(5, 5, 0.6)
     lk = orc.lsf_kernel(0.5, 1.25)
-    d = tng_subset
+    d = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
     out = ops.pipeline_host(plans["cubic"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"],
                             edges, 25, pk, lk)
     ref = c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, 25,
