@@ -1,0 +1,179 @@
+"""rubix/core/pipeline.py mirror: ``RubixPipeline(config).run()`` for the particle -> datacube path.
+
+The reference registers its stage closures by ``__name__`` in a ``LinearTransformerPipeline``
+(rubix/pipeline/linear_pipeline.py:56-157), orders them by the YAML ``depends_on`` chain of
+``pipeline_config.yml`` and composes them into one expression; this class does the same ordering
+and composition for the stages this package implements (no jax.jit: every stage enqueues CUDA
+kernels on the current stream, the only synchronisation is at the end of ``run``).
+
+Stages of ``calc_ifu`` that are outside the hot path (``rotate_galaxy``, ``apply_noise``; SURVEY.md
+section 8(f) "next") have no CUDA implementation here.  By default they are skipped with a
+warning; pass your own callables through ``extra_functions`` to run them.
+"""
+
+from __future__ import annotations
+
+import copy
+import os
+import time
+from typing import Callable, Dict, Iterable, List, Optional, Union
+
+import numpy as np
+
+from ..h5lite import H5File
+from ..logger import get_logger
+from ..utils import get_config, get_pipeline_config
+from .data import RubixData, get_reshape_data, make_rubix_data
+from .ifu import (get_calculate_datacube, get_calculate_spectra, get_doppler_shift_and_resampling,
+                  get_scale_spectrum_by_mass)
+from .lsf import get_convolve_lsf
+from .psf import get_convolve_psf
+from .ssp import get_ssp
+from .telescope import get_filter_particles, get_spaxel_assignment, get_telescope
+
+#: calc_ifu nodes that are not part of the accelerated path
+NOT_ON_PATH = ("rotate_galaxy", "apply_noise")
+
+
+def order_by_depends_on(pipeline_config: dict) -> List[str]:
+    """rubix/pipeline/linear_pipeline.py:56-138: exactly one root (``depends_on: null``), every
+    other node depends on exactly one node, no branching."""
+    nodes = pipeline_config["Transformers"]
+    roots = [k for k, v in nodes.items() if v.get("depends_on") is None]
+    if len(roots) != 1:
+        raise ValueError("There must be exactly one starting point in a linear pipeline")
+    children: Dict[str, str] = {}
+    for k, v in nodes.items():
+        dep = v.get("depends_on")
+        if dep is None:
+            continue
+        if dep not in nodes:
+            raise ValueError(f"Node {k} depends on unknown node {dep}")
+        if dep in children:
+            raise ValueError("Branching is not allowed in a linear pipeline")
+        children[dep] = k
+    order, cur = [], roots[0]
+    while cur is not None:
+        order.append(cur)
+        cur = children.get(cur)
+    if len(order) != len(nodes):
+        raise ValueError("The pipeline is not a single linear chain")
+    return order
+
+
+def load_rubix_galaxy(path: str, particle_types: Iterable[str] = ("stars",)) -> dict:
+    """Read a ``rubix_galaxy.h5`` written by the reference's input handlers
+    (rubix/galaxy/input_handler/base.py:16-76: ``galaxy/*``, ``particles/<type>/<field>``) with the
+    numpy-only reader; the layout restated from rubix/core/data.py:508-540."""
+    out = {"particle_data": {}}
+    with H5File(path) as f:
+        g = f["galaxy"]
+        out["redshift"] = float(np.asarray(g["redshift"].read()).reshape(-1)[0])
+        out["subhalo_center"] = np.asarray(g["center"].read(), dtype=np.float32)
+        out["subhalo_halfmassrad_stars"] = float(np.asarray(g["halfmassrad_stars"].read()).reshape(-1)[0])
+        parts = f["particles"]
+        for t in particle_types:
+            if t in parts.keys():
+                grp = parts[t]
+                out["particle_data"][t] = {k: np.asarray(grp[k].read(), dtype=np.float32) for k in grp.keys()}
+    return out
+
+
+def prepare_input(config: dict) -> RubixData:
+    """rubix/core/data.py:491-603: load ``<output_path>/rubix_galaxy.h5``, centre the particles on
+    the subhalo centre (rubix/galaxy/alignment.py:14-64), optional seed-42 subset."""
+    logger = get_logger(config.get("logger", None))
+    path = os.path.join(config["output_path"], "rubix_galaxy.h5")
+    types = config["data"]["args"]["particle_type"] if "data" in config else ["stars"]
+    raw = load_rubix_galaxy(path, types)
+    st = raw["particle_data"].get("stars")
+    if st is None:
+        raise ValueError("Neither stars nor gas coordinates are available.")
+    center = raw["subhalo_center"].astype(np.float32)
+    coords = st["coords"]
+    if np.any(center < coords.min(0)) or np.any(center > coords.max(0)):
+        raise ValueError("Center is not within the bounds of the galaxy")
+    logger.info("Centering stars particles")
+    arrays = dict(coords=(coords - center).astype(np.float32), velocity=st["velocity"], mass=st["mass"],
+                  metallicity=st["metallicity"], age=st["age"])
+    sub = config.get("data", {}).get("subset", {})
+    if sub.get("use_subset"):
+        np.random.seed(42)  # rubix/core/data.py:565
+        idx = np.random.choice(np.arange(len(arrays["coords"])), size=sub["subset_size"], replace=False)
+        arrays = {k: v[idx] for k, v in arrays.items()}
+        logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for stars")
+    rd = make_rubix_data(**arrays, device=False)
+    rd.galaxy.redshift = raw["redshift"]
+    rd.galaxy.center = center
+    rd.galaxy.halfmassrad_stars = raw["subhalo_halfmassrad_stars"]
+    return rd
+
+
+class RubixPipeline:
+    """``RubixPipeline(user_config).run()`` (rubix/core/pipeline.py:30-208).
+
+    ``data`` may be a ready :class:`RubixData` (host or device arrays); otherwise it is loaded from
+    ``<output_path>/rubix_galaxy.h5`` like the reference's ``prepare_input``.
+    """
+
+    def __init__(self, user_config: Union[dict, str], data: Optional[RubixData] = None,
+                 extra_functions: Optional[List[Callable]] = None):
+        self.user_config = get_config(user_config)
+        self.pipeline_config = get_pipeline_config(self.user_config["pipeline"]["name"])
+        self.logger = get_logger(self.user_config.get("logger"))
+        self.ssp = get_ssp(self.user_config)
+        self.telescope = get_telescope(self.user_config)
+        self.extra_functions = list(extra_functions or [])
+        self.data = data if data is not None else self._prepare_data()
+        self.func = None
+
+    def _prepare_data(self) -> RubixData:
+        self.logger.info("Getting rubix data...")
+        rd = prepare_input(self.user_config)
+        n = len(rd.stars.coords) if rd.stars.coords is not None else 0
+        self.logger.info(f"Data loaded with {n} star particles and 0 gas particles.")
+        return rd
+
+    def _get_pipeline_functions(self) -> list:
+        self.logger.info("Setting up the pipeline...")
+        c = self.user_config
+        return [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
+                get_scale_spectrum_by_mass(c), get_doppler_shift_and_resampling(c), get_calculate_datacube(c),
+                get_convolve_psf(c), get_convolve_lsf(c)] + self.extra_functions
+
+    def assemble(self) -> List[Callable]:
+        registry: Dict[str, Callable] = {}
+        for fn in self._get_pipeline_functions():
+            if fn.__name__ in registry:  # rubix/pipeline/abstract_pipeline.py:80-82
+                raise ValueError("A transformer with this name is already present")
+            registry[fn.__name__] = fn
+        chain = []
+        for name in order_by_depends_on(self.pipeline_config):
+            if name in registry:
+                chain.append(copy.deepcopy(registry[name]))  # rubix/pipeline/transformer.py:18
+            elif name in NOT_ON_PATH:
+                self.logger.warning(f"stage {name} is outside the B200 hot path and was not supplied: skipped")
+            else:
+                raise RuntimeError(f"Transformer {name} not found in the registered functions")
+        return chain
+
+    def run(self) -> RubixData:
+        import torch
+        t0 = time.time()
+        self.logger.info("Assembling the pipeline...")
+        chain = self.assemble()
+
+        def expr(x):
+            for fn in chain:
+                x = fn(x)
+            return x
+
+        self.func = expr
+        self.logger.info("Running the pipeline on the input data...")
+        output = self.func(self.data)
+        torch.cuda.synchronize()
+        self.logger.info("Pipeline run completed in %.2f seconds.", time.time() - t0)
+        return output
+
+    def gradient(self):
+        raise NotImplementedError("Gradient calculation is not implemented yet")

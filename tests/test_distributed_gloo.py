@@ -1,0 +1,75 @@
+"""World-size-2 test (gloo, CPU) of the multi-GPU host logic: contiguous particle shards
+(rubix/core/data.py:471-482), per-rank partial cubes, one sum-reduce (rubix/core/ifu.py:333), and the
+wavelength-slab split used for the PSF/LSF stage.  The partial cubes come from the CPU oracle here
+(the checker); on the GPU box the same plumbing carries the CUDA cubes (bench.py --gpus N)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import c_oracle
+        from oracle import rubix_oracle as orc
+        from rubix_b200 import parallel, synthetic
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        tpl = np.load(os.path.join(root, "tests", "golden", "bc03lr_f32.npz"))
+        wave = synthetic.muse_wave()[:400]
+        edges = synthetic.spatial_edges(5)
+        data = synthetic.bench_g(3001, seed=42)  # odd count: the last shard is shorter
+        mine = parallel.shard_particles(data, rank, world)
+        cube = c_oracle.particles_to_cube(mine["coords"], mine["velocity"], mine["mass"], mine["metallicity"],
+                                          mine["age"], edges, 5, tpl["metallicity"], tpl["age"], tpl["wavelength"],
+                                          tpl["flux"], wave, 0.1, method="linear", dtype=np.float64, n_threads=1)
+        t = torch.from_numpy(np.ascontiguousarray(cube))
+        parallel.allreduce_cube(t)
+        # PSF + LSF sharded by wavelength slab with a +-12 channel halo, then gathered
+        pk = orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)
+        lo, hi = parallel.wavelength_slab(len(wave), rank, world)
+        hlo, hhi = max(lo - 12, 0), min(hi + 12, len(wave))
+        slab = orc.apply_lsf(orc.apply_psf(t.numpy()[:, :, hlo:hhi], pk), 0.5, 1.25)[:, :, lo - hlo:lo - hlo + hi - lo]
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, hi, slab))
+        if rank == 0:
+            full = np.concatenate([p[2] for p in sorted(parts, key=lambda p: p[0])], axis=2)
+            np.savez(os.path.join(out_dir, "out.npz"), cube=t.numpy(), conv=full)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_shard_reduce_and_slab_convolution(tmp_path, bc03):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    from oracle import c_oracle
+    from oracle import rubix_oracle as orc
+    from rubix_b200 import synthetic
+    wave = synthetic.muse_wave()[:400]
+    edges = synthetic.spatial_edges(5)
+    d = synthetic.bench_g(3001, seed=42)
+    ref = c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, 5,
+                                     bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], wave, 0.1,
+                                     method="linear", dtype=np.float64, n_threads=1)
+    assert ref.max() > 0
+    assert np.abs(got["cube"] - ref).max() <= 1e-12 * ref.max()
+    conv = orc.apply_lsf(orc.apply_psf(ref, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
+    # slab-wise LSF with a 12-channel halo is exact (the kernel reaches +-12 channels)
+    assert np.abs(got["conv"] - conv).max() <= 1e-12 * conv.max()

@@ -1,0 +1,119 @@
+"""GPU tests of the drop-in factories (the rubix.core mirror): the staged path reproduces the
+reference's observable intermediates (tests/test_core_ifu.py shapes / exact mass scaling / zero spectra
+for out-of-grid Z), the fused path gives the same cube, and RubixPipeline runs the whole chain."""
+
+import copy
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle  # noqa: E402
+from oracle import rubix_oracle as orc  # noqa: E402
+
+CONFIG = {
+    "pipeline": {"name": "calc_ifu"},
+    "logger": {"log_level": "WARNING", "log_file_path": None,
+               "format": "%(asctime)s - %(name)s - %(levelname)s - %(message)s"},
+    "telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6}, "lsf": {"sigma": 0.5}},
+    "cosmology": {"name": "PLANCK15"},
+    "galaxy": {"dist_z": 0.1},
+    "ssp": {"template": {"name": "BruzualCharlot2003"}},
+}
+
+
+@pytest.fixture(scope="module")
+def core():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rubix_b200 import core as _core
+    return _core
+
+
+def _run_chain(core, cfg, data):
+    rd = core.make_rubix_data(**data)
+    for get in (core.get_filter_particles, core.get_spaxel_assignment, core.get_reshape_data,
+                core.get_calculate_spectra, core.get_scale_spectrum_by_mass,
+                core.get_doppler_shift_and_resampling, core.get_calculate_datacube):
+        rd = get(cfg)(rd)
+    return rd
+
+
+def _oracle_cube(cfg, data, bc03, muse_wave, method):
+    from rubix_b200.core.telescope import get_spatial_bin_edges
+    edges = get_spatial_bin_edges(cfg)
+    nb = len(edges) - 1
+    # the reference's segment_sum keeps ids < sbin^2 of x + nb*y (rubix/core/ifu.py:320)
+    m, z, a, _ = orc.filter_particles(data["coords"], data["mass"], data["metallicity"], data["age"], edges)
+    pix = orc.square_spaxel_assignment(data["coords"], edges)
+    spec = orc.calculate_spectra(bc03, z, a, method=method, dtype=np.float64)
+    spec = orc.scale_spectrum_by_mass(spec, m.astype(np.float64))
+    res = orc.doppler_shift_and_resampling(spec, data["velocity"], bc03["wavelength"], muse_wave, 0.1,
+                                           dtype=np.float64)
+    return orc.calculate_cube(res, pix, 25), nb
+
+
+def test_staged_intermediates_match_reference_contract(core, bc03, muse_wave, tng_subset):
+    cfg = copy.deepcopy(CONFIG)
+    cfg["b200"] = {"fused": False}
+    d = {k: v[:300].copy() for k, v in tng_subset.items()}
+    d["metallicity"][:5] = 0.1  # above the grid -> zero spectra (tests/test_core_ifu.py:207-246)
+    rd = core.make_rubix_data(**d)
+    rd = core.get_filter_particles(cfg)(rd)
+    rd = core.get_spaxel_assignment(cfg)(rd)
+    rd = core.get_reshape_data(cfg)(rd)
+    assert rd.stars.coords.shape == (1, 300, 3) and rd.stars.pixel_assignment.dtype == torch.int32
+    rd = core.get_calculate_spectra(cfg)(rd)
+    spec = rd.stars.spectra
+    assert tuple(spec.shape) == (1, 300, 842)
+    assert not torch.isnan(spec).any()
+    assert float(spec[0, :5].abs().max()) == 0.0
+    before = spec.clone()
+    rd = core.get_scale_spectrum_by_mass(cfg)(rd)
+    # tests/test_core_ifu.py:277-279: exactly spectra * mass[..., None]
+    assert torch.equal(rd.stars.spectra, before * rd.stars.mass[..., None])
+    rd = core.get_doppler_shift_and_resampling(cfg)(rd)
+    assert tuple(rd.stars.spectra.shape) == (1, 300, 3721) and not torch.isnan(rd.stars.spectra).any()
+    rd = core.get_calculate_datacube(cfg)(rd)
+    assert tuple(rd.stars.datacube.shape) == (25, 25, 3721)
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_fused_and_staged_factories_agree_with_oracle(core, bc03, muse_wave, tng_subset, method):
+    from tests.test_gpu_parity import _cube_close, _well_conditioned
+    d = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
+    cubes = {}
+    for fused in (False, True):
+        cfg = copy.deepcopy(CONFIG)
+        cfg["ssp"]["method"] = method
+        cfg["b200"] = {"fused": fused}
+        rd = _run_chain(core, cfg, d)
+        if fused:
+            from rubix_b200.core.ifu import DeferredSpectra
+            assert isinstance(rd.stars.spectra, DeferredSpectra) and rd.stars.spectra.shape == (1, len(d["mass"]), 3721)
+        cubes[fused] = rd.stars.datacube.cpu().numpy()
+    ref, nb = _oracle_cube(cfg, d, bc03, muse_wave, method)
+    if nb == 25:  # 26 edges: x + 25*y is the cube layout; with 27 edges ids >= 625 are dropped on both sides
+        _cube_close(cubes[True], ref, f"factory fused {method}")
+    _cube_close(cubes[True], cubes[False].astype(np.float64), f"factory fused vs staged {method}", rtol_max=1e-5)
+
+
+def test_rubix_pipeline_end_to_end(core, bc03, muse_wave, tng_subset):
+    from tests.test_gpu_parity import _cube_close, _well_conditioned
+    d = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
+    outs = {}
+    for fused in (False, True):
+        cfg = copy.deepcopy(CONFIG)
+        cfg["b200"] = {"fused": fused}
+        pipe = core.RubixPipeline(cfg, data=core.make_rubix_data(**d, device=False))
+        out = pipe.run()
+        cube = out.stars.datacube
+        assert tuple(cube.shape) == (25, 25, 3721) and not torch.isnan(cube).any()
+        outs[fused] = cube.cpu().numpy()
+    raw, nb = _oracle_cube(cfg, d, bc03, muse_wave, "cubic")
+    ref = orc.apply_lsf(orc.apply_psf(raw, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
+    if nb == 25:
+        _cube_close(outs[True], ref, "RubixPipeline fused")
+    _cube_close(outs[True], outs[False].astype(np.float64), "RubixPipeline fused vs staged", rtol_max=1e-5)
