@@ -41,25 +41,35 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     }                                                                                       \
   } while (0)
 
-constexpr int kChunk = 16;           // targets per chunk in the fused kernel
-constexpr int kFusedThreads = 256;   // one thread per chunk -> W <= 4096
-constexpr int kMaxWindow = 512;      // SSP knots the fused kernel can hold per particle
+constexpr int kMaxLutBuckets = 8192;  // channel-lookup buckets the fused kernel keeps in shared memory
 constexpr float kSpeedOfLight = 299792.458f;  // rubix/config/rubix_config.yml:8
 
 // Device view of a plan (passed by value to kernels).
 struct PlanView {
-  int nz, na, L, Lp, W, method, vel_comp, nchunks;
-  float tmin, tmax;
+  int nz, na, L, Lp, W, method, vel_comp;
+  int nb;                      // number of channel-lookup buckets
+  float tmin, tmax, trange;    // telescope band; trange = tmax - tmin
+  float lut_scale;             // (2*nb - 1) / trange, see bucket_offset()
+  float tref;                  // reference wavelength of the q table (band centre)
   const float *zgrid, *agrid;  // SSP metallicity / age axes
   const float *tab[4];         // f, fx, fy, fxy: (nz*na, Lp) float32, rows 16-byte aligned
   const float *lamz;           // (L)  (1+z)*wavelength                       rubix/spectra/ifu.py:80
   const float *rdl;            // (L)  1/(lamz[j+1]-lamz[j]); 0 for the last knot or zero width
   const float *t;              // (W)  telescope wave_seq
   const float *dt;             // (W)  diff0(t): [0, t1-t0, ...]                rubix/spectra/ifu.py:84-102
-  const float *tau;            // (W)  t[w] - tc[w / kChunk]   (exact in f32)
-  const float2 *suf;           // (W)  suffix sums inside the chunk: (sum dt, sum tau*dt) over k' >= k
-  const float *tc;             // (nchunks) chunk reference wavelength
+  const uint16_t *lut;         // (nb)  number of channels whose bucket is smaller than b
+  const float2 *tt;            // (W)   (t[max(w-1,0)], t[w])
+  const float2 *q;             // (W+1) double-float prefix sums of dt[w]*(t[w]-tref) over w < k
 };
+
+// Monotone map wavelength -> 2 * bucket (a byte offset into the uint16 lut), without F2I: the
+// rounded product lands in the mantissa of 1.5 * 2^23.  The lut is built on the device with this
+// very function (plan.cu), so host/device rounding differences cannot arise.
+__device__ __forceinline__ int bucket_offset(float x, float tmin, float trange, float scale) {
+  float xs = fminf(fmaxf(__fsub_rn(x, tmin), 0.f), trange);
+  float y = __fmaf_rn(xs, scale, 12582912.f);
+  return __float_as_int(y) & 0x3FFFFE;
+}
 
 }  // namespace rbx
 
@@ -68,6 +78,8 @@ struct rbx_plan {
   std::vector<void *> allocs;
   std::vector<float> h_lamz, h_t;
   int device;
+  int lut_ok;        // every telescope channel has a bucket of its own
+  float min_dt, max_dt;
 };
 
 namespace rbx {

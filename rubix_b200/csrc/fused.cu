@@ -7,32 +7,32 @@
 //   segment_kernel   one block: segment starts, work items (segments split into <= psub particles),
 //                    SSP knot window for the observed Doppler range
 //   gather_kernel    sorted per-particle records {d, 1/d, template row, interpolation weights * mass}
-//   fused_cube_kernel persistent CTAs pull work items; per item the spaxel's spectrum is accumulated
-//                    in registers + shared memory (no global atomics) and written once
+//   fused_cube_kernel persistent CTAs (one per SM); warp groups pull work items; per item the spaxel's
+//                    spectrum is accumulated in shared memory (no global atomics) and written once
 //   reduce_partials_kernel  spaxels that were split over several items: fixed-order sum of partial rows
 //
-// Algorithm of fused_cube_kernel.  For one particle the reference evaluates, for every telescope
-// channel t_w,  p_w = jnp.interp(t_w, lam' = lam_z * d, s)  and then rescales by total/new
-// (rubix/spectra/ifu.py:241-260).  p is piecewise linear in t with break points at the Doppler-shifted
-// SSP knots, so instead of touching all W channels per particle we accumulate, per chunk of 16
-// channels, the line that is valid at the chunk's first channel (base: value at the chunk reference
-// wavelength + slope) and, for every SSP knot that falls inside the chunk, the change of line at the
-// first channel behind the knot (step).  Lines are continuous at knots, so the step is
-// (dA, dB) = (-(m_j - m_{j-1}) * tau_x, m_j - m_{j-1}) in chunk-local coordinates tau = t - tc.
-// The spaxel spectrum is recovered once per work item by a 16-long prefix sum of the steps.
-// Work per particle is O(#knots in band + W/16) instead of O(W * log L); every quantity that is
-// summed is bounded by the spectrum itself (chunk-local coordinates), so float32 accumulation is as
-// benign as the reference's.  sum_w p_w * dt_w (the "new total") comes from the same lines through
-// per-chunk suffix tables of dt and tau*dt.
+// The algorithm of fused_cube_kernel is described above the kernel.  In short: for one particle the
+// reference evaluates p_w = jnp.interp(t_w, lam' = lam_z * d, s) for every telescope channel and rescales
+// by total/new (rubix/spectra/ifu.py:241-260).  p is piecewise linear in t with break points at the
+// Doppler-shifted SSP knots, so a particle is fully described by its ~220 knots: work per particle is
+// O(#knots in band), not O(W log L), and nothing per-channel is touched until the spaxel is finished.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 
 namespace rbx {
 
-constexpr int NB = 4;  // particles per batch (between block barriers)
-constexpr int kStepPitch = kChunk + 1;
 constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
+constexpr int NB = 4;                 // particles per batch (between group barriers)
+constexpr int KPL = 2;                // knot slots per lane
+constexpr int OWN = 30;               // owner lanes per warp
+constexpr int kCtaThreads = 512;
+constexpr int kCtaWarps = kCtaThreads / 32;
+constexpr int kMaxGroups = 4;
+constexpr int kMaxGroupWarps = 8;
+constexpr int kRegionSlack = 64;      // spare cells per warp region
+constexpr int kMaxKnots = KPL * OWN * kMaxGroupWarps - 3;  // widest knot window [ja, jb) a group can hold
+
 
 struct Item { int start, count, spaxel, slot; };
 
@@ -131,7 +131,7 @@ __global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, in
       while (b < p.L && p.lamz[b] <= hi_l) ++b;  // one past the last knot that can be in the band
       ja = max(0, a - 3);
       jb = min(p.L, b + 3);
-      if (jb - ja > kMaxWindow) err = 2;
+      if (jb - ja > kMaxKnots) err = 2;
     }
     ctrl[C_NITEMS] = err ? 0 : rb;
     ctrl[C_JA] = ja;
@@ -187,236 +187,420 @@ __global__ void gather_kernel(PlanView p, const uint32_t *__restrict__ idx_sorte
 }
 
 // ---- the fused kernel -----------------------------------------------------------------------------
+// Thread mapping.  A CTA (one per SM, 512 threads) holds the telescope lookup tables in shared memory
+// (staged once with TMA bulk copies) and runs up to kMaxGroups independent *groups*; a group is
+// NWG = ceil((KW + 2) / 60) warps that pull work items (<= psub particles of one spaxel) from a
+// global queue.  Inside a group the SSP knot window is laid out along the lanes: lane l of warp wg
+// owns the KPL = 2 consecutive knot slots s = 2 * (30 * wg + l - 1) + {0, 1} (lanes 0 and 31 are
+// halos that only feed their neighbours through shuffles), slot s <-> SSP index jbase + s.  All
+// per-knot constants (lam_z, 1/dlam_z, template offset) live in registers for the whole kernel.
+//
+// Per particle a lane evaluates, for its two knots: the mass-weighted spectrum S (template rows
+// through the read-only path), the shifted position x = lam_z * d, the first telescope channel at or
+// above x (k, via the bucket table -- no search, no F2I), the slope m of the segment to the next
+// knot and the kink dm = m - m_prev.  The reference's two normalisation sums are evaluated per knot
+// segment: total = sum S_j (x_j - x_{j-1}) [x_j in band] and
+// new = sum_w p(t_w) dt_w = sum_j S_j D_j + m_j (Q_j - (x_j - tref) D_j), with D_j = t[k_{j+1}-1] -
+// t[k_j-1] (dt telescopes exactly in float32) and Q from the double-float prefix table.  One
+// transposed warp reduction + one named barrier per batch of NB = 4 particles gives the scales.
+//
+// Accumulation.  p(t) is piecewise linear, so the spaxel spectrum is kept as (a) per channel cell k the
+// summed kinks (sum dm * (t[k-1] - x), sum dm) of all knots that fell into (t[k-1], t[k]] and (b) per
+// chunk of CH channels the summed line (value at the chunk's first channel, slope) -- re-anchoring
+// every chunk keeps float32 rounding from growing with wavelength distance.  Each warp adds into its
+// own cell region (the channel range its knots can reach for the Doppler factors present), so the
+// adds are plain shared-memory read-modify-writes in a fixed order: no atomics, bit-reproducible.
+// Configurations where knots of one warp can share a channel (SSP grid finer than the telescope's)
+// or where the regions do not fit use one shared region and 64-bit CAS adds instead.
+// Once per work item the cells are expanded with two warp scans per 32 channels and stored coalesced.
+struct FusedLayout {  // shared-memory layout (byte offsets), computed on the host
+  int off_mbar, off_lut, off_tt, off_q, off_group, group_stride;
+  int g_step, g_base, g_rec, g_red, g_misc;  // offsets inside a group's block
+  int lut_bytes, tt_bytes, q_bytes;          // multiples of 16 (TMA bulk copy sizes)
+  int cap;         // step cells per group
+  int nch, chs;    // chunks per row, log2(channels per chunk)
+  int max_groups;
+  int collide;     // two knots of one warp can fall into the same channel -> CAS adds
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// number of channels below x, and t[k-1] (t[0] for k = 0)
+__device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsigned char *s_lut,
+                                          const float2 *s_tt, float &e) {
+  const int off = bucket_offset(x, p.tmin, p.trange, p.lut_scale);
+  const int l = *reinterpret_cast<const uint16_t *>(s_lut + off);
+  const float2 t2 = s_tt[l];
+  const bool up = t2.y < x;
+  e = up ? t2.y : t2.x;
+  return l + (up ? 1 : 0);
+}
+
+__device__ __forceinline__ void cell_add(float2 *cell, float a, float b, bool cas) {
+  if (!cas) {
+    float2 v = *cell;
+    v.x += a; v.y += b;
+    *cell = v;
+  } else {
+    unsigned long long *addr = reinterpret_cast<unsigned long long *>(cell);
+    unsigned long long old = *addr, assumed;
+    do {
+      assumed = old;
+      float lo = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + a;
+      float hi = __uint_as_float((unsigned)(assumed >> 32)) + b;
+      unsigned long long nv = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+      old = atomicCAS(addr, assumed, nv);
+    } while (old != assumed);
+  }
+}
+
 template <int METHOD>
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kCtaThreads, 1)
 fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
-                  float *__restrict__ cube, float *__restrict__ partials, int Wp) {
-  constexpr int NW = METHOD == RBX_METHOD_LINEAR ? 4 : 16;
-  constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;
-  constexpr int NWARP = kFusedThreads / 32;
-  extern __shared__ __align__(16) unsigned char smraw[];
+                  float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay) {
+  constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
+  constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage the lookup tables (TMA bulk copies, one elected thread) -----------------------------
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + lay.off_mbar);
+  unsigned char *s_lut = smem + lay.off_lut;
+  const float2 *s_tt = reinterpret_cast<const float2 *>(smem + lay.off_tt);
+  const float2 *s_q = reinterpret_cast<const float2 *>(smem + lay.off_q);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t total = (uint32_t)(lay.lut_bytes + lay.tt_bytes + lay.q_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(total) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_lut)), "l"(p.lut), "r"((uint32_t)lay.lut_bytes), "r"(smem_u32(mbar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_tt)), "l"(p.tt), "r"((uint32_t)lay.tt_bytes), "r"(smem_u32(mbar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_q)), "l"(p.q), "r"((uint32_t)lay.q_bytes), "r"(smem_u32(mbar)) : "memory");
+  }
+
+  // ---- group geometry (runtime: depends on the knot window found by segment_kernel) ---------------
   const int ja = ctrl[C_JA], jb = ctrl[C_JB];
-  const int KW = jb - ja;      // real knots in the window, u = j - ja + 1 in [1, KW]
-  const int KP = KW + 2;       // + one sentinel each side
-  float *s_lamz = reinterpret_cast<float *>(smraw);
-  float *s_rdl = s_lamz + KP;
-  float *s_S = s_rdl + KP;                         // [2][NB][KP]
-  float2 *s_step = reinterpret_cast<float2 *>(s_S + 2 * NB * KP + ((2 * NB * KP + 2 * KP) & 1));  // 8B aligned
-  float *s_rec = reinterpret_cast<float *>(s_step + kFusedThreads * kStepPitch);  // [2][NB][RS]
-  float *s_red = s_rec + 2 * NB * RS;              // [2][NWARP][NB]  (tot, new)
-  float *s_scale = s_red + 2 * NWARP * NB;         // [NB]
-  __shared__ int s_item;
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_items = ctrl[C_NITEMS];
+  const int jbase = (ja - 1) & ~1;                 // even; slot s <-> SSP index jbase + s
+  const int need = jb - jbase + 1;                 // slots that must be owned
+  const int NWG = max(1, (need + KPL * OWN - 1) / (KPL * OWN));
+  const int ngroups = min(min(lay.max_groups, kCtaWarps / NWG), kMaxGroups);
+  const int grp = warp / NWG, wg = warp - grp * NWG;
+  const bool active = grp < ngroups;
+  const int gthreads = NWG * 32;
+  const int gt = wg * 32 + lane;                   // thread index inside the group
 
-  // window tables (+ sentinels: knots at -inf / +inf carrying the end values, slope 0 beyond)
-  for (int u = tid; u < KP; u += kFusedThreads) {
-    float lz, rd;
-    if (u == 0) { lz = -1.0e30f; rd = 0.f; }
-    else if (u == KP - 1) { lz = 1.0e30f; rd = 0.f; }
-    else { lz = p.lamz[ja + u - 1]; rd = (u == KP - 2) ? ((jb == p.L) ? 0.f : p.rdl[jb - 1]) : p.rdl[ja + u - 1]; }
-    s_lamz[u] = lz;
-    s_rdl[u] = rd;
-  }
-  for (int q = tid; q < kFusedThreads * kStepPitch; q += kFusedThreads) s_step[q] = make_float2(0.f, 0.f);
+  unsigned char *gbase = smem + lay.off_group + (size_t)(active ? grp : 0) * lay.group_stride;
+  float2 *s_step = reinterpret_cast<float2 *>(gbase + lay.g_step);   // [cap]
+  float2 *s_base = reinterpret_cast<float2 *>(gbase + lay.g_base);   // [NWG][nch]
+  float *s_rec = reinterpret_cast<float *>(gbase + lay.g_rec);       // [2][NB][RS]
+  float *s_red = reinterpret_cast<float *>(gbase + lay.g_red);       // [2][2*NB][kMaxGroupWarps]
+  int *s_misc = reinterpret_cast<int *>(gbase + lay.g_misc);         // [0]=item, [2..10)=region klo, [12..20)=region khi
 
-  // per-thread chunk constants
-  const int c = tid;
-  const bool has_chunk = c < p.nchunks;
-  const int w0 = c * kChunk;
-  const int nk = has_chunk ? min(kChunk, p.W - w0) : 0;
-  float tcc = 0.f, tfirst = 0.f, tlast = 0.f, rdtc = 0.f, D0 = 0.f, T0 = 0.f;
-  if (has_chunk) {
-    tcc = p.tc[c];
-    tfirst = p.tau[w0];
-    tlast = p.tau[w0 + nk - 1];
-    rdtc = nk > 1 ? (float)(nk - 1) / (tlast - tfirst) : 0.f;
-    float2 s0 = p.suf[w0];
-    D0 = s0.x; T0 = s0.y;
+  if (active) {
+    for (int q = gt; q < lay.cap; q += gthreads) s_step[q] = make_float2(0.f, 0.f);
+    for (int q = gt; q < NWG * lay.nch; q += gthreads) s_base[q] = make_float2(0.f, 0.f);
   }
-  int ug = 1;  // running guess of the knot at/below the chunk's first channel
-  float2 *my_step = s_step + (size_t)c * kStepPitch;
+
+  // ---- per-lane knot constants ---------------------------------------------------------------------
+  const bool owner = lane >= 1 && lane <= OWN;
+  const int s0 = KPL * (OWN * wg + lane - 1);      // first slot of this lane (halo lanes included)
+  const int j0 = jbase + s0;                       // SSP index of slot 0 (even)
+  // template offset of the pair load (clamped into the padded row) and which half each slot reads
+  const int jpair = min(max(j0, 0), ((p.L - 1) & ~1));
+  float lz[KPL], rdlv[KPL];
+  bool take_hi[KPL];
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const int j = j0 + r;
+    const int jc = min(max(j, 0), p.L - 1);
+    take_hi[r] = (jc - jpair) != 0;
+    lz[r] = j < 0 ? -1.0e30f : (j >= p.L ? 1.0e30f : p.lamz[j]);
+    rdlv[r] = (j < 0 || j >= p.L - 1) ? 0.f : p.rdl[j];
+  }
+  // previous knot of slot 0 for the "total" difference; diff0's first element is 0 (rubix/spectra/ifu.py:84-102)
+  const float lzprev = (j0 - 1 >= 0 && j0 - 1 < p.L) ? p.lamz[j0 - 1] : lz[0];
+  const bool pair_plain = !take_hi[0] && take_hi[1];
+  const bool any_odd = __any_sync(0xffffffffu, !pair_plain);
+
+  // wait for the tables
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                   : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
+    }
+  }
+  if (!active) return;  // spare warps (no __syncthreads below this line)
+
+  // ---- cell regions: the channel range each warp can reach for the Doppler factors present --------
+  const float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+  {
+    float e;
+    int klo = owner ? channel_of(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e) : 0x7fffffff;
+    int khi = owner ? channel_of(__fmul_rn(lz[KPL - 1], dmax), p, s_lut, s_tt, e) : -1;
+    // widest lane span at dmax: must hold at most one chunk start (see the base deposit below)
+    float lznext = __shfl_down_sync(0xffffffffu, lz[0], 1);
+    int kfirst = channel_of(__fmul_rn(lz[0], dmax), p, s_lut, s_tt, e);
+    int knext = channel_of(__fmul_rn(lznext, dmax), p, s_lut, s_tt, e);
+    int span = owner ? knext - kfirst + 2 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+      khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+      span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
+    }
+    if (lane == 0) {
+      s_misc[2 + wg] = klo;
+      s_misc[12 + wg] = khi;
+      if (span >= (1 << lay.chs)) atomicExch(ctrl + C_ERROR, 3);
+    }
+  }
+  group_barrier(1 + grp, gthreads);
+  // regions are packed back to back: offset of region w = sum of the sizes before it
+  int total_cells = 0, my_off = 0;
+  for (int w = 0; w < NWG; ++w) {
+    if (w == wg) my_off = total_cells;
+    total_cells += s_misc[12 + w] - s_misc[2 + w] + 1;
+  }
+  const bool shared_mode = lay.collide != 0 || total_cells > lay.cap;
+  const int my_klo = shared_mode ? 0 : s_misc[2 + wg];
+  const int cellbase = shared_mode ? 0 : my_off - my_klo;
+  const int nreg = shared_mode ? 1 : NWG;
+  float2 *my_base = s_base + (size_t)wg * lay.nch;
+  const int CH = 1 << lay.chs;
+
+  const float *tab[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) tab[t] = p.tab[t] + jpair;
+  const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
 
   while (true) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(ctrl + C_WORK, 1);
-    __syncthreads();
-    const int item_id = s_item;
+    group_barrier(1 + grp, gthreads);
+    if (gt == 0) s_misc[0] = atomicAdd(ctrl + C_WORK, 1);
+    group_barrier(1 + grp, gthreads);
+    const int item_id = s_misc[0];
     if (item_id >= n_items) break;
     const Item it = items[item_id];
-    float baseA = 0.f, baseB = 0.f;
     const int nbatch = (it.count + NB - 1) / NB;
 
     // records of batch 0
-    for (int q = tid; q < NB * RS; q += kFusedThreads) {
+    for (int q = gt; q < NB * RS; q += gthreads) {
       int b = q / RS;
-      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q % RS)] : 0.f;
+      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q - b * RS)] : 0.f;
     }
-    __syncthreads();
+    group_barrier(1 + grp, gthreads);
 
     for (int bt = 0; bt < nbatch; ++bt) {
       const int buf = bt & 1;
       const float *r_cur = s_rec + buf * NB * RS;
-      float *S_cur = s_S + buf * NB * KP;
-      // prefetch the next batch's records
-      if (bt + 1 < nbatch) {
-        for (int q = tid; q < NB * RS; q += kFusedThreads) {
-          int b = (bt + 1) * NB + q / RS;
-          s_rec[(buf ^ 1) * NB * RS + q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q % RS)] : 0.f;
+      if (bt + 1 < nbatch) {  // prefetch the next batch's records
+        for (int q = gt; q < NB * RS; q += gthreads) {
+          int b = q / RS;
+          int pb = (bt + 1) * NB + b;
+          s_rec[(buf ^ 1) * NB * RS + q] = (pb < it.count) ? rec[(size_t)(it.start + pb) * RS + (q - b * RS)] : 0.f;
         }
       }
 
-      // ---- phase K: mass-weighted SSP spectrum at the window knots; "total" partial sums -------
-      float tot[NB];
-#pragma unroll
-      for (int b = 0; b < NB; ++b) tot[b] = 0.f;
-      for (int u = tid + 1; u <= KW; u += kFusedThreads) {
-        const int j = ja + u - 1;
-        const float lz = s_lamz[u], lzm = s_lamz[u - 1];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const float *rb = r_cur + b * RS;
-          const int row = __float_as_int(rb[2]);
-          float S = 0.f;
-          if (METHOD == RBX_METHOD_LINEAR) {
-            const float *f = p.tab[0] + (size_t)row * p.Lp + j;
-            S = rb[4] * __ldg(f);
-            S = fmaf(rb[5], __ldg(f + p.Lp), S);
-            S = fmaf(rb[6], __ldg(f + (size_t)p.na * p.Lp), S);
-            S = fmaf(rb[7], __ldg(f + (size_t)(p.na + 1) * p.Lp), S);
-          } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float *f = p.tab[t] + (size_t)row * p.Lp + j;
-              // weight order (jj, ii) = (0,0),(0,1),(1,0),(1,1): rows +0, +na, +1, +na+1
-              S = fmaf(rb[4 + 4 * t + 0], __ldg(f), S);
-              S = fmaf(rb[4 + 4 * t + 1], __ldg(f + (size_t)p.na * p.Lp), S);
-              S = fmaf(rb[4 + 4 * t + 2], __ldg(f + p.Lp), S);
-              S = fmaf(rb[4 + 4 * t + 3], __ldg(f + (size_t)(p.na + 1) * p.Lp), S);
-            }
-          }
-          S_cur[b * KP + u] = S;
-          if (u == 1) S_cur[b * KP] = S;
-          if (u == KW) S_cur[b * KP + KW + 1] = S;
-          // total luminosity in band: sum s_j * (x_j - x_{j-1}) * [tmin <= x_j <= tmax]
-          const float d = rb[0];
-          const float x = __fmul_rn(lz, d);
-          if (j > 0 && x >= p.tmin && x <= p.tmax) tot[b] = fmaf(S, x - __fmul_rn(lzm, d), tot[b]);
-        }
-      }
+      // ---- phase 1: per-knot quantities and the two normalisation sums ----------------------------
+      unsigned kk[NB];                 // k of slot 0 | k of slot 1 << 16
+      float g0[NB], g1[NB], dm0[NB], dm1[NB];
+      int cb[NB];                      // chunk whose base this lane deposits (-1: none)
+      float bv[NB], bm[NB];            // its line: value at the chunk's first channel, slope
+      float red[2 * NB];               // tot[0..NB), new[0..NB)
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        float v = warp_sum(tot[b]);
-        if (lane == 0) s_red[wid * NB + b] = v;
+        const float *rb = r_cur + b * RS;
+        const float4 r0 = *reinterpret_cast<const float4 *>(rb);  // d, 1/d, row, -
+        const float d = r0.x, rd = r0.y;
+        const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
+        float Sa = 0.f, Sb = 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
+          const float *f = tab[t] + row;
+          const float2 fA = __ldg(reinterpret_cast<const float2 *>(f));
+          const float2 fB = __ldg(reinterpret_cast<const float2 *>(f + (METHOD == RBX_METHOD_LINEAR ? rowB : rowC)));
+          const float2 fC = __ldg(reinterpret_cast<const float2 *>(f + (METHOD == RBX_METHOD_LINEAR ? rowC : rowB)));
+          const float2 fD = __ldg(reinterpret_cast<const float2 *>(f + rowD));
+          // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
+          Sa = fmaf(w.x, fA.x, Sa); Sb = fmaf(w.x, fA.y, Sb);
+          Sa = fmaf(w.y, fB.x, Sa); Sb = fmaf(w.y, fB.y, Sb);
+          Sa = fmaf(w.z, fC.x, Sa); Sb = fmaf(w.z, fC.y, Sb);
+          Sa = fmaf(w.w, fD.x, Sa); Sb = fmaf(w.w, fD.y, Sb);
+        }
+        float S0 = Sa, S1 = Sb;
+        if (any_odd) {  // lanes at the true ends of the SSP grid: clamped copies (jnp.interp end values)
+          S0 = take_hi[0] ? Sb : Sa;
+          S1 = take_hi[1] ? Sb : Sa;
+        }
+        const float x0 = __fmul_rn(lz[0], d), x1 = __fmul_rn(lz[1], d);
+        float e0, e1;
+        const int k0 = channel_of(x0, p, s_lut, s_tt, e0);
+        const int k1 = channel_of(x1, p, s_lut, s_tt, e1);
+        const float2 q0 = s_q[k0], q1 = s_q[k1];
+        // right neighbour's first knot, left neighbour's last slope
+        const float S2 = __shfl_down_sync(0xffffffffu, S0, 1);
+        const int k2 = __shfl_down_sync(0xffffffffu, k0, 1);
+        const float e2 = __shfl_down_sync(0xffffffffu, e0, 1);
+        const float q2x = __shfl_down_sync(0xffffffffu, q0.x, 1);
+        const float q2y = __shfl_down_sync(0xffffffffu, q0.y, 1);
+        const float m0 = (S1 - S0) * rdlv[0] * rd;
+        const float m1 = (S2 - S1) * rdlv[1] * rd;
+        const float mp = __shfl_up_sync(0xffffffffu, m1, 1);
+        // total: sum S_j (x_j - x_{j-1}) over knots inside the band   (rubix/spectra/ifu.py:241-247)
+        float tot = 0.f;
+        if (x0 >= p.tmin && x0 <= p.tmax) tot = S0 * (x0 - __fmul_rn(lzprev, d));
+        if (x1 >= p.tmin && x1 <= p.tmax) tot = fmaf(S1, x1 - x0, tot);
+        // new: sum_w p(t_w) dt_w over the channels of my two segments   (rubix/spectra/ifu.py:249-251)
+        const float D0 = e1 - e0, D1 = e2 - e1;
+        const float T0 = fmaf(-(x0 - p.tref), D0, (q1.x - q0.x) + (q1.y - q0.y));
+        const float T1 = fmaf(-(x1 - p.tref), D1, (q2x - q1.x) + (q2y - q1.y));
+        float nw = fmaf(m0, T0, S0 * D0);
+        nw += fmaf(m1, T1, S1 * D1);
+        red[b] = owner ? tot : 0.f;
+        red[NB + b] = owner ? nw : 0.f;
+        // kinks
+        const float d0 = m0 - mp, d1 = m1 - m0;
+        dm0[b] = d0; dm1[b] = d1;
+        g0[b] = d0 * (e0 - x0);
+        g1[b] = d1 * (e1 - x1);
+        kk[b] = (unsigned)k0 | ((unsigned)k1 << 16);
+        // chunk base: the line valid at the first chunk start inside [k0, k2)
+        const int c = (k0 + CH - 1) >> lay.chs;
+        const int chan = c << lay.chs;
+        const bool has = owner && chan < k2 && chan < p.W;
+        const bool second = chan >= k1;
+        const float Sr = second ? S1 : S0, mr = second ? m1 : m0, xr = second ? x1 : x0;
+        const float tch = s_tt[has ? chan : 0].y;
+        cb[b] = has ? c : -1;
+        bv[b] = fmaf(mr, tch - xr, Sr);
+        bm[b] = mr;
       }
-      __syncthreads();  // (A) S_cur, tot partials visible
 
-      // ---- phase C1: lines of this particle on my chunk; "new total" partial sums -------------
-      float A0[NB], B0[NB], dA1[NB], dB1[NB];
-      int k1[NB], nbp[NB], u0[NB];
+      // ---- transposed warp reduction of the 2*NB sums ----------------------------------------------
+      // after the three folding steps lane l holds value index ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1)
+      float v4[4], v2[2], v1;
+      {
+        const bool hi = lane & 16;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        float np = 0.f;
-        A0[b] = B0[b] = dA1[b] = dB1[b] = 0.f;
-        k1[b] = 0; nbp[b] = 0; u0[b] = 0;
-        if (has_chunk && bt * NB + b < it.count) {
-          const float *rb = r_cur + b * RS;
-          const float d = rb[0], rd = rb[1];
-          const float *S = S_cur + b * KP;
-          // knot at or below the first channel (chunk-local: tau_x = lam_z * d - tc, one rounding)
-          while (fmaf(s_lamz[ug + 1], d, -tcc) <= tfirst) ++ug;
-          while (fmaf(s_lamz[ug], d, -tcc) > tfirst) --ug;
-          u0[b] = ug;
-          const float Sa = S[ug];
-          const float m0 = (S[ug + 1] - Sa) * s_rdl[ug] * rd;
-          const float tx0 = fmaf(s_lamz[ug], d, -tcc);
-          A0[b] = fmaf(-m0, tx0, Sa);  // value of the line at tau = 0
-          B0[b] = m0;
-          np = fmaf(A0[b], D0, m0 * T0);
-          float mprev = m0;
-          for (int u = ug + 1;; ++u) {
-            const float tx = fmaf(s_lamz[u], d, -tcc);
-            if (!(tx <= tlast)) break;
-            int k = (int)ceilf((tx - tfirst) * rdtc);
-            k = min(max(k, 0), nk - 1);
-            while (k > 0 && p.tau[w0 + k - 1] >= tx) --k;
-            while (k < nk - 1 && p.tau[w0 + k] < tx) ++k;
-            const float m = (S[u + 1] - S[u]) * s_rdl[u] * rd;
-            const float dB = m - mprev;
-            const float dA = -dB * tx;
-            const float2 sf = p.suf[w0 + k];
-            np = fmaf(dA, sf.x, np);
-            np = fmaf(dB, sf.y, np);
-            if (nbp[b] == 0) { k1[b] = k; dA1[b] = dA; dB1[b] = dB; }
-            ++nbp[b];
-            mprev = m;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float keep = hi ? red[i + 4] : red[i], send = hi ? red[i] : red[i + 4];
+          v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
-        float v = warp_sum(np);
-        if (lane == 0) s_red[NWARP * NB + wid * NB + b] = v;
       }
-      __syncthreads();  // (B) new partials visible
-      if (tid < NB) {
-        float a = 0.f, bsum = 0.f;
+      {
+        const bool hi = lane & 8;
 #pragma unroll
-        for (int k = 0; k < NWARP; ++k) { a += s_red[k * NB + tid]; bsum += s_red[NWARP * NB + k * NB + tid]; }
-        s_scale[tid] = nan_to_num0(a / bsum);  // rubix/spectra/ifu.py:252-255
+        for (int i = 0; i < 2; ++i) {
+          const float keep = hi ? v4[i + 2] : v4[i], send = hi ? v4[i] : v4[i + 2];
+          v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
       }
-      __syncthreads();  // (C) scale visible
+      {
+        const bool hi = lane & 4;
+        const float keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
+        v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+      float *red_cur = s_red + buf * (2 * NB * kMaxGroupWarps);
+      if ((lane & 3) == 0) {
+        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        red_cur[idx * kMaxGroupWarps + wg] = v1;
+      }
+      group_barrier(1 + grp, gthreads);
+      // every warp: lane i < 2*NB sums value i over the group's warps in warp order
+      float scale = 0.f;
+      {
+        float acc = 0.f;
+        if (lane < 2 * NB)
+          for (int w = 0; w < NWG; ++w) acc += red_cur[lane * kMaxGroupWarps + w];
+        const float nwv = __shfl_down_sync(0xffffffffu, acc, NB);
+        scale = nan_to_num0(acc / nwv);  // lanes 0..NB-1: total / new   (rubix/spectra/ifu.py:252-255)
+      }
 
-      // ---- phase C2: accumulate the scaled lines ---------------------------------------------
+      // ---- phase 2: scaled kinks and chunk bases ----------------------------------------------------
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        if (has_chunk && bt * NB + b < it.count) {
-          const float sc = s_scale[b];
-          baseA = fmaf(sc, A0[b], baseA);
-          baseB = fmaf(sc, B0[b], baseB);
-          if (nbp[b] > 0) {
-            float2 st = my_step[k1[b]];
-            st.x = fmaf(sc, dA1[b], st.x);
-            st.y = fmaf(sc, dB1[b], st.y);
-            my_step[k1[b]] = st;
-          }
-          if (nbp[b] > 1) {  // fine SSP grids: more than one knot per chunk -> replay the rest
-            const float *rb = r_cur + b * RS;
-            const float d = rb[0], rd = rb[1];
-            const float *S = S_cur + b * KP;
-            int u = u0[b] + 1;
-            float mprev = (S[u + 1] - S[u]) * s_rdl[u] * rd;
-            for (++u;; ++u) {
-              const float tx = fmaf(s_lamz[u], d, -tcc);
-              if (!(tx <= tlast)) break;
-              int k = (int)ceilf((tx - tfirst) * rdtc);
-              k = min(max(k, 0), nk - 1);
-              while (k > 0 && p.tau[w0 + k - 1] >= tx) --k;
-              while (k < nk - 1 && p.tau[w0 + k] < tx) ++k;
-              const float m = (S[u + 1] - S[u]) * s_rdl[u] * rd;
-              const float dB = m - mprev;
-              float2 st = my_step[k];
-              st.x = fmaf(sc, -dB * tx, st.x);
-              st.y = fmaf(sc, dB, st.y);
-              my_step[k] = st;
-              mprev = m;
-            }
-          }
+        const float sc = __shfl_sync(0xffffffffu, scale, b);
+        if (owner && bt * NB + b < it.count) {
+          const int k0 = (int)(kk[b] & 0xffffu), k1 = (int)(kk[b] >> 16);
+          cell_add(s_step + cellbase + k0, sc * g0[b], sc * dm0[b], shared_mode);
+          cell_add(s_step + cellbase + k1, sc * g1[b], sc * dm1[b], shared_mode);
+          if (cb[b] >= 0) cell_add(my_base + cb[b], sc * bv[b], sc * bm[b], false);
         }
+        __syncwarp();
       }
     }  // batches
+    group_barrier(1 + grp, gthreads);
 
-    // ---- expand lines + steps into the spaxel spectrum and store it ------------------------------
-    if (has_chunk) {
-      float *row = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
-      float pa = baseA, pb = baseB;
-      for (int k = 0; k < nk; ++k) {
-        float2 st = my_step[k];
-        my_step[k] = make_float2(0.f, 0.f);
-        pa += st.x; pb += st.y;
-        row[w0 + k] = fmaf(pb, p.tau[w0 + k], pa);
+    // ---- expand the cells into the spaxel spectrum and store it -----------------------------------
+    float *row = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
+    for (int c = wg; c < lay.nch; c += NWG) {
+      float vcar = 0.f, scar = 0.f;
+      for (int w = 0; w < NWG; ++w) {
+        const float2 bs = s_base[(size_t)w * lay.nch + c];
+        vcar += bs.x; scar += bs.y;
+      }
+      __syncwarp();
+      if (lane < NWG) s_base[(size_t)lane * lay.nch + c] = make_float2(0.f, 0.f);
+      for (int h = 0; h < CH; h += 32) {
+        const int ch = (c << lay.chs) + h + lane;
+        float A = 0.f, B = 0.f;
+        if (ch <= p.W) {
+          int off = 0;
+          for (int w = 0; w < nreg; ++w) {
+            const int klo_w = shared_mode ? 0 : s_misc[2 + w];
+            const int size_w = shared_mode ? p.W + 1 : s_misc[12 + w] - klo_w + 1;
+            const int idx = ch - klo_w;
+            if ((unsigned)idx < (unsigned)size_w) {
+              float2 *cellp = s_step + off + idx;
+              const float2 cv = *cellp;
+              A += cv.x; B += cv.y;
+              *cellp = make_float2(0.f, 0.f);
+            }
+            off += size_w;
+          }
+        }
+        const bool valid = ch < p.W;
+        const bool start = (h + lane) == 0;   // the chunk's first channel takes the base line itself
+        if (start || !valid) { A = 0.f; B = 0.f; }
+        const float2 t2 = s_tt[valid ? ch : 0];
+        const float dtc = start ? 0.f : t2.y - t2.x;
+        // slope after the kinks of this channel, then the value increments
+        float sB = B;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, sB, o);
+          if (lane >= o) sB += n;
+        }
+        const float s = scar + sB;
+        float inc = fmaf(s, dtc, A);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += n;
+        }
+        const float v = vcar + inc;
+        if (valid) row[ch] = v;
+        scar = __shfl_sync(0xffffffffu, s, 31);
+        vcar = __shfl_sync(0xffffffffu, v, 31);
       }
     }
   }
 }
+
 
 // cube[s] = sum over the spaxel's items, in item order (deterministic two-level reduction)
 __global__ void reduce_partials_kernel(const int *__restrict__ item_start, const Item *__restrict__ items,
@@ -523,17 +707,12 @@ extern "C" int rbx_profile_fused(double *mean_ms, int64_t *launches, int reset) 
   return RBX_OK;
 }
 
-static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
+// Shared-memory layout and static limits of fused_cube_kernel for this plan.
+static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_bytes) {
   const PlanView &v = plan->v;
-  if (v.nchunks > kFusedThreads) {
-    set_error("rbx_build_cube: more than 4096 telescope channels; use the stage calls");
-    return RBX_ERR_UNSUPPORTED;
-  }
-  // knots inside the band at rest (+25% head-room for Doppler spread) must fit the window
-  int inband = 0;
-  for (int l = 0; l < v.L; ++l) inband += (plan->h_lamz[l] >= v.tmin && plan->h_lamz[l] <= v.tmax);
-  if (inband + inband / 4 + 8 > kMaxWindow) {
-    set_error("rbx_build_cube: SSP grid too fine for the fused kernel's knot window; use the stage calls");
+  if (!plan->lut_ok || v.nb <= 0 || v.W + 1 >= 65535) {
+    set_error("rbx_build_cube: telescope wavelength grid not supported by the fused kernel (too long, or too "
+              "uneven for the channel lookup table); use the stage calls");
     return RBX_ERR_UNSUPPORTED;
   }
   for (int w = 1; w < v.W; ++w)
@@ -546,6 +725,70 @@ static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
       set_error("rbx_build_cube: SSP wavelength grid must be non-decreasing");
       return RBX_ERR_UNSUPPORTED;
     }
+  // knots that can reach the band for |v| up to ~0.03 c
+  const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
+  int inband = 0;
+  double min2 = 1e300, max2 = 0.0;  // extremes of lam_z[j+2] - lam_z[j] among those knots
+  for (int l = 0; l < v.L; ++l) {
+    const double x = plan->h_lamz[l];
+    if (x < lo || x > hi) continue;
+    ++inband;
+    if (l + 2 < v.L) {
+      const double d2 = (double)plan->h_lamz[l + 2] - x;
+      min2 = std::fmin(min2, d2);
+      max2 = std::fmax(max2, d2);
+    }
+  }
+  if (inband + 8 > kMaxKnots) {
+    set_error("rbx_build_cube: SSP grid too fine for the fused kernel's knot window; use the stage calls");
+    return RBX_ERR_UNSUPPORTED;
+  }
+  // channels per chunk: a lane's two segments must hold at most one chunk start
+  const double span = max2 > 0.0 ? max2 * 1.03 / (double)plan->min_dt + 4.0 : 4.0;
+  int chs = 6;
+  while (chs <= 8 && span >= (double)(1 << chs)) ++chs;
+  if (chs > 8) {
+    set_error("rbx_build_cube: SSP grid too coarse relative to the telescope channels for the fused kernel; "
+              "use the stage calls");
+    return RBX_ERR_UNSUPPORTED;
+  }
+  lay.chs = chs;
+  lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
+  lay.collide = (min2 * 0.97 <= (double)plan->max_dt) ? 1 : 0;
+  lay.cap = v.W + 1 + kMaxGroupWarps * kRegionSlack;
+  auto a16 = [](int x) { return (x + 15) & ~15; };
+  auto a128 = [](int x) { return (x + 127) & ~127; };
+  lay.lut_bytes = a16(2 * v.nb);
+  lay.tt_bytes = a16(8 * v.W);
+  lay.q_bytes = a16(8 * (v.W + 1));
+  lay.off_mbar = 0;
+  lay.off_lut = 16;
+  lay.off_tt = lay.off_lut + lay.lut_bytes;
+  lay.off_q = lay.off_tt + lay.tt_bytes;
+  lay.off_group = a128(lay.off_q + lay.q_bytes);
+  const int rs = v.method == RBX_METHOD_LINEAR ? 8 : 20;
+  lay.g_step = 0;
+  lay.g_base = a16(lay.cap * 8);
+  lay.g_rec = lay.g_base + a16(kMaxGroupWarps * lay.nch * 8);
+  lay.g_red = lay.g_rec + a16(2 * NB * rs * 4);
+  lay.g_misc = lay.g_red + a16(2 * 2 * NB * kMaxGroupWarps * 4);
+  lay.group_stride = a128(lay.g_misc + 32 * 4);
+  const int budget = 227 * 1024;
+  lay.max_groups = std::min(kMaxGroups, (budget - lay.off_group) / lay.group_stride);
+  if (lay.max_groups < 1) {
+    set_error("rbx_build_cube: telescope wavelength grid too long for the fused kernel's shared memory; use the "
+              "stage calls");
+    return RBX_ERR_UNSUPPORTED;
+  }
+  smem_bytes = (size_t)lay.off_group + (size_t)lay.max_groups * lay.group_stride;
+  return RBX_OK;
+}
+
+static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
+  FusedLayout lay;
+  size_t smem = 0;
+  int rc = fused_layout(plan, lay, smem);
+  if (rc != RBX_OK) return rc;
   if (num_spaxels < 1 || (int64_t)num_spaxels * num_spaxels > (1 << 24)) {
     set_error("rbx_build_cube: num_spaxels out of range");
     return RBX_ERR_INVALID_ARGUMENT;
@@ -608,24 +851,23 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   count_launch();
   RBX_LAUNCH_OK();
 
-  const int KPmax = kMaxWindow + 2;
-  const int RS = ws.rec_stride;
-  size_t smem = sizeof(float) * (2 * KPmax + 2 * NB * KPmax + 2) + sizeof(float2) * kFusedThreads * kStepPitch +
-                sizeof(float) * (2 * NB * RS + 2 * (kFusedThreads / 32) * NB + NB) + 64;
+  FusedLayout lay;
+  size_t smem = 0;
+  rc = fused_layout(plan, lay, smem);
+  if (rc != RBX_OK) return rc;
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  int ctas_per_sm = 2;
   const bool prof = g_profile.load() != 0;
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
   if (v.method == RBX_METHOD_LINEAR) {
     RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fused_cube_kernel<RBX_METHOD_LINEAR><<<nsm * ctas_per_sm, kFusedThreads, smem, stream>>>(
-        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp);
+    fused_cube_kernel<RBX_METHOD_LINEAR><<<nsm, kCtaThreads, smem, stream>>>(
+        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
   } else {
     RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fused_cube_kernel<RBX_METHOD_CUBIC><<<nsm * ctas_per_sm, kFusedThreads, smem, stream>>>(
-        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp);
+    fused_cube_kernel<RBX_METHOD_CUBIC><<<nsm, kCtaThreads, smem, stream>>>(
+        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
   }
   count_launch();
   RBX_LAUNCH_OK();

@@ -40,6 +40,32 @@ __global__ void approx_df_kernel(const float *__restrict__ x, const float *__res
   out[tid] = v;
 }
 
+// Channel lookup table of the fused kernel.  bucket[w] = bucket of channel w under bucket_offset();
+// lut[b] = number of channels whose bucket is < b.  With at most one channel per bucket,
+// #channels below x is lut[b(x)] + (t[lut[b(x)]] < x) for every x, because b() is monotone.
+__global__ void lut_bucket_kernel(const float *__restrict__ t, int W, float tmin, float trange, float scale,
+                                  int *__restrict__ bucket, int *__restrict__ ok) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  int b = bucket_offset(t[w], tmin, trange, scale) >> 1;
+  bucket[w] = b;
+  if (w > 0) {
+    int bp = bucket_offset(t[w - 1], tmin, trange, scale) >> 1;
+    if (bp >= b) atomicExch(ok, 0);
+  }
+}
+
+__global__ void lut_fill_kernel(const int *__restrict__ bucket, int W, int nb, uint16_t *__restrict__ lut) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int lo = 0, hi = W;  // first w with bucket[w] >= b
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (bucket[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  lut[b] = (uint16_t)lo;
+}
+
 }  // namespace rbx
 
 using namespace rbx;
@@ -77,7 +103,6 @@ extern "C" int rbx_plan_create(rbx_plan **out, const float *h_met, int nz, const
   std::memset(&v, 0, sizeof(v));
   v.nz = nz; v.na = na; v.L = L; v.W = W; v.method = method; v.vel_comp = vel_component;
   v.Lp = (L + 3) & ~3;
-  v.nchunks = (W + kChunk - 1) / kChunk;
   int rc;
 #define TRY(x) do { rc = (x); if (rc != RBX_OK) { rbx_plan_destroy(pl); return rc; } } while (0)
 
@@ -124,31 +149,61 @@ extern "C" int rbx_plan_create(rbx_plan **out, const float *h_met, int nz, const
 
   // telescope grid
   pl->h_t.assign(h_t, h_t + W);
-  std::vector<float> dt(W, 0.f), tau(W), tc(v.nchunks);
-  std::vector<float2> suf(W);
-  float tmin = h_t[0], tmax = h_t[0];
+  std::vector<float> dt(W, 0.f);
+  std::vector<float2> tt(W), q(W + 1);
+  float tmin = h_t[0], tmax = h_t[0], min_dt = 3.0e38f, max_dt = 0.f;
   for (int w = 0; w < W; ++w) {
-    if (w > 0) dt[w] = h_t[w] - h_t[w - 1];
+    if (w > 0) {
+      dt[w] = h_t[w] - h_t[w - 1];
+      min_dt = std::fmin(min_dt, dt[w]);
+      max_dt = std::fmax(max_dt, dt[w]);
+    }
     tmin = std::fmin(tmin, h_t[w]);
     tmax = std::fmax(tmax, h_t[w]);
+    tt[w] = make_float2(h_t[w > 0 ? w - 1 : 0], h_t[w]);
   }
-  v.tmin = tmin; v.tmax = tmax;
-  for (int c = 0; c < v.nchunks; ++c) {
-    int w0 = c * kChunk, w1 = std::min(W, w0 + kChunk);
-    tc[c] = h_t[std::min(W - 1, w0 + kChunk / 2)];
-    double sd = 0, st = 0;
-    for (int w = w1 - 1; w >= w0; --w) {
-      tau[w] = h_t[w] - tc[c];
-      sd += (double)dt[w];
-      st += (double)tau[w] * (double)dt[w];
-      suf[w] = make_float2((float)sd, (float)st);
+  v.tmin = tmin; v.tmax = tmax; v.trange = tmax - tmin;
+  v.tref = h_t[W / 2];
+  pl->min_dt = min_dt; pl->max_dt = max_dt;
+  {  // q[k] = sum_{w<k} dt[w] * (t[w] - tref) as an unevaluated float pair (hi, lo)
+    double acc = 0.0;
+    for (int k = 0; k <= W; ++k) {
+      float hi = (float)acc;
+      q[k] = make_float2(hi, (float)(acc - (double)hi));
+      if (k < W) acc += (double)dt[k] * ((double)h_t[k] - (double)v.tref);
     }
   }
   TRY(upload(pl, h_t, (size_t)W, &v.t, stream));
   TRY(upload(pl, dt.data(), (size_t)W, &v.dt, stream));
-  TRY(upload(pl, tau.data(), (size_t)W, &v.tau, stream));
-  TRY(upload(pl, suf.data(), (size_t)W, &v.suf, stream));
-  TRY(upload(pl, tc.data(), (size_t)v.nchunks, &v.tc, stream));
+  TRY(upload(pl, tt.data(), (size_t)W, &v.tt, stream));
+  TRY(upload(pl, q.data(), (size_t)W + 1, &v.q, stream));
+  // channel lookup table, built on the device with the kernel's own bucket function
+  pl->lut_ok = 0;
+  v.nb = 0; v.lut = nullptr; v.lut_scale = 0.f;
+  if (W >= 2 && min_dt > 0.f && v.trange > 0.f) {
+    double want = (double)v.trange / (double)min_dt * 1.03 + 4.0;
+    if (want <= (double)kMaxLutBuckets) {
+      v.nb = (int)want;
+      v.lut_scale = (float)((2.0 * v.nb - 1.0) / (double)v.trange);
+      void *d_bucket = nullptr, *d_ok = nullptr, *d_lut = nullptr;
+      if (cudaMalloc(&d_bucket, sizeof(int) * W) != cudaSuccess || cudaMalloc(&d_ok, sizeof(int)) != cudaSuccess ||
+          cudaMalloc(&d_lut, sizeof(uint16_t) * v.nb + 16) != cudaSuccess) {
+        set_error("rbx_plan_create: cudaMalloc failed");
+        rbx_plan_destroy(pl);
+        return RBX_ERR_CUDA;
+      }
+      pl->allocs.push_back(d_bucket); pl->allocs.push_back(d_ok); pl->allocs.push_back(d_lut);
+      int one = 1;
+      cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, stream);
+      lut_bucket_kernel<<<(W + 255) / 256, 256, 0, stream>>>(v.t, W, v.tmin, v.trange, v.lut_scale, (int *)d_bucket, (int *)d_ok);
+      lut_fill_kernel<<<(v.nb + 255) / 256, 256, 0, stream>>>((const int *)d_bucket, W, v.nb, (uint16_t *)d_lut);
+      count_launch(2);
+      int ok = 0;
+      cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, stream);
+      if (cudaStreamSynchronize(stream) == cudaSuccess) pl->lut_ok = ok;
+      v.lut = (const uint16_t *)d_lut;
+    }
+  }
 #undef TRY
   // the staging vectors above die at return: make sure the async copies have consumed them
   if (cudaStreamSynchronize(stream) != cudaSuccess) {

@@ -45,14 +45,11 @@ def _oracle_cube(cfg, data, bc03, muse_wave, method):
     from rubix_b200.core.telescope import get_spatial_bin_edges
     edges = get_spatial_bin_edges(cfg)
     nb = len(edges) - 1
-    # the reference's segment_sum keeps ids < sbin^2 of x + nb*y (rubix/core/ifu.py:320)
-    m, z, a, _ = orc.filter_particles(data["coords"], data["mass"], data["metallicity"], data["age"], edges)
-    pix = orc.square_spaxel_assignment(data["coords"], edges)
-    spec = orc.calculate_spectra(bc03, z, a, method=method, dtype=np.float64)
-    spec = orc.scale_spectrum_by_mass(spec, m.astype(np.float64))
-    res = orc.doppler_shift_and_resampling(spec, data["velocity"], bc03["wavelength"], muse_wave, 0.1,
-                                           dtype=np.float64)
-    return orc.calculate_cube(res, pix, 25), nb
+    # ids are x + nb*y; the reference's segment_sum keeps ids < sbin^2 (rubix/core/ifu.py:320)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], muse_wave, 0.1, method=method, dtype=np.float64, n_threads=8)
+    return ref, nb
 
 
 def test_staged_intermediates_match_reference_contract(core, bc03, muse_wave, tng_subset):
@@ -82,7 +79,7 @@ def test_staged_intermediates_match_reference_contract(core, bc03, muse_wave, tn
 
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_fused_and_staged_factories_agree_with_oracle(core, bc03, muse_wave, tng_subset, method):
-    from tests.test_gpu_parity import _cube_close, _well_conditioned
+    from helpers import cube_close as _cube_close, well_conditioned as _well_conditioned
     d = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
     cubes = {}
     for fused in (False, True):
@@ -95,13 +92,13 @@ def test_fused_and_staged_factories_agree_with_oracle(core, bc03, muse_wave, tng
             assert isinstance(rd.stars.spectra, DeferredSpectra) and rd.stars.spectra.shape == (1, len(d["mass"]), 3721)
         cubes[fused] = rd.stars.datacube.cpu().numpy()
     ref, nb = _oracle_cube(cfg, d, bc03, muse_wave, method)
-    if nb == 25:  # 26 edges: x + 25*y is the cube layout; with 27 edges ids >= 625 are dropped on both sides
-        _cube_close(cubes[True], ref, f"factory fused {method}")
+    # with 27 float32 edges (nb = 26) ids >= 625 are dropped on both sides, like segment_sum does
+    _cube_close(cubes[True], ref, f"factory fused {method} (nb={nb})")
     _cube_close(cubes[True], cubes[False].astype(np.float64), f"factory fused vs staged {method}", rtol_max=1e-5)
 
 
 def test_rubix_pipeline_end_to_end(core, bc03, muse_wave, tng_subset):
-    from tests.test_gpu_parity import _cube_close, _well_conditioned
+    from helpers import cube_close as _cube_close, well_conditioned as _well_conditioned
     d = _well_conditioned(tng_subset, np.float32(1.1) * bc03["wavelength"], muse_wave)
     outs = {}
     for fused in (False, True):
@@ -114,6 +111,5 @@ def test_rubix_pipeline_end_to_end(core, bc03, muse_wave, tng_subset):
         outs[fused] = cube.cpu().numpy()
     raw, nb = _oracle_cube(cfg, d, bc03, muse_wave, "cubic")
     ref = orc.apply_lsf(orc.apply_psf(raw, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
-    if nb == 25:
-        _cube_close(outs[True], ref, "RubixPipeline fused")
+    _cube_close(outs[True], ref, f"RubixPipeline fused (nb={nb})")
     _cube_close(outs[True], outs[False].astype(np.float64), "RubixPipeline fused vs staged", rtol_max=1e-5)
