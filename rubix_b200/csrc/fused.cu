@@ -214,7 +214,7 @@ __global__ void gather_kernel(PlanView p, const uint32_t *__restrict__ idx_sorte
 // or where the regions do not fit use one shared region and 64-bit CAS adds instead.
 // Once per work item the cells are expanded with two warp scans per 32 channels and stored coalesced.
 struct FusedLayout {  // shared-memory layout (byte offsets), computed on the host
-  int off_mbar, off_lut, off_tt, off_q, off_group, group_stride;
+  int off_mbar, off_lut, off_tt, off_q, off_tc, off_group, group_stride;
   int g_step, g_base, g_rec, g_red, g_misc;  // offsets inside a group's block
   int lut_bytes, tt_bytes, q_bytes;          // multiples of 16 (TMA bulk copy sizes)
   int cap;         // step cells per group
@@ -240,8 +240,9 @@ __device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsi
   return l + (up ? 1 : 0);
 }
 
-__device__ __forceinline__ void cell_add(float2 *cell, float a, float b, bool cas) {
-  if (!cas) {
+template <bool CAS>
+__device__ __forceinline__ void cell_add(float2 *cell, float a, float b) {
+  if (!CAS) {
     float2 v = *cell;
     v.x += a; v.y += b;
     *cell = v;
@@ -272,6 +273,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   unsigned char *s_lut = smem + lay.off_lut;
   const float2 *s_tt = reinterpret_cast<const float2 *>(smem + lay.off_tt);
   const float2 *s_q = reinterpret_cast<const float2 *>(smem + lay.off_q);
+  float *s_tc = reinterpret_cast<float *>(smem + lay.off_tc);   // [nch] wavelength of each chunk's first channel
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -302,14 +304,16 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
 
   unsigned char *gbase = smem + lay.off_group + (size_t)(active ? grp : 0) * lay.group_stride;
   float2 *s_step = reinterpret_cast<float2 *>(gbase + lay.g_step);   // [cap]
-  float2 *s_base = reinterpret_cast<float2 *>(gbase + lay.g_base);   // [NWG][nch]
+  float2 *s_base = reinterpret_cast<float2 *>(gbase + lay.g_base);   // [NWG][nch + 32]
   float *s_rec = reinterpret_cast<float *>(gbase + lay.g_rec);       // [2][NB][RS]
   float *s_red = reinterpret_cast<float *>(gbase + lay.g_red);       // [2][2*NB][kMaxGroupWarps]
   int *s_misc = reinterpret_cast<int *>(gbase + lay.g_misc);         // [0]=item, [2..10)=region klo, [12..20)=region khi
 
   if (active) {
-    for (int q = gt; q < lay.cap; q += gthreads) s_step[q] = make_float2(0.f, 0.f);
-    for (int q = gt; q < NWG * lay.nch; q += gthreads) s_base[q] = make_float2(0.f, 0.f);
+    const int nbase = lay.nch + 32;  // per warp: one line per chunk + one dummy per lane
+    for (int q = gt; q < lay.cap + kMaxGroupWarps * 32; q += gthreads) s_step[q] = make_float2(0.f, 0.f);
+    for (int q = gt; q < NWG * nbase; q += gthreads) s_base[q] = make_float2(0.f, 0.f);
+    for (int q = gt; q < 2 * 2 * NB * kMaxGroupWarps; q += gthreads) s_red[q] = 0.f;
   }
 
   // ---- per-lane knot constants ---------------------------------------------------------------------
@@ -341,6 +345,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
                    : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
     }
   }
+  for (int c = tid; c < lay.nch; c += kCtaThreads) s_tc[c] = s_tt[min(c << lay.chs, p.W - 1)].y;
+  __syncthreads();
   if (!active) return;  // spare warps (no __syncthreads below this line)
 
   // ---- cell regions: the channel range each warp can reach for the Doppler factors present --------
@@ -375,9 +381,13 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   }
   const bool shared_mode = lay.collide != 0 || total_cells > lay.cap;
   const int my_klo = shared_mode ? 0 : s_misc[2 + wg];
-  const int cellbase = shared_mode ? 0 : my_off - my_klo;
   const int nreg = shared_mode ? 1 : NWG;
-  float2 *my_base = s_base + (size_t)wg * lay.nch;
+  const int nbase = lay.nch + 32;
+  // halo lanes add zeros-by-construction into a dummy cell of their own, so phase 2 needs no predicate
+  const int own = owner ? 1 : 0;
+  float2 *my_cells = s_step + (owner ? (shared_mode ? 0 : my_off - my_klo) : lay.cap + wg * 32 + lane);
+  float2 *my_base = s_base + (size_t)wg * nbase;
+  const int base_dummy = lay.nch + lane;
   const int CH = 1 << lay.chs;
 
   const float *tab[NT];
@@ -397,7 +407,11 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
     // records of batch 0
     for (int q = gt; q < NB * RS; q += gthreads) {
       int b = q / RS;
-      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + (q - b * RS)] : 0.f;
+      const int col = q - b * RS;
+      // padding slots repeat the item's first particle with zero weights: their knots stay inside the
+      // warps' cell regions and they add exact zeros
+      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + col]
+                                : (col < 4 ? rec[(size_t)it.start * RS + col] : 0.f);
     }
     group_barrier(1 + grp, gthreads);
 
@@ -408,14 +422,16 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         for (int q = gt; q < NB * RS; q += gthreads) {
           int b = q / RS;
           int pb = (bt + 1) * NB + b;
-          s_rec[(buf ^ 1) * NB * RS + q] = (pb < it.count) ? rec[(size_t)(it.start + pb) * RS + (q - b * RS)] : 0.f;
+          const int col = q - b * RS;
+          s_rec[(buf ^ 1) * NB * RS + q] = (pb < it.count) ? rec[(size_t)(it.start + pb) * RS + col]
+                                                           : (col < 4 ? rec[(size_t)it.start * RS + col] : 0.f);
         }
       }
 
       // ---- phase 1: per-knot quantities and the two normalisation sums ----------------------------
-      unsigned kk[NB];                 // k of slot 0 | k of slot 1 << 16
+      int ka[NB], kb[NB];              // cell of slot 0 / slot 1 (times `own`)
       float g0[NB], g1[NB], dm0[NB], dm1[NB];
-      int cb[NB];                      // chunk whose base this lane deposits (-1: none)
+      int cb[NB];                      // chunk whose base this lane deposits (a dummy slot if none)
       float bv[NB], bm[NB];            // its line: value at the chunk's first channel, slope
       float red[2 * NB];               // tot[0..NB), new[0..NB)
 #pragma unroll
@@ -459,9 +475,9 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         const float m1 = (S2 - S1) * rdlv[1] * rd;
         const float mp = __shfl_up_sync(0xffffffffu, m1, 1);
         // total: sum S_j (x_j - x_{j-1}) over knots inside the band   (rubix/spectra/ifu.py:241-247)
-        float tot = 0.f;
-        if (x0 >= p.tmin && x0 <= p.tmax) tot = S0 * (x0 - __fmul_rn(lzprev, d));
-        if (x1 >= p.tmin && x1 <= p.tmax) tot = fmaf(S1, x1 - x0, tot);
+        const float w0 = (x0 >= p.tmin && x0 <= p.tmax) ? x0 - __fmul_rn(lzprev, d) : 0.f;
+        const float w1 = (x1 >= p.tmin && x1 <= p.tmax) ? x1 - x0 : 0.f;
+        const float tot = fmaf(S1, w1, S0 * w0);
         // new: sum_w p(t_w) dt_w over the channels of my two segments   (rubix/spectra/ifu.py:249-251)
         const float D0 = e1 - e0, D1 = e2 - e1;
         const float T0 = fmaf(-(x0 - p.tref), D0, (q1.x - q0.x) + (q1.y - q0.y));
@@ -475,15 +491,15 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         dm0[b] = d0; dm1[b] = d1;
         g0[b] = d0 * (e0 - x0);
         g1[b] = d1 * (e1 - x1);
-        kk[b] = (unsigned)k0 | ((unsigned)k1 << 16);
+        ka[b] = k0 * own; kb[b] = k1 * own;
         // chunk base: the line valid at the first chunk start inside [k0, k2)
         const int c = (k0 + CH - 1) >> lay.chs;
         const int chan = c << lay.chs;
         const bool has = owner && chan < k2 && chan < p.W;
         const bool second = chan >= k1;
         const float Sr = second ? S1 : S0, mr = second ? m1 : m0, xr = second ? x1 : x0;
-        const float tch = s_tt[has ? chan : 0].y;
-        cb[b] = has ? c : -1;
+        const float tch = s_tc[min(c, lay.nch - 1)];
+        cb[b] = has ? c : base_dummy;
         bv[b] = fmaf(mr, tch - xr, Sr);
         bm[b] = mr;
       }
@@ -523,24 +539,34 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
       // every warp: lane i < 2*NB sums value i over the group's warps in warp order
       float scale = 0.f;
       {
-        float acc = 0.f;
-        if (lane < 2 * NB)
-          for (int w = 0; w < NWG; ++w) acc += red_cur[lane * kMaxGroupWarps + w];
+        // slots of warps beyond NWG stay zero, so the sum always runs over all kMaxGroupWarps entries
+        const float4 *rp = reinterpret_cast<const float4 *>(red_cur + (lane & (2 * NB - 1)) * kMaxGroupWarps);
+        const float4 ra = rp[0], rb4 = rp[1];
+        const float acc = ((ra.x + ra.y) + (ra.z + ra.w)) + ((rb4.x + rb4.y) + (rb4.z + rb4.w));
         const float nwv = __shfl_down_sync(0xffffffffu, acc, NB);
         scale = nan_to_num0(acc / nwv);  // lanes 0..NB-1: total / new   (rubix/spectra/ifu.py:252-255)
+        if (bt * NB + lane >= it.count) scale = 0.f;  // padding slots of the last batch add nothing
       }
 
       // ---- phase 2: scaled kinks and chunk bases ----------------------------------------------------
+      if (!shared_mode) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const float sc = __shfl_sync(0xffffffffu, scale, b);
-        if (owner && bt * NB + b < it.count) {
-          const int k0 = (int)(kk[b] & 0xffffu), k1 = (int)(kk[b] >> 16);
-          cell_add(s_step + cellbase + k0, sc * g0[b], sc * dm0[b], shared_mode);
-          cell_add(s_step + cellbase + k1, sc * g1[b], sc * dm1[b], shared_mode);
-          if (cb[b] >= 0) cell_add(my_base + cb[b], sc * bv[b], sc * bm[b], false);
+        for (int b = 0; b < NB; ++b) {
+          const float sc = __shfl_sync(0xffffffffu, scale, b);
+          cell_add<false>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
+          cell_add<false>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
+          cell_add<false>(my_base + cb[b], sc * bv[b], sc * bm[b]);
+          __syncwarp();
         }
-        __syncwarp();
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float sc = __shfl_sync(0xffffffffu, scale, b);
+          cell_add<true>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
+          cell_add<true>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
+          cell_add<false>(my_base + cb[b], sc * bv[b], sc * bm[b]);
+          __syncwarp();
+        }
       }
     }  // batches
     group_barrier(1 + grp, gthreads);
@@ -550,11 +576,11 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
     for (int c = wg; c < lay.nch; c += NWG) {
       float vcar = 0.f, scar = 0.f;
       for (int w = 0; w < NWG; ++w) {
-        const float2 bs = s_base[(size_t)w * lay.nch + c];
+        const float2 bs = s_base[(size_t)w * nbase + c];
         vcar += bs.x; scar += bs.y;
       }
       __syncwarp();
-      if (lane < NWG) s_base[(size_t)lane * lay.nch + c] = make_float2(0.f, 0.f);
+      if (lane < NWG) s_base[(size_t)lane * nbase + c] = make_float2(0.f, 0.f);
       for (int h = 0; h < CH; h += 32) {
         const int ch = (c << lay.chs) + h + lane;
         float A = 0.f, B = 0.f;
@@ -765,11 +791,12 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
   lay.off_lut = 16;
   lay.off_tt = lay.off_lut + lay.lut_bytes;
   lay.off_q = lay.off_tt + lay.tt_bytes;
-  lay.off_group = a128(lay.off_q + lay.q_bytes);
+  lay.off_tc = lay.off_q + lay.q_bytes;
+  lay.off_group = a128(lay.off_tc + a16(4 * lay.nch));
   const int rs = v.method == RBX_METHOD_LINEAR ? 8 : 20;
   lay.g_step = 0;
-  lay.g_base = a16(lay.cap * 8);
-  lay.g_rec = lay.g_base + a16(kMaxGroupWarps * lay.nch * 8);
+  lay.g_base = a16((lay.cap + kMaxGroupWarps * 32) * 8);  // + one dummy cell per lane (halo lanes)
+  lay.g_rec = lay.g_base + a16(kMaxGroupWarps * (lay.nch + 32) * 8);
   lay.g_red = lay.g_rec + a16(2 * NB * rs * 4);
   lay.g_misc = lay.g_red + a16(2 * 2 * NB * kMaxGroupWarps * 4);
   lay.group_stride = a128(lay.g_misc + 32 * 4);
