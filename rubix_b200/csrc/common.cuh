@@ -51,6 +51,8 @@ struct PlanView {
   float tmin, tmax, trange;    // telescope band; trange = tmax - tmin
   float lut_scale;             // (2*nb - 1) / trange, see bucket_offset()
   float tref;                  // reference wavelength of the q table (band centre)
+  int affine;                  // t[w] == fadd(fmul(w, tdelta), t0) for every channel (numpy/jnp arange grids)
+  float t0, tdelta, tinv;      // affine grid parameters (tinv = 1 / tdelta)
   const float *zgrid, *agrid;  // SSP metallicity / age axes
   const float *tab[4];         // f, fx, fy, fxy: (nz*na, Lp) float32, rows 16-byte aligned
   const float *lamz;           // (L)  (1+z)*wavelength                       rubix/spectra/ifu.py:80

@@ -59,7 +59,12 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
                             const float *__restrict__ met, const float *__restrict__ age,
                             const int32_t *__restrict__ pixel, int n, int nseg, int ncell,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
-                            int *__restrict__ ctrl) {
+                            int *__restrict__ ctrl, int smem_hist) {
+  extern __shared__ int s_hist[];  // per-block spaxel histogram (when it fits): one global atomic per bin
+  if (smem_hist) {
+    for (int s = threadIdx.x; s < nseg; s += blockDim.x) s_hist[s] = 0;
+    __syncthreads();
+  }
   float dmin = 3.0e38f, dmax = 0.f;
   int nvalid = 0;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
@@ -73,7 +78,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     if (valid) {
       uint32_t cell = (uint32_t)((i - 1) * (p.na - 1) + (j - 1));
       key = (uint32_t)px * (uint32_t)ncell + (ncell > 1 ? cell : 0u);
-      atomicAdd(counts + px, 1);
+      atomicAdd(smem_hist ? s_hist + px : counts + px, 1);
       dmin = fminf(dmin, d);
       dmax = fmaxf(dmax, d);
       ++nvalid;
@@ -92,6 +97,13 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     atomicMin(ctrl + C_DMIN, __float_as_int(dmin));
     atomicMax(ctrl + C_DMAX, __float_as_int(dmax));
     atomicAdd(ctrl + C_NVALID, nvalid);
+  }
+  if (smem_hist) {
+    __syncthreads();
+    for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
+      const int c = s_hist[s];
+      if (c) atomicAdd(counts + s, c);
+    }
   }
 }
 
@@ -125,10 +137,11 @@ __global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, in
     if (ra > 0) {
       float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
       float lo_l = p.tmin / dmax, hi_l = p.tmax / dmin;
-      int a = 0;
-      while (a < p.L && p.lamz[a] < lo_l) ++a;  // first knot that can reach the band
-      int b = a;
-      while (b < p.L && p.lamz[b] <= hi_l) ++b;  // one past the last knot that can be in the band
+      // first knot that can reach the band / one past the last knot that can be in it
+      int a = 0, hi_a = p.L;
+      while (a < hi_a) { int mid = (a + hi_a) >> 1; if (p.lamz[mid] < lo_l) a = mid + 1; else hi_a = mid; }
+      int b = ss_right(p.lamz, p.L, hi_l);
+      b = max(b, a);
       ja = max(0, a - 3);
       jb = min(p.L, b + 3);
       if (jb - ja > kMaxKnots) err = 2;
@@ -221,6 +234,7 @@ struct FusedLayout {  // shared-memory layout (byte offsets), computed on the ho
   int nch, chs;    // chunks per row, log2(channels per chunk)
   int max_groups;
   int collide;     // two knots of one warp can fall into the same channel -> CAS adds
+  int force_lut;   // use the lookup-table channel search even on an affine grid (RBX_FUSED_FORCE_LUT=1, tests)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -229,9 +243,19 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// number of channels below x, and t[k-1] (t[0] for k = 0)
+// number of channels below x, and t[k-1] (t[0] for k = 0).
+// AFFINE grids: k = ceil((x - t0) / delta) in float32.  Within ~1e-3 A of a channel wavelength the
+// rounded quotient may pick the neighbouring cell; the kink is then booked one channel off with the
+// matching e, which changes that single channel by dm * (t_k - x) <= dm * 1e-3 A: p(t) is continuous.
+template <bool AFFINE>
 __device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsigned char *s_lut,
                                           const float2 *s_tt, float &e) {
+  if (AFFINE) {
+    const float v = fminf(fmaxf((x - p.t0) * p.tinv, 0.f), (float)p.W);
+    const int k = __float2int_ru(v);
+    e = __fadd_rn(__fmul_rn((float)max(k - 1, 0), p.tdelta), p.t0);
+    return k;
+  }
   const int off = bucket_offset(x, p.tmin, p.trange, p.lut_scale);
   const int l = *reinterpret_cast<const uint16_t *>(s_lut + off);
   const float2 t2 = s_tt[l];
@@ -259,7 +283,7 @@ __device__ __forceinline__ void cell_add(float2 *cell, float a, float b) {
   }
 }
 
-template <int METHOD>
+template <int METHOD, bool AFFINE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
                   float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay) {
@@ -280,14 +304,16 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   }
   __syncthreads();
   if (tid == 0) {
-    const uint32_t total = (uint32_t)(lay.lut_bytes + lay.tt_bytes + lay.q_bytes);
+    const uint32_t total = (uint32_t)(lay.q_bytes + (AFFINE ? 0 : lay.lut_bytes + lay.tt_bytes));
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(total) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(s_lut)), "l"(p.lut), "r"((uint32_t)lay.lut_bytes), "r"(smem_u32(mbar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(s_tt)), "l"(p.tt), "r"((uint32_t)lay.tt_bytes), "r"(smem_u32(mbar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(s_q)), "l"(p.q), "r"((uint32_t)lay.q_bytes), "r"(smem_u32(mbar)) : "memory");
+    if (!AFFINE) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(s_lut)), "l"(p.lut), "r"((uint32_t)lay.lut_bytes), "r"(smem_u32(mbar)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(s_tt)), "l"(p.tt), "r"((uint32_t)lay.tt_bytes), "r"(smem_u32(mbar)) : "memory");
+    }
   }
 
   // ---- group geometry (runtime: depends on the knot window found by segment_kernel) ---------------
@@ -345,7 +371,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
                    : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
     }
   }
-  for (int c = tid; c < lay.nch; c += kCtaThreads) s_tc[c] = s_tt[min(c << lay.chs, p.W - 1)].y;
+  for (int c = tid; c < lay.nch; c += kCtaThreads) s_tc[c] = p.t[min(c << lay.chs, p.W - 1)];
   __syncthreads();
   if (!active) return;  // spare warps (no __syncthreads below this line)
 
@@ -353,12 +379,12 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   const float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
   {
     float e;
-    int klo = owner ? channel_of(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e) : 0x7fffffff;
-    int khi = owner ? channel_of(__fmul_rn(lz[KPL - 1], dmax), p, s_lut, s_tt, e) : -1;
+    int klo = owner ? channel_of<AFFINE>(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e) : 0x7fffffff;
+    int khi = owner ? channel_of<AFFINE>(__fmul_rn(lz[KPL - 1], dmax), p, s_lut, s_tt, e) : -1;
     // widest lane span at dmax: must hold at most one chunk start (see the base deposit below)
     float lznext = __shfl_down_sync(0xffffffffu, lz[0], 1);
-    int kfirst = channel_of(__fmul_rn(lz[0], dmax), p, s_lut, s_tt, e);
-    int knext = channel_of(__fmul_rn(lznext, dmax), p, s_lut, s_tt, e);
+    int kfirst = channel_of<AFFINE>(__fmul_rn(lz[0], dmax), p, s_lut, s_tt, e);
+    int knext = channel_of<AFFINE>(__fmul_rn(lznext, dmax), p, s_lut, s_tt, e);
     int span = owner ? knext - kfirst + 2 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -387,8 +413,18 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   const int own = owner ? 1 : 0;
   float2 *my_cells = s_step + (owner ? (shared_mode ? 0 : my_off - my_klo) : lay.cap + wg * 32 + lane);
   float2 *my_base = s_base + (size_t)wg * nbase;
-  const int base_dummy = lay.nch + lane;
   const int CH = 1 << lay.chs;
+  // chunk lines are summed in registers: over the Doppler range present a lane's first knot moves by
+  // less than one chunk, so the chunk start inside its span is chunk cA or cA + 1
+  int cA = 0;
+  {
+    float e;
+    const int kmin0 = channel_of<AFFINE>(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e);
+    const int kmax0 = channel_of<AFFINE>(__fmul_rn(lz[0], dmax), p, s_lut, s_tt, e);
+    cA = (kmin0 + CH - 1) >> lay.chs;
+    if (owner && ((kmax0 + CH - 1) >> lay.chs) > cA + 1) atomicExch(ctrl + C_ERROR, 3);
+  }
+  float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
   const float *tab[NT];
 #pragma unroll
@@ -431,7 +467,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
       // ---- phase 1: per-knot quantities and the two normalisation sums ----------------------------
       int ka[NB], kb[NB];              // cell of slot 0 / slot 1 (times `own`)
       float g0[NB], g1[NB], dm0[NB], dm1[NB];
-      int cb[NB];                      // chunk whose base this lane deposits (a dummy slot if none)
+      int cb[NB];                      // chunk line this lane adds: 0 none, 1 -> chunk cA, 2 -> chunk cA + 1
       float bv[NB], bm[NB];            // its line: value at the chunk's first channel, slope
       float red[2 * NB];               // tot[0..NB), new[0..NB)
 #pragma unroll
@@ -462,8 +498,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         }
         const float x0 = __fmul_rn(lz[0], d), x1 = __fmul_rn(lz[1], d);
         float e0, e1;
-        const int k0 = channel_of(x0, p, s_lut, s_tt, e0);
-        const int k1 = channel_of(x1, p, s_lut, s_tt, e1);
+        const int k0 = channel_of<AFFINE>(x0, p, s_lut, s_tt, e0);
+        const int k1 = channel_of<AFFINE>(x1, p, s_lut, s_tt, e1);
         const float2 q0 = s_q[k0], q1 = s_q[k1];
         // right neighbour's first knot, left neighbour's last slope
         const float S2 = __shfl_down_sync(0xffffffffu, S0, 1);
@@ -499,7 +535,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         const bool second = chan >= k1;
         const float Sr = second ? S1 : S0, mr = second ? m1 : m0, xr = second ? x1 : x0;
         const float tch = s_tc[min(c, lay.nch - 1)];
-        cb[b] = has ? c : base_dummy;
+        cb[b] = has ? 1 + (c - cA) : 0;
         bv[b] = fmaf(mr, tch - xr, Sr);
         bm[b] = mr;
       }
@@ -555,7 +591,9 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
           const float sc = __shfl_sync(0xffffffffu, scale, b);
           cell_add<false>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
           cell_add<false>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
-          cell_add<false>(my_base + cb[b], sc * bv[b], sc * bm[b]);
+          const float cv = sc * bv[b], cm = sc * bm[b];
+          accAv += cb[b] == 1 ? cv : 0.f; accAm += cb[b] == 1 ? cm : 0.f;
+          accBv += cb[b] == 2 ? cv : 0.f; accBm += cb[b] == 2 ? cm : 0.f;
           __syncwarp();
         }
       } else {
@@ -564,11 +602,22 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
           const float sc = __shfl_sync(0xffffffffu, scale, b);
           cell_add<true>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
           cell_add<true>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
-          cell_add<false>(my_base + cb[b], sc * bv[b], sc * bm[b]);
+          const float cv = sc * bv[b], cm = sc * bm[b];
+          accAv += cb[b] == 1 ? cv : 0.f; accAm += cb[b] == 1 ? cm : 0.f;
+          accBv += cb[b] == 2 ? cv : 0.f; accBm += cb[b] == 2 ? cm : 0.f;
           __syncwarp();
         }
       }
     }  // batches
+    // flush the register chunk lines, one lane after the other (neighbouring lanes can share a chunk)
+    for (int l = 1; l <= OWN; ++l) {
+      if (lane == l) {
+        if (cA < lay.nch) cell_add<false>(my_base + cA, accAv, accAm);
+        if (cA + 1 < lay.nch) cell_add<false>(my_base + cA + 1, accBv, accBm);
+      }
+      __syncwarp();
+    }
+    accAv = accAm = accBv = accBm = 0.f;
     group_barrier(1 + grp, gthreads);
 
     // ---- expand the cells into the spaxel spectrum and store it -----------------------------------
@@ -602,8 +651,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         const bool valid = ch < p.W;
         const bool start = (h + lane) == 0;   // the chunk's first channel takes the base line itself
         if (start || !valid) { A = 0.f; B = 0.f; }
-        const float2 t2 = s_tt[valid ? ch : 0];
-        const float dtc = start ? 0.f : t2.y - t2.x;
+        const float dtc = (start || !valid) ? 0.f : __ldg(p.dt + ch);
         // slope after the kinks of this channel, then the value increments
         float sB = B;
 #pragma unroll
@@ -736,7 +784,7 @@ extern "C" int rbx_profile_fused(double *mean_ms, int64_t *launches, int reset) 
 // Shared-memory layout and static limits of fused_cube_kernel for this plan.
 static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_bytes) {
   const PlanView &v = plan->v;
-  if (!plan->lut_ok || v.nb <= 0 || v.W + 1 >= 65535) {
+  if ((!v.affine && (!plan->lut_ok || v.nb <= 0)) || v.W + 1 >= 65535) {
     set_error("rbx_build_cube: telescope wavelength grid not supported by the fused kernel (too long, or too "
               "uneven for the channel lookup table); use the stage calls");
     return RBX_ERR_UNSUPPORTED;
@@ -781,10 +829,16 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
   lay.chs = chs;
   lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
   lay.collide = (min2 * 0.97 <= (double)plan->max_dt) ? 1 : 0;
+  {
+    const char *e = getenv("RBX_FUSED_FORCE_LUT");
+    lay.force_lut = (e && e[0] == '1') ? 1 : 0;
+    const char *c = getenv("RBX_FUSED_FORCE_CAS");
+    if (c && c[0] == '1') lay.collide = 1;
+  }
   lay.cap = v.W + 1 + kMaxGroupWarps * kRegionSlack;
   auto a16 = [](int x) { return (x + 15) & ~15; };
   auto a128 = [](int x) { return (x + 127) & ~127; };
-  lay.lut_bytes = a16(2 * v.nb);
+  lay.lut_bytes = a16(2 * std::max(v.nb, 0));
   lay.tt_bytes = a16(8 * v.W);
   lay.q_bytes = a16(8 * (v.W + 1));
   lay.off_mbar = 0;
@@ -861,8 +915,17 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
 
   const int threads = 256;
   int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
-  prep_kernel<<<blocks, threads, 0, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n, nseg, ws.ncell,
-                                               ws.keys_in, ws.idx_in, ws.counts, ws.ctrl);
+  {
+    const size_t hist_bytes = sizeof(int) * (size_t)nseg;
+    const int smem_hist = hist_bytes <= 160 * 1024 ? 1 : 0;
+    // the per-block histogram is flushed with one atomic per non-empty bin: fewer blocks for big cubes
+    int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, nseg <= 4096 ? 148 * 8 : 148 * 2) : blocks;
+    if (smem_hist && hist_bytes > 48 * 1024)
+      RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+    prep_kernel<<<pblocks, threads, smem_hist ? hist_bytes : 0, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n,
+                                                                          nseg, ws.ncell, ws.keys_in, ws.idx_in,
+                                                                          ws.counts, ws.ctrl, smem_hist);
+  }
   count_launch();
   RBX_LAUNCH_OK();
   size_t cb = ws.cub_bytes;
@@ -887,15 +950,17 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const bool prof = g_profile.load() != 0;
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
-  if (v.method == RBX_METHOD_LINEAR) {
-    RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fused_cube_kernel<RBX_METHOD_LINEAR><<<nsm, kCtaThreads, smem, stream>>>(
-        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
-  } else {
-    RBX_CUDA_OK(cudaFuncSetAttribute(fused_cube_kernel<RBX_METHOD_CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fused_cube_kernel<RBX_METHOD_CUBIC><<<nsm, kCtaThreads, smem, stream>>>(
-        v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
-  }
+  auto launch = [&](auto kernel) -> int {
+    RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
+    return RBX_OK;
+  };
+  const bool affine = v.affine != 0 && !lay.force_lut;
+  if (v.method == RBX_METHOD_LINEAR)
+    rc = affine ? launch(fused_cube_kernel<RBX_METHOD_LINEAR, true>) : launch(fused_cube_kernel<RBX_METHOD_LINEAR, false>);
+  else
+    rc = affine ? launch(fused_cube_kernel<RBX_METHOD_CUBIC, true>) : launch(fused_cube_kernel<RBX_METHOD_CUBIC, false>);
+  if (rc != RBX_OK) return rc;
   count_launch();
   RBX_LAUNCH_OK();
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }

@@ -2,14 +2,42 @@
 // filter_particles -> spaxel_assignment -> fused cube -> PSF + LSF, with the H2D copies of the
 // particle arrays and the D2H copy of the cube inside the call.  Device scratch comes from the
 // stream-ordered allocator (cudaMallocAsync), so repeated calls reuse the pool without cudaMalloc.
+#include <mutex>
+
 #include "common.cuh"
 
 using namespace rbx;
 
 namespace {
+// One stream-ordered pool per device that never trims: with the default release threshold (0) the
+// driver hands the scratch back to the OS at every synchronisation and the next call pays for
+// mapping hundreds of MB again (measured: 6 ms .. 1.1 s per call at 10^6 .. 10^7 particles).
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+
+int scratch_pool(cudaMemPool_t *out) {
+  int dev = 0;
+  RBX_CUDA_OK(cudaGetDevice(&dev));
+  RBX_REQUIRE(dev >= 0 && dev < 64, "rbx_pipeline_host: device ordinal out of range");
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    RBX_CUDA_OK(cudaMemPoolCreate(&g_pools[dev], &props));
+    uint64_t keep = UINT64_MAX;
+    RBX_CUDA_OK(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  *out = g_pools[dev];
+  return RBX_OK;
+}
+
 struct Scratch {
   std::vector<void *> ptrs;
   cudaStream_t s;
+  cudaMemPool_t pool = nullptr;
   explicit Scratch(cudaStream_t st) : s(st) {}
   ~Scratch() {
     for (void *p : ptrs) cudaFreeAsync(p, s);
@@ -17,7 +45,11 @@ struct Scratch {
   template <typename T>
   int get(T **out, size_t count) {
     void *p = nullptr;
-    RBX_CUDA_OK(cudaMallocAsync(&p, count * sizeof(T) + 256, s));
+    if (!pool) {
+      int rc = scratch_pool(&pool);
+      if (rc != RBX_OK) return rc;
+    }
+    RBX_CUDA_OK(cudaMallocFromPoolAsync(&p, count * sizeof(T) + 256, pool, s));
     ptrs.push_back(p);
     *out = (T *)p;
     return RBX_OK;

@@ -55,6 +55,15 @@ __global__ void lut_bucket_kernel(const float *__restrict__ t, int W, float tmin
   }
 }
 
+// Is the telescope grid exactly t0 + w * delta evaluated in float32 (multiply, then add)?  That is how
+// numpy / jnp.arange fill a float32 range (rubix/telescope/utils.py:53), so it holds for every
+// telescope of the reference; the fused kernel then finds channels arithmetically.
+__global__ void affine_check_kernel(const float *__restrict__ t, int W, float t0, float delta, int *__restrict__ ok) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  if (t[w] != __fadd_rn(__fmul_rn((float)w, delta), t0)) atomicExch(ok, 0);
+}
+
 __global__ void lut_fill_kernel(const int *__restrict__ bucket, int W, int nb, uint16_t *__restrict__ lut) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
@@ -177,6 +186,23 @@ extern "C" int rbx_plan_create(rbx_plan **out, const float *h_met, int nz, const
   TRY(upload(pl, dt.data(), (size_t)W, &v.dt, stream));
   TRY(upload(pl, tt.data(), (size_t)W, &v.tt, stream));
   TRY(upload(pl, q.data(), (size_t)W + 1, &v.q, stream));
+  // affine grid test (on the device: same float32 operations as the kernel)
+  v.affine = 0; v.t0 = h_t[0]; v.tdelta = W > 1 ? h_t[1] - h_t[0] : 1.f; v.tinv = 1.f / v.tdelta;
+  if (W >= 2 && v.tdelta > 0.f) {
+    void *d_ok = nullptr;
+    if (cudaMalloc(&d_ok, sizeof(int)) != cudaSuccess) {
+      set_error("rbx_plan_create: cudaMalloc failed");
+      rbx_plan_destroy(pl);
+      return RBX_ERR_CUDA;
+    }
+    pl->allocs.push_back(d_ok);
+    int one = 1, ok = 0;
+    cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, stream);
+    affine_check_kernel<<<(W + 255) / 256, 256, 0, stream>>>(v.t, W, v.t0, v.tdelta, (int *)d_ok);
+    count_launch();
+    cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (cudaStreamSynchronize(stream) == cudaSuccess) v.affine = ok;
+  }
   // channel lookup table, built on the device with the kernel's own bucket function
   pl->lut_ok = 0;
   v.nb = 0; v.lut = nullptr; v.lut_scale = 0.f;

@@ -208,6 +208,40 @@ def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
     _cube_close(out, ref, f"fused {gen} {method}")
 
 
+@pytest.mark.parametrize("env", ["RBX_FUSED_FORCE_LUT", "RBX_FUSED_FORCE_CAS"])
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env, monkeypatch):
+    """The kernel's general paths -- lookup-table channel search for non-arange telescope grids, one
+    shared cell region with CAS adds for SSP grids finer than the telescope's -- forced on the MUSE
+    configuration (they are otherwise only taken by configurations the oracle is slow on)."""
+    from rubix_b200 import synthetic
+    monkeypatch.setenv(env, "1")
+    edges = synthetic.spatial_edges(25)
+    data = _well_conditioned(synthetic.bench_g(20000, seed=5), np.float32(1.1) * bc03["wavelength"], muse_wave)
+    out = _run_fused(ops, plans[method], data, edges, 25)
+    monkeypatch.delenv(env)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], muse_wave, 0.1, method=method, dtype=np.float64, n_threads=8)
+    _cube_close(out, ref, f"fused {env} {method}")
+
+
+def test_fused_cube_non_affine_grid(ops, bc03):
+    """A telescope grid that is not an arange (slowly growing channel width) takes the lookup-table path."""
+    from rubix_b200 import synthetic
+    rng = np.random.default_rng(3)
+    steps = (1.25 * (1 + 0.2 * np.linspace(0, 1, 1500)) + rng.uniform(0, 0.01, 1500)).astype(np.float32)
+    wave = (np.float32(5000.0) + np.cumsum(steps, dtype=np.float64)).astype(np.float32)
+    plan = ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], wave, 0.05, method="linear")
+    edges = synthetic.spatial_edges(9)
+    data = _well_conditioned(synthetic.bench_g(6000, seed=9), np.float32(1.05) * bc03["wavelength"], wave)
+    out = _run_fused(ops, plan, data, edges, 9)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 9, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], wave, 0.05, method="linear", dtype=np.float64, n_threads=8)
+    _cube_close(out, ref, "fused non-affine grid")
+
+
 def test_fused_equals_stage_path(ops, plans, tng_subset):
     """The fused kernel and the materialising stage kernels are two CUDA implementations of the same
     stages; they must agree to float32 rounding."""
