@@ -31,6 +31,7 @@ constexpr int kCtaWarps = kCtaThreads / 32;
 constexpr int kMaxGroups = 4;
 constexpr int kMaxGroupWarps = 8;
 constexpr int kRegionSlack = 64;      // spare cells per warp region
+constexpr int kRedStride = 12;        // floats per reduction slot (8 warps + padding: conflict-free LDS.128)
 constexpr int kMaxKnots = KPL * OWN * kMaxGroupWarps - 3;  // widest knot window [ja, jb) a group can hold
 
 
@@ -304,11 +305,11 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
   }
   __syncthreads();
   if (tid == 0) {
-    const uint32_t total = (uint32_t)(lay.q_bytes + (AFFINE ? 0 : lay.lut_bytes + lay.tt_bytes));
+    const uint32_t total = AFFINE ? 0u : (uint32_t)(lay.q_bytes + lay.lut_bytes + lay.tt_bytes);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(total) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(s_q)), "l"(p.q), "r"((uint32_t)lay.q_bytes), "r"(smem_u32(mbar)) : "memory");
     if (!AFFINE) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(s_q)), "l"(p.q), "r"((uint32_t)lay.q_bytes), "r"(smem_u32(mbar)) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(smem_u32(s_lut)), "l"(p.lut), "r"((uint32_t)lay.lut_bytes), "r"(smem_u32(mbar)) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -339,7 +340,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
     const int nbase = lay.nch + 32;  // per warp: one line per chunk + one dummy per lane
     for (int q = gt; q < lay.cap + kMaxGroupWarps * 32; q += gthreads) s_step[q] = make_float2(0.f, 0.f);
     for (int q = gt; q < NWG * nbase; q += gthreads) s_base[q] = make_float2(0.f, 0.f);
-    for (int q = gt; q < 2 * 2 * NB * kMaxGroupWarps; q += gthreads) s_red[q] = 0.f;
+    for (int q = gt; q < 2 * 2 * NB * kRedStride; q += gthreads) s_red[q] = 0.f;
   }
 
   // ---- per-lane knot constants ---------------------------------------------------------------------
@@ -500,13 +501,10 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         float e0, e1;
         const int k0 = channel_of<AFFINE>(x0, p, s_lut, s_tt, e0);
         const int k1 = channel_of<AFFINE>(x1, p, s_lut, s_tt, e1);
-        const float2 q0 = s_q[k0], q1 = s_q[k1];
         // right neighbour's first knot, left neighbour's last slope
         const float S2 = __shfl_down_sync(0xffffffffu, S0, 1);
         const int k2 = __shfl_down_sync(0xffffffffu, k0, 1);
         const float e2 = __shfl_down_sync(0xffffffffu, e0, 1);
-        const float q2x = __shfl_down_sync(0xffffffffu, q0.x, 1);
-        const float q2y = __shfl_down_sync(0xffffffffu, q0.y, 1);
         const float m0 = (S1 - S0) * rdlv[0] * rd;
         const float m1 = (S2 - S1) * rdlv[1] * rd;
         const float mp = __shfl_up_sync(0xffffffffu, m1, 1);
@@ -514,10 +512,27 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         const float w0 = (x0 >= p.tmin && x0 <= p.tmax) ? x0 - __fmul_rn(lzprev, d) : 0.f;
         const float w1 = (x1 >= p.tmin && x1 <= p.tmax) ? x1 - x0 : 0.f;
         const float tot = fmaf(S1, w1, S0 * w0);
-        // new: sum_w p(t_w) dt_w over the channels of my two segments   (rubix/spectra/ifu.py:249-251)
+        // new: sum_w p(t_w) dt_w over the channels [k_j, k_{j+1}) of my two segments
+        // (rubix/spectra/ifu.py:249-251): S_j D_j + m_j T_j with D_j = sum dt_w = e_{j+1} - e_j (dt
+        // telescopes exactly in float32) and T_j = sum dt_w (t_w - x_j).
         const float D0 = e1 - e0, D1 = e2 - e1;
-        const float T0 = fmaf(-(x0 - p.tref), D0, (q1.x - q0.x) + (q1.y - q0.y));
-        const float T1 = fmaf(-(x1 - p.tref), D1, (q2x - q1.x) + (q2y - q1.y));
+        const float gx0 = e0 - x0, gx1 = e1 - x1;   // t[k-1] - x, in (-dt, 0]
+        float T0, T1;
+        if (AFFINE) {
+          // dt_w (t_w - x) = ((t_w - x)^2 - (t_{w-1} - x)^2) / 2 + dt_w^2 / 2: the squares telescope, and on
+          // an arange grid sum dt_w^2 = 2 delta D - n delta^2 up to O(n ulp^2)
+          const float n0 = (float)(max(k1, 1) - max(k0, 1)), n1 = (float)(max(k2, 1) - max(k1, 1));
+          const float hd2 = 0.5f * p.tdelta * p.tdelta;
+          T0 = fmaf(D0, fmaf(0.5f, D0, gx0 + p.tdelta), -hd2 * n0);
+          T1 = fmaf(D1, fmaf(0.5f, D1, gx1 + p.tdelta), -hd2 * n1);
+        } else {
+          // general grid: T_j = Q[k_{j+1}] - Q[k_j] - (x_j - tref) D_j, Q = double-float prefix of dt_w (t_w - tref)
+          const float2 q0 = s_q[k0], q1 = s_q[k1];
+          const float q2x = __shfl_down_sync(0xffffffffu, q0.x, 1);
+          const float q2y = __shfl_down_sync(0xffffffffu, q0.y, 1);
+          T0 = fmaf(-(x0 - p.tref), D0, (q1.x - q0.x) + (q1.y - q0.y));
+          T1 = fmaf(-(x1 - p.tref), D1, (q2x - q1.x) + (q2y - q1.y));
+        }
         float nw = fmaf(m0, T0, S0 * D0);
         nw += fmaf(m1, T1, S1 * D1);
         red[b] = owner ? tot : 0.f;
@@ -525,8 +540,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
         // kinks
         const float d0 = m0 - mp, d1 = m1 - m0;
         dm0[b] = d0; dm1[b] = d1;
-        g0[b] = d0 * (e0 - x0);
-        g1[b] = d1 * (e1 - x1);
+        g0[b] = d0 * gx0;
+        g1[b] = d1 * gx1;
         ka[b] = k0 * own; kb[b] = k1 * own;
         // chunk base: the line valid at the first chunk start inside [k0, k2)
         const int c = (k0 + CH - 1) >> lay.chs;
@@ -566,17 +581,17 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
       }
       v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
       v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-      float *red_cur = s_red + buf * (2 * NB * kMaxGroupWarps);
+      float *red_cur = s_red + buf * (2 * NB * kRedStride);
       if ((lane & 3) == 0) {
         const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        red_cur[idx * kMaxGroupWarps + wg] = v1;
+        red_cur[idx * kRedStride + wg] = v1;
       }
       group_barrier(1 + grp, gthreads);
       // every warp: lane i < 2*NB sums value i over the group's warps in warp order
       float scale = 0.f;
       {
         // slots of warps beyond NWG stay zero, so the sum always runs over all kMaxGroupWarps entries
-        const float4 *rp = reinterpret_cast<const float4 *>(red_cur + (lane & (2 * NB - 1)) * kMaxGroupWarps);
+        const float4 *rp = reinterpret_cast<const float4 *>(red_cur + (lane & (2 * NB - 1)) * kRedStride);
         const float4 ra = rp[0], rb4 = rp[1];
         const float acc = ((ra.x + ra.y) + (ra.z + ra.w)) + ((rb4.x + rb4.y) + (rb4.z + rb4.w));
         const float nwv = __shfl_down_sync(0xffffffffu, acc, NB);
@@ -852,7 +867,7 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
   lay.g_base = a16((lay.cap + kMaxGroupWarps * 32) * 8);  // + one dummy cell per lane (halo lanes)
   lay.g_rec = lay.g_base + a16(kMaxGroupWarps * (lay.nch + 32) * 8);
   lay.g_red = lay.g_rec + a16(2 * NB * rs * 4);
-  lay.g_misc = lay.g_red + a16(2 * 2 * NB * kMaxGroupWarps * 4);
+  lay.g_misc = lay.g_red + a16(2 * 2 * NB * kRedStride * 4);
   lay.group_stride = a128(lay.g_misc + 32 * 4);
   const int budget = 227 * 1024;
   lay.max_groups = std::min(kMaxGroups, (budget - lay.off_group) / lay.group_stride);
