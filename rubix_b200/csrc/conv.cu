@@ -126,6 +126,103 @@ __global__ void psf_lsf_kernel(const float *__restrict__ in, float *__restrict__
   }
 }
 
+// ---- fused PSF + LSF, register tiled ---------------------------------------------------------------
+// Block = TY x TX spaxels x TL output channels; one thread per channel of the tile *including* the
+// spectral halo (TL + K - 1 channels).  PSF: every input voxel of the (TY+P-1) x (TX+P-1) spatial
+// neighbourhood is loaded once (coalesced along lambda) into a register and used for up to P*P
+// FMAs into TY*TX register accumulators; the taps sit in registers too.  The PSF result goes to
+// shared memory only, the LSF then runs along lambda with 4 outputs per thread (7 LDS.128 for 100
+// FMAs) and stores coalesced.  HBM traffic is the algorithmic 8 bytes / voxel as long as the
+// (TY+P-1) spaxel rows being worked on stay in L2 (blocks walk x, then lambda, then y).
+template <int TY, int TX, int P, int KMAX>
+__global__ void __launch_bounds__(160)
+psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W,
+                   const float *__restrict__ Kp, const float *__restrict__ kl, int K, int ext, int TL) {
+  extern __shared__ __align__(16) float s_mid[];  // [TY*TX][pitch]
+  const int TLH = TL + K - 1;
+  const int pitch = (TLH + 3 + 4) & ~3;            // room for the 4-wide LSF reads of the last group
+  const int tiles_x = (nx + TX - 1) / TX;
+  const int x0 = (blockIdx.x % tiles_x) * TX;
+  const int w0 = (blockIdx.x / tiles_x) * TL;
+  const int y0 = blockIdx.y * TY;
+  constexpr int C = (P - 1) / 2;                   // jax "same": out[y] = sum_m K[m] in[y - m + C]
+  __shared__ float s_kp[P * P];
+  for (int i = threadIdx.x; i < P * P; i += blockDim.x) s_kp[i] = Kp[i];
+  __syncthreads();
+
+  // ---- PSF into shared memory -------------------------------------------------------------------
+  for (int c = threadIdx.x; c < TLH; c += blockDim.x) {
+    const int q = w0 + ext - (K - 1) + c;          // input channel of tile column c
+    float acc[TY][TX];
+#pragma unroll
+    for (int a = 0; a < TY; ++a)
+#pragma unroll
+      for (int b = 0; b < TX; ++b) acc[a][b] = 0.f;
+    if (q >= 0 && q < W) {
+#pragma unroll 1
+      for (int iy = 0; iy < TY + P - 1; ++iy) {    // rolled: keeps the live set at one input row
+        const int yy = y0 + iy - (P - 1 - C);
+        if (yy < 0 || yy >= ny) continue;
+        float v[TX + P - 1];
+#pragma unroll
+        for (int ix = 0; ix < TX + P - 1; ++ix) {
+          const int xx = x0 + ix - (P - 1 - C);
+          v[ix] = (xx >= 0 && xx < nx) ? __ldg(in + ((size_t)yy * nx + xx) * W + q) : 0.f;
+        }
+#pragma unroll
+        for (int oy = 0; oy < TY; ++oy) {
+          const int m = oy + P - 1 - iy;           // tap row feeding output row oy (block-uniform)
+          if (m < 0 || m >= P) continue;
+#pragma unroll
+          for (int n = 0; n < P; ++n) {
+            const float kv = s_kp[m * P + n];
+#pragma unroll
+            for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(kv, v[ox + P - 1 - n], acc[oy][ox]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < TY; ++a)
+#pragma unroll
+      for (int b = 0; b < TX; ++b) s_mid[(a * TX + b) * pitch + c] = acc[a][b];
+  }
+  // zero the pad columns read by the last 4-wide group
+  for (int i = threadIdx.x; i < TY * TX * (pitch - TLH); i += blockDim.x) {
+    const int pix = i / (pitch - TLH), c = TLH + i % (pitch - TLH);
+    s_mid[pix * pitch + c] = 0.f;
+  }
+  __syncthreads();
+
+  // ---- LSF: out[w0 + j] = sum_m kl[m] mid[j + K - 1 - m] -----------------------------------------
+  float krev[KMAX];  // taps reversed and zero padded: krev[u] = kl[K - 1 - u]
+#pragma unroll
+  for (int u = 0; u < KMAX; ++u) krev[u] = u < K ? __ldg(kl + (K - 1 - u)) : 0.f;
+  const int groups = (TL + 3) / 4;
+  for (int item = threadIdx.x; item < TY * TX * groups; item += blockDim.x) {
+    const int pix = item / groups, j0 = (item - pix * groups) * 4;
+    const int y = y0 + pix / TX, x = x0 + pix % TX;
+    if (y >= ny || x >= nx) continue;
+    const float4 *mp = reinterpret_cast<const float4 *>(s_mid + pix * pitch + j0);
+    float win[KMAX + 3 + 1];
+#pragma unroll
+    for (int i = 0; i < (KMAX + 3 + 3) / 4; ++i) {
+      const float4 t4 = (4 * i < K + 3) ? mp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      win[4 * i] = t4.x; win[4 * i + 1] = t4.y; win[4 * i + 2] = t4.z; win[4 * i + 3] = t4.w;
+    }
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    // out[j0 + r] = sum_m kl[m] * mid[j0 + r + K - 1 - m];  with u = K - 1 - m: kl[K-1-u] * win[r + u]
+#pragma unroll
+    for (int u = 0; u < KMAX; ++u)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) o[r] = fmaf(krev[u], win[r + u], o[r]);
+    float *dst = out + ((size_t)y * nx + x) * W + w0 + j0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (j0 + r < TL && w0 + j0 + r < W) dst[r] = o[r];
+  }
+}
+
 // rubix/telescope/psf/kernels.py:26-31 in float32; single block
 __global__ void gaussian_psf_kernel(int m, int n, float sigma, float *__restrict__ out) {
   __shared__ float ssum;
@@ -201,6 +298,24 @@ extern "C" int rbx_psf_lsf(const float *d_in, float *d_out, int ny, int nx, int 
   RBX_REQUIRE(K == 2 * ext + 1, "rbx_psf_lsf: LSF kernel length must be 2*extend_factor+1");
   RBX_REQUIRE((M <= ny && N <= nx) || (M >= ny && N >= nx),
               "One input must be smaller than the other in every dimension.");
+  if (M == N && (M == 3 || M == 5 || M == 7) && K <= 25) {
+    const int TLr = 128;
+    auto run = [&](auto kernel, int ty, int tx) -> int {
+      const int pitch = (TLr + K - 1 + 3 + 4) & ~3;
+      const size_t smem = sizeof(float) * (size_t)ty * tx * pitch;
+      if (smem > 48 * 1024) RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid(((nx + tx - 1) / tx) * ((W + TLr - 1) / TLr), (ny + ty - 1) / ty);
+      kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(d_in, d_out, ny, nx, W, d_psf, d_lsf, K, ext, TLr);
+      count_launch();
+      RBX_LAUNCH_OK();
+      return RBX_OK;
+    };
+    const bool five = (nx % 5 == 0) && (ny % 5 == 0) && M == 5;
+    if (five) return run(psf_lsf_reg_kernel<5, 5, 5, 25>, 5, 5);
+    if (M == 3) return run(psf_lsf_reg_kernel<4, 8, 3, 25>, 4, 8);
+    if (M == 5) return run(psf_lsf_reg_kernel<4, 8, 5, 25>, 4, 8);
+    return run(psf_lsf_reg_kernel<4, 8, 7, 25>, 4, 8);
+  }
   constexpr int TY = 5, TX = 5;
   int TL = 128;
   auto smem_for = [&](int tl) {

@@ -339,19 +339,33 @@ def test_lsf_matches_oracle(ops):
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("S,W", [(25, 3721), (13, 517), (31, 130)])
-def test_fused_psf_lsf(ops, S, W):
+@pytest.mark.parametrize("S,W,P", [(25, 3721, 5), (13, 517, 5), (31, 130, 5), (12, 700, 3), (17, 300, 7), (9, 200, 4)])
+def test_fused_psf_lsf(ops, S, W, P):
+    """P = 3/5/7 take the register-tiled kernel (5x5 and 4x8 spaxel tiles), P = 4 the generic one."""
     rng = np.random.default_rng(8)
     cube = rng.random((S, S, W)).astype(np.float32)
-    pk = orc.gaussian_kernel_2d(5, 5, 0.6)
+    pk = orc.gaussian_kernel_2d(P, P, 0.6) if P != 4 else rng.random((4, 4)).astype(np.float32)
     lk = orc.lsf_kernel(0.5, 1.25)
     out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
     ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
     err = np.abs(out - ref).max()
-    print(f"[psf+lsf {S}x{W}] max|d|={err:.3e}")
+    print(f"[psf+lsf {S}x{W} P={P}] max|d|={err:.3e}")
     assert err <= 2e-6 * np.abs(ref).max()
     two = ops.convolve_lsf(ops.convolve_psf(cube, pk), lk).cpu().numpy()
     assert np.abs(two - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_fused_psf_lsf_asymmetric_kernels(ops):
+    """Non-symmetric taps: catches flipped or transposed kernels (a Gaussian cannot)."""
+    rng = np.random.default_rng(11)
+    cube = rng.random((10, 15, 333)).astype(np.float32)
+    pk = rng.random((5, 5)).astype(np.float32)
+    lk = rng.random(25).astype(np.float32)
+    out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+    mid = orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64))
+    ref = np.stack([[np.convolve(mid[y, x], lk.astype(np.float64), mode="full")[12:12 + 333] for x in range(15)]
+                    for y in range(10)])
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
 def test_gaussian_kernels_on_device(ops):
