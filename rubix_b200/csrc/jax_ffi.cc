@@ -1,0 +1,119 @@
+// XLA FFI handlers around the C ABI (include/rubix_b200.h) so that the path can be called with
+// jax.ffi.ffi_call from inside rubix's single jax.jit (rubix/pipeline/abstract_pipeline.py:126-130).
+//
+// NOT BUILT IN THIS IMAGE: neither jax nor the XLA FFI headers (xla/ffi/api/ffi.h, shipped inside
+// jaxlib: `python -c "import jax.ffi; print(jax.ffi.include_dir())"`) exist here, so this file is
+// compiled only when the header is found (`make -C rubix_b200/csrc jax_ffi XLA_FFI_INCLUDE=...`)
+// and has not been exercised.  The C ABI underneath is what the GPU tests cover.
+//
+// Conventions: every handler takes the CUDA stream from the platform context, device buffers from
+// XLA, and writes into XLA-owned result buffers; the workspace of rbx_build_cube is one more result
+// buffer (uint8) sized on the Python side with rbx_build_cube_workspace_bytes, so nothing is
+// allocated here and nothing synchronises.  The plan handle (rbx_plan*, created once per
+// configuration outside jit) travels as an int64 attribute.
+#if defined(__has_include)
+#if __has_include("xla/ffi/api/ffi.h")
+#define RBX_HAVE_XLA_FFI 1
+#endif
+#endif
+
+#ifdef RBX_HAVE_XLA_FFI
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "rubix_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static ffi::Error status(int rc) {
+  if (rc == RBX_OK) return ffi::Error::Success();
+  return ffi::Error(ffi::ErrorCode::kInternal, std::string("rubix_b200: ") + rbx_last_error());
+}
+
+// a0: coords (n,3), edges (e,) -> pixel (n,) int32      replaces rubix/telescope/utils.py:138-151
+static ffi::Error SpaxelAssignImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> coords, ffi::Buffer<ffi::F32> edges,
+                                   ffi::ResultBuffer<ffi::S32> pixel) {
+  const int64_t n = coords.dimensions()[0];
+  return status(rbx_spaxel_assign(coords.typed_data(), n, edges.typed_data(), (int)edges.element_count(),
+                                  pixel->typed_data(), nullptr, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxSpaxelAssign, SpaxelAssignImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>());
+
+// a1..a5 fused: velocity (n,3), mass, metallicity, age (n,), pixel (n,) -> cube (S,S,W), workspace
+// replaces rubix/core/ifu.py:95-118,152-154,269-293,327-339
+static ffi::Error BuildCubeImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> velocity, ffi::Buffer<ffi::F32> mass,
+                                ffi::Buffer<ffi::F32> metallicity, ffi::Buffer<ffi::F32> age,
+                                ffi::Buffer<ffi::S32> pixel, ffi::ResultBuffer<ffi::F32> cube,
+                                ffi::ResultBuffer<ffi::U8> workspace, int64_t plan, int32_t num_spaxels) {
+  const int64_t n = mass.element_count();
+  return status(rbx_build_cube(reinterpret_cast<const rbx_plan *>(plan), velocity.typed_data(), mass.typed_data(),
+                               metallicity.typed_data(), age.typed_data(), pixel.typed_data(), n, num_spaxels,
+                               cube->typed_data(), workspace->typed_data(), workspace->size_bytes(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxBuildCube, BuildCubeImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<int32_t>("num_spaxels"));
+
+// stage calls for the stepwise path (stars.spectra observable between stages)
+static ffi::Error SspLookupImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> metallicity, ffi::Buffer<ffi::F32> age,
+                                ffi::ResultBuffer<ffi::F32> spectra, int64_t plan) {
+  return status(rbx_ssp_lookup(reinterpret_cast<const rbx_plan *>(plan), metallicity.typed_data(), age.typed_data(),
+                               (int64_t)metallicity.element_count(), spectra->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxSspLookup, SspLookupImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int64_t>("plan"));
+
+static ffi::Error DopplerResampleImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> spectra,
+                                      ffi::Buffer<ffi::F32> velocity, ffi::ResultBuffer<ffi::F32> out, int64_t plan) {
+  const int64_t n = velocity.element_count() / 3;
+  return status(rbx_doppler_resample(reinterpret_cast<const rbx_plan *>(plan), spectra.typed_data(),
+                                     velocity.typed_data(), n, out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxDopplerResample, DopplerResampleImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int64_t>("plan"));
+
+// a6 + a7: cube (ny,nx,W), psf (M,N), lsf (K,) -> out (ny,nx,W)
+// replaces rubix/telescope/psf/psf.py:56-57 and rubix/telescope/lsf/lsf.py:96-105
+static ffi::Error PsfLsfImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> cube, ffi::Buffer<ffi::F32> psf,
+                             ffi::Buffer<ffi::F32> lsf, ffi::ResultBuffer<ffi::F32> out, int32_t ext) {
+  auto d = cube.dimensions();
+  auto k = psf.dimensions();
+  return status(rbx_psf_lsf(cube.typed_data(), out->typed_data(), (int)d[0], (int)d[1], (int)d[2], psf.typed_data(),
+                            (int)k[0], (int)k[1], lsf.typed_data(), (int)lsf.element_count(), ext, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxPsfLsf, PsfLsfImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("ext"));
+#endif  // RBX_HAVE_XLA_FFI

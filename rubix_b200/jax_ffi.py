@@ -1,0 +1,64 @@
+"""jax.ffi binding of the path (the JAX-side half of rubix_b200/csrc/jax_ffi.cc).
+
+Needs jax >= 0.4.38 and ``librubix_b200_jax.so`` (``make -C rubix_b200/csrc jax_ffi``); neither is
+available in the build image, so this module is not imported by the package and has not been
+executed.  It shows the binding a rubix maintainer would use: the handlers are registered once and
+``build_cube`` / ``psf_lsf`` become traceable functions that can sit inside rubix's ``jax.jit``.
+The plan (device tables of one configuration) is created eagerly, outside jit, through the ctypes
+binding in :mod:`rubix_b200._lib`; only its address travels as a static attribute.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_TARGETS = {"rbx_spaxel_assign": "RbxSpaxelAssign", "rbx_build_cube": "RbxBuildCube",
+            "rbx_ssp_lookup": "RbxSspLookup", "rbx_doppler_resample": "RbxDopplerResample",
+            "rbx_psf_lsf": "RbxPsfLsf"}
+_registered = False
+
+
+def register():
+    global _registered
+    if _registered:
+        return
+    import jax
+    lib = ctypes.CDLL(os.path.join(_HERE, "librubix_b200_jax.so"))
+    for name, symbol in _TARGETS.items():
+        jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(lib, symbol)), platform="CUDA")
+    _registered = True
+
+
+def spaxel_assign(coords, edges):
+    import jax
+    import jax.numpy as jnp
+    register()
+    out = jax.ShapeDtypeStruct(coords.shape[:1], jnp.int32)
+    return jax.ffi.ffi_call("rbx_spaxel_assign", out)(coords, edges)
+
+
+def build_cube(plan_handle: int, workspace_bytes: int, velocity, mass, metallicity, age, pixel, num_spaxels: int,
+               n_wave: int):
+    """calculate_spectra -> scale_spectrum_by_mass -> doppler_shift_and_resampling -> calculate_datacube
+    (rubix/core/ifu.py) as one custom call.  ``plan_handle``/``workspace_bytes`` come from
+    ``ops.Plan(...).handle.value`` and ``rbx_build_cube_workspace_bytes``."""
+    import jax
+    import jax.numpy as jnp
+    import numpy as np
+    register()
+    outs = (jax.ShapeDtypeStruct((num_spaxels, num_spaxels, n_wave), jnp.float32),
+            jax.ShapeDtypeStruct((workspace_bytes,), jnp.uint8))
+    cube, _ = jax.ffi.ffi_call("rbx_build_cube", outs)(velocity, mass, metallicity, age, pixel,
+                                                       plan=np.int64(plan_handle),
+                                                       num_spaxels=np.int32(num_spaxels))
+    return cube
+
+
+def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12):
+    import jax
+    import numpy as np
+    register()
+    return jax.ffi.ffi_call("rbx_psf_lsf", jax.ShapeDtypeStruct(cube.shape, cube.dtype))(
+        cube, psf_kernel, lsf_kernel, ext=np.int32(ext))
