@@ -23,12 +23,15 @@
 namespace rbx {
 
 constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
-constexpr int NB = 4;                 // particles per batch (between group barriers)
+#ifndef RBX_NB
+#define RBX_NB 4
+#endif
+constexpr int NB = RBX_NB;            // particles per batch (between group barriers)
 constexpr int KPL = 2;                // knot slots per lane
 constexpr int OWN = 30;               // owner lanes per warp
-constexpr int kCtaThreads = 512;
+constexpr int kCtaThreads = NB == 4 ? 512 : 640;   // NB = 2 needs fewer registers: one more group per SM
 constexpr int kCtaWarps = kCtaThreads / 32;
-constexpr int kMaxGroups = 4;
+constexpr int kMaxGroups = NB == 4 ? 4 : 5;
 constexpr int kMaxGroupWarps = 8;
 constexpr int kRegionSlack = 64;      // spare cells per warp region
 constexpr int kRedStride = 12;        // floats per reduction slot (8 warps + padding: conflict-free LDS.128)
@@ -281,6 +284,18 @@ __device__ __forceinline__ void cell_add(float2 *cell, float a, float b) {
       unsigned long long nv = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
       old = atomicCAS(addr, assumed, nv);
     } while (old != assumed);
+  }
+}
+
+// cell += sc * (a, b)
+template <bool CAS>
+__device__ __forceinline__ void cell_fma(float2 *cell, float sc, float a, float b) {
+  if (!CAS) {
+    float2 v = *cell;
+    v.x = fmaf(sc, a, v.x); v.y = fmaf(sc, b, v.y);
+    *cell = v;
+  } else {
+    cell_add<true>(cell, sc * a, sc * b);
   }
 }
 
@@ -557,35 +572,59 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
 
       // ---- transposed warp reduction of the 2*NB sums ----------------------------------------------
       // after the three folding steps lane l holds value index ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1)
-      float v4[4], v2[2], v1;
-      {
-        const bool hi = lane & 16;
+      float v1;
+      int red_idx;
+      bool red_writer;
+      if (NB == 4) {
+        float v4[4], v2[2];
+        {
+          const bool hi = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float keep = hi ? red[i + 4] : red[i], send = hi ? red[i] : red[i + 4];
-          v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          for (int i = 0; i < 4; ++i) {
+            const float keep = hi ? red[(i + 4) % (2 * NB)] : red[i], send = hi ? red[i] : red[(i + 4) % (2 * NB)];
+            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
         }
-      }
-      {
-        const bool hi = lane & 8;
+        {
+          const bool hi = lane & 8;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float keep = hi ? v4[i + 2] : v4[i], send = hi ? v4[i] : v4[i + 2];
-          v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          for (int i = 0; i < 2; ++i) {
+            const float keep = hi ? v4[i + 2] : v4[i], send = hi ? v4[i] : v4[i + 2];
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
         }
+        {
+          const bool hi = lane & 4;
+          const float keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
+          v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        red_idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        red_writer = (lane & 3) == 0;
+      } else {  // NB == 2: four sums
+        float v2[2];
+        {
+          const bool hi = lane & 16;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float keep = hi ? red[(i + 2) % (2 * NB)] : red[i], send = hi ? red[i] : red[(i + 2) % (2 * NB)];
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+        }
+        {
+          const bool hi = lane & 8;
+          const float keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
+          v1 = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        red_idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        red_writer = (lane & 7) == 0;
       }
-      {
-        const bool hi = lane & 4;
-        const float keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
-        v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
       float *red_cur = s_red + buf * (2 * NB * kRedStride);
-      if ((lane & 3) == 0) {
-        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        red_cur[idx * kRedStride + wg] = v1;
-      }
+      if (red_writer) red_cur[red_idx * kRedStride + wg] = v1;
       group_barrier(1 + grp, gthreads);
       // every warp: lane i < 2*NB sums value i over the group's warps in warp order
       float scale = 0.f;
@@ -604,22 +643,22 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const float sc = __shfl_sync(0xffffffffu, scale, b);
-          cell_add<false>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
-          cell_add<false>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
-          const float cv = sc * bv[b], cm = sc * bm[b];
-          accAv += cb[b] == 1 ? cv : 0.f; accAm += cb[b] == 1 ? cm : 0.f;
-          accBv += cb[b] == 2 ? cv : 0.f; accBm += cb[b] == 2 ? cm : 0.f;
+          cell_fma<false>(my_cells + ka[b], sc, g0[b], dm0[b]);
+          cell_fma<false>(my_cells + kb[b], sc, g1[b], dm1[b]);
+          const float sA = cb[b] == 1 ? sc : 0.f, sB = cb[b] == 2 ? sc : 0.f;
+          accAv = fmaf(sA, bv[b], accAv); accAm = fmaf(sA, bm[b], accAm);
+          accBv = fmaf(sB, bv[b], accBv); accBm = fmaf(sB, bm[b], accBm);
           __syncwarp();
         }
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const float sc = __shfl_sync(0xffffffffu, scale, b);
-          cell_add<true>(my_cells + ka[b], sc * g0[b], sc * dm0[b]);
-          cell_add<true>(my_cells + kb[b], sc * g1[b], sc * dm1[b]);
-          const float cv = sc * bv[b], cm = sc * bm[b];
-          accAv += cb[b] == 1 ? cv : 0.f; accAm += cb[b] == 1 ? cm : 0.f;
-          accBv += cb[b] == 2 ? cv : 0.f; accBm += cb[b] == 2 ? cm : 0.f;
+          cell_fma<true>(my_cells + ka[b], sc, g0[b], dm0[b]);
+          cell_fma<true>(my_cells + kb[b], sc, g1[b], dm1[b]);
+          const float sA = cb[b] == 1 ? sc : 0.f, sB = cb[b] == 2 ? sc : 0.f;
+          accAv = fmaf(sA, bv[b], accAv); accAm = fmaf(sA, bm[b], accAm);
+          accBv = fmaf(sB, bv[b], accBv); accBm = fmaf(sB, bm[b], accBm);
           __syncwarp();
         }
       }
