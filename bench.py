@@ -223,10 +223,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
 
     def step():
-        # filter_particles works in place: restore the three arrays it touches (part of the step)
-        mass.copy_(mass0); met.copy_(met0); age.copy_(age0)
-        ops.filter_particles(coords, edges, mass, met, age)
-        pix = ops.spaxel_assign(coords, edges)
+        pix = ops.filter_and_assign(coords, edges)  # filter_particles + spaxel_assignment, one pass
         ops.build_cube(plan, vel, mass, met, age, pix, S, out=cube)
         if world > 1:
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
@@ -292,8 +289,7 @@ def main():
             dcoords.copy_(hp["coords"], non_blocking=True); dvel.copy_(hp["velocity"], non_blocking=True)
             mass.copy_(hp["mass"], non_blocking=True); met.copy_(hp["metallicity"], non_blocking=True)
             age.copy_(hp["age"], non_blocking=True)
-            ops.filter_particles(dcoords, edges, mass, met, age)
-            pix = ops.spaxel_assign(dcoords, edges)
+            pix = ops.filter_and_assign(dcoords, edges)
             ops.build_cube(plan, dvel, mass, met, age, pix, S, out=cube)
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:

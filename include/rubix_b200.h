@@ -82,6 +82,14 @@ int rbx_filter_particles(const float *d_coords, int64_t n, const float *d_edges,
                          float *d_mass, float *d_metallicity, float *d_age, uint8_t *d_mask,
                          void *stream);
 
+/* filter_particles + spaxel_assignment in one pass over coords (rubix/core/telescope.py:155-174 followed
+ * by rubix/telescope/utils.py:138-151).  With d_mass / d_metallicity / d_age given they are zeroed in
+ * place outside the aperture like rbx_filter_particles; with all three NULL nothing is modified and
+ * particles outside the aperture get pixel = -1 instead, which rbx_build_cube / rbx_segment_sum drop --
+ * the same cube, because a zero-mass particle contributes exactly 0. */
+int rbx_filter_and_assign(const float *d_coords, int64_t n, const float *d_edges, int n_edges, float *d_mass,
+                          float *d_metallicity, float *d_age, int32_t *d_pixel, uint8_t *d_mask, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage calls: one per reference stage, materialising the same intermediates as the reference.
  * Used by the stepwise (notebook) path and for stage-level parity.

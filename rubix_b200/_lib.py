@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 EXPORTED = [
     "rbx_last_error", "rbx_version", "rbx_launch_count",
     "rbx_plan_create", "rbx_plan_destroy", "rbx_plan_dims",
-    "rbx_spaxel_assign", "rbx_filter_particles",
+    "rbx_spaxel_assign", "rbx_filter_particles", "rbx_filter_and_assign",
     "rbx_ssp_lookup", "rbx_scale_by_mass", "rbx_doppler_resample", "rbx_segment_sum",
     "rbx_build_cube_workspace_bytes", "rbx_build_cube",
     "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf",
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         "rbx_plan_dims": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "rbx_spaxel_assign": [vp, i64, vp, i32, vp, vp, vp],
         "rbx_filter_particles": [vp, i64, vp, i32, vp, vp, vp, vp, vp],
+        "rbx_filter_and_assign": [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp],
         "rbx_ssp_lookup": [vp, vp, vp, i64, vp, vp],
         "rbx_scale_by_mass": [vp, vp, i64, i32, vp, vp],
         "rbx_doppler_resample": [vp, vp, vp, i64, vp, vp],

@@ -93,8 +93,10 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
     RBX_CUDA_OK(cudaMemcpyAsync(d_met, h_metallicity, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
     RBX_CUDA_OK(cudaMemcpyAsync(d_age, h_age, sizeof(float) * n, cudaMemcpyHostToDevice, stream));
   }
-  if (apply_filter) TRY(rbx_filter_particles(d_coords, n, d_edges, n_edges, d_mass, d_met, d_age, nullptr, stream));
-  TRY(rbx_spaxel_assign(d_coords, n, d_edges, n_edges, d_pixel, nullptr, stream));
+  if (apply_filter)  // particles outside the aperture get pixel -1 (same cube as zeroing their mass)
+    TRY(rbx_filter_and_assign(d_coords, n, d_edges, n_edges, nullptr, nullptr, nullptr, d_pixel, nullptr, stream));
+  else
+    TRY(rbx_spaxel_assign(d_coords, n, d_edges, n_edges, d_pixel, nullptr, stream));
   TRY(rbx_build_cube(plan, d_vel, d_mass, d_met, d_age, d_pixel, n, num_spaxels, d_cube, d_ws, ws_bytes, stream));
   float *result = d_cube;
   if (h_psf || h_lsf) TRY(sc.get(&d_cube2, cube_elems));

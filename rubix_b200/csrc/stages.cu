@@ -15,7 +15,7 @@ __global__ void spaxel_assign_kernel(const float *__restrict__ coords, int64_t n
                                      const float *__restrict__ edges, int n_edges,
                                      int32_t *__restrict__ pixel, uint8_t *__restrict__ mask,
                                      float *__restrict__ mass, float *__restrict__ met,
-                                     float *__restrict__ age) {
+                                     float *__restrict__ age, int mark_outside) {
   extern __shared__ float s_edges[];
   const float *e = edges;
   if (n_edges <= kMaxEdgesSmem) {
@@ -36,6 +36,7 @@ __global__ void spaxel_assign_kernel(const float *__restrict__ coords, int64_t n
     }
     bool in = (x >= lo) && (x <= hi) && (y >= lo) && (y <= hi);
     if (mask) mask[p] = in ? 1 : 0;
+    if (mark_outside && !in && pixel) pixel[p] = -1;  // dropped downstream like a zero-mass particle
     if (!in) {
       if (mass) mass[p] = 0.f;
       if (met) met[p] = 0.f;
@@ -161,13 +162,14 @@ static int grid_for(int64_t n, int per_block) {
 using namespace rbx;
 
 static int spaxel_common(const float *d_coords, int64_t n, const float *d_edges, int n_edges, int32_t *d_pixel,
-                         uint8_t *d_mask, float *mass, float *met, float *age, cudaStream_t stream) {
+                         uint8_t *d_mask, float *mass, float *met, float *age, cudaStream_t stream,
+                         int mark_outside = 0) {
   RBX_REQUIRE(n >= 0 && n_edges >= 2, "spaxel assignment: need n >= 0 and at least 2 bin edges");
   if (n == 0) return RBX_OK;
   RBX_REQUIRE(d_coords && d_edges, "spaxel assignment: null pointer");
   size_t smem = n_edges <= kMaxEdgesSmem ? sizeof(float) * n_edges : 0;
   spaxel_assign_kernel<<<grid_for(n, 256), 256, smem, stream>>>(d_coords, n, d_edges, n_edges, d_pixel, d_mask,
-                                                                 mass, met, age);
+                                                                 mass, met, age, mark_outside);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;
@@ -182,6 +184,14 @@ extern "C" int rbx_spaxel_assign(const float *d_coords, int64_t n, const float *
 extern "C" int rbx_filter_particles(const float *d_coords, int64_t n, const float *d_edges, int n_edges,
                                     float *d_mass, float *d_met, float *d_age, uint8_t *d_mask, void *stream) {
   return spaxel_common(d_coords, n, d_edges, n_edges, nullptr, d_mask, d_mass, d_met, d_age, (cudaStream_t)stream);
+}
+
+extern "C" int rbx_filter_and_assign(const float *d_coords, int64_t n, const float *d_edges, int n_edges,
+                                     float *d_mass, float *d_met, float *d_age, int32_t *d_pixel, uint8_t *d_mask,
+                                     void *stream) {
+  RBX_REQUIRE(d_pixel || n == 0, "rbx_filter_and_assign: null output");
+  const int mark = (!d_mass && !d_met && !d_age) ? 1 : 0;
+  return spaxel_common(d_coords, n, d_edges, n_edges, d_pixel, d_mask, d_mass, d_met, d_age, (cudaStream_t)stream, mark);
 }
 
 extern "C" int rbx_ssp_lookup(const rbx_plan *plan, const float *d_met, const float *d_age, int64_t n,

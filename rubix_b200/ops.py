@@ -112,6 +112,17 @@ def filter_particles(coords, edges, mass=None, metallicity=None, age=None):
     return mask.bool()
 
 
+def filter_and_assign(coords, edges, mass=None, metallicity=None, age=None) -> torch.Tensor:
+    """filter_particles + spaxel_assignment in one pass.  Without mass / metallicity / age nothing is
+    modified and particles outside the aperture get pixel -1 (dropped by build_cube / segment_sum)."""
+    coords, edges = dev(coords), dev(edges)
+    n = coords.shape[0]
+    pixel = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().rbx_filter_and_assign(_p(coords), n, _p(edges), edges.numel(), _p(mass), _p(metallicity),
+                                                _p(age), _p(pixel), None, _stream()))
+    return pixel
+
+
 def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
     n = metallicity.numel()

@@ -96,6 +96,23 @@ def test_filter_particles(ops):
     assert np.array_equal(age.cpu().numpy(), ea)
 
 
+def test_filter_and_assign_one_pass(ops):
+    from rubix_b200.synthetic import bench_g, spatial_edges
+    d = bench_g(50000, sigma_kpc=3.0)
+    edges = spatial_edges(25)
+    ref_idx, ref_mask = c_oracle.spaxel_assign(d["coords"], edges)
+    assert (~ref_mask).sum() > 100
+    # marking mode: nothing modified, pixel -1 outside the aperture
+    pix = ops.filter_and_assign(d["coords"], edges).cpu().numpy()
+    assert np.array_equal(pix[ref_mask], ref_idx[ref_mask]) and (pix[~ref_mask] == -1).all()
+    # in-place mode: same as filter_particles followed by spaxel_assign
+    mass, met, age = ops.dev(d["mass"]).clone(), ops.dev(d["metallicity"]).clone(), ops.dev(d["age"]).clone()
+    pix2 = ops.filter_and_assign(d["coords"], edges, mass, met, age).cpu().numpy()
+    assert np.array_equal(pix2, ref_idx)
+    for t, h in ((mass, d["mass"]), (met, d["metallicity"]), (age, d["age"])):
+        assert np.array_equal(t.cpu().numpy(), np.where(ref_mask, h, np.float32(0)))
+
+
 # ---- a1 -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_ssp_lookup_nodes_and_outside(ops, plans, bc03, method):
