@@ -137,8 +137,9 @@ __global__ void psf_lsf_kernel(const float *__restrict__ in, float *__restrict__
 template <int TY, int TX, int P, int KMAX>
 __global__ void __launch_bounds__(160)
 psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W,
-                   const float *__restrict__ Kp, const float *__restrict__ kl, int K, int ext, int TL) {
-  extern __shared__ __align__(16) float s_mid[];  // [TY*TX][pitch]
+                   const float *__restrict__ Kp, const float *__restrict__ kl, int K, int ext) {
+  constexpr int TL = 128;                          // output channels per block
+  extern __shared__ __align__(16) float s_mid[];   // [TY*TX][pitch]
   const int TLH = TL + K - 1;
   const int pitch = (TLH + 3 + 4) & ~3;            // room for the 4-wide LSF reads of the last group
   const int tiles_x = (nx + TX - 1) / TX;
@@ -146,9 +147,12 @@ psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny
   const int w0 = (blockIdx.x / tiles_x) * TL;
   const int y0 = blockIdx.y * TY;
   constexpr int C = (P - 1) / 2;                   // jax "same": out[y] = sum_m K[m] in[y - m + C]
-  __shared__ float s_kp[P * P];
-  for (int i = threadIdx.x; i < P * P; i += blockDim.x) s_kp[i] = Kp[i];
-  __syncthreads();
+  constexpr int H = P - 1 - C;                     // rows / columns of halo before the tile
+  float kp[P * P];                                 // PSF taps in registers (static indices below)
+#pragma unroll
+  for (int i = 0; i < P * P; ++i) kp[i] = Kp ? __ldg(Kp + i) : 1.f;   // Kp == NULL: identity (P == 1)
+  const bool interior = y0 - H >= 0 && y0 + TY + C <= ny && x0 - H >= 0 && x0 + TX + C <= nx;
+  const size_t rowstride = (size_t)nx * W;
 
   // ---- PSF into shared memory -------------------------------------------------------------------
   for (int c = threadIdx.x; c < TLH; c += blockDim.x) {
@@ -159,27 +163,33 @@ psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny
 #pragma unroll
       for (int b = 0; b < TX; ++b) acc[a][b] = 0.f;
     if (q >= 0 && q < W) {
-#pragma unroll 1
-      for (int iy = 0; iy < TY + P - 1; ++iy) {    // rolled: keeps the live set at one input row
-        const int yy = y0 + iy - (P - 1 - C);
-        if (yy < 0 || yy >= ny) continue;
-        float v[TX + P - 1];
+      const float *base = in + ((ptrdiff_t)(y0 - H) * nx + (x0 - H)) * W + q;   // voxel (iy = 0, ix = 0)
 #pragma unroll
-        for (int ix = 0; ix < TX + P - 1; ++ix) {
-          const int xx = x0 + ix - (P - 1 - C);
-          v[ix] = (xx >= 0 && xx < nx) ? __ldg(in + ((size_t)yy * nx + xx) * W + q) : 0.f;
+      for (int iy = 0; iy < TY + P - 1; ++iy) {
+        const int yy = y0 + iy - H;
+        float v[TX + P - 1];
+        if (interior) {
+#pragma unroll
+          for (int ix = 0; ix < TX + P - 1; ++ix) v[ix] = __ldg(base + iy * rowstride + (size_t)ix * W);
+        } else {
+          const bool rowok = yy >= 0 && yy < ny;
+#pragma unroll
+          for (int ix = 0; ix < TX + P - 1; ++ix) {
+            const int xx = x0 + ix - H;
+            v[ix] = (rowok && xx >= 0 && xx < nx) ? __ldg(base + iy * rowstride + (ptrdiff_t)ix * W) : 0.f;
+          }
         }
 #pragma unroll
         for (int oy = 0; oy < TY; ++oy) {
-          const int m = oy + P - 1 - iy;           // tap row feeding output row oy (block-uniform)
+          const int m = oy + P - 1 - iy;           // tap row feeding output row oy (compile time)
           if (m < 0 || m >= P) continue;
 #pragma unroll
-          for (int n = 0; n < P; ++n) {
-            const float kv = s_kp[m * P + n];
+          for (int n = 0; n < P; ++n)
 #pragma unroll
-            for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(kv, v[ox + P - 1 - n], acc[oy][ox]);
-          }
+            for (int ox = 0; ox < TX; ++ox) acc[oy][ox] = fmaf(kp[m * P + n], v[ox + P - 1 - n], acc[oy][ox]);
         }
+        // keep the loads of the next input row behind this row's FMAs: hoisting them all costs ~250 registers
+        asm volatile("" ::: "memory");
       }
     }
 #pragma unroll
@@ -197,10 +207,10 @@ psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny
   // ---- LSF: out[w0 + j] = sum_m kl[m] mid[j + K - 1 - m] -----------------------------------------
   float krev[KMAX];  // taps reversed and zero padded: krev[u] = kl[K - 1 - u]
 #pragma unroll
-  for (int u = 0; u < KMAX; ++u) krev[u] = u < K ? __ldg(kl + (K - 1 - u)) : 0.f;
-  const int groups = (TL + 3) / 4;
-  for (int item = threadIdx.x; item < TY * TX * groups; item += blockDim.x) {
-    const int pix = item / groups, j0 = (item - pix * groups) * 4;
+  for (int u = 0; u < KMAX; ++u) krev[u] = u < K ? (kl ? __ldg(kl + (K - 1 - u)) : 1.f) : 0.f;  // kl == NULL: identity (K == 1)
+  constexpr int G = TL / 4;                        // 4-channel groups per spaxel
+  for (int item = threadIdx.x; item < TY * TX * G; item += blockDim.x) {
+    const int pix = item / G, j0 = (item % G) * 4;
     const int y = y0 + pix / TX, x = x0 + pix % TX;
     if (y >= ny || x >= nx) continue;
     const float4 *mp = reinterpret_cast<const float4 *>(s_mid + pix * pitch + j0);
@@ -217,9 +227,13 @@ psf_lsf_reg_kernel(const float *__restrict__ in, float *__restrict__ out, int ny
 #pragma unroll
       for (int r = 0; r < 4; ++r) o[r] = fmaf(krev[u], win[r + u], o[r]);
     float *dst = out + ((size_t)y * nx + x) * W + w0 + j0;
+    if (w0 + j0 + 3 < W) {
+      dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
+    } else {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if (j0 + r < TL && w0 + j0 + r < W) dst[r] = o[r];
+      for (int r = 0; r < 4; ++r)
+        if (w0 + j0 + r < W) dst[r] = o[r];
+    }
   }
 }
 
@@ -265,6 +279,38 @@ __global__ void gaussian_lsf_kernel(float sigma, float wr, int factor, int K, fl
 
 using namespace rbx;
 
+// Launch the register-tiled kernel when it covers the configuration (square PSF of 1/3/5/7 taps per side,
+// LSF of <= 25 taps, or identity for either); RBX_ERR_UNSUPPORTED otherwise (no error text set).
+static int psf_lsf_reg_dispatch(const float *d_in, float *d_out, int ny, int nx, int W, const float *d_psf, int M,
+                                int N, const float *d_lsf, int K, int ext, cudaStream_t stream) {
+  if (!(M == N && (M == 1 || M == 3 || M == 5 || M == 7) && (K <= 25))) return RBX_ERR_UNSUPPORTED;
+  const int TLr = 128;
+  auto run = [&](auto kernel, int ty, int tx) -> int {
+    const int pitch = (TLr + K - 1 + 3 + 4) & ~3;
+    const size_t smem = sizeof(float) * (size_t)ty * tx * pitch;
+    if (smem > 48 * 1024) RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(((nx + tx - 1) / tx) * ((W + TLr - 1) / TLr), (ny + ty - 1) / ty);
+    kernel<<<grid, 160, smem, stream>>>(d_in, d_out, ny, nx, W, d_psf, d_lsf, K, ext);
+    count_launch();
+    RBX_LAUNCH_OK();
+    return RBX_OK;
+  };
+  const bool five = (nx % 5 == 0) && (ny % 5 == 0);
+  if (K == 1) {  // PSF only
+    if (M == 3) return run(psf_lsf_reg_kernel<4, 8, 3, 1>, 4, 8);
+    if (M == 5) return five ? run(psf_lsf_reg_kernel<5, 5, 5, 1>, 5, 5) : run(psf_lsf_reg_kernel<4, 8, 5, 1>, 4, 8);
+    if (M == 7) return run(psf_lsf_reg_kernel<4, 8, 7, 1>, 4, 8);
+    return RBX_ERR_UNSUPPORTED;
+  }
+  if (M == 1) return five ? run(psf_lsf_reg_kernel<5, 5, 1, 25>, 5, 5) : run(psf_lsf_reg_kernel<4, 8, 1, 25>, 4, 8);
+  if (M == 3) return run(psf_lsf_reg_kernel<4, 8, 3, 25>, 4, 8);
+  if (M == 5) {
+    if (five && nx % 10 == 0 && nx >= 50) return run(psf_lsf_reg_kernel<5, 10, 5, 25>, 5, 10);
+    return five ? run(psf_lsf_reg_kernel<5, 5, 5, 25>, 5, 5) : run(psf_lsf_reg_kernel<4, 8, 5, 25>, 4, 8);
+  }
+  return run(psf_lsf_reg_kernel<4, 8, 7, 25>, 4, 8);
+}
+
 extern "C" int rbx_convolve_psf(const float *d_in, float *d_out, int ny, int nx, int W, const float *d_kernel,
                                 int M, int N, void *stream) {
   RBX_REQUIRE(d_in && d_out && d_kernel && d_in != d_out, "rbx_convolve_psf: bad pointers (no aliasing)");
@@ -272,6 +318,10 @@ extern "C" int rbx_convolve_psf(const float *d_in, float *d_out, int ny, int nx,
   // jax.scipy.signal.convolve2d: "One input must be smaller than the other in every dimension."
   RBX_REQUIRE((M <= ny && N <= nx) || (M >= ny && N >= nx),
               "One input must be smaller than the other in every dimension.");
+  {  // register-tiled kernel with an identity LSF
+    int rc = psf_lsf_reg_dispatch(d_in, d_out, ny, nx, W, d_kernel, M, N, nullptr, 1, 0, (cudaStream_t)stream);
+    if (rc != RBX_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid((W + 255) / 256, ny * nx);
   psf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, ny, nx, W, d_kernel, M, N);
   count_launch();
@@ -284,6 +334,13 @@ extern "C" int rbx_convolve_lsf(const float *d_in, float *d_out, int64_t rows, i
   RBX_REQUIRE(d_in && d_out && d_kernel && d_in != d_out, "rbx_convolve_lsf: bad pointers (no aliasing)");
   RBX_REQUIRE(rows > 0 && W > 0 && K > 0 && K <= kMaxTaps, "rbx_convolve_lsf: bad shape");
   RBX_REQUIRE(K == 2 * ext + 1, "rbx_convolve_lsf: kernel length must be 2*extend_factor+1");
+  if (rows < (1 << 30)) {  // register-tiled kernel with an identity PSF
+    int fx = 1;  // any factorisation rows = fy * fx is a valid "image" for an identity PSF: pick one that fills tiles
+    for (int d : {40, 25, 20, 10, 8, 5, 4, 2})
+      if (rows % d == 0) { fx = d; break; }
+    int rc = psf_lsf_reg_dispatch(d_in, d_out, (int)(rows / fx), fx, W, nullptr, 1, 1, d_kernel, K, ext, (cudaStream_t)stream);
+    if (rc != RBX_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid((W + 255) / 256, (unsigned)(rows < 65535 ? rows : 65535));
   lsf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, rows, W, d_kernel, K, ext);
   count_launch();
@@ -298,23 +355,9 @@ extern "C" int rbx_psf_lsf(const float *d_in, float *d_out, int ny, int nx, int 
   RBX_REQUIRE(K == 2 * ext + 1, "rbx_psf_lsf: LSF kernel length must be 2*extend_factor+1");
   RBX_REQUIRE((M <= ny && N <= nx) || (M >= ny && N >= nx),
               "One input must be smaller than the other in every dimension.");
-  if (M == N && (M == 3 || M == 5 || M == 7) && K <= 25) {
-    const int TLr = 128;
-    auto run = [&](auto kernel, int ty, int tx) -> int {
-      const int pitch = (TLr + K - 1 + 3 + 4) & ~3;
-      const size_t smem = sizeof(float) * (size_t)ty * tx * pitch;
-      if (smem > 48 * 1024) RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dim3 grid(((nx + tx - 1) / tx) * ((W + TLr - 1) / TLr), (ny + ty - 1) / ty);
-      kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(d_in, d_out, ny, nx, W, d_psf, d_lsf, K, ext, TLr);
-      count_launch();
-      RBX_LAUNCH_OK();
-      return RBX_OK;
-    };
-    const bool five = (nx % 5 == 0) && (ny % 5 == 0) && M == 5;
-    if (five) return run(psf_lsf_reg_kernel<5, 5, 5, 25>, 5, 5);
-    if (M == 3) return run(psf_lsf_reg_kernel<4, 8, 3, 25>, 4, 8);
-    if (M == 5) return run(psf_lsf_reg_kernel<4, 8, 5, 25>, 4, 8);
-    return run(psf_lsf_reg_kernel<4, 8, 7, 25>, 4, 8);
+  {
+    int rc = psf_lsf_reg_dispatch(d_in, d_out, ny, nx, W, d_psf, M, N, d_lsf, K, ext, (cudaStream_t)stream);
+    if (rc != RBX_ERR_UNSUPPORTED) return rc;
   }
   constexpr int TY = 5, TX = 5;
   int TL = 128;

@@ -259,6 +259,24 @@ def test_fused_cube_non_affine_grid(ops, bc03):
     _cube_close(out, ref, "fused non-affine grid")
 
 
+def test_fused_cube_large_fov_150(ops, plans, bc03, muse_wave):
+    """BASELINE config 4 geometry (150 x 150 spaxels x 3721 channels) at a particle count the oracle
+    finishes in seconds: many small spaxel segments, 335 MB cube."""
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(150)
+    data = _well_conditioned(synthetic.bench_g(60000, seed=21), np.float32(1.1) * bc03["wavelength"], muse_wave)
+    out = _run_fused(ops, plans["linear"], data, edges, 150)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 150, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], muse_wave, 0.1, method="linear", dtype=np.float64, n_threads=8)
+    _cube_close(out, ref, "fused 150x150")
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    conv = ops.psf_lsf(out.astype(np.float32), pk, lk).cpu().numpy()
+    sl = slice(40, 110)  # oracle convolution of the central region only (the full 335 MB cube is slow in numpy)
+    refc = orc.apply_lsf(orc.apply_psf(ref[sl, sl], pk.astype(np.float64)), 0.5, 1.25)[2:-2, 2:-2]
+    assert np.abs(conv[sl, sl][2:-2, 2:-2] - refc).max() <= 5e-6 * np.abs(refc).max()
+
+
 def test_fused_equals_stage_path(ops, plans, tng_subset):
     """The fused kernel and the materialising stage kernels are two CUDA implementations of the same
     stages; they must agree to float32 rounding."""
