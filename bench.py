@@ -228,7 +228,7 @@ def main():
         if world > 1:
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
-            return ops.psf_lsf(cube, pk, lk)
+            return ops.psf_lsf(cube, pk_h, lk_h)  # host taps, as the reference builds them
         return cube
 
     def barrier():
@@ -293,7 +293,7 @@ def main():
             ops.build_cube(plan, dvel, mass, met, age, pix, S, out=cube)
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
-                hcube.copy_(ops.psf_lsf(cube, pk, lk), non_blocking=True)
+                hcube.copy_(ops.psf_lsf(cube, pk_h, lk_h), non_blocking=True)
             torch.cuda.synchronize()
             return float(hcube[S // 2, S // 2, 100]) if rank == 0 else 0.0
         e2e_api = "device ops through the C ABI with pinned host shards, NCCL reduce, cube to rank 0's host"

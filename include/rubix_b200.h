@@ -139,6 +139,13 @@ int rbx_convolve_lsf(const float *d_in, float *d_out, int64_t rows, int W, const
                      int K, int ext, void *stream);
 int rbx_psf_lsf(const float *d_in, float *d_out, int ny, int nx, int W, const float *d_psf, int M,
                 int N, const float *d_lsf, int K, int ext, void *stream);
+/* The same pass with HOST taps (the reference builds both kernels on the host from the config:
+ * rubix/telescope/psf/kernels.py:5-31, rubix/telescope/lsf/lsf.py:12-26).  h_psf (M, N) or NULL for no PSF,
+ * h_lsf (K = 2 ext + 1) or NULL for no LSF.  Knowing the taps at launch lets the library run an
+ * outer-product PSF as two 1-D passes and drop LSF taps below 1e-14 of the largest (they cannot change a
+ * float32 sum); returns RBX_ERR_UNSUPPORTED when the taps need the general kernels (rbx_psf_lsf). */
+int rbx_psf_lsf_taps(const float *d_in, float *d_out, int ny, int nx, int W, const float *h_psf, int M,
+                     int N, const float *h_lsf, int K, int ext, void *stream);
 /* gaussian_kernel_2d (rubix/telescope/psf/kernels.py:26-31) and _get_kernel
  * (rubix/telescope/lsf/lsf.py:12-26) evaluated in float32 on the device. */
 int rbx_gaussian_psf_kernel(int m, int n, float sigma, float *d_kernel, void *stream);

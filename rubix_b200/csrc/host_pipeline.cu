@@ -99,31 +99,41 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
     TRY(rbx_spaxel_assign(d_coords, n, d_edges, n_edges, d_pixel, nullptr, stream));
   TRY(rbx_build_cube(plan, d_vel, d_mass, d_met, d_age, d_pixel, n, num_spaxels, d_cube, d_ws, ws_bytes, stream));
   float *result = d_cube;
-  if (h_psf || h_lsf) TRY(sc.get(&d_cube2, cube_elems));
-  if (h_psf) {
-    TRY(sc.get(&d_psf, (size_t)M * N));
-    RBX_CUDA_OK(cudaMemcpyAsync(d_psf, h_psf, sizeof(float) * M * N, cudaMemcpyHostToDevice, stream));
-  }
-  if (h_lsf) {
-    TRY(sc.get(&d_lsf, (size_t)K));
-    RBX_CUDA_OK(cudaMemcpyAsync(d_lsf, h_lsf, sizeof(float) * K, cudaMemcpyHostToDevice, stream));
-  }
-  if (h_psf && h_lsf) {
-    int rc = rbx_psf_lsf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, d_lsf, K, ext, stream);
-    if (rc == RBX_ERR_UNSUPPORTED) {  // taps too large for the fused tile: two passes
-      TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
-      TRY(rbx_convolve_lsf(d_cube2, d_cube, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
-      result = d_cube;
-    } else {
-      TRY(rc);
+  if (h_psf || h_lsf) {
+    TRY(sc.get(&d_cube2, cube_elems));
+    // host-known taps: separable PSF + pruned LSF in one marching pass (conv_march.cu)
+    int rc = rbx_psf_lsf_taps(d_cube, d_cube2, num_spaxels, num_spaxels, W, h_psf, M, N, h_lsf, K, ext, stream);
+    if (rc == RBX_OK) {
       result = d_cube2;
+    } else if (rc != RBX_ERR_UNSUPPORTED) {
+      return rc;
+    } else {  // general taps: device-tap kernels
+      if (h_psf) {
+        TRY(sc.get(&d_psf, (size_t)M * N));
+        RBX_CUDA_OK(cudaMemcpyAsync(d_psf, h_psf, sizeof(float) * M * N, cudaMemcpyHostToDevice, stream));
+      }
+      if (h_lsf) {
+        TRY(sc.get(&d_lsf, (size_t)K));
+        RBX_CUDA_OK(cudaMemcpyAsync(d_lsf, h_lsf, sizeof(float) * K, cudaMemcpyHostToDevice, stream));
+      }
+      if (h_psf && h_lsf) {
+        rc = rbx_psf_lsf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, d_lsf, K, ext, stream);
+        if (rc == RBX_ERR_UNSUPPORTED) {  // taps too large for the fused tile: two passes
+          TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
+          TRY(rbx_convolve_lsf(d_cube2, d_cube, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
+          result = d_cube;
+        } else {
+          TRY(rc);
+          result = d_cube2;
+        }
+      } else if (h_psf) {
+        TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
+        result = d_cube2;
+      } else {
+        TRY(rbx_convolve_lsf(d_cube, d_cube2, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
+        result = d_cube2;
+      }
     }
-  } else if (h_psf) {
-    TRY(rbx_convolve_psf(d_cube, d_cube2, num_spaxels, num_spaxels, W, d_psf, M, N, stream));
-    result = d_cube2;
-  } else if (h_lsf) {
-    TRY(rbx_convolve_lsf(d_cube, d_cube2, (int64_t)num_spaxels * num_spaxels, W, d_lsf, K, ext, stream));
-    result = d_cube2;
   }
   RBX_CUDA_OK(cudaMemcpyAsync(h_cube, result, sizeof(float) * cube_elems, cudaMemcpyDeviceToHost, stream));
   RBX_CUDA_OK(cudaStreamSynchronize(stream));  // the caller reads h_cube right after this returns

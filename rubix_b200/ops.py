@@ -196,28 +196,67 @@ def build_cube(plan: Plan, velocity, mass, metallicity, age, pixel, num_spaxels:
     return cube
 
 
-def convolve_psf(cube, kernel) -> torch.Tensor:
-    cube, kernel = dev(cube), dev(kernel)
+def _host_taps(k):
+    """float32 host copy of a kernel given as numpy / list (None for CUDA tensors: those stay on the device)."""
+    if k is None or (isinstance(k, torch.Tensor) and k.is_cuda):
+        return None
+    if isinstance(k, torch.Tensor):
+        k = k.numpy()
+    return np.ascontiguousarray(np.asarray(k), dtype=np.float32)
+
+
+def _taps_call(cube, out, pk, lk, ext) -> bool:
+    """rbx_psf_lsf_taps (host-known taps: separable PSF, pruned LSF).  False when the taps need the
+    general device-tap kernels."""
+    ny, nx, W = cube.shape
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    M, N = pk.shape if pk is not None else (0, 0)
+    K = lk.size if lk is not None else 0
+    rc = _lib.lib().rbx_psf_lsf_taps(_p(cube), _p(out), ny, nx, W, vp(pk), M, N, vp(lk), K, ext, _stream())
+    if rc == _lib.RBX_ERR_UNSUPPORTED:
+        return False
+    _lib.check(rc)
+    return True
+
+
+def convolve_psf(cube, kernel, host_taps: bool = True) -> torch.Tensor:
+    """a6.  A kernel given on the host (numpy) takes the host-tap kernel when it is an outer product."""
+    cube = dev(cube)
     ny, nx, W = cube.shape
     out = torch.empty_like(cube)
+    hk = _host_taps(kernel) if host_taps else None
+    if hk is not None and hk.ndim == 2 and _taps_call(cube, out, hk, None, 0):
+        return out
+    kernel = dev(kernel)
     _lib.check(_lib.lib().rbx_convolve_psf(_p(cube), _p(out), ny, nx, W, _p(kernel), kernel.shape[0],
                                            kernel.shape[1], _stream()))
     return out
 
 
-def convolve_lsf(cube, kernel, ext: int = 12) -> torch.Tensor:
-    cube, kernel = dev(cube), dev(kernel).reshape(-1)
+def convolve_lsf(cube, kernel, ext: int = 12, host_taps: bool = True) -> torch.Tensor:
+    """a7.  A kernel given on the host (numpy) takes the host-tap kernel (negligible taps dropped)."""
+    cube = dev(cube)
     W = cube.shape[-1]
     rows = cube.numel() // W
     out = torch.empty_like(cube)
+    hk = _host_taps(kernel) if host_taps else None
+    if hk is not None and cube.ndim == 3 and hk.size == 2 * ext + 1 and _taps_call(cube, out, None, hk.reshape(-1), ext):
+        return out
+    kernel = dev(kernel).reshape(-1)
     _lib.check(_lib.lib().rbx_convolve_lsf(_p(cube), _p(out), rows, W, _p(kernel), kernel.numel(), ext, _stream()))
     return out
 
 
-def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12) -> torch.Tensor:
-    cube, pk, lk = dev(cube), dev(psf_kernel), dev(lsf_kernel).reshape(-1)
+def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12, host_taps: bool = True) -> torch.Tensor:
+    """a6 + a7 in one pass.  Kernels given on the host (numpy, as the reference builds them) take
+    rbx_psf_lsf_taps; CUDA tensors, or taps it does not cover, take the device-tap kernels."""
+    cube = dev(cube)
     ny, nx, W = cube.shape
     out = torch.empty_like(cube)
+    hp, hl = (_host_taps(psf_kernel), _host_taps(lsf_kernel)) if host_taps else (None, None)
+    if hp is not None and hl is not None and hp.ndim == 2 and _taps_call(cube, out, hp, hl.reshape(-1), ext):
+        return out
+    pk, lk = dev(psf_kernel), dev(lsf_kernel).reshape(-1)
     rc = _lib.lib().rbx_psf_lsf(_p(cube), _p(out), ny, nx, W, _p(pk), pk.shape[0], pk.shape[1], _p(lk),
                                 lk.numel(), ext, _stream())
     if rc == _lib.RBX_ERR_UNSUPPORTED:  # taps too large for the fused tile: two CUDA passes

@@ -340,54 +340,91 @@ def test_fused_linearity_and_sharding(ops, plans):
 
 
 # ---- a6 / a7 ----------------------------------------------------------------------------------------
-def test_psf_matches_oracle(ops):
+@pytest.mark.parametrize("host_taps", [True, False])
+def test_psf_matches_oracle(ops, host_taps):
     rng = np.random.default_rng(6)
     cube = rng.random((25, 25, 300)).astype(np.float32)
     for shape in ((5, 5), (3, 3), (4, 4), (3, 5)):
         k = rng.random(shape).astype(np.float32)
-        out = ops.convolve_psf(cube, k).cpu().numpy()
+        out = ops.convolve_psf(cube, k, host_taps=host_taps).cpu().numpy()
         ref = orc.apply_psf(cube.astype(np.float64), k.astype(np.float64))
         assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
     # tests/test_telescope_psf.py:22-54
     c = np.zeros((10, 10, 3), dtype=np.float32)
     c[5, 5, :] = 1
-    out = ops.convolve_psf(c, np.ones((3, 3), dtype=np.float32)).cpu().numpy()
+    out = ops.convolve_psf(c, np.ones((3, 3), dtype=np.float32), host_taps=host_taps).cpu().numpy()
     assert np.array_equal(out, orc.apply_psf(c, np.ones((3, 3), dtype=np.float32)))
+    # separable (outer-product) kernels: the host-tap path runs them as two 1-D passes
+    for P in (3, 5, 7):
+        k = orc.gaussian_kernel_2d(P, P, 0.9)
+        out = ops.convolve_psf(cube, k, host_taps=host_taps).cpu().numpy()
+        ref = orc.apply_psf(cube.astype(np.float64), k.astype(np.float64))
+        assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-def test_lsf_matches_oracle(ops):
+@pytest.mark.parametrize("host_taps", [True, False])
+def test_lsf_matches_oracle(ops, host_taps):
     # tests/test_telescope_lsf.py:6-60 (delta -> normalised gaussian, atol 1e-5)
     for pos in (20, 50, 75):
         s = np.zeros((1, 1, 100), dtype=np.float32)
         s[0, 0, pos] = 1
         k = orc.lsf_kernel(2.0, 1.0)
-        out = ops.convolve_lsf(s, k).cpu().numpy()[0, 0]
+        out = ops.convolve_lsf(s, k, host_taps=host_taps).cpu().numpy()[0, 0]
         x = np.arange(100)
         g = np.exp(-0.5 * ((x - pos) ** 2) / 4.0)
         assert np.allclose(out, g / g.sum(), atol=1e-5)
     rng = np.random.default_rng(7)
     cube = rng.random((7, 9, 500)).astype(np.float32)
     k = orc.lsf_kernel(0.5, 1.25)
-    out = ops.convolve_lsf(cube, k).cpu().numpy()
+    out = ops.convolve_lsf(cube, k, host_taps=host_taps).cpu().numpy()
     ref = orc.apply_lsf(cube.astype(np.float64), 0.5, 1.25)
     assert out.shape == cube.shape
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    # wide LSF (sigma 3 A: all 25 taps matter) and a medium one (13-tap window)
+    for sigma in (3.0, 1.2):
+        k = orc.lsf_kernel(sigma, 1.25)
+        out = ops.convolve_lsf(cube, k, host_taps=host_taps).cpu().numpy()
+        ref = orc.apply_lsf(cube.astype(np.float64), sigma, 1.25)
+        assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("S,W,P", [(25, 3721, 5), (13, 517, 5), (31, 130, 5), (12, 700, 3), (17, 300, 7), (9, 200, 4)])
-def test_fused_psf_lsf(ops, S, W, P):
-    """P = 3/5/7 take the register-tiled kernel (5x5 and 4x8 spaxel tiles), P = 4 the generic one."""
+@pytest.mark.parametrize("host_taps", [True, False])
+@pytest.mark.parametrize("S,W,P", [(25, 3721, 5), (13, 517, 5), (31, 130, 5), (12, 700, 3), (17, 300, 7), (9, 200, 4),
+                                   (47, 250, 5), (3, 40, 3)])
+def test_fused_psf_lsf(ops, S, W, P, host_taps):
+    """Device taps: P = 3/5/7 take the register-tiled kernel (5x5 and 4x8 spaxel tiles), P = 4 the generic
+    one.  Host taps: the marching kernel (separable PSF, pruned LSF; TX = 5 below 40 columns, 10 above)."""
     rng = np.random.default_rng(8)
     cube = rng.random((S, S, W)).astype(np.float32)
     pk = orc.gaussian_kernel_2d(P, P, 0.6) if P != 4 else rng.random((4, 4)).astype(np.float32)
     lk = orc.lsf_kernel(0.5, 1.25)
-    out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+    out = ops.psf_lsf(cube, pk, lk, host_taps=host_taps).cpu().numpy()
     ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
     err = np.abs(out - ref).max()
-    print(f"[psf+lsf {S}x{W} P={P}] max|d|={err:.3e}")
+    print(f"[psf+lsf {S}x{W} P={P} host_taps={host_taps}] max|d|={err:.3e}")
     assert err <= 2e-6 * np.abs(ref).max()
-    two = ops.convolve_lsf(ops.convolve_psf(cube, pk), lk).cpu().numpy()
+    two = ops.convolve_lsf(ops.convolve_psf(cube, pk, host_taps=host_taps), lk, host_taps=host_taps).cpu().numpy()
     assert np.abs(two - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_psf_lsf_taps_wide_cube(ops):
+    """150 x 150 spaxels (config 4's cube shape, fewer channels): several y segments and x strips, the
+    spectral tile boundary, a non-square cube; the host-tap kernel against the device-tap kernel and the
+    float64 oracle.  A delta cube checks every tap lands where the reference puts it."""
+    rng = np.random.default_rng(12)
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    for shape in ((150, 150, 260), (37, 150, 131)):
+        cube = rng.random(shape).astype(np.float32)
+        out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+        dev_taps = ops.psf_lsf(cube, pk, lk, host_taps=False).cpu().numpy()
+        ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
+        assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+        assert np.abs(out - dev_taps).max() <= 2e-6 * np.abs(ref).max()
+    d = np.zeros((150, 150, 130), dtype=np.float32)
+    d[0, 0, 0] = d[149, 149, 129] = d[74, 9, 121] = d[49, 10, 122] = 1.0
+    out = ops.psf_lsf(d, pk, lk).cpu().numpy()
+    ref = orc.apply_lsf(orc.apply_psf(d.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
+    assert np.abs(out - ref).max() <= 2e-7
 
 
 def test_fused_psf_lsf_asymmetric_kernels(ops):
@@ -396,11 +433,21 @@ def test_fused_psf_lsf_asymmetric_kernels(ops):
     cube = rng.random((10, 15, 333)).astype(np.float32)
     pk = rng.random((5, 5)).astype(np.float32)
     lk = rng.random(25).astype(np.float32)
+    out = ops.psf_lsf(cube, pk, lk).cpu().numpy()   # not an outer product: falls through to the device taps
+    mid = orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64))
+    ref = np.stack([[np.convolve(mid[y, x], lk.astype(np.float64), mode="full")[12:12 + 333] for x in range(15)]
+                    for y in range(10)])
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    # asymmetric outer-product PSF + asymmetric 7-tap LSF: the marching kernel's tap orientation
+    pk = np.outer(rng.random(5) + 0.1, rng.random(5) + 0.1).astype(np.float32)
+    lk = np.zeros(25, dtype=np.float32)
+    lk[9:16] = rng.random(7).astype(np.float32) + 0.1
     out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
     mid = orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64))
     ref = np.stack([[np.convolve(mid[y, x], lk.astype(np.float64), mode="full")[12:12 + 333] for x in range(15)]
                     for y in range(10)])
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(ops.psf_lsf(cube, pk, lk, host_taps=False).cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
 def test_gaussian_kernels_on_device(ops):

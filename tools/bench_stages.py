@@ -13,6 +13,7 @@ from rubix_b200 import ops, synthetic  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--particles", type=int, default=1_000_000)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--conv-only", action="store_true")
 args = ap.parse_args()
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -35,9 +36,19 @@ tpl = np.load(os.path.join(ROOT, "tests", "golden", "bc03lr_f32.npz"))
 wave = synthetic.muse_wave()
 pk = ops.dev(np.load(os.path.join(ROOT, "tests", "golden", "muse_wave.npy"))[:1])  # placeholder, replaced below
 from rubix_b200.telescope import gaussian_kernel_2d, lsf_kernel  # noqa: E402
-pk, lk = ops.dev(gaussian_kernel_2d(5, 5, 0.6)), ops.dev(lsf_kernel(0.5, 1.25))
+pk_h, lk_h = gaussian_kernel_2d(5, 5, 0.6), lsf_kernel(0.5, 1.25)
+pk, lk = ops.dev(pk_h), ops.dev(lk_h)
 for S in (25, 150):
     cube = torch.rand((S, S, 3721), device="cuda")
+    byts = 8 * cube.numel()
+    for name, fn in (("psf_lsf_taps", lambda: ops.psf_lsf(cube, pk_h, lk_h)),
+                     ("psf_only_taps", lambda: ops.convolve_psf(cube, pk_h)),
+                     ("lsf_only_taps", lambda: ops.convolve_lsf(cube, lk_h)),
+                     ("copy", lambda: cube.clone())):
+        med, mn = timeit(fn)
+        out[f"{name}_S{S}"] = {"ms_median": med, "ms_min": mn, "algorithmic_bytes": byts,
+                               "achieved_gbs": byts / (med * 1e-3) / 1e9,
+                               "frac_of_measured_hbm": byts / (med * 1e-3) / 1e9 / peak}
     med, mn = timeit(lambda: ops.psf_lsf(cube, pk, lk))
     byts = 8 * cube.numel()
     out[f"psf_lsf_S{S}"] = {"ms_median": med, "ms_min": mn, "algorithmic_bytes": byts,
@@ -47,6 +58,9 @@ for S in (25, 150):
     med, mn = timeit(lambda: ops.convolve_lsf(cube, lk))
     out[f"lsf_only_S{S}"] = {"ms_median": med, "achieved_gbs": byts / (med * 1e-3) / 1e9}
     del cube
+if args.conv_only:
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 n = args.particles
 d = synthetic.bench_g(n)
 for S in (25, 150):
