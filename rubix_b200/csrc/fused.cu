@@ -18,6 +18,8 @@
 // O(#knots in band), not O(W log L), and nothing per-channel is touched until the spaxel is finished.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace rbx {
@@ -731,6 +733,313 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
 }
 
 
+// ---- warp-per-particle variant ----------------------------------------------------------------------
+// One WARP holds the whole knot window: lane l owns the WK = 8 consecutive SSP knots jbase + 8 l + {0..7}
+// (256 slots), so the two normalisation sums of a particle are a lane-local sum plus one butterfly
+// reduction -- no group barrier, no shared-memory exchange -- and the eight knots of a lane are eight
+// independent instruction chains.  Every warp owns a private cell array (W + 1 cells) in shared memory
+// and works on its own work item, so the warps of a CTA never synchronise after start-up.  A lane's
+// knots fall into distinct cells (SSP spacing > channel spacing, checked on the host; the group kernel
+// above with its CAS mode covers everything else), hence the eight read-modify-writes of a particle are
+// issued as 8 loads, 16 FMAs, 8 stores: one shared-memory round trip per particle instead of one per
+// knot.  Affine (arange) telescope grids only.
+constexpr int WK = 8;
+constexpr int kWarpSlots = WK * 32;
+
+struct WarpLayout {
+  int off_tc;        // [nch] wavelength of each chunk's first channel
+  int off_warp;      // first warp block
+  int warp_stride;   // bytes per warp: cells [(W + 2)] float2, then chunk lines [nch] float2
+  int w_base;        // offset of the chunk lines inside a warp block
+  int nch, chs;      // chunks per row, log2(channels per chunk)
+  int nwarps;        // warps per CTA
+  unsigned skew;     // cell index = k + floor(k * skew / 2^32): makes the lane stride an odd number of cells
+  int ncells;        // cells per warp (W + 2 + skew of the last one)
+};
+
+__device__ __forceinline__ int skewed(int k, unsigned skew) {
+  unsigned r;
+  asm("mad.hi.u32 %0, %1, %2, %1;" : "=r"(r) : "r"((unsigned)k), "r"(skew));
+  return (int)r;
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(256, 1)
+fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
+                       float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay) {
+  constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
+  constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float *s_tc = reinterpret_cast<float *>(smem + lay.off_tc);
+  float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride);
+  float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_base);
+  const int CH = 1 << lay.chs;
+
+  for (int c = tid; c < lay.nch; c += blockDim.x) s_tc[c] = p.t[min(c << lay.chs, p.W - 1)];
+  for (int q = lane; q < lay.ncells; q += 32) cells[q] = make_float2(0.f, 0.f);
+  for (int q = lane; q < lay.nch; q += 32) base[q] = make_float2(0.f, 0.f);
+  __syncthreads();
+
+  // ---- per-lane knot constants -------------------------------------------------------------------
+  const int ja = ctrl[C_JA], jb = ctrl[C_JB];
+  const int n_items = ctrl[C_NITEMS];
+  const int jbase = (ja - 1) & ~3;               // multiple of 4 (16-byte template loads); slot s <-> knot jbase + s
+  if (jb - jbase + 1 > kWarpSlots) {             // the knot window does not fit one warp: fail loudly (poison_kernel)
+    if (tid == 0) atomicExch(ctrl + C_ERROR, 2);
+    return;
+  }
+  const int j0 = jbase + WK * lane;
+  const bool interior = j0 >= 0 && j0 + WK <= p.L;   // all eight knots inside the SSP grid: two 16-byte loads per row
+  float lz[WK], rdl[WK];
+  int jc[WK];                                     // clamped knot index (jnp.interp end values)
+#pragma unroll
+  for (int r = 0; r < WK; ++r) {
+    const int j = j0 + r;
+    jc[r] = min(max(j, 0), p.L - 1);
+    lz[r] = j < 0 ? -1.0e30f : (j >= p.L ? 1.0e30f : p.lamz[j]);
+    rdl[r] = (j < 0 || j >= p.L - 1) ? 0.f : p.rdl[j];
+  }
+  if (lane == 31) rdl[WK - 1] = 0.f;              // the segment leaving the window (always beyond the band)
+  // previous knot of slot 0 for the "total" difference; diff0's first element is 0 (rubix/spectra/ifu.py:84-102)
+  const float lzprev = (j0 - 1 >= 0 && j0 - 1 < p.L) ? p.lamz[j0 - 1] : lz[0];
+
+  const float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+  // chunk lines are summed in registers: a lane's span [k_0, k_8) holds at most one chunk start, and over
+  // the Doppler range present that start is chunk cA or cA + 1
+  int cA = 0;
+  {
+    float e;
+    const int kmin0 = channel_of<true>(__fmul_rn(lz[0], dmin), p, nullptr, nullptr, e);
+    const int kmax0 = channel_of<true>(__fmul_rn(lz[0], dmax), p, nullptr, nullptr, e);
+    const float lznext = __shfl_down_sync(0xffffffffu, lz[0], 1);
+    const int knext = lane == 31 ? kmax0 : channel_of<true>(__fmul_rn(lznext, dmax), p, nullptr, nullptr, e);
+    cA = (kmin0 + CH - 1) >> lay.chs;
+    if (((kmax0 + CH - 1) >> lay.chs) > cA + 1 || knext - kmax0 + 2 >= CH) atomicExch(ctrl + C_ERROR, 3);
+  }
+  float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
+
+  const float *tab[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) tab[t] = p.tab[t];
+  const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
+  const float hd2 = 0.5f * p.tdelta * p.tdelta;
+
+  while (true) {
+    int item_id = 0;
+    if (lane == 0) item_id = atomicAdd(ctrl + C_WORK, 1);
+    item_id = __shfl_sync(0xffffffffu, item_id, 0);
+    if (item_id >= n_items) break;
+    const Item it = items[item_id];
+
+    // Software pipeline: the record and (linear method, interior lanes) the eight template vectors of the
+    // NEXT particle are in flight while the current one is processed.
+    constexpr bool PF = METHOD == RBX_METHOD_LINEAR;
+    float4 nr0, nwt[NT];
+    float4 nf[PF ? 8 : 1];
+    auto fetch = [&](int q) {
+      const float *rb = rec + (size_t)(it.start + q) * RS;
+      nr0 = __ldg(reinterpret_cast<const float4 *>(rb));
+#pragma unroll
+      for (int t = 0; t < NT; ++t) nwt[t] = __ldg(reinterpret_cast<const float4 *>(rb + 4 + 4 * t));
+    };
+    auto fetch_rows = [&]() {   // needs nr0 (the row index): issued one step behind the record itself
+      if (PF && interior) {
+        const float *f = tab[0] + (size_t)__float_as_int(nr0.z) * p.Lp + j0;
+        nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
+        nf[1] = __ldg(reinterpret_cast<const float4 *>(f + 4));
+        nf[2] = __ldg(reinterpret_cast<const float4 *>(f + rowB));
+        nf[3] = __ldg(reinterpret_cast<const float4 *>(f + rowB + 4));
+        nf[4] = __ldg(reinterpret_cast<const float4 *>(f + rowC));
+        nf[5] = __ldg(reinterpret_cast<const float4 *>(f + rowC + 4));
+        nf[6] = __ldg(reinterpret_cast<const float4 *>(f + rowD));
+        nf[7] = __ldg(reinterpret_cast<const float4 *>(f + rowD + 4));
+      }
+    };
+    fetch(0);
+    fetch_rows();
+    for (int q = 0; q < it.count; ++q) {
+      const float4 r0 = nr0;   // d, 1/d, row, -
+      float4 wq[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) wq[t] = nwt[t];
+      const float d = r0.x, rd = r0.y;
+      const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
+
+      // ---- mass-weighted spectrum at my eight knots ------------------------------------------------
+      float S[WK + 1];
+#pragma unroll
+      for (int r = 0; r < WK; ++r) S[r] = 0.f;
+      if (PF && interior) {
+        // linear weights are ordered rows (+0, +1, +na, +na+1)
+        const float wv[4] = {wq[0].x, wq[0].y, wq[0].z, wq[0].w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float4 lo = nf[PF ? 2 * a : 0], hi = nf[PF ? 2 * a + 1 : 0];
+          S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
+          S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
+          S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
+          S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
+        }
+        if (q + 1 < it.count) { fetch(q + 1); fetch_rows(); }
+      } else {
+        if (q + 1 < it.count) fetch(q + 1);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
+          const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
+          const float wv[4] = {wq[t].x, wq[t].y, wq[t].z, wq[t].w};
+          const float *f = tab[t] + row;
+          if (interior) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float4 lo = __ldg(reinterpret_cast<const float4 *>(f + off[a] + j0));
+              const float4 hi = __ldg(reinterpret_cast<const float4 *>(f + off[a] + j0 + 4));
+              S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
+              S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
+              S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
+              S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int r = 0; r < WK; ++r) S[r] = fmaf(wv[a], __ldg(f + off[a] + jc[r]), S[r]);
+          }
+        }
+      }
+
+      // ---- shifted positions, first channel at or above each knot ------------------------------------
+      float x[WK], e[WK + 1];
+      int k[WK + 1];
+#pragma unroll
+      for (int r = 0; r < WK; ++r) {
+        x[r] = __fmul_rn(lz[r], d);
+        k[r] = channel_of<true>(x[r], p, nullptr, nullptr, e[r]);
+      }
+      S[WK] = __shfl_down_sync(0xffffffffu, S[0], 1);
+      k[WK] = __shfl_down_sync(0xffffffffu, k[0], 1);
+      e[WK] = __shfl_down_sync(0xffffffffu, e[0], 1);
+      if (lane == 31) { S[WK] = S[WK - 1]; k[WK] = k[WK - 1]; e[WK] = e[WK - 1]; }
+
+      // ---- slopes, the two normalisation sums (rubix/spectra/ifu.py:241-251) -------------------------
+      float m[WK], gx[WK];
+      float tot = 0.f, nw = 0.f;
+#pragma unroll
+      for (int r = 0; r < WK; ++r) {
+        m[r] = (S[r + 1] - S[r]) * rdl[r] * rd;
+        const float xprev = r == 0 ? __fmul_rn(lzprev, d) : x[r - 1];
+        const float wd = (x[r] >= p.tmin && x[r] <= p.tmax) ? x[r] - xprev : 0.f;
+        tot = fmaf(S[r], wd, tot);
+        // sum_w p(t_w) dt_w over the channels [k_r, k_{r+1}): S D + m T, D = sum dt_w (telescopes exactly in
+        // float32), T = sum dt_w (t_w - x) in closed form on the arange grid
+        const float D = e[r + 1] - e[r];
+        gx[r] = e[r] - x[r];
+        const float nn = (float)(max(k[r + 1], 1) - max(k[r], 1));
+        const float T = fmaf(D, fmaf(0.5f, D, gx[r] + p.tdelta), -hd2 * nn);
+        nw += fmaf(m[r], T, S[r] * D);
+      }
+      float mp = __shfl_up_sync(0xffffffffu, m[WK - 1], 1);
+      if (lane == 0) mp = m[0];   // slot 0 of the window lies below the band for every Doppler factor present
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        nw += __shfl_xor_sync(0xffffffffu, nw, o);
+      }
+      const float sc = nan_to_num0(tot / nw);   // total / new   (rubix/spectra/ifu.py:252-255)
+
+      // ---- chunk line: the segment valid at the first chunk start inside [k_0, k_8) ---------------------
+      {
+        const int c = (k[0] + CH - 1) >> lay.chs;
+        const int chan = c << lay.chs;
+        const bool has = chan < k[WK] && chan < p.W;
+        float Sr = S[0], mr = m[0], xr = x[0];
+#pragma unroll
+        for (int r = 1; r < WK; ++r) {
+          const bool take = k[r] <= chan;
+          Sr = take ? S[r] : Sr; mr = take ? m[r] : mr; xr = take ? x[r] : xr;
+        }
+        const float tch = s_tc[min(c, lay.nch - 1)];
+        const float bv = fmaf(mr, tch - xr, Sr);
+        const int sel = has ? 1 + (c - cA) : 0;
+        const float sA = sel == 1 ? sc : 0.f, sB = sel == 2 ? sc : 0.f;
+        accAv = fmaf(sA, bv, accAv); accAm = fmaf(sA, mr, accAm);
+        accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
+      }
+
+      // ---- scaled kinks into my cells: 8 loads, 16 FMAs, 8 stores -----------------------------------------
+      float2 cv[WK];
+      int ka[WK];
+#pragma unroll
+      for (int r = 0; r < WK; ++r) ka[r] = skewed(k[r], lay.skew);
+#pragma unroll
+      for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+#pragma unroll
+      for (int r = 0; r < WK; ++r) {
+        const float dm = m[r] - (r == 0 ? mp : m[r - 1]);
+        cv[r].x = fmaf(sc, dm * gx[r], cv[r].x);
+        cv[r].y = fmaf(sc, dm, cv[r].y);
+      }
+#pragma unroll
+      for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
+      __syncwarp();
+    }  // particles
+
+    // flush the register chunk lines, one lane after the other (neighbouring lanes can share a chunk)
+    for (int l = 0; l < 32; ++l) {
+      if (lane == l) {
+        if (cA < lay.nch) cell_add<false>(base + cA, accAv, accAm);
+        if (cA + 1 < lay.nch) cell_add<false>(base + cA + 1, accBv, accBm);
+      }
+      __syncwarp();
+    }
+    accAv = accAm = accBv = accBm = 0.f;
+
+    // ---- expand the cells into the spaxel spectrum and store it ---------------------------------------
+    float *rowp = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
+    for (int c = 0; c < lay.nch; ++c) {
+      const float2 bs = base[c];
+      float vcar = bs.x, scar = bs.y;
+      __syncwarp();
+      if (lane == 0) base[c] = make_float2(0.f, 0.f);
+      for (int h = 0; h < CH; h += 32) {
+        const int ch = (c << lay.chs) + h + lane;
+        if ((c << lay.chs) + h > p.W) break;
+        float A = 0.f, B = 0.f;
+        if (ch <= p.W) {
+          const int ca = skewed(ch, lay.skew);
+          const float2 cvv = cells[ca];
+          A = cvv.x; B = cvv.y;
+          cells[ca] = make_float2(0.f, 0.f);
+        }
+        const bool valid = ch < p.W;
+        const bool start = (h + lane) == 0;   // the chunk's first channel takes the base line itself
+        if (start || !valid) { A = 0.f; B = 0.f; }
+        const float dtc = (start || !valid) ? 0.f : __ldg(p.dt + ch);
+        // slope after the kinks of this channel, then the value increments
+        float sB = B;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, sB, o);
+          if (lane >= o) sB += n;
+        }
+        const float sl = scar + sB;
+        float inc = fmaf(sl, dtc, A);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += n;
+        }
+        const float v = vcar + inc;
+        if (valid) rowp[ch] = v;
+        scar = __shfl_sync(0xffffffffu, sl, 31);
+        vcar = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // cube[s] = sum over the spaxel's items, in item order (deterministic two-level reduction)
 __global__ void reduce_partials_kernel(const int *__restrict__ item_start, const Item *__restrict__ items,
                                        const float *__restrict__ partials, int Wp, int W, int nseg,
@@ -930,6 +1239,68 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
   return RBX_OK;
 }
 
+// Static limits and shared-memory layout of fused_cube_warp_kernel.  false: the plan needs the group kernel.
+static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_bytes) {
+  const PlanView &v = plan->v;
+  if (!v.affine || v.W + 2 >= (1 << 20)) return false;
+  if (const char *e = getenv("RBX_FUSED_IMPL")) {
+    if (!strcmp(e, "group")) return false;
+  }
+  if (const char *e = getenv("RBX_FUSED_FORCE_LUT")) if (e[0] == '1') return false;
+  if (const char *e = getenv("RBX_FUSED_FORCE_CAS")) if (e[0] == '1') return false;
+  // knots that can reach the band for |v| up to ~0.03 c
+  const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
+  int inband = 0;
+  double min1 = 1e300, max8 = 0.0;   // extremes of lam_z[j+1] - lam_z[j] and lam_z[j+8] - lam_z[j] among those knots
+  for (int l = 0; l < v.L; ++l) {
+    const double x = plan->h_lamz[l];
+    if (x < lo || x > hi) continue;
+    ++inband;
+    if (l + 1 < v.L) min1 = std::fmin(min1, (double)plan->h_lamz[l + 1] - x);
+    max8 = std::fmax(max8, (double)plan->h_lamz[std::min(l + WK, v.L - 1)] - x);
+  }
+  if (inband + 16 > kWarpSlots) return false;
+  if (!(min1 * 0.97 > (double)plan->max_dt)) return false;   // two knots of a lane could share a cell
+  const double span = max8 * 1.03 / (double)plan->min_dt + 4.0;
+  int chs = 6;
+  while (chs <= 10 && span >= (double)(1 << chs)) ++chs;
+  if (chs > 10) return false;
+  if (const char *e = getenv("RBX_FUSED_CHS")) chs = std::max(chs, atoi(e));
+  auto a128 = [](int x) { return (x + 127) & ~127; };
+  lay.chs = chs;
+  lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
+  lay.off_tc = 0;
+  lay.off_warp = a128(4 * lay.nch);
+  // bank skew: the lane stride in cells (8 knots) becomes the next odd integer, so the 16 lanes of a
+  // 64-bit shared-memory wavefront hit 16 different banks
+  {
+    double sum = 0.0;
+    int cnt = 0;
+    for (int l = 0; l + 1 < v.L; ++l) {
+      const double x = plan->h_lamz[l];
+      if (x < lo || x > hi) continue;
+      sum += (double)plan->h_lamz[l + 1] - x;
+      ++cnt;
+    }
+    const double mean_dt = (double)v.trange / std::max(1, v.W - 1);
+    const double stride = cnt ? WK * (sum / cnt) / mean_dt : 0.0;
+    double target = std::ceil(stride);
+    if (((long long)target & 1) == 0) target += 1.0;
+    double alpha = stride > 1.0 ? (target - stride) / stride : 0.0;
+    if (getenv("RBX_FUSED_NO_SKEW")) alpha = 0.0;
+    lay.skew = (unsigned)std::llround(std::fmin(alpha, 0.25) * 4294967296.0);
+    lay.ncells = v.W + 2 + (int)(((unsigned long long)(v.W + 2) * lay.skew) >> 32) + 1;
+  }
+  lay.w_base = a128(8 * lay.ncells);
+  lay.warp_stride = lay.w_base + a128(8 * lay.nch);
+  int nw = std::min(8, (227 * 1024 - lay.off_warp) / lay.warp_stride);
+  if (const char *e = getenv("RBX_FUSED_WARPS")) nw = std::min(nw, std::max(1, atoi(e)));
+  if (nw < 4) return false;
+  lay.nwarps = nw;
+  smem_bytes = (size_t)lay.off_warp + (size_t)nw * lay.warp_stride;
+  return true;
+}
+
 static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
   FusedLayout lay;
   size_t smem = 0;
@@ -1021,7 +1392,17 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
     return RBX_OK;
   };
   const bool affine = v.affine != 0 && !lay.force_lut;
-  if (v.method == RBX_METHOD_LINEAR)
+  WarpLayout wlay;
+  size_t wsmem = 0;
+  if (warp_layout(plan, wlay, wsmem)) {
+    auto wlaunch = [&](auto kernel) -> int {
+      RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, wlay);
+      return RBX_OK;
+    };
+    rc = v.method == RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR>)
+                                       : wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC>);
+  } else if (v.method == RBX_METHOD_LINEAR)
     rc = affine ? launch(fused_cube_kernel<RBX_METHOD_LINEAR, true>) : launch(fused_cube_kernel<RBX_METHOD_LINEAR, false>);
   else
     rc = affine ? launch(fused_cube_kernel<RBX_METHOD_CUBIC, true>) : launch(fused_cube_kernel<RBX_METHOD_CUBIC, false>);
