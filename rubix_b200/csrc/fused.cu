@@ -751,6 +751,7 @@ struct WarpLayout {
   int off_warp;      // first warp block
   int warp_stride;   // bytes per warp: cells [(W + 2)] float2, then chunk lines [nch] float2
   int w_base;        // offset of the chunk lines inside a warp block
+  int w_rec;         // offset of the record batch [32][RS] inside a warp block
   int nch, chs;      // chunks per row, log2(channels per chunk)
   int nwarps;        // warps per CTA
   unsigned skew;     // cell index = k + floor(k * skew / 2^32): makes the lane stride an odd number of cells
@@ -774,6 +775,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
   float *s_tc = reinterpret_cast<float *>(smem + lay.off_tc);
   float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride);
   float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_base);
+  float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_rec);   // [32][RS]
   const int CH = 1 << lay.chs;
 
   for (int c = tid; c < lay.nch; c += blockDim.x) s_tc[c] = p.t[min(c << lay.chs, p.W - 1)];
@@ -832,37 +834,40 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
     if (item_id >= n_items) break;
     const Item it = items[item_id];
 
-    // Software pipeline: the record and (linear method, interior lanes) the eight template vectors of the
-    // NEXT particle are in flight while the current one is processed.
-    constexpr bool PF = METHOD == RBX_METHOD_LINEAR;
-    float4 nr0, nwt[NT];
-    float4 nf[PF ? 8 : 1];
-    auto fetch = [&](int q) {
-      const float *rb = rec + (size_t)(it.start + q) * RS;
-      nr0 = __ldg(reinterpret_cast<const float4 *>(rb));
+    // Software pipeline.  Records: a batch of 32 sorted records is loaded coalesced (lane l loads record l)
+    // and parked in the warp's shared-memory slot, so every particle's record is a broadcast read away.
+    // Template rows: the eight 16-byte vectors of the NEXT (particle, table) group are in flight while the
+    // current group is folded in and, for the last table, during the whole knot arithmetic of the particle.
+    for (int b0 = 0; b0 < it.count; b0 += 32) {
+      const int nb = min(32, it.count - b0);
+      __syncwarp();
+      if (lane < nb) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)(it.start + b0 + lane) * RS);
+        float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RS);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) nwt[t] = __ldg(reinterpret_cast<const float4 *>(rb + 4 + 4 * t));
-    };
-    auto fetch_rows = [&]() {   // needs nr0 (the row index): issued one step behind the record itself
-      if (PF && interior) {
-        const float *f = tab[0] + (size_t)__float_as_int(nr0.z) * p.Lp + j0;
-        nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
-        nf[1] = __ldg(reinterpret_cast<const float4 *>(f + 4));
-        nf[2] = __ldg(reinterpret_cast<const float4 *>(f + rowB));
-        nf[3] = __ldg(reinterpret_cast<const float4 *>(f + rowB + 4));
-        nf[4] = __ldg(reinterpret_cast<const float4 *>(f + rowC));
-        nf[5] = __ldg(reinterpret_cast<const float4 *>(f + rowC + 4));
-        nf[6] = __ldg(reinterpret_cast<const float4 *>(f + rowD));
-        nf[7] = __ldg(reinterpret_cast<const float4 *>(f + rowD + 4));
+        for (int u = 0; u < RS / 4; ++u) dst[u] = __ldg(src + u);
       }
-    };
-    fetch(0);
-    fetch_rows();
-    for (int q = 0; q < it.count; ++q) {
-      const float4 r0 = nr0;   // d, 1/d, row, -
-      float4 wq[NT];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) wq[t] = nwt[t];
+      __syncwarp();
+      float4 nf[8];
+      auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
+        if (interior) {
+          const float *f = tab[t] + (size_t)__float_as_int(s_rec[i * RS + 2]) * p.Lp + j0;
+          // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
+          const size_t o1 = METHOD == RBX_METHOD_LINEAR ? rowB : rowC, o2 = METHOD == RBX_METHOD_LINEAR ? rowC : rowB;
+          nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
+          nf[1] = __ldg(reinterpret_cast<const float4 *>(f + 4));
+          nf[2] = __ldg(reinterpret_cast<const float4 *>(f + o1));
+          nf[3] = __ldg(reinterpret_cast<const float4 *>(f + o1 + 4));
+          nf[4] = __ldg(reinterpret_cast<const float4 *>(f + o2));
+          nf[5] = __ldg(reinterpret_cast<const float4 *>(f + o2 + 4));
+          nf[6] = __ldg(reinterpret_cast<const float4 *>(f + rowD));
+          nf[7] = __ldg(reinterpret_cast<const float4 *>(f + rowD + 4));
+        }
+      };
+      issue_rows(0, 0);
+    for (int qi = 0; qi < nb; ++qi) {
+      const float *rb = s_rec + qi * RS;
+      const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, -
       const float d = r0.x, rd = r0.y;
       const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
 
@@ -870,42 +875,32 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
       float S[WK + 1];
 #pragma unroll
       for (int r = 0; r < WK; ++r) S[r] = 0.f;
-      if (PF && interior) {
-        // linear weights are ordered rows (+0, +1, +na, +na+1)
-        const float wv[4] = {wq[0].x, wq[0].y, wq[0].z, wq[0].w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const float4 lo = nf[PF ? 2 * a : 0], hi = nf[PF ? 2 * a + 1 : 0];
-          S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
-          S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
-          S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
-          S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
-        }
-        if (q + 1 < it.count) { fetch(q + 1); fetch_rows(); }
-      } else {
-        if (q + 1 < it.count) fetch(q + 1);
+      for (int t = 0; t < NT; ++t) {
+        const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+        if (interior) {
+          float4 cur[8];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
-          const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
-          const float wv[4] = {wq[t].x, wq[t].y, wq[t].z, wq[t].w};
-          const float *f = tab[t] + row;
-          if (interior) {
+          for (int u = 0; u < 8; ++u) cur[u] = nf[u];
+          if (t + 1 < NT) issue_rows(qi, t + 1);
+          else if (qi + 1 < nb) issue_rows(qi + 1, 0);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              const float4 lo = __ldg(reinterpret_cast<const float4 *>(f + off[a] + j0));
-              const float4 hi = __ldg(reinterpret_cast<const float4 *>(f + off[a] + j0 + 4));
-              S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
-              S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
-              S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
-              S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
-            }
-          } else {
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int r = 0; r < WK; ++r) S[r] = fmaf(wv[a], __ldg(f + off[a] + jc[r]), S[r]);
+          for (int a = 0; a < 4; ++a) {
+            const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
+            S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
+            S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
+            S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
+            S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
           }
+        } else {
+          // lanes at the ends of the SSP grid: clamped scalar loads (jnp.interp end values)
+          const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
+          const float *f = tab[t] + row;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int r = 0; r < WK; ++r) S[r] = fmaf(wv[a], __ldg(f + off[a] + jc[r]), S[r]);
         }
       }
 
@@ -941,49 +936,61 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
       }
       float mp = __shfl_up_sync(0xffffffffu, m[WK - 1], 1);
       if (lane == 0) mp = m[0];   // slot 0 of the window lies below the band for every Doppler factor present
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        nw += __shfl_xor_sync(0xffffffffu, nw, o);
-      }
-      const float sc = nan_to_num0(tot / nw);   // total / new   (rubix/spectra/ifu.py:252-255)
 
-      // ---- chunk line: the segment valid at the first chunk start inside [k_0, k_8) ---------------------
-      {
-        const int c = (k[0] + CH - 1) >> lay.chs;
-        const int chan = c << lay.chs;
-        const bool has = chan < k[WK] && chan < p.W;
-        float Sr = S[0], mr = m[0], xr = x[0];
-#pragma unroll
-        for (int r = 1; r < WK; ++r) {
-          const bool take = k[r] <= chan;
-          Sr = take ? S[r] : Sr; mr = take ? m[r] : mr; xr = take ? x[r] : xr;
-        }
-        const float tch = s_tc[min(c, lay.nch - 1)];
-        const float bv = fmaf(mr, tch - xr, Sr);
-        const int sel = has ? 1 + (c - cA) : 0;
-        const float sA = sel == 1 ? sc : 0.f, sB = sel == 2 ? sc : 0.f;
-        accAv = fmaf(sA, bv, accAv); accAm = fmaf(sA, mr, accAm);
-        accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
-      }
-
-      // ---- scaled kinks into my cells: 8 loads, 16 FMAs, 8 stores -----------------------------------------
+      // Everything that does not need the scale is issued BEFORE the reduction, so that the cell loads and
+      // the chunk-line selection overlap the shuffle latency.
+      // ---- kinks and their cells: 8 loads now, 16 FMAs + 8 stores after the scale ------------------------
       float2 cv[WK];
+      float dmv[WK];
       int ka[WK];
 #pragma unroll
       for (int r = 0; r < WK; ++r) ka[r] = skewed(k[r], lay.skew);
 #pragma unroll
       for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
 #pragma unroll
+      for (int r = 0; r < WK; ++r) dmv[r] = m[r] - (r == 0 ? mp : m[r - 1]);
+      // ---- chunk line: the segment valid at the first chunk start inside [k_0, k_8) ---------------------
+      float bv, mr;
+      int sel;
+      {
+        const int c = (k[0] + CH - 1) >> lay.chs;
+        const int chan = c << lay.chs;
+        const bool has = chan < k[WK] && chan < p.W;
+        float Sr = S[0], xr = x[0];
+        mr = m[0];
+#pragma unroll
+        for (int r = 1; r < WK; ++r) {
+          const bool take = k[r] <= chan;
+          Sr = take ? S[r] : Sr; mr = take ? m[r] : mr; xr = take ? x[r] : xr;
+        }
+        const float tch = s_tc[min(c, lay.nch - 1)];
+        bv = fmaf(mr, tch - xr, Sr);
+        sel = has ? 1 + (c - cA) : 0;
+      }
+
+      // ---- total / new   (rubix/spectra/ifu.py:252-255) -----------------------------------------------
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        nw += __shfl_xor_sync(0xffffffffu, nw, o);
+      }
+      const float sc = nan_to_num0(tot / nw);
+
+      {
+        const float sA = sel == 1 ? sc : 0.f, sB = sel == 2 ? sc : 0.f;
+        accAv = fmaf(sA, bv, accAv); accAm = fmaf(sA, mr, accAm);
+        accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
+      }
+#pragma unroll
       for (int r = 0; r < WK; ++r) {
-        const float dm = m[r] - (r == 0 ? mp : m[r - 1]);
-        cv[r].x = fmaf(sc, dm * gx[r], cv[r].x);
-        cv[r].y = fmaf(sc, dm, cv[r].y);
+        cv[r].x = fmaf(sc, dmv[r] * gx[r], cv[r].x);
+        cv[r].y = fmaf(sc, dmv[r], cv[r].y);
       }
 #pragma unroll
       for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
       __syncwarp();
     }  // particles
+    }  // record batches
 
     // flush the register chunk lines, one lane after the other (neighbouring lanes can share a chunk)
     for (int l = 0; l < 32; ++l) {
@@ -1292,7 +1299,8 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
     lay.ncells = v.W + 2 + (int)(((unsigned long long)(v.W + 2) * lay.skew) >> 32) + 1;
   }
   lay.w_base = a128(8 * lay.ncells);
-  lay.warp_stride = lay.w_base + a128(8 * lay.nch);
+  lay.w_rec = lay.w_base + a128(8 * lay.nch);
+  lay.warp_stride = lay.w_rec + a128(4 * 32 * (v.method == RBX_METHOD_LINEAR ? 8 : 20));
   int nw = std::min(8, (227 * 1024 - lay.off_warp) / lay.warp_stride);
   if (const char *e = getenv("RBX_FUSED_WARPS")) nw = std::min(nw, std::max(1, atoi(e)));
   if (nw < 4) return false;
