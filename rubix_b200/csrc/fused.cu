@@ -2,11 +2,10 @@
 //
 // Pipeline (all on the caller's stream, no host synchronisation):
 //   prep_kernel      validity, template cell, sort key = spaxel * ncell + cell, per-spaxel histogram,
-//                    min/max Doppler factor
+//                    min/max Doppler factor, per-particle record {d, 1/d, template row, weights * mass}
 //   cub radix sort   (key, particle index) pairs -- stable, so the summation order is deterministic
 //   segment_kernel   one block: segment starts, work items (segments split into <= psub particles),
 //                    SSP knot window for the observed Doppler range
-//   gather_kernel    sorted per-particle records {d, 1/d, template row, interpolation weights * mass}
 //   fused_cube_kernel persistent CTAs (one per SM); warp groups pull work items; per item the spaxel's
 //                    spectrum is accumulated in shared memory (no global atomics) and written once
 //   reduce_partials_kernel  spaxels that were split over several items: fixed-order sum of partial rows
@@ -62,11 +61,13 @@ struct FusedWs {
 __device__ __forceinline__ int rec_stride_for(int method) { return method == RBX_METHOD_LINEAR ? 8 : 20; }
 
 // ---- prep ---------------------------------------------------------------------------------------
+// record (floats, original particle order): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=unused
+// [4..]=interpolation weights * mass.  The cube kernels fetch records through the sorted index.
 __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const float *__restrict__ mass,
                             const float *__restrict__ met, const float *__restrict__ age,
                             const int32_t *__restrict__ pixel, int n, int nseg, int cell_bits, int cell_shift,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
-                            int *__restrict__ ctrl, int smem_hist) {
+                            int *__restrict__ ctrl, int smem_hist, float *__restrict__ rec, int stride) {
   extern __shared__ int s_hist[];  // per-block spaxel histogram (when it fits): one global atomic per bin
   if (smem_hist) {
     for (int s = threadIdx.x; s < nseg; s += blockDim.x) s_hist[s] = 0;
@@ -89,6 +90,16 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
       dmin = fminf(dmin, d);
       dmax = fmaxf(dmax, d);
       ++nvalid;
+      SspTerms tm;
+      ssp_terms(p, met[q], age[q], mass[q], tm);
+      float4 *r = reinterpret_cast<float4 *>(rec + (size_t)q * stride);
+      r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), 0.f);
+      r[1] = make_float4(tm.w[0], tm.w[1], tm.w[2], tm.w[3]);
+      if (p.method != RBX_METHOD_LINEAR) {
+        r[2] = make_float4(tm.w[4], tm.w[5], tm.w[6], tm.w[7]);
+        r[3] = make_float4(tm.w[8], tm.w[9], tm.w[10], tm.w[11]);
+        r[4] = make_float4(tm.w[12], tm.w[13], tm.w[14], tm.w[15]);
+      }
     }
     keys[q] = key;
     idx[q] = (uint32_t)q;
@@ -115,10 +126,41 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
 }
 
 // ---- segments / items / knot window (one block) -----------------------------------------------
-__global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
+// exclusive block scan of three ints per thread (1024 threads): warp shuffles + one shared hop
+__device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int *s_w, int &ta, int &tb, int &tc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int ia = a, ib = b, ic = c;   // inclusive
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o),
+              nc = __shfl_up_sync(0xffffffffu, ic, o);
+    if (lane >= o) { ia += na; ib += nb; ic += nc; }
+  }
+  if (lane == 31) { s_w[warp] = ia; s_w[32 + warp] = ib; s_w[64 + warp] = ic; }
+  __syncthreads();
+  if (warp == 0) {
+    int wa = s_w[lane], wb = s_w[32 + lane], wc = s_w[64 + lane];
+    int xa = wa, xb = wb, xc = wc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int na = __shfl_up_sync(0xffffffffu, xa, o), nb = __shfl_up_sync(0xffffffffu, xb, o),
+                nc = __shfl_up_sync(0xffffffffu, xc, o);
+      if (lane >= o) { xa += na; xb += nb; xc += nc; }
+    }
+    s_w[lane] = xa - wa; s_w[32 + lane] = xb - wb; s_w[64 + lane] = xc - wc;   // exclusive warp offsets
+    if (lane == 31) { s_w[96] = xa; s_w[97] = xb; s_w[98] = xc; }             // totals
+  }
+  __syncthreads();
+  a = s_w[warp] + ia - a; b = s_w[32 + warp] + ib - b; c = s_w[64 + warp] + ic - c;
+  ta = s_w[96]; tb = s_w[97]; tc = s_w[98];
+}
+
+__global__ void __launch_bounds__(1024)
+segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl) {
-  __shared__ int s_a[1024], s_b[1024], s_c[1024];
+  __shared__ int s_w[100];
+  __shared__ int s_err;
   const int T = blockDim.x, t = threadIdx.x;
   const int per = (nseg + T - 1) / T;
   const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
@@ -128,20 +170,14 @@ __global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, in
     int ni = (c + psub - 1) / psub;
     ca += c; cb += ni; cc += ni > 1 ? ni : 0;
   }
-  s_a[t] = ca; s_b[t] = cb; s_c[t] = cc;
-  __syncthreads();
-  if (t == 0) {  // tiny serial exclusive scan over <= 1024 partials
-    int ra = 0, rb = 0, rc = 0;
-    for (int k = 0; k < T; ++k) {
-      int a = s_a[k], b = s_b[k], c = s_c[k];
-      s_a[k] = ra; s_b[k] = rb; s_c[k] = rc;
-      ra += a; rb += b; rc += c;
-    }
+  int ra = ca, rb = cb, rc = cc, ta, tb, tc;
+  block_scan3(ra, rb, rc, s_w, ta, tb, tc);   // ra, rb, rc: exclusive prefixes; ta, tb, tc: totals
+  if (t == 0) {
     int err = 0;
-    if (rb > max_items || rc > max_split) err = 1;
+    if (tb > max_items || tc > max_split) err = 1;
     // SSP knot window for the Doppler factors actually present
     int ja = 0, jb = 0;
-    if (ra > 0) {
+    if (ta > 0) {
       float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
       float lo_l = p.tmin / dmax, hi_l = p.tmax / dmin;
       // first knot that can reach the band / one past the last knot that can be in it
@@ -153,18 +189,18 @@ __global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, in
       jb = min(p.L, b + 3);
       if (jb - ja > kMaxKnots) err = 2;
     }
-    ctrl[C_NITEMS] = err ? 0 : rb;
+    ctrl[C_NITEMS] = err ? 0 : tb;
     ctrl[C_JA] = ja;
     ctrl[C_JB] = jb;
     ctrl[C_ERROR] = err;
     ctrl[C_WORK] = 0;
-    ctrl[C_NSPLIT] = rc;
-    seg_start[nseg] = ra;
-    item_start[nseg] = rb;
+    ctrl[C_NSPLIT] = tc;
+    seg_start[nseg] = ta;
+    item_start[nseg] = tb;
+    s_err = err;
   }
   __syncthreads();
-  int ra = s_a[t], rb = s_b[t], rc = s_c[t];
-  const bool err = ctrl[C_ERROR] != 0;
+  const bool err = s_err != 0;
   for (int s = lo; s < hi; ++s) {
     int c = counts[s];
     int ni = (c + psub - 1) / psub;
@@ -181,28 +217,6 @@ __global__ void segment_kernel(PlanView p, int nseg, int psub, int max_items, in
       }
     }
     ra += c; rb += ni; rc += ni > 1 ? ni : 0;
-  }
-}
-
-// ---- gather sorted records ----------------------------------------------------------------------
-// record (floats): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=unused  [4..]=weights * mass
-__global__ void gather_kernel(PlanView p, const uint32_t *__restrict__ idx_sorted, const int *__restrict__ ctrl,
-                              const float *__restrict__ vel, const float *__restrict__ mass,
-                              const float *__restrict__ met, const float *__restrict__ age,
-                              float *__restrict__ rec, int stride) {
-  const int nvalid = ctrl[C_NVALID];
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nvalid; q += gridDim.x * blockDim.x) {
-    uint32_t src = idx_sorted[q];
-    SspTerms tm;
-    ssp_terms(p, met[src], age[src], mass[src], tm);
-    float d = expf(vel[3 * (size_t)src + p.vel_comp] / kSpeedOfLight);
-    float *r = rec + (size_t)q * stride;
-    r[0] = d;
-    r[1] = 1.f / d;
-    r[2] = __int_as_float(tm.n ? tm.row[0] : 0);
-    r[3] = 0.f;
-    const int nw = p.method == RBX_METHOD_LINEAR ? 4 : 16;
-    for (int k = 0; k < nw; ++k) r[4 + k] = tm.n ? tm.w[k] : 0.f;
   }
 }
 
@@ -304,7 +318,8 @@ __device__ __forceinline__ void cell_fma(float2 *cell, float sc, float a, float 
 
 template <int METHOD, bool AFFINE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
-fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
+fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
+                  const Item *__restrict__ items, int *__restrict__ ctrl,
                   float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
@@ -465,8 +480,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
       const int col = q - b * RS;
       // padding slots repeat the item's first particle with zero weights: their knots stay inside the
       // warps' cell regions and they add exact zeros
-      s_rec[q] = (b < it.count) ? rec[(size_t)(it.start + b) * RS + col]
-                                : (col < 4 ? rec[(size_t)it.start * RS + col] : 0.f);
+      s_rec[q] = (b < it.count) ? rec[(size_t)sidx[it.start + b] * RS + col]
+                                : (col < 4 ? rec[(size_t)sidx[it.start] * RS + col] : 0.f);
     }
     group_barrier(1 + grp, gthreads);
 
@@ -478,8 +493,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const Item *__restr
           int b = q / RS;
           int pb = (bt + 1) * NB + b;
           const int col = q - b * RS;
-          s_rec[(buf ^ 1) * NB * RS + q] = (pb < it.count) ? rec[(size_t)(it.start + pb) * RS + col]
-                                                           : (col < 4 ? rec[(size_t)it.start * RS + col] : 0.f);
+          s_rec[(buf ^ 1) * NB * RS + q] = (pb < it.count) ? rec[(size_t)sidx[it.start + pb] * RS + col]
+                                                           : (col < 4 ? rec[(size_t)sidx[it.start] * RS + col] : 0.f);
         }
       }
 
@@ -766,7 +781,8 @@ __device__ __forceinline__ int skewed(int k, unsigned skew) {
 
 template <int METHOD>
 __global__ void __launch_bounds__(256, 1)
-fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__restrict__ items, int *__restrict__ ctrl,
+fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
+                       const Item *__restrict__ items, int *__restrict__ ctrl,
                        float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
@@ -825,7 +841,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
 #pragma unroll
   for (int t = 0; t < NT; ++t) tab[t] = p.tab[t];
   const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
-  const float hd2 = 0.5f * p.tdelta * p.tdelta;
+  const float hdelta = 0.5f * p.tdelta;
 
   while (true) {
     int item_id = 0;
@@ -838,16 +854,25 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
     // and parked in the warp's shared-memory slot, so every particle's record is a broadcast read away.
     // Template rows: the eight 16-byte vectors of the NEXT (particle, table) group are in flight while the
     // current group is folded in and, for the last table, during the whole knot arithmetic of the particle.
+    float4 nrec[RS / 4];   // my record of the NEXT batch, in flight during the current one
+    auto fetch_rec = [&](int b0) {
+      if (b0 + lane < it.count) {
+        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)__ldg(sidx + it.start + b0 + lane) * RS);
+#pragma unroll
+        for (int u = 0; u < RS / 4; ++u) nrec[u] = __ldg(src + u);
+      }
+    };
+    fetch_rec(0);
     for (int b0 = 0; b0 < it.count; b0 += 32) {
       const int nb = min(32, it.count - b0);
       __syncwarp();
       if (lane < nb) {
-        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)(it.start + b0 + lane) * RS);
         float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RS);
 #pragma unroll
-        for (int u = 0; u < RS / 4; ++u) dst[u] = __ldg(src + u);
+        for (int u = 0; u < RS / 4; ++u) dst[u] = nrec[u];
       }
       __syncwarp();
+      if (b0 + 32 < it.count) fetch_rec(b0 + 32);
       float4 nf[8];
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
         if (interior) {
@@ -928,11 +953,12 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const Item *__
         tot = fmaf(S[r], wd, tot);
         // sum_w p(t_w) dt_w over the channels [k_r, k_{r+1}): S D + m T, D = sum dt_w (telescopes exactly in
         // float32), T = sum dt_w (t_w - x) in closed form on the arange grid
+        // (the old n delta^2 / 2 term: on an arange grid n delta = D to first order in the channel-width
+        // rounding, so T = D (D/2 + (t[k-1] - x) + delta/2) and S D + m T = D (S + m T'))
         const float D = e[r + 1] - e[r];
         gx[r] = e[r] - x[r];
-        const float nn = (float)(max(k[r + 1], 1) - max(k[r], 1));
-        const float T = fmaf(D, fmaf(0.5f, D, gx[r] + p.tdelta), -hd2 * nn);
-        nw += fmaf(m[r], T, S[r] * D);
+        const float Tp = fmaf(0.5f, D, gx[r] + hdelta);
+        nw = fmaf(D, fmaf(m[r], Tp, S[r]), nw);
       }
       float mp = __shfl_up_sync(0xffffffffu, m[WK - 1], 1);
       if (lane == 0) mp = m[0];   // slot 0 of the window lies below the band for every Doppler factor present
@@ -1368,7 +1394,7 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
       RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
     prep_kernel<<<pblocks, threads, smem_hist ? hist_bytes : 0, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n,
                                                                           nseg, ws.cell_bits, ws.cell_shift, ws.keys_in, ws.idx_in,
-                                                                          ws.counts, ws.ctrl, smem_hist);
+                                                                          ws.counts, ws.ctrl, smem_hist, ws.rec, ws.rec_stride);
   }
   count_launch();
   RBX_LAUNCH_OK();
@@ -1380,11 +1406,6 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
                                           ws.item_start, ws.items, ws.ctrl);
   count_launch();
   RBX_LAUNCH_OK();
-  gather_kernel<<<blocks, threads, 0, stream>>>(v, ws.idx_out, ws.ctrl, d_vel, d_mass, d_met, d_age, ws.rec,
-                                                 ws.rec_stride);
-  count_launch();
-  RBX_LAUNCH_OK();
-
   FusedLayout lay;
   size_t smem = 0;
   rc = fused_layout(plan, lay, smem);
@@ -1396,7 +1417,7 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
   auto launch = [&](auto kernel) -> int {
     RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
+    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
     return RBX_OK;
   };
   const bool affine = v.affine != 0 && !lay.force_lut;
@@ -1405,7 +1426,7 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   if (warp_layout(plan, wlay, wsmem)) {
     auto wlaunch = [&](auto kernel) -> int {
       RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, wlay);
+      kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, wlay);
       return RBX_OK;
     };
     rc = v.method == RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR>)
