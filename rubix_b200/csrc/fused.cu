@@ -320,7 +320,7 @@ template <int METHOD, bool AFFINE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                   const Item *__restrict__ items, int *__restrict__ ctrl,
-                  float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay) {
+                  float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay, int accumulate) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
   extern __shared__ __align__(128) unsigned char smem[];
@@ -739,7 +739,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
           if (lane >= o) inc += n;
         }
         const float v = vcar + inc;
-        if (valid) row[ch] = v;
+        if (valid) row[ch] = (accumulate && it.slot < 0) ? row[ch] + v : v;
         scar = __shfl_sync(0xffffffffu, s, 31);
         vcar = __shfl_sync(0xffffffffu, v, 31);
       }
@@ -783,7 +783,7 @@ template <int METHOD>
 __global__ void __launch_bounds__(256, 1)
 fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                        const Item *__restrict__ items, int *__restrict__ ctrl,
-                       float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay) {
+                       float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay, int accumulate) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1064,7 +1064,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           if (lane >= o) inc += n;
         }
         const float v = vcar + inc;
-        if (valid) rowp[ch] = v;
+        if (valid) rowp[ch] = (accumulate && it.slot < 0) ? rowp[ch] + v : v;
         scar = __shfl_sync(0xffffffffu, sl, 31);
         vcar = __shfl_sync(0xffffffffu, v, 31);
       }
@@ -1076,14 +1076,14 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 // cube[s] = sum over the spaxel's items, in item order (deterministic two-level reduction)
 __global__ void reduce_partials_kernel(const int *__restrict__ item_start, const Item *__restrict__ items,
                                        const float *__restrict__ partials, int Wp, int W, int nseg,
-                                       const int *__restrict__ ctrl, float *__restrict__ cube) {
+                                       const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate) {
   if (ctrl[C_ERROR]) return;
   for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
     const int i0 = item_start[s], i1 = item_start[s + 1];
     if (i1 - i0 < 2) continue;
     const int slot0 = items[i0].slot;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
-      float acc = 0.f;
+      float acc = accumulate ? cube[(size_t)s * W + w] : 0.f;
       for (int k = 0; k < i1 - i0; ++k) acc += partials[(size_t)(slot0 + k) * Wp + w];
       cube[(size_t)s * W + w] = acc;
     }
@@ -1358,6 +1358,15 @@ extern "C" size_t rbx_build_cube_workspace_bytes(const rbx_plan *plan, int64_t n
 extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
                               const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels,
                               float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
+  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, d_pixel, n, num_spaxels, d_cube, d_ws, ws_bytes,
+                              stream_, 0);
+}
+
+// accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in chunks so that the
+// host-to-device copy of one chunk overlaps the kernels of the previous one)
+int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
+                         const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube,
+                         void *d_ws, size_t ws_bytes, void *stream_, int accumulate) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RBX_REQUIRE(plan && d_cube, "rbx_build_cube: null plan or cube");
   RBX_REQUIRE(n >= 0 && n < (1ll << 31) - 1, "rbx_build_cube: n out of range");
@@ -1365,7 +1374,7 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   if (rc != RBX_OK) return rc;
   const PlanView &v = plan->v;
   const int nseg = num_spaxels * num_spaxels;
-  RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)nseg * v.W, stream));
+  if (!accumulate) RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)nseg * v.W, stream));
   if (n == 0) return RBX_OK;
   RBX_REQUIRE(d_vel && d_mass && d_met && d_age && d_pixel && d_ws, "rbx_build_cube: null pointer");
   FusedWs ws;
@@ -1417,7 +1426,8 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
   auto launch = [&](auto kernel) -> int {
     RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay);
+    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay,
+                                               accumulate);
     return RBX_OK;
   };
   const bool affine = v.affine != 0 && !lay.force_lut;
@@ -1426,7 +1436,8 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   if (warp_layout(plan, wlay, wsmem)) {
     auto wlaunch = [&](auto kernel) -> int {
       RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, wlay);
+      kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp,
+                                                       wlay, accumulate);
       return RBX_OK;
     };
     rc = v.method == RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR>)
@@ -1440,7 +1451,8 @@ extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const fl
   RBX_LAUNCH_OK();
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
-  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.items, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube);
+  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.items, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube,
+                                                    accumulate);
   count_launch();
   RBX_LAUNCH_OK();
   poison_kernel<<<148, 256, 0, stream>>>(ws.ctrl, d_cube, (size_t)nseg * v.W);
