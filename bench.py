@@ -222,9 +222,19 @@ def main():
     cube = torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
 
+    # N > 1, two exchange patterns: a MUSE-size cube (9.3 MB) is summed onto rank 0, which applies
+    # PSF + LSF (14 us); a large-FOV cube (S = 150: 335 MB) is all-reduced and every rank convolves its own
+    # wavelength slab in place (+-12 channel halo), the result staying sharded by wavelength.
+    from rubix_b200 import parallel
+    slab_mode = world > 1 and cube.numel() * 4 > (64 << 20)
+    slab_lo, slab_hi = parallel.wavelength_slab(plan.W, rank, world)
+
     def step():
         pix = ops.filter_and_assign(coords, edges)  # filter_particles + spaxel_assignment, one pass
         ops.build_cube(plan, vel, mass, met, age, pix, S, out=cube)
+        if slab_mode:
+            dist.all_reduce(cube, op=dist.ReduceOp.SUM)
+            return ops.psf_lsf_slab(cube, slab_lo, slab_hi, pk_h, lk_h)
         if world > 1:
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
@@ -291,12 +301,20 @@ def main():
             age.copy_(hp["age"], non_blocking=True)
             pix = ops.filter_and_assign(dcoords, edges)
             ops.build_cube(plan, dvel, mass, met, age, pix, S, out=cube)
+            if slab_mode:
+                dist.all_reduce(cube, op=dist.ReduceOp.SUM)
+                hslab.copy_(ops.psf_lsf_slab(cube, slab_lo, slab_hi, pk_h, lk_h), non_blocking=True)
+                torch.cuda.synchronize()
+                return float(hslab[S // 2, S // 2, 0])
             dist.reduce(cube, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 hcube.copy_(ops.psf_lsf(cube, pk_h, lk_h), non_blocking=True)
             torch.cuda.synchronize()
             return float(hcube[S // 2, S // 2, 100]) if rank == 0 else 0.0
-        e2e_api = "device ops through the C ABI with pinned host shards, NCCL reduce, cube to rank 0's host"
+        hslab = torch.empty((S, S, slab_hi - slab_lo), dtype=torch.float32).pin_memory() if slab_mode else None
+        e2e_api = ("device ops through the C ABI with pinned host shards, NCCL all-reduce, PSF+LSF per wavelength slab, "
+                   "each slab to its rank's host" if slab_mode else
+                   "device ops through the C ABI with pinned host shards, NCCL reduce, cube to rank 0's host")
 
     for _ in range(2):
         e2e_step()
@@ -315,7 +333,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * n / float(te.item())
     h2d = sum(v.nbytes for v in hnp.values()) + edges_h.nbytes + pk_h.nbytes + lk_h.nbytes
-    d2h = hcube.numel() * 4
+    d2h = (hslab.numel() if (world > 1 and slab_mode) else hcube.numel()) * 4
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -345,7 +363,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "template": tpl_name, "method": args.method,
                        "particles_per_gpu": n, "l2": "flushed (256 MB fill) between timed steps",
-                       "parallelism": f"particle-sharded x{world}, one NCCL reduce of the partial cubes"},
+                       "parallelism": (f"particle-sharded x{world}, one NCCL all-reduce of the partial cubes, PSF+LSF "
+                                       "sharded by wavelength slab" if slab_mode else
+                                       f"particle-sharded x{world}, one NCCL reduce of the partial cubes")},
             "cube_build_ms": ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu.get("dram_bytes_per_launch"),

@@ -146,6 +146,13 @@ int rbx_psf_lsf(const float *d_in, float *d_out, int ny, int nx, int W, const fl
  * float32 sum); returns RBX_ERR_UNSUPPORTED when the taps need the general kernels (rbx_psf_lsf). */
 int rbx_psf_lsf_taps(const float *d_in, float *d_out, int ny, int nx, int W, const float *h_psf, int M,
                      int N, const float *h_lsf, int K, int ext, void *stream);
+/* The same on a wavelength SLAB of a cube (the multi-GPU PSF / LSF stage shards by wavelength):
+ * W channels starting at d_in / d_out, consecutive spaxels in_pitch / out_pitch floats apart (>= W).
+ * Channels outside the slab count as zero, so a rank passes its slab plus a halo of `ext` channels taken
+ * from the summed cube and keeps the interior. */
+int rbx_psf_lsf_taps_pitched(const float *d_in, int in_pitch, float *d_out, int out_pitch, int ny, int nx,
+                             int W, const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                             void *stream);
 /* gaussian_kernel_2d (rubix/telescope/psf/kernels.py:26-31) and _get_kernel
  * (rubix/telescope/lsf/lsf.py:12-26) evaluated in float32 on the device. */
 int rbx_gaussian_psf_kernel(int m, int n, float sigma, float *d_kernel, void *stream);

@@ -20,7 +20,7 @@ EXPORTED = [
     "rbx_spaxel_assign", "rbx_filter_particles", "rbx_filter_and_assign",
     "rbx_ssp_lookup", "rbx_scale_by_mass", "rbx_doppler_resample", "rbx_segment_sum",
     "rbx_build_cube_workspace_bytes", "rbx_build_cube",
-    "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf", "rbx_psf_lsf_taps",
+    "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf", "rbx_psf_lsf_taps", "rbx_psf_lsf_taps_pitched",
     "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
     "rbx_pipeline_host",
     "rbx_profile_enable", "rbx_profile_fused",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         "rbx_convolve_lsf": [vp, vp, i64, i32, vp, i32, i32, vp],
         "rbx_psf_lsf": [vp, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp],
         "rbx_psf_lsf_taps": [vp, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp],
+        "rbx_psf_lsf_taps_pitched": [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp],
         "rbx_gaussian_psf_kernel": [i32, i32, f32, vp, vp],
         "rbx_gaussian_lsf_kernel": [f32, f32, i32, vp, vp],
         "rbx_pipeline_host": [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp],

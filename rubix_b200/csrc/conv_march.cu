@@ -94,7 +94,7 @@ struct Cols {
 // EDGE = false: every column, channel and store of the block is inside the cube (no predicates at all).
 template <int P, int KE, int TX, int NT, bool EDGE>
 __device__ __forceinline__ void march_body(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W,
-                                           int x0, int w0, int ya, int yb, const MarchTaps &tp,
+                                           int pin, int pout, int x0, int w0, int ya, int yb, const MarchTaps &tp,
                                            float (&s_mid)[2][TX][NT]) {
   constexpr int TL = NT - (KE - 1);      // output channels per block
   constexpr int HE = (KE - 1) / 2;       // spectral halo on each side
@@ -107,8 +107,8 @@ __device__ __forceinline__ void march_body(const float *__restrict__ in, float *
   const int nsteps = (yb - ya) + P - 1;
   const bool lsf_thread = c < TL && w0 + c < W;
   const int nvalid = lsf_thread ? min(TX, nx - x0) : 0;   // output columns this thread stores
-  const unsigned W4 = 4u * (unsigned)W;                   // column stride in bytes
-  const size_t rowstride = (size_t)nx * W;
+  const unsigned W4 = 4u * (unsigned)pin, W4o = 4u * (unsigned)pout;   // column strides in bytes (in, out)
+  const size_t rowstride = (size_t)nx * pin, rowstride_o = (size_t)nx * pout;
   unsigned colmask = 0;
   if (EDGE) {
 #pragma unroll
@@ -116,7 +116,7 @@ __device__ __forceinline__ void march_body(const float *__restrict__ in, float *
       if (qok && x0 - H + ix >= 0 && x0 - H + ix < nx) colmask |= 1u << ix;
   }
   // input row `yy` of this thread's channel: IX columns starting at x0 - H (only called for rows inside the cube)
-  const float *in0 = in + ((ptrdiff_t)(x0 - H) * W + q);
+  const float *in0 = in + ((ptrdiff_t)(x0 - H) * pin + q);
   auto load_row = [&](int yy, float (&v)[IX]) {
     const float *rowp = in0 + (ptrdiff_t)yy * (ptrdiff_t)rowstride;
     if (EDGE) Cols<0, IX>::load_masked(rowp, W4, colmask, v);
@@ -182,9 +182,9 @@ __device__ __forceinline__ void march_body(const float *__restrict__ in, float *
             for (int t = 1; t < KE; ++t) acc = fmaf(tp.kl[t], s_mid[buf][ox][c + t], acc);
             o[ox] = acc;
           }
-          float *dst = out + (size_t)oy * rowstride + (size_t)x0 * W + (w0 + c);
-          if (EDGE) Cols<0, TX>::store_n(dst, W4, o, nvalid);
-          else if (c < TL) Cols<0, TX>::store(dst, W4, o);
+          float *dst = out + (size_t)oy * rowstride_o + (size_t)x0 * pout + (w0 + c);
+          if (EDGE) Cols<0, TX>::store_n(dst, W4o, o, nvalid);
+          else if (c < TL) Cols<0, TX>::store(dst, W4o, o);
         }
         buf ^= 1;
       }
@@ -261,7 +261,7 @@ __device__ __forceinline__ void y_pass_dyn(int u, float (&A)[P][TX], const float
 
 template <int P, int KE, int TX, int NT>
 __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, float *__restrict__ out, int ny, int nx,
-                                                int W, int x0, int w0, int ya, int yb, const MarchTaps &tp,
+                                                int W, int pin, int pout, int x0, int w0, int ya, int yb, const MarchTaps &tp,
                                                 float (&s_mid)[2][TX][NT],
                                                 float (&s_in)[kMarchStages][TX + P - 1][kMarchRowFloats],
                                                 uint64_t (&s_bar)[kMarchStages + 2]) {
@@ -276,8 +276,8 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
   const int c = threadIdx.x;
   const int q0 = w0 - HE;                // first input channel of the tile (the caller checked the window fits)
   const int nsteps = (yb - ya) + P - 1;
-  const unsigned W4 = 4u * (unsigned)W;
-  const size_t rowstride = (size_t)nx * W;
+  const unsigned W4o = 4u * (unsigned)pout;
+  const size_t rowstride = (size_t)nx * pin, rowstride_o = (size_t)nx * pout;
   const int nvalid = min(TX, nx - x0);
   const int yfirst = max(ya - H, 0), ylast = min(yb + C, ny);   // valid input rows [yfirst, ylast)
   unsigned colmask = 0;
@@ -306,7 +306,7 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
   const uint64_t in_words = (uint64_t)(uintptr_t)in >> 2;
   const int lane = c & 31, warp = c >> 5;
   const bool copy_lane = lane < IX && ((colmask >> lane) & 1u);
-  const uint64_t e_lane = in_words + (uint64_t)(copy_lane ? x0 - H + lane : 0) * (uint64_t)W + (uint64_t)q0;
+  const uint64_t e_lane = in_words + (uint64_t)(copy_lane ? x0 - H + lane : 0) * (uint64_t)pin + (uint64_t)q0;
   // Row k is issued by warp k % 4 (the copy work rotates over the warps, i.e. over the SM's four
   // schedulers): lane 0 arms the stage's barrier, lane ix copies column ix.
   auto issue_row = [&](int yy) {
@@ -348,9 +348,9 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
           o[ox] = acc;
         }
       }
-      float *dst = out + (size_t)oy * rowstride + (size_t)x0 * W + (w0 + c);
-      if (nvalid == TX) Cols<0, TX>::store(dst, W4, o);
-      else Cols<0, TX>::store_n(dst, W4, o, nvalid);
+      float *dst = out + (size_t)oy * rowstride_o + (size_t)x0 * pout + (w0 + c);
+      if (nvalid == TX) Cols<0, TX>::store(dst, W4o, o);
+      else Cols<0, TX>::store_n(dst, W4o, o, nvalid);
     }
   };
 
@@ -376,12 +376,12 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
       mbar_wait(smem_addr(&s_bar[st]), (uint32_t)((k / NST) & 1));
       // alignment shift of column ix: ((row, column, q0) element index) mod 4, warp-uniform
       const uint32_t e0 = (uint32_t)(in_words & 3u) + (uint32_t)(q0 & 3) +
-                          (uint32_t)((((uint64_t)yy * nx + (uint64_t)(x0 - H + IX)) * (uint64_t)W) & 3u);
+                          (uint32_t)((((uint64_t)yy * nx + (uint64_t)(x0 - H + IX)) * (uint64_t)pin) & 3u);
       float v[IX];
 #pragma unroll
       for (int ix = 0; ix < IX; ++ix) {
-        // (x0 - H + ix) * W = (x0 - H + IX) * W - (IX - ix) * W, and -x == 3x (mod 4)
-        const uint32_t sh = (e0 + (uint32_t)((IX - ix) * 3) * (uint32_t)(W & 3)) & 3u;
+        // (x0 - H + ix) * pitch = (x0 - H + IX) * pitch - (IX - ix) * pitch, and -x == 3x (mod 4)
+        const uint32_t sh = (e0 + (uint32_t)((IX - ix) * 3) * (uint32_t)(pin & 3)) & 3u;
         v[ix] = s_in[st][ix][sh + c];
       }
 #pragma unroll
@@ -424,7 +424,7 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
 
 template <int P, int KE, int TX, int NT>
 __global__ void __launch_bounds__(NT, RBX_MARCH_MINB * 128 / NT)
-psf_lsf_march_kernel(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W,
+psf_lsf_march_kernel(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W, int pin, int pout,
                      int rows_per_seg, int use_bulk, const __grid_constant__ MarchTaps tp) {
   constexpr int TL = NT - (KE - 1);
   constexpr int HE = (KE - 1) / 2;
@@ -438,8 +438,8 @@ psf_lsf_march_kernel(const float *__restrict__ in, float *__restrict__ out, int 
   const int yb = min(ya + rows_per_seg, ny);
   // bulk path: the whole 132-float staging window of every column lies inside its spaxel's spectrum
   const bool lam_in = w0 - HE >= 0 && w0 - HE + kMarchRowFloats <= W;
-  if (use_bulk && lam_in) march_body_bulk<P, KE, TX, NT>(in, out, ny, nx, W, x0, w0, ya, yb, tp, s_mid, s_in, s_bar);
-  else march_body<P, KE, TX, NT, true>(in, out, ny, nx, W, x0, w0, ya, yb, tp, s_mid);
+  if (use_bulk && lam_in) march_body_bulk<P, KE, TX, NT>(in, out, ny, nx, W, pin, pout, x0, w0, ya, yb, tp, s_mid, s_in, s_bar);
+  else march_body<P, KE, TX, NT, true>(in, out, ny, nx, W, pin, pout, x0, w0, ya, yb, tp, s_mid);
 }
 
 }  // namespace rbx
@@ -473,7 +473,8 @@ bool separable_factors(const float *K, int M, int N, float *ky, float *kx) {
 }
 
 template <int P, int KE, int TX, int NT>
-int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, const MarchTaps &taps, cudaStream_t stream) {
+int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, int pin, int pout, const MarchTaps &taps,
+                 cudaStream_t stream) {
   auto kernel = psf_lsf_march_kernel<P, KE, TX, NT>;
   constexpr int TL = NT - (KE - 1);
   static int slots_cached[64] = {};
@@ -503,27 +504,29 @@ int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, const M
   dim3 grid(bx, (ny + rows - 1) / rows);
   // bulk copies need 16-byte aligned global addresses: the staging aligns down relative to d_in
   static const bool no_bulk = getenv("RBX_MARCH_NO_BULK") != nullptr;
-  const int use_bulk = (((uintptr_t)d_in & 15u) == 0 && !no_bulk) ? 1 : 0;
-  kernel<<<grid, NT, 0, stream>>>(d_in, d_out, ny, nx, W, rows, use_bulk, taps);
+  // (an unaligned slab start inside a wider cube is fine: the bytes before it belong to the same cube)
+  const int use_bulk = ((((uintptr_t)d_in & 15u) == 0 || pin > W) && !no_bulk) ? 1 : 0;
+  kernel<<<grid, NT, 0, stream>>>(d_in, d_out, ny, nx, W, pin, pout, rows, use_bulk, taps);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;
 }
 
 template <int P, int KE>
-int launch_march_tx(const float *d_in, float *d_out, int ny, int nx, int W, const MarchTaps &taps, cudaStream_t stream) {
-  if (nx >= 40) return launch_march<P, KE, 10, 128>(d_in, d_out, ny, nx, W, taps, stream);
-  return launch_march<P, KE, 5, 128>(d_in, d_out, ny, nx, W, taps, stream);
+int launch_march_tx(const float *d_in, float *d_out, int ny, int nx, int W, int pin, int pout, const MarchTaps &taps,
+                    cudaStream_t stream) {
+  if (nx >= 40) return launch_march<P, KE, 10, 128>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
+  return launch_march<P, KE, 5, 128>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
 }
 
 template <int P>
-int launch_march_ke(int KE, const float *d_in, float *d_out, int ny, int nx, int W, const MarchTaps &taps,
-                    cudaStream_t stream) {
+int launch_march_ke(int KE, const float *d_in, float *d_out, int ny, int nx, int W, int pin, int pout,
+                    const MarchTaps &taps, cudaStream_t stream) {
   switch (KE) {
-    case 1: return launch_march_tx<P, 1>(d_in, d_out, ny, nx, W, taps, stream);
-    case 7: return launch_march_tx<P, 7>(d_in, d_out, ny, nx, W, taps, stream);
-    case 13: return launch_march_tx<P, 13>(d_in, d_out, ny, nx, W, taps, stream);
-    default: return launch_march_tx<P, 25>(d_in, d_out, ny, nx, W, taps, stream);
+    case 1: return launch_march_tx<P, 1>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
+    case 7: return launch_march_tx<P, 7>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
+    case 13: return launch_march_tx<P, 13>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
+    default: return launch_march_tx<P, 25>(d_in, d_out, ny, nx, W, pin, pout, taps, stream);
   }
 }
 
@@ -535,8 +538,17 @@ int launch_march_ke(int KE, const float *d_in, float *d_out, int ny, int nx, int
 // device-tap kernels of conv.cu.
 extern "C" int rbx_psf_lsf_taps(const float *d_in, float *d_out, int ny, int nx, int W, const float *h_psf, int M,
                                 int N, const float *h_lsf, int K, int ext, void *stream) {
+  return rbx_psf_lsf_taps_pitched(d_in, W, d_out, W, ny, nx, W, h_psf, M, N, h_lsf, K, ext, stream);
+}
+
+// The same on a wavelength SLAB of a cube: W channels starting at d_in / d_out, consecutive spaxels
+// in_pitch / out_pitch floats apart (>= W).  Channels outside [0, W) of the slab count as zero.
+extern "C" int rbx_psf_lsf_taps_pitched(const float *d_in, int in_pitch, float *d_out, int out_pitch, int ny, int nx,
+                                        int W, const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                                        void *stream) {
+  const int pin = in_pitch, pout = out_pitch;
   RBX_REQUIRE(d_in && d_out && d_in != d_out, "rbx_psf_lsf_taps: bad pointers (no aliasing)");
-  RBX_REQUIRE(ny > 0 && nx > 0 && W > 0, "rbx_psf_lsf_taps: bad shape");
+  RBX_REQUIRE(ny > 0 && nx > 0 && W > 0 && pin >= W && pout >= W, "rbx_psf_lsf_taps: bad shape");
   RBX_REQUIRE(h_psf || h_lsf, "rbx_psf_lsf_taps: at least one kernel is needed");
   TapPlan tp = {};
   tp.P = 1; tp.KE = 1;
@@ -573,9 +585,9 @@ extern "C" int rbx_psf_lsf_taps(const float *d_in, float *d_out, int ny, int nx,
   for (int i = 0; i < kMarchMaxK; ++i) tp.taps.kl2[i] = make_float2(tp.taps.kl[i], tp.taps.kl[i]);
   cudaStream_t s = (cudaStream_t)stream;
   switch (tp.P) {
-    case 1: return launch_march_ke<1>(tp.KE, d_in, d_out, ny, nx, W, tp.taps, s);
-    case 3: return launch_march_ke<3>(tp.KE, d_in, d_out, ny, nx, W, tp.taps, s);
-    case 5: return launch_march_ke<5>(tp.KE, d_in, d_out, ny, nx, W, tp.taps, s);
-    default: return launch_march_ke<7>(tp.KE, d_in, d_out, ny, nx, W, tp.taps, s);
+    case 1: return launch_march_ke<1>(tp.KE, d_in, d_out, ny, nx, W, pin, pout, tp.taps, s);
+    case 3: return launch_march_ke<3>(tp.KE, d_in, d_out, ny, nx, W, pin, pout, tp.taps, s);
+    case 5: return launch_march_ke<5>(tp.KE, d_in, d_out, ny, nx, W, pin, pout, tp.taps, s);
+    default: return launch_march_ke<7>(tp.KE, d_in, d_out, ny, nx, W, pin, pout, tp.taps, s);
   }
 }

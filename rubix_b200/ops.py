@@ -219,6 +219,29 @@ def _taps_call(cube, out, pk, lk, ext) -> bool:
     return True
 
 
+def psf_lsf_slab(cube, lo: int, hi: int, psf_kernel, lsf_kernel, ext: int = 12) -> torch.Tensor:
+    """PSF + LSF of the wavelength slab [lo, hi) of a full (ny, nx, W) cube: the multi-GPU PSF / LSF stage
+    shards by wavelength.  The slab is read in place with a halo of ``ext`` channels on each
+    side (strided view, no copy) and the (ny, nx, hi - lo) interior is returned."""
+    cube = dev(cube)
+    ny, nx, W = cube.shape
+    hp, hl = _host_taps(psf_kernel), _host_taps(lsf_kernel)
+    if hp is None or hl is None:
+        raise ValueError("psf_lsf_slab needs host (numpy) kernels")
+    hlo, hhi = max(lo - ext, 0), min(hi + ext, W)
+    ws = hhi - hlo
+    out = torch.empty((ny, nx, ws), dtype=torch.float32, device="cuda")
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    src = C.c_void_p(cube.data_ptr() + 4 * hlo)
+    rc = _lib.lib().rbx_psf_lsf_taps_pitched(src, W, _p(out), ws, ny, nx, ws, vp(hp), hp.shape[0], hp.shape[1],
+                                             vp(hl.reshape(-1)), hl.size, ext, _stream())
+    if rc == _lib.RBX_ERR_UNSUPPORTED:  # general taps: device-tap kernels on a contiguous copy of the slab
+        out = psf_lsf(cube[:, :, hlo:hhi].contiguous(), psf_kernel, lsf_kernel, ext, host_taps=False)
+    else:
+        _lib.check(rc)
+    return out[:, :, lo - hlo:lo - hlo + (hi - lo)]
+
+
 def convolve_psf(cube, kernel, host_taps: bool = True) -> torch.Tensor:
     """a6.  A kernel given on the host (numpy) takes the host-tap kernel when it is an outer product."""
     cube = dev(cube)

@@ -450,6 +450,27 @@ def test_fused_psf_lsf_asymmetric_kernels(ops):
     assert np.abs(ops.psf_lsf(cube, pk, lk, host_taps=False).cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+def test_psf_lsf_wavelength_slabs(ops):
+    """The multi-GPU PSF / LSF stage: every rank convolves its wavelength slab (read in place, +-12 channel
+    halo) of the summed cube; the slabs put together equal the convolution of the whole cube."""
+    from rubix_b200 import parallel
+    rng = np.random.default_rng(13)
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    for shape, world in (((25, 25, 1001), 3), ((50, 40, 517), 8)):
+        cube = rng.random(shape).astype(np.float32)
+        whole = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+        dcube = ops.dev(cube)
+        parts = []
+        for r in range(world):
+            lo, hi = parallel.wavelength_slab(shape[2], r, world)
+            parts.append(ops.psf_lsf_slab(dcube, lo, hi, pk, lk).cpu().numpy())
+        got = np.concatenate(parts, axis=2)
+        assert got.shape == whole.shape
+        assert np.abs(got - whole).max() <= 1e-6 * np.abs(whole).max()
+        ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
 def test_gaussian_kernels_on_device(ops):
     from rubix_b200 import _lib
     import ctypes as C
