@@ -159,6 +159,22 @@ int rbx_gaussian_psf_kernel(int m, int n, float sigma, float *d_kernel, void *st
 int rbx_gaussian_lsf_kernel(float sigma, float wave_res, int factor, float *d_kernel, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * rotate_galaxy, the stage right before the path (rubix/core/rotation.py:76-115 ->
+ * rubix/galaxy/alignment.py:233-265): moment-of-inertia tensor of the particles within the half-mass
+ * radius (alignment.py:67-125, including its index-0 padding), eigenvectors by ascending eigenvalue
+ * (:128-146), then (p @ R) @ E for coordinates and velocities (:149-229).  h_euler is the (3, 3) row-major
+ * Euler matrix R_z R_y R_x of the configured angles (alignment.py:164-209), float32 on the HOST.
+ * d_rotation (9 floats) receives R; eigenvector signs are normalised (largest component positive) because
+ * eigh's signs are backend-dependent in the reference.  d_velocity / d_velocity_out may both be NULL.
+ * Outputs may not alias inputs.  Workspace: rbx_rotate_galaxy_workspace_bytes().
+ * ------------------------------------------------------------------------------------------- */
+size_t rbx_rotate_galaxy_workspace_bytes(void);
+int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity, const float *d_mass, int64_t n,
+                      float halfmass_radius, const float *h_euler, float *d_coords_out,
+                      float *d_velocity_out, float *d_rotation, void *d_workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience call: the whole path (filter -> spaxel -> fused cube -> PSF -> LSF) for
  * callers that hold numpy / host arrays.  Copies inputs H2D, runs the kernels, copies the cube
  * back; h_cube is (num_spaxels, num_spaxels, W).  h_psf (M,N) / h_lsf (K,) may be NULL to skip.

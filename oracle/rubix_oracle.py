@@ -406,6 +406,63 @@ def apply_lsf(datacube, lsf_sigma, wave_resolution, extend_factor=12):
 # --------------------------------------------------------------------------------------
 # grids
 # --------------------------------------------------------------------------------------
+
+# ---- rotate_galaxy: the stage before the path (rubix/galaxy/alignment.py) -----------------------------
+def moment_of_inertia_tensor(positions, masses, halfmass_radius, dtype=np.float64):
+    """rubix/galaxy/alignment.py:67-125.  The reference selects the particles inside the half-mass
+    radius with ``jnp.where(mask, size=N)[0]``, which pads the index list with 0 up to N entries: particle
+    0 is therefore added (N - n_inside) more times.  Reproduced, not fixed."""
+    pos32 = np.asarray(positions, dtype=np.float32)
+    dist = np.sqrt(np.sum(pos32 ** 2, axis=1, dtype=np.float32))
+    inside = dist <= np.float32(halfmass_radius)
+    idx = np.nonzero(inside)[0]
+    idx = np.concatenate([idx, np.zeros(len(pos32) - len(idx), dtype=idx.dtype)])
+    p = np.asarray(positions, dtype=dtype)[idx]
+    m = np.asarray(masses, dtype=dtype)[idx]
+    I = np.zeros((3, 3), dtype=dtype)
+    for i in range(3):
+        for j in range(3):
+            if i == j:
+                I[i, j] = np.sum(m * np.sum(p ** 2, axis=1) - m * p[:, i] ** 2)
+            else:
+                I[i, j] = -np.sum(m * p[:, i] * p[:, j])
+    return I
+
+
+def rotation_matrix_from_inertia_tensor(I, normalise_signs=True):
+    """rubix/galaxy/alignment.py:128-146: eigh, eigenvectors ordered by ascending eigenvalue.  eigh's
+    eigenvector signs are backend-dependent (LAPACK / cuSOLVER) in the reference itself; with
+    ``normalise_signs`` every eigenvector gets its largest-magnitude component positive (the convention of
+    the CUDA path), otherwise numpy's LAPACK signs are kept."""
+    w, v = np.linalg.eigh(np.asarray(I, dtype=np.float64))
+    R = v[:, np.argsort(w, kind="stable")]
+    if normalise_signs:
+        for c in range(3):
+            if R[np.argmax(np.abs(R[:, c])), c] < 0:
+                R[:, c] = -R[:, c]
+    return R
+
+
+def euler_rotation_matrix(alpha, beta, gamma):
+    """rubix/galaxy/alignment.py:164-209: Rotation.from_euler about x, y, z (degrees), R = R_z R_y R_x."""
+    a, b, g = np.deg2rad([alpha, beta, gamma])
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(g), -np.sin(g), 0], [np.sin(g), np.cos(g), 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def rotate_galaxy(positions, velocities, masses, halfmass_radius, alpha, beta, gamma, dtype=np.float64,
+                  normalise_signs=True):
+    """rubix/galaxy/alignment.py:233-265: (p @ R) @ E for coordinates and velocities."""
+    I = moment_of_inertia_tensor(positions, masses, halfmass_radius, dtype=np.float64)
+    R = rotation_matrix_from_inertia_tensor(I, normalise_signs).astype(dtype)
+    E = euler_rotation_matrix(alpha, beta, gamma).astype(dtype)
+    pos = (np.asarray(positions, dtype=dtype) @ R) @ E
+    vel = (np.asarray(velocities, dtype=dtype) @ R) @ E
+    return pos, vel, R
+
+
 def calculate_wave_seq(wave_range, wave_res, dtype=np.float32):
     """rubix/telescope/utils.py:53 (``jnp.arange`` in f32).  Pinned bit-exactly by the ``wave``
     dataset of the reference's notebooks/data/dummy_datacube.h5 (tests/golden/muse_wave.npy)."""

@@ -23,6 +23,7 @@ EXPORTED = [
     "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf", "rbx_psf_lsf_taps", "rbx_psf_lsf_taps_pitched",
     "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
     "rbx_pipeline_host",
+    "rbx_rotate_galaxy", "rbx_rotate_galaxy_workspace_bytes",
     "rbx_profile_enable", "rbx_profile_fused",
 ]
 
@@ -85,6 +86,9 @@ def lib() -> C.CDLL:
         "rbx_gaussian_lsf_kernel": [f32, f32, i32, vp, vp],
         "rbx_pipeline_host": [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp],
     }
+    sigs["rbx_rotate_galaxy"] = [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp, sz, vp]
+    L.rbx_rotate_galaxy_workspace_bytes.argtypes = []
+    L.rbx_rotate_galaxy_workspace_bytes.restype = sz
     for name, args in sigs.items():
         fn = getattr(L, name)
         fn.argtypes = args

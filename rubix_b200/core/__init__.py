@@ -8,3 +8,4 @@ from .ssp import get_lookup_interpolation, get_ssp  # noqa: F401
 from .telescope import (get_filter_particles, get_spatial_bin_edges, get_spaxel_assignment,  # noqa: F401
                         get_telescope)
 from .pipeline import RubixPipeline  # noqa: F401
+from .rotation import get_galaxy_rotation  # noqa: F401

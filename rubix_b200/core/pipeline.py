@@ -6,9 +6,9 @@ The reference registers its stage closures by ``__name__`` in a ``LinearTransfor
 and composition for the stages this package implements (no jax.jit: every stage enqueues CUDA
 kernels on the current stream, the only synchronisation is at the end of ``run``).
 
-Stages of ``calc_ifu`` that are outside the hot path (``rotate_galaxy``, ``apply_noise``; SURVEY.md
-section 8(f) "next") have no CUDA implementation here.  By default they are skipped with a
-warning; pass your own callables through ``extra_functions`` to run them.
+``rotate_galaxy`` (the stage right before the path) runs on the device when the
+config carries ``galaxy.rotation``; ``apply_noise`` (8(f) #3) has no CUDA implementation here and is
+skipped with a warning unless supplied through ``extra_functions``.
 """
 
 from __future__ import annotations
@@ -28,6 +28,7 @@ from .ifu import (get_calculate_datacube, get_calculate_spectra, get_doppler_shi
                   get_scale_spectrum_by_mass)
 from .lsf import get_convolve_lsf
 from .psf import get_convolve_psf
+from .rotation import get_galaxy_rotation
 from .ssp import get_ssp
 from .telescope import get_filter_particles, get_spaxel_assignment, get_telescope
 
@@ -137,7 +138,8 @@ class RubixPipeline:
     def _get_pipeline_functions(self) -> list:
         self.logger.info("Setting up the pipeline...")
         c = self.user_config
-        return [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
+        rot = [get_galaxy_rotation(c)] if "rotation" in c.get("galaxy", {}) else []
+        return rot + [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
                 get_scale_spectrum_by_mass(c), get_doppler_shift_and_resampling(c), get_calculate_datacube(c),
                 get_convolve_psf(c), get_convolve_lsf(c)] + self.extra_functions
 

@@ -123,6 +123,35 @@ def filter_and_assign(coords, edges, mass=None, metallicity=None, age=None) -> t
     return pixel
 
 
+def euler_rotation_matrix(alpha: float, beta: float, gamma: float) -> np.ndarray:
+    """rubix/galaxy/alignment.py:164-209: R = R_z R_y R_x (degrees), float32."""
+    a, b, g = np.deg2rad([alpha, beta, gamma])
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(g), -np.sin(g), 0], [np.sin(g), np.cos(g), 0], [0, 0, 1]])
+    return np.ascontiguousarray(Rz @ Ry @ Rx, dtype=np.float32)
+
+
+def rotate_galaxy(coords, velocity, mass, halfmass_radius: float, alpha: float, beta: float, gamma: float):
+    """rubix/galaxy/alignment.py:233-265 on the device: inertia tensor of the particles within the
+    half-mass radius, eigenvector alignment, Euler rotation.  Returns (coords, velocity, R)."""
+    coords, mass = dev(coords), dev(mass).reshape(-1)
+    velocity = None if velocity is None else dev(velocity)
+    n = coords.shape[0]
+    if coords.ndim != 2 or coords.shape[1] != 3 or mass.numel() != n or (velocity is not None and velocity.shape != coords.shape):
+        raise ValueError("rotate_galaxy: coords / velocity must be (n, 3) and mass (n,)")
+    out_c = torch.empty_like(coords)
+    out_v = None if velocity is None else torch.empty_like(velocity)
+    R = torch.empty(9, dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    ws = _workspace(L.rbx_rotate_galaxy_workspace_bytes())
+    E = euler_rotation_matrix(alpha, beta, gamma)
+    _lib.check(L.rbx_rotate_galaxy(_p(coords), _p(velocity), _p(mass), n, float(np.float32(halfmass_radius)),
+                                   E.ctypes.data_as(C.c_void_p), _p(out_c), _p(out_v), _p(R), _p(ws), ws.numel(),
+                                   _stream()))
+    return out_c, out_v, R.reshape(3, 3)
+
+
 def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
     n = metallicity.numel()

@@ -495,3 +495,58 @@ def test_pipeline_host_end_to_end(ops, plans, bc03, muse_wave, tng_subset):
                                      0.1, method="cubic", dtype=np.float64, n_threads=8)
     ref = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
     _cube_close(out, ref, "pipeline_host cubic + psf + lsf")
+
+
+# ---- rotate_galaxy ---------------------------------------------------------------------
+@pytest.mark.parametrize("n,angles", [(3, (90.0, 0.0, 0.0)), (5000, (0.0, 0.0, 0.0)), (200000, (33.0, 71.0, 152.0))])
+def test_rotate_galaxy_matches_oracle(ops, n, angles):
+    """Inertia tensor (with the reference's index-0 padding), eigenvector alignment, Euler rotation against
+    the float64 oracle.  tests/test_galaxy_alignment.py:160-190 is the n = 3 case."""
+    rng = np.random.default_rng(21)
+    if n == 3:
+        pos, vel, m, r = np.eye(3, dtype=np.float32), np.roll(np.eye(3, dtype=np.float32), 1, axis=1), np.ones(3, np.float32), 2.0
+    else:
+        # a flattened, tilted disc: distinct principal axes
+        pos = (rng.normal(size=(n, 3)) * np.array([4.0, 2.5, 0.6])).astype(np.float32)
+        tilt = orc.euler_rotation_matrix(25.0, -40.0, 10.0).astype(np.float32)
+        pos = (pos @ tilt).astype(np.float32)
+        vel = rng.normal(scale=150.0, size=(n, 3)).astype(np.float32)
+        m = (rng.random(n) + 0.5).astype(np.float32)
+        r = 3.0
+    c, v, R = ops.rotate_galaxy(pos, vel, m, r, *angles)
+    c, v, R = c.cpu().numpy(), v.cpu().numpy(), R.cpu().numpy()
+    pref, vref, Rref = orc.rotate_galaxy(pos, vel, m, r, *angles)
+    if n == 3:  # degenerate tensor: any orthonormal basis is valid; check the rotation is one and was applied
+        assert np.allclose(R.T @ R, np.eye(3), atol=1e-6)
+        E = orc.euler_rotation_matrix(*angles)
+        assert np.allclose(c, (pos.astype(np.float64) @ R) @ E, atol=1e-6)
+        return
+    assert np.abs(R - Rref).max() <= 2e-6
+    assert np.abs(c - pref).max() <= 1e-5 * np.abs(pref).max()
+    assert np.abs(v - vref).max() <= 1e-5 * np.abs(vref).max()
+    # bit-identical reruns (fixed reduction order)
+    c2, v2, R2 = ops.rotate_galaxy(pos, vel, m, r, *angles)
+    assert torch.equal(c2, torch.from_numpy(c).cuda()) and torch.equal(R2.cpu(), torch.from_numpy(R))
+
+
+def test_rotate_then_bin(ops, plans, bc03, muse_wave):
+    """rotate_galaxy -> filter -> spaxel assignment -> cube through the factories' operators: an edge-on
+    rotation of a thin disc puts the flux into a band of spaxel rows."""
+    from rubix_b200.synthetic import spatial_edges
+    rng = np.random.default_rng(22)
+    n = 20000
+    pos = (rng.normal(size=(n, 3)) * np.array([1.5, 1.5, 0.05])).astype(np.float32)
+    vel = rng.normal(scale=50.0, size=(n, 3)).astype(np.float32)
+    m = np.ones(n, np.float32)
+    met = np.full(n, 0.02, np.float32)
+    age = np.full(n, 9.0, np.float32)
+    edges = spatial_edges(25)
+    cubes = {}
+    for name, ang in (("face", (0.0, 0.0, 0.0)), ("edge", (90.0, 0.0, 0.0))):
+        c, v, _ = ops.rotate_galaxy(pos, vel, m, 2.0, *ang)
+        pix = ops.filter_and_assign(c, edges)
+        cubes[name] = ops.build_cube(plans["linear"], v, m, met, age, pix, 25).sum(dim=2).cpu().numpy()
+    # the principal-axis frame orders axes by ascending moment: x, y span the disc for "face-on" output
+    rows_face = (cubes["face"].sum(axis=1) > 0).sum() + (cubes["face"].sum(axis=0) > 0).sum()
+    rows_edge = min((cubes["edge"].sum(axis=1) > 0).sum(), (cubes["edge"].sum(axis=0) > 0).sum())
+    assert rows_edge <= 3 and rows_face >= 20

@@ -167,3 +167,25 @@ def test_tng_fixture_fields(tng_subset):
     for k in ("coords", "velocity", "mass", "metallicity", "age"):
         assert tng_subset[k].dtype == np.float32
     assert tng_subset["coords"].shape[1] == 3
+
+
+# ---- rubix/core/rotation.py ------------------------------------------------------------------------
+@pytest.mark.parametrize("galaxy,msg", [
+    ({"dist_z": 0.1}, "Rotation information not provided in galaxy config"),
+    ({"rotation": {"beta": 0, "gamma": 0}}, "alpha not provided in rotation information"),
+    ({"rotation": {"alpha": 0, "gamma": 0}}, "beta not provided in rotation information"),
+    ({"rotation": {"alpha": 0, "beta": 0}}, "gamma not provided in rotation information"),
+    ({"rotation": {"type": "sideways"}}, "Invalid type provided in rotation information"),
+])
+def test_rotation_config_errors(galaxy, msg):
+    """tests/test_core_rotation.py:15-46."""
+    from rubix_b200.core import get_galaxy_rotation
+    with pytest.raises(ValueError, match=msg):
+        get_galaxy_rotation({"galaxy": galaxy, "data": {"args": {"particle_type": ["stars"]}}})
+
+
+def test_rotation_factory_name():
+    from rubix_b200.core import get_galaxy_rotation
+    for rot in ({"type": "face-on"}, {"type": "edge-on"}, {"alpha": 10, "beta": 20, "gamma": 30}):
+        fn = get_galaxy_rotation({"galaxy": {"rotation": rot}, "data": {"args": {"particle_type": ["stars"]}}})
+        assert fn.__name__ == "rotate_galaxy"  # the YAML node name (pipeline_config.yml)

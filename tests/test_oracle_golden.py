@@ -236,3 +236,42 @@ def test_f32_oracle_tracks_f64(bc03, muse_wave, tng_subset, method):
     assert np.array_equal(i32, i64)
     assert c64.max() > 0
     assert np.abs(c32 - c64).max() <= 2e-5 * np.abs(c64).max()
+
+
+# ---- rotate_galaxy (the stage before the path) ---------------------------------------------------
+def test_rotation_known_answers():
+    """tests/test_galaxy_alignment.py: inertia tensor of three unit masses on the axes = diag(2, 2, 2)
+    (:67-80), eigenvectors of diag(1, 2, 3) = identity (:83-99), euler (90, 0, 0) =
+    [[1,0,0],[0,0,-1],[0,1,0]] (:120-134), apply_rotation / rotate_galaxy of the unit vectors (:137-190)."""
+    pos = np.eye(3)
+    I = orc.moment_of_inertia_tensor(pos, np.ones(3), 2.0)
+    assert np.array_equal(I, 2.0 * np.eye(3))
+    assert np.allclose(orc.rotation_matrix_from_inertia_tensor(np.diag([1.0, 2.0, 3.0])), np.eye(3))
+    E = orc.euler_rotation_matrix(90.0, 0.0, 0.0)
+    assert np.allclose(E, [[1, 0, 0], [0, 0, -1], [0, 1, 0]], atol=1e-15)
+    assert np.allclose(pos @ E, [[1, 0, 0], [0, 0, -1], [0, 1, 0]], atol=1e-15)
+    vel = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+    p, v, R = orc.rotate_galaxy(pos, vel, np.ones(3), 2.0, 90.0, 0.0, 0.0)
+    # a degenerate tensor (all eigenvalues equal): any orthonormal R is an eigenbasis; LAPACK returns the identity
+    assert np.allclose(R, np.eye(3))
+    assert np.allclose(p, [[1, 0, 0], [0, 0, -1], [0, 1, 0]], atol=1e-15)
+    assert np.allclose(v, [[0, 0, -1], [0, 1, 0], [1, 0, 0]], atol=1e-15)
+
+
+def test_inertia_tensor_padding_quirk():
+    """jnp.where(mask, size=N) pads with index 0 (alignment.py:103-106): particle 0 is added once per
+    particle outside the radius."""
+    rng = np.random.default_rng(3)
+    pos = rng.normal(size=(50, 3))
+    m = rng.random(50) + 0.5
+    r = 1.2
+    inside = np.linalg.norm(pos.astype(np.float32), axis=1) <= np.float32(r)
+    def tensor(p, w):
+        return np.array([[np.sum(w * (np.sum(p ** 2, 1) - p[:, i] ** 2)) if i == j else -np.sum(w * p[:, i] * p[:, j])
+                          for j in range(3)] for i in range(3)])
+    want = tensor(pos[inside], m[inside]) + (50 - inside.sum()) * tensor(pos[:1], m[:1])
+    assert np.allclose(orc.moment_of_inertia_tensor(pos, m, r), want, rtol=1e-12)
+    R = orc.rotation_matrix_from_inertia_tensor(want)
+    assert np.allclose(R.T @ R, np.eye(3), atol=1e-12)
+    w = np.diag(R.T @ want @ R)
+    assert np.all(np.diff(w) >= 0)
