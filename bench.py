@@ -12,7 +12,7 @@ Doppler shift / flux-conserving resample / cube accumulation -> PSF -> LSF.
              around each step on the launch stream, L2 flushed between steps, max over ranks).
 * ``e2e``    the same metric through the host-buffer C-ABI call (``rbx_pipeline_host``): pinned host
              arrays in, host cube out, H2D + D2H inside the timed region.
-* ``roofline``  the dominant kernel (fused_cube_kernel), timed by CUDA events inside the library on
+* ``roofline``  the dominant kernel (fused_cube_warp_kernel), timed by CUDA events inside the library on
              its launch stream; achieved = algorithmic HBM bytes / duration against the measured
              copy bandwidth in MEASURED_PEAKS.json.  The kernel is instruction-issue bound, not HBM
              bound, so ``frac`` is small by construction; ``issue`` adds the
@@ -369,12 +369,13 @@ def main():
             "cube_build_ms": ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu.get("dram_bytes_per_launch"),
-                         "kernel": "fused_cube_kernel",
+                         "kernel": "fused_cube_warp_kernel",
                          "kernel_ms": mean_ms.value, "kernel_launches_timed": int(nl.value),
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "issue": issue,
-                         "note": "this kernel is bound by instruction issue and the shared-memory pipe, not by HBM "
-                                 "(DESIGN.md section 5): 40 B and ~830 warp instructions per particle; kernel share "
-                                 f"of step = {mean_ms.value / ms_per_step:.2f}"},
+                         "note": "this kernel is bound by instruction issue and the shared-memory (LSU wavefront) pipe, "
+                                 "not by HBM (DESIGN.md section 5): 40 B and "
+                                 f"~{ncu.get('warp_inst_per_particle', 460):.0f} warp instructions per particle; kernel "
+                                 f"share of step = {mean_ms.value / ms_per_step:.2f}"},
             "e2e": {"value": e2e_val, "unit": "particles/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
                     "api": e2e_api},

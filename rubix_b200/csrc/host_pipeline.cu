@@ -117,7 +117,7 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
   // (fixed ranges, fixed order: the result stays deterministic).
   // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges; at 10^6 the
   // per-range launch overhead eats the overlap, 2.13 -> 2.09 ms with 2)
-  int chunks = n >= 3000000 ? 5 : (n >= 600000 ? 2 : 1);
+  int chunks = n >= 3000000 ? 5 : (n >= 1500000 ? 2 : 1);
   if (const char *e = getenv("RBX_HOST_CHUNKS")) chunks = std::max(1, std::min(16, atoi(e)));
   if (n == 0) chunks = 1;
   CopyLane *lane = nullptr;
