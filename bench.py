@@ -171,6 +171,10 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if getattr(args, "galaxies", 1) > 1:
+        return (f"survey batch: {args.galaxies} synthetic galaxies per GPU x {args.particles} star particles, each "
+                f"rotated to its own inclination, MUSE {args.spaxels}x{args.spaxels} spaxels x 3721 channels, BC03 SSP, "
+                f"ssp.method={args.method}, gaussian PSF 5/0.6 + LSF sigma 0.5")
     return (f"{args.particles} synthetic star particles per GPU (bench-G), MUSE {args.spaxels}x{args.spaxels} "
             f"spaxels x 3721 channels, BC03 SSP, ssp.method={args.method}, gaussian PSF 5/0.6 + LSF sigma 0.5")
 
@@ -186,6 +190,9 @@ def main():
     ap.add_argument("--spaxels", type=int, default=25)
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--galaxies", type=int, default=1,
+                    help="survey batch (config 5): galaxies per GPU and step, each with its own inclination "
+                         "(rotate_galaxy on the device); replicas only, no collective")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -229,7 +236,29 @@ def main():
     slab_mode = world > 1 and cube.numel() * 4 > (64 << 20)
     slab_lo, slab_hi = parallel.wavelength_slab(plan.W, rank, world)
 
+    G = max(1, args.galaxies)
+    if G > 1:   # survey batch: a flattened disc per galaxy, its own Euler angles
+        rng = np.random.default_rng(1000 + rank)
+        gal = []
+        for g in range(G):
+            dg = synthetic.bench_g(n, seed=4200 + 64 * rank + g)
+            dg["coords"][:, 2] *= 0.2
+            gal.append(dict(coords=ops.dev(dg["coords"]), velocity=ops.dev(dg["velocity"]), mass=ops.dev(dg["mass"]),
+                            metallicity=ops.dev(dg["metallicity"]), age=ops.dev(dg["age"]),
+                            angles=tuple(float(a) for a in rng.uniform(0.0, 180.0, 3))))
+
+    def survey_step():
+        out = None
+        for g in gal:   # independent galaxies: no collective (SURVEY 8e "replicas only")
+            c, v, _ = ops.rotate_galaxy(g["coords"], g["velocity"], g["mass"], 1.5, *g["angles"])
+            pix = ops.filter_and_assign(c, edges)
+            ops.build_cube(plan, v, g["mass"], g["metallicity"], g["age"], pix, S, out=cube)
+            out = ops.psf_lsf(cube, pk_h, lk_h)
+        return out
+
     def step():
+        if G > 1:
+            return survey_step()
         pix = ops.filter_and_assign(coords, edges)  # filter_particles + spaxel_assignment, one pass
         ops.build_cube(plan, vel, mass, met, age, pix, S, out=cube)
         if slab_mode:
@@ -276,7 +305,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
+    value = world * G * n / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (rank-local galaxy; N>1 reduces on the device) -------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -362,7 +391,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "template": tpl_name, "method": args.method,
-                       "particles_per_gpu": n, "l2": "flushed (256 MB fill) between timed steps",
+                       "particles_per_gpu": n * G, "galaxies_per_gpu": G,
+                       "l2": "flushed (256 MB fill) between timed steps",
                        "parallelism": (f"particle-sharded x{world}, one NCCL all-reduce of the partial cubes, PSF+LSF "
                                        "sharded by wavelength slab" if slab_mode else
                                        f"particle-sharded x{world}, one NCCL reduce of the partial cubes")},
