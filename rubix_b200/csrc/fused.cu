@@ -126,58 +126,89 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
 }
 
 // ---- segments / items / knot window (one block) -----------------------------------------------
-// exclusive block scan of three ints per thread (1024 threads): warp shuffles + one shared hop
-__device__ __forceinline__ void block_scan3(int &a, int &b, int &c, int *s_w, int &ta, int &tb, int &tc) {
+// exclusive block scan of NV ints per thread (1024 threads): warp shuffles + one shared hop
+template <int NV>
+__device__ __forceinline__ void block_scan(int (&v)[NV], int (&total)[NV], int *s_w /* [33 * NV] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int ia = a, ib = b, ic = c;   // inclusive
+  int inc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) inc[q] = v[q];
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o),
-              nc = __shfl_up_sync(0xffffffffu, ic, o);
-    if (lane >= o) { ia += na; ib += nb; ic += nc; }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const int nb = __shfl_up_sync(0xffffffffu, inc[q], o);
+      if (lane >= o) inc[q] += nb;
+    }
   }
-  if (lane == 31) { s_w[warp] = ia; s_w[32 + warp] = ib; s_w[64 + warp] = ic; }
+  if (lane == 31) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s_w[q * 33 + warp] = inc[q];
+  }
   __syncthreads();
   if (warp == 0) {
-    int wa = s_w[lane], wb = s_w[32 + lane], wc = s_w[64 + lane];
-    int xa = wa, xb = wb, xc = wc;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int na = __shfl_up_sync(0xffffffffu, xa, o), nb = __shfl_up_sync(0xffffffffu, xb, o),
-                nc = __shfl_up_sync(0xffffffffu, xc, o);
-      if (lane >= o) { xa += na; xb += nb; xc += nc; }
+    for (int q = 0; q < NV; ++q) {
+      const int w = s_w[q * 33 + lane];
+      int x = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += nb;
+      }
+      __syncwarp();
+      s_w[q * 33 + lane] = x - w;             // exclusive warp offsets
+      if (lane == 31) s_w[q * 33 + 32] = x;   // total
     }
-    s_w[lane] = xa - wa; s_w[32 + lane] = xb - wb; s_w[64 + lane] = xc - wc;   // exclusive warp offsets
-    if (lane == 31) { s_w[96] = xa; s_w[97] = xb; s_w[98] = xc; }             // totals
   }
   __syncthreads();
-  a = s_w[warp] + ia - a; b = s_w[32 + warp] + ib - b; c = s_w[64 + warp] + ic - c;
-  ta = s_w[96]; tb = s_w[97]; tc = s_w[98];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    v[q] = s_w[q * 33 + warp] + inc[q] - v[q];
+    total[q] = s_w[q * 33 + 32];
+  }
 }
 
+// How a spaxel's `c` sorted particles are cut into work items.  The bulk goes into items of `psub`
+// particles; the last eighth goes into items a quarter of that size, and ALL small items sit behind ALL
+// bulk items in the work queue, so that the warps that finish their last bulk item early fill up on small
+// ones (the tail of the persistent kernel shrinks from half a bulk item to half a small one).
+struct Cut { int bulk, tail, nb, ns, psmall; };
+__device__ __forceinline__ Cut cut_spaxel(int c, int psub) {
+  Cut k;
+  k.psmall = max(32, psub >> 2);
+  k.tail = 0;
+  if (c > psub) k.tail = min(c, ((c >> 3) + k.psmall - 1) / k.psmall * k.psmall);
+  k.bulk = c - k.tail;
+  k.nb = (k.bulk + psub - 1) / psub;
+  k.ns = (k.tail + k.psmall - 1) / k.psmall;
+  return k;
+}
+
+// item_start[s] .. item_start[s+1]: the spaxel's rows in `partials` (none when it is a single item)
 __global__ void __launch_bounds__(1024)
 segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl) {
-  __shared__ int s_w[100];
+  __shared__ int s_w[33 * 4];
   __shared__ int s_err;
   const int T = blockDim.x, t = threadIdx.x;
   const int per = (nseg + T - 1) / T;
   const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
-  int ca = 0, cb = 0, cc = 0;  // particles, items, split rows
+  int v[4] = {0, 0, 0, 0}, tot[4];  // particles, bulk items, small items, split rows
   for (int s = lo; s < hi; ++s) {
-    int c = counts[s];
-    int ni = (c + psub - 1) / psub;
-    ca += c; cb += ni; cc += ni > 1 ? ni : 0;
+    const int c = counts[s];
+    const Cut k = cut_spaxel(c, psub);
+    const int ni = k.nb + k.ns;
+    v[0] += c; v[1] += k.nb; v[2] += k.ns; v[3] += ni > 1 ? ni : 0;
   }
-  int ra = ca, rb = cb, rc = cc, ta, tb, tc;
-  block_scan3(ra, rb, rc, s_w, ta, tb, tc);   // ra, rb, rc: exclusive prefixes; ta, tb, tc: totals
+  block_scan<4>(v, tot, s_w);   // v: exclusive prefixes; tot: totals
   if (t == 0) {
     int err = 0;
-    if (tb > max_items || tc > max_split) err = 1;
+    if (tot[1] + tot[2] > max_items || tot[3] > max_split) err = 1;
     // SSP knot window for the Doppler factors actually present
     int ja = 0, jb = 0;
-    if (ta > 0) {
+    if (tot[0] > 0) {
       float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
       float lo_l = p.tmin / dmax, hi_l = p.tmax / dmin;
       // first knot that can reach the band / one past the last knot that can be in it
@@ -189,34 +220,44 @@ segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
       jb = min(p.L, b + 3);
       if (jb - ja > kMaxKnots) err = 2;
     }
-    ctrl[C_NITEMS] = err ? 0 : tb;
+    ctrl[C_NITEMS] = err ? 0 : tot[1] + tot[2];
     ctrl[C_JA] = ja;
     ctrl[C_JB] = jb;
     ctrl[C_ERROR] = err;
     ctrl[C_WORK] = 0;
-    ctrl[C_NSPLIT] = tc;
-    seg_start[nseg] = ta;
-    item_start[nseg] = tb;
+    ctrl[C_NSPLIT] = tot[3];
+    seg_start[nseg] = tot[0];
+    item_start[nseg] = tot[3];
     s_err = err;
   }
   __syncthreads();
   const bool err = s_err != 0;
+  int ra = v[0], rb = v[1], rs = tot[1] + v[2], rc = v[3];
   for (int s = lo; s < hi; ++s) {
-    int c = counts[s];
-    int ni = (c + psub - 1) / psub;
+    const int c = counts[s];
+    const Cut k = cut_spaxel(c, psub);
+    const int ni = k.nb + k.ns;
     seg_start[s] = ra;
-    item_start[s] = rb;
+    item_start[s] = rc;
     if (!err) {
-      for (int k = 0; k < ni; ++k) {
+      for (int q = 0; q < k.nb; ++q) {   // bulk items: front of the queue
         Item it;
-        it.start = ra + k * psub;
-        it.count = min(psub, c - k * psub);
+        it.start = ra + q * psub;
+        it.count = min(psub, k.bulk - q * psub);
         it.spaxel = s;
-        it.slot = ni > 1 ? rc + k : -1;
-        items[rb + k] = it;
+        it.slot = ni > 1 ? rc + q : -1;
+        items[rb + q] = it;
+      }
+      for (int q = 0; q < k.ns; ++q) {   // small items: behind every bulk item
+        Item it;
+        it.start = ra + k.bulk + q * k.psmall;
+        it.count = min(k.psmall, k.tail - q * k.psmall);
+        it.spaxel = s;
+        it.slot = rc + k.nb + q;         // ns > 0 implies ni > 1
+        items[rs + q] = it;
       }
     }
-    ra += c; rb += ni; rc += ni > 1 ? ni : 0;
+    ra += c; rb += k.nb; rs += k.ns; rc += ni > 1 ? ni : 0;
   }
 }
 
@@ -1018,73 +1059,103 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
     }  // particles
     }  // record batches
 
-    // flush the register chunk lines, one lane after the other (neighbouring lanes can share a chunk)
-    for (int l = 0; l < 32; ++l) {
-      if (lane == l) {
-        if (cA < lay.nch) cell_add<false>(base + cA, accAv, accAm);
-        if (cA + 1 < lay.nch) cell_add<false>(base + cA + 1, accBv, accBm);
-      }
-      __syncwarp();
+    // flush the register chunk lines: cA is non-decreasing along the lanes, so lanes that share a chunk form
+    // runs; a segmented shuffle scan sums each run in a fixed order and its last lane adds the total
+    {
+      auto flush = [&](int key, float v, float m) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int kk = __shfl_up_sync(0xffffffffu, key, o);
+          const float vv = __shfl_up_sync(0xffffffffu, v, o), mm = __shfl_up_sync(0xffffffffu, m, o);
+          if (lane >= o && kk == key) { v += vv; m += mm; }
+        }
+        const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+        if ((lane == 31 || knext != key) && key < lay.nch) cell_add<false>(base + key, v, m);
+        __syncwarp();
+      };
+      flush(cA, accAv, accAm);
+      flush(cA + 1, accBv, accBm);
     }
     accAv = accAm = accBv = accBm = 0.f;
 
     // ---- expand the cells into the spaxel spectrum and store it ---------------------------------------
+    // Per chunk: slope_k = scar + sum_{j<=k} B_j and value_k = vcar + sum_{j<=k} (slope_j dt_j + A_j)
+    //   = vcar + scar (t_k - t_ref) + sum_{j<=k} (sB_j dt_j + A_j)      (sum dt_j telescopes exactly)
+    // so the two warp scans of a 32-channel group do not depend on the carries: four groups are scanned
+    // at once (four independent shuffle chains) and the carries are applied afterwards.
     float *rowp = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
+    const bool add_to_row = accumulate && it.slot < 0;
     for (int c = 0; c < lay.nch; ++c) {
       const float2 bs = base[c];
       float vcar = bs.x, scar = bs.y;
       __syncwarp();
       if (lane == 0) base[c] = make_float2(0.f, 0.f);
-      for (int h = 0; h < CH; h += 32) {
-        const int ch = (c << lay.chs) + h + lane;
-        if ((c << lay.chs) + h > p.W) break;
-        float A = 0.f, B = 0.f;
-        if (ch <= p.W) {
-          const int ca = skewed(ch, lay.skew);
-          const float2 cvv = cells[ca];
-          A = cvv.x; B = cvv.y;
-          cells[ca] = make_float2(0.f, 0.f);
+      const int cstart = c << lay.chs;
+      for (int h = 0; h < CH; h += 128) {
+        if (cstart + h > p.W) break;
+        float A[4], sB[4], dtc[4], tk[4], tref[4];
+        bool valid[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int gstart = cstart + h + 32 * g;
+          const int ch = gstart + lane;
+          A[g] = 0.f; sB[g] = 0.f;
+          if (ch <= p.W) {
+            const int ca = skewed(ch, lay.skew);
+            const float2 cvv = cells[ca];
+            A[g] = cvv.x; sB[g] = cvv.y;
+            cells[ca] = make_float2(0.f, 0.f);
+          }
+          valid[g] = ch < p.W;
+          const bool start = ch == cstart;      // the chunk's first channel takes the base line itself
+          if (start || !valid[g]) { A[g] = 0.f; sB[g] = 0.f; }
+          dtc[g] = (start || !valid[g]) ? 0.f : __ldg(p.dt + ch);
+          tk[g] = __ldg(p.t + min(ch, p.W - 1));
+          tref[g] = __ldg(p.t + min(max(gstart - 1, cstart), p.W - 1));
         }
-        const bool valid = ch < p.W;
-        const bool start = (h + lane) == 0;   // the chunk's first channel takes the base line itself
-        if (start || !valid) { A = 0.f; B = 0.f; }
-        const float dtc = (start || !valid) ? 0.f : __ldg(p.dt + ch);
-        // slope after the kinks of this channel, then the value increments
-        float sB = B;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const float n = __shfl_up_sync(0xffffffffu, sB, o);
-          if (lane >= o) sB += n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float n = __shfl_up_sync(0xffffffffu, sB[g], o);
+            if (lane >= o) sB[g] += n;
+          }
         }
-        const float sl = scar + sB;
-        float inc = fmaf(sl, dtc, A);
+        float inc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) inc[g] = fmaf(sB[g], dtc[g], A[g]);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const float n = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float n = __shfl_up_sync(0xffffffffu, inc[g], o);
+            if (lane >= o) inc[g] += n;
+          }
         }
-        const float v = vcar + inc;
-        if (valid) rowp[ch] = (accumulate && it.slot < 0) ? rowp[ch] + v : v;
-        scar = __shfl_sync(0xffffffffu, sl, 31);
-        vcar = __shfl_sync(0xffffffffu, v, 31);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = cstart + h + 32 * g + lane;
+          const float v = vcar + fmaf(scar, tk[g] - tref[g], inc[g]);
+          if (valid[g]) rowp[ch] = add_to_row ? rowp[ch] + v : v;
+          scar += __shfl_sync(0xffffffffu, sB[g], 31);
+          vcar = __shfl_sync(0xffffffffu, v, 31);
+        }
       }
     }
     __syncwarp();
   }
 }
 
-// cube[s] = sum over the spaxel's items, in item order (deterministic two-level reduction)
-__global__ void reduce_partials_kernel(const int *__restrict__ item_start, const Item *__restrict__ items,
-                                       const float *__restrict__ partials, int Wp, int W, int nseg,
-                                       const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate) {
+// cube[s] = sum over the spaxel's partial rows, in sub-range order (deterministic two-level reduction)
+__global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const float *__restrict__ partials, int Wp, int W,
+                                       int nseg, const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate) {
   if (ctrl[C_ERROR]) return;
   for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
-    const int i0 = item_start[s], i1 = item_start[s + 1];
+    const int i0 = slot_start[s], i1 = slot_start[s + 1];
     if (i1 - i0 < 2) continue;
-    const int slot0 = items[i0].slot;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
       float acc = accumulate ? cube[(size_t)s * W + w] : 0.f;
-      for (int k = 0; k < i1 - i0; ++k) acc += partials[(size_t)(slot0 + k) * Wp + w];
+      for (int k = i0; k < i1; ++k) acc += partials[(size_t)k * Wp + w];
       cube[(size_t)s * W + w] = acc;
     }
   }
@@ -1126,8 +1197,10 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
   ws.end_bit = seg_bits + ws.cell_bits;
   ws.rec_stride = v.method == RBX_METHOD_LINEAR ? 8 : 20;
   ws.psub = choose_psub(n);
-  ws.max_split = (int)(2 * (n / ws.psub) + 2);
-  ws.max_items = nseg + (int)(n / ws.psub) + 2;
+  // a spaxel is cut only when it holds more than psub particles (at most n / psub of them), into at most
+  // 2 c / psub + 2 items (cut_spaxel)
+  ws.max_split = (int)(4 * (n / ws.psub) + 4);
+  ws.max_items = nseg + (int)(4 * (n / ws.psub)) + 4;
   ws.Wp = (v.W + 3) & ~3;
   ws.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, ws.cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
@@ -1451,8 +1524,7 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   RBX_LAUNCH_OK();
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
-  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.items, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube,
-                                                    accumulate);
+  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube, accumulate);
   count_launch();
   RBX_LAUNCH_OK();
   poison_kernel<<<148, 256, 0, stream>>>(ws.ctrl, d_cube, (size_t)nseg * v.W);
