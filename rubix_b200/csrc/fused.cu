@@ -174,11 +174,11 @@ __device__ __forceinline__ void block_scan(int (&v)[NV], int (&total)[NV], int *
 // bulk items in the work queue, so that the warps that finish their last bulk item early fill up on small
 // ones (the tail of the persistent kernel shrinks from half a bulk item to half a small one).
 struct Cut { int bulk, tail, nb, ns, psmall; };
-__device__ __forceinline__ Cut cut_spaxel(int c, int psub) {
+__device__ __forceinline__ Cut cut_spaxel(int c, int psub, int small_shift, int tail_shift) {
   Cut k;
-  k.psmall = max(32, psub >> 2);
+  k.psmall = max(32, psub >> small_shift);
   k.tail = 0;
-  if (c > psub) k.tail = min(c, ((c >> 3) + k.psmall - 1) / k.psmall * k.psmall);
+  if (c > psub) k.tail = min(c, ((c >> tail_shift) + k.psmall - 1) / k.psmall * k.psmall);
   k.bulk = c - k.tail;
   k.nb = (k.bulk + psub - 1) / psub;
   k.ns = (k.tail + k.psmall - 1) / k.psmall;
@@ -187,7 +187,7 @@ __device__ __forceinline__ Cut cut_spaxel(int c, int psub) {
 
 // item_start[s] .. item_start[s+1]: the spaxel's rows in `partials` (none when it is a single item)
 __global__ void __launch_bounds__(1024)
-segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
+segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl) {
   __shared__ int s_w[33 * 4];
@@ -198,7 +198,7 @@ segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
   int v[4] = {0, 0, 0, 0}, tot[4];  // particles, bulk items, small items, split rows
   for (int s = lo; s < hi; ++s) {
     const int c = counts[s];
-    const Cut k = cut_spaxel(c, psub);
+    const Cut k = cut_spaxel(c, psub, small_shift, tail_shift);
     const int ni = k.nb + k.ns;
     v[0] += c; v[1] += k.nb; v[2] += k.ns; v[3] += ni > 1 ? ni : 0;
   }
@@ -235,7 +235,7 @@ segment_kernel(PlanView p, int nseg, int psub, int max_items, int max_split,
   int ra = v[0], rb = v[1], rs = tot[1] + v[2], rc = v[3];
   for (int s = lo; s < hi; ++s) {
     const int c = counts[s];
-    const Cut k = cut_spaxel(c, psub);
+    const Cut k = cut_spaxel(c, psub, small_shift, tail_shift);
     const int ni = k.nb + k.ns;
     seg_start[s] = ra;
     item_start[s] = rc;
@@ -1171,10 +1171,14 @@ __global__ void poison_kernel(const int *__restrict__ ctrl, float *__restrict__ 
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Particles per bulk work item.  Measured on B200 (tools/gpu_sweep.sh, profiles/r01_item_sweep.txt): every item
+// costs a fixed ~10 us of expansion, so few large items win as long as the quarter-size tail items behind them
+// keep the end of the persistent kernel short: 512 at 10^6 particles, 2048 at 10^7.
 static int choose_psub(int64_t n) {
-  int64_t t = n / 4096;
+  if (const char *e = getenv("RBX_PSUB")) return std::max(32, atoi(e));
+  int64_t t = n / 2048;
   int ps = 256;
-  while (ps < t && ps < 8192) ps <<= 1;
+  while (ps < t && ps < 2048) ps <<= 1;
   return ps;
 }
 
@@ -1484,7 +1488,10 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, cb, ws.keys_in, ws.keys_out, ws.idx_in, ws.idx_out,
                                               (int)n, 0, ws.end_bit, stream));
   count_launch(3);
-  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, ws.max_items, ws.max_split, ws.counts, ws.seg_start,
+  int small_shift = 2, tail_shift = 3;
+  if (const char *e = getenv("RBX_SMALL_SHIFT")) small_shift = std::max(0, std::min(5, atoi(e)));
+  if (const char *e = getenv("RBX_TAIL_SHIFT")) tail_shift = std::max(1, std::min(6, atoi(e)));
+  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts, ws.seg_start,
                                           ws.item_start, ws.items, ws.ctrl);
   count_launch();
   RBX_LAUNCH_OK();
