@@ -225,14 +225,17 @@ def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
     _cube_close(out, ref, f"fused {gen} {method}")
 
 
-@pytest.mark.parametrize("env", ["RBX_FUSED_FORCE_LUT", "RBX_FUSED_FORCE_CAS"])
+@pytest.mark.parametrize("env", ["RBX_FUSED_FORCE_LUT=1", "RBX_FUSED_FORCE_CAS=1", "RBX_FUSED_IMPL=group",
+                                 "RBX_PSUB=64", "RBX_SMALL_SHIFT=1", "RBX_FUSED_NO_SKEW=1"])
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env, monkeypatch):
-    """The kernel's general paths -- lookup-table channel search for non-arange telescope grids, one
-    shared cell region with CAS adds for SSP grids finer than the telescope's -- forced on the MUSE
-    configuration (they are otherwise only taken by configurations the oracle is slow on)."""
+    """The general paths -- the group kernel (RBX_FUSED_IMPL=group), its lookup-table channel search for
+    non-arange telescope grids and its shared cell region with CAS adds for SSP grids finer than the
+    telescope's -- forced on the MUSE configuration (they are otherwise only taken by configurations the
+    oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew."""
     from rubix_b200 import synthetic
-    monkeypatch.setenv(env, "1")
+    env, val = env.split("=")
+    monkeypatch.setenv(env, val)
     edges = synthetic.spatial_edges(25)
     data = _well_conditioned(synthetic.bench_g(20000, seed=5), np.float32(1.1) * bc03["wavelength"], muse_wave)
     out = _run_fused(ops, plans[method], data, edges, 25)
@@ -469,6 +472,29 @@ def test_psf_lsf_wavelength_slabs(ops):
         assert np.abs(got - whole).max() <= 1e-6 * np.abs(whole).max()
         ref = orc.apply_lsf(orc.apply_psf(cube.astype(np.float64), pk.astype(np.float64)), 0.5, 1.25)
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_pipeline_host_particle_ranges(ops, plans, bc03, muse_wave, monkeypatch):
+    """rbx_pipeline_host bins a galaxy in particle ranges (copy / compute overlap, accumulating cube build):
+    1, 2 and 5 ranges give the same cube, equal to the oracle's."""
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(25)
+    d = _well_conditioned(synthetic.bench_g(30011, seed=9), np.float32(1.1) * bc03["wavelength"], muse_wave)
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    outs = {}
+    for c in (1, 2, 5):
+        monkeypatch.setenv("RBX_HOST_CHUNKS", str(c))
+        outs[c] = ops.pipeline_host(plans["linear"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"],
+                                    edges, 25, pk, lk).copy()
+    monkeypatch.delenv("RBX_HOST_CHUNKS")
+    ref = c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, 25,
+                                     bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave,
+                                     0.1, method="linear", dtype=np.float64, n_threads=8)
+    ref = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
+    for c, out in outs.items():
+        _cube_close(out, ref, f"pipeline_host {c} ranges")
+    assert np.abs(outs[2] - outs[1]).max() <= 2e-6 * np.abs(ref).max()
+    assert np.abs(outs[5] - outs[1]).max() <= 2e-6 * np.abs(ref).max()
 
 
 def test_gaussian_kernels_on_device(ops):
