@@ -251,16 +251,15 @@ def main():
         out = None
         for g in gal:   # independent galaxies: no collective (SURVEY 8e "replicas only")
             c, v, _ = ops.rotate_galaxy(g["coords"], g["velocity"], g["mass"], 1.5, *g["angles"])
-            pix = ops.filter_and_assign(c, edges)
-            ops.build_cube(plan, v, g["mass"], g["metallicity"], g["age"], pix, S, out=cube)
+            ops.assign_build_cube(plan, c, edges, v, g["mass"], g["metallicity"], g["age"], S, out=cube)
             out = ops.psf_lsf(cube, pk_h, lk_h)
         return out
 
     def step():
         if G > 1:
             return survey_step()
-        pix = ops.filter_and_assign(coords, edges)  # filter_particles + spaxel_assignment, one pass
-        ops.build_cube(plan, vel, mass, met, age, pix, S, out=cube)
+        # filter_particles + spaxel_assignment inside the first kernel of the fused cube build
+        ops.assign_build_cube(plan, coords, edges, vel, mass, met, age, S, out=cube)
         if slab_mode:
             dist.all_reduce(cube, op=dist.ReduceOp.SUM)
             return ops.psf_lsf_slab(cube, slab_lo, slab_hi, pk_h, lk_h)
@@ -328,8 +327,7 @@ def main():
             dcoords.copy_(hp["coords"], non_blocking=True); dvel.copy_(hp["velocity"], non_blocking=True)
             mass.copy_(hp["mass"], non_blocking=True); met.copy_(hp["metallicity"], non_blocking=True)
             age.copy_(hp["age"], non_blocking=True)
-            pix = ops.filter_and_assign(dcoords, edges)
-            ops.build_cube(plan, dvel, mass, met, age, pix, S, out=cube)
+            ops.assign_build_cube(plan, dcoords, edges, dvel, mass, met, age, S, out=cube)
             if slab_mode:
                 dist.all_reduce(cube, op=dist.ReduceOp.SUM)
                 hslab.copy_(ops.psf_lsf_slab(cube, slab_lo, slab_hi, pk_h, lk_h), non_blocking=True)

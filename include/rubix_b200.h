@@ -125,6 +125,15 @@ int rbx_build_cube(const rbx_plan *plan, const float *d_velocity, const float *d
                    int num_spaxels, float *d_cube, void *d_workspace, size_t workspace_bytes,
                    void *stream);
 
+/* a0 + a1..a5 in one call: spaxel assignment (and, with apply_filter, the aperture filter: particles outside
+ * get pixel -1, the same cube as zeroing their mass) happens inside the first kernel of the cube build, so the
+ * particle arrays are read once.  d_pixel_out (n,) may be NULL.  Same workspace as rbx_build_cube. */
+int rbx_assign_build_cube(const rbx_plan *plan, const float *d_coords, const float *d_edges, int n_edges,
+                          int apply_filter, const float *d_velocity, const float *d_mass,
+                          const float *d_metallicity, const float *d_age, int64_t n, int num_spaxels,
+                          int32_t *d_pixel_out, float *d_cube, void *d_workspace, size_t workspace_bytes,
+                          void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a6 apply_psf (rubix/telescope/psf/psf.py:56-57): per wavelength slice
  *    convolve2d(slice, kernel, mode="same"); d_kernel is (M, N) row-major on the device.

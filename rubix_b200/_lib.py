@@ -19,7 +19,7 @@ EXPORTED = [
     "rbx_plan_create", "rbx_plan_destroy", "rbx_plan_dims",
     "rbx_spaxel_assign", "rbx_filter_particles", "rbx_filter_and_assign",
     "rbx_ssp_lookup", "rbx_scale_by_mass", "rbx_doppler_resample", "rbx_segment_sum",
-    "rbx_build_cube_workspace_bytes", "rbx_build_cube",
+    "rbx_build_cube_workspace_bytes", "rbx_build_cube", "rbx_assign_build_cube",
     "rbx_convolve_psf", "rbx_convolve_lsf", "rbx_psf_lsf", "rbx_psf_lsf_taps", "rbx_psf_lsf_taps_pitched",
     "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
     "rbx_pipeline_host",
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "rbx_doppler_resample": [vp, vp, vp, i64, vp, vp],
         "rbx_segment_sum": [vp, vp, i64, i32, i32, vp, i32, vp],
         "rbx_build_cube": [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp],
+        "rbx_assign_build_cube": [vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp],
         "rbx_convolve_psf": [vp, vp, i32, i32, i32, vp, i32, i32, vp],
         "rbx_convolve_lsf": [vp, vp, i64, i32, vp, i32, i32, vp],
         "rbx_psf_lsf": [vp, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp],

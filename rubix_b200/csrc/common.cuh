@@ -86,10 +86,11 @@ struct rbx_plan {
 
 namespace rbx {
 
-// rbx_build_cube with an accumulate switch (fused.cu; used by rbx_pipeline_host's chunked overlap)
+// rbx_build_cube with an accumulate switch and optional in-kernel spaxel assignment (fused.cu)
 int build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
-                    const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube, void *d_ws,
-                    size_t ws_bytes, void *stream, int accumulate);
+                    const float *d_age, int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube, void *d_ws,
+                    size_t ws_bytes, void *stream, int accumulate, const float *d_coords, const float *d_edges,
+                    int n_edges, int mark_outside);
 
 // ---- small device helpers ---------------------------------------------------------------------
 // searchsorted(a, v, side='right') on a sorted array: number of elements <= v (NaN v -> n, like numpy/XLA

@@ -63,15 +63,39 @@ __device__ __forceinline__ int rec_stride_for(int method) { return method == RBX
 // ---- prep ---------------------------------------------------------------------------------------
 // record (floats, original particle order): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=unused
 // [4..]=interpolation weights * mass.  The cube kernels fetch records through the sorted index.
+constexpr int kDminBias = 0x7f7fffff;   // ctrl[C_DMIN] holds kDminBias - bits(dmin): a zeroed ctrl means "no particle yet"
+
+// With `coords` the spaxel assignment (rubix/telescope/utils.py:138-151, same searches as
+// spaxel_assign_kernel: bit-exact) and the aperture filter (rubix/core/telescope.py:155-174, as pixel -1)
+// happen here, so the particle arrays are read once; `pixel` then is an optional output.
 __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const float *__restrict__ mass,
                             const float *__restrict__ met, const float *__restrict__ age,
-                            const int32_t *__restrict__ pixel, int n, int nseg, int cell_bits, int cell_shift,
+                            int32_t *__restrict__ pixel, int n, int nseg, int cell_bits, int cell_shift,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
-                            int *__restrict__ ctrl, int smem_hist, float *__restrict__ rec, int stride) {
-  extern __shared__ int s_hist[];  // per-block spaxel histogram (when it fits): one global atomic per bin
-  if (smem_hist) {
+                            int *__restrict__ ctrl, int smem_hist, float *__restrict__ rec, int stride,
+                            const float *__restrict__ coords, const float *__restrict__ edges, int n_edges,
+                            int mark_outside, int edges_smem) {
+  extern __shared__ int s_dyn[];
+  int *s_hist = s_dyn;                                  // per-block spaxel histogram (when it fits)
+  float *s_axes = reinterpret_cast<float *>(s_dyn + (smem_hist ? nseg : 0));   // SSP metallicity and age axes
+  float *s_edges = s_axes + p.nz + p.na;
+  if (smem_hist)
     for (int s = threadIdx.x; s < nseg; s += blockDim.x) s_hist[s] = 0;
-    __syncthreads();
+  for (int s = threadIdx.x; s < p.nz; s += blockDim.x) s_axes[s] = p.zgrid[s];
+  for (int s = threadIdx.x; s < p.na; s += blockDim.x) s_axes[p.nz + s] = p.agrid[s];
+  const float *e = edges;
+  if (coords && edges_smem) {
+    for (int s = threadIdx.x; s < n_edges; s += blockDim.x) s_edges[s] = edges[s];
+    e = s_edges;
+  }
+  __syncthreads();
+  p.zgrid = s_axes;
+  p.agrid = s_axes + p.nz;
+  float elo = 0.f, ehi = 0.f;
+  const int nb = n_edges - 1;
+  if (coords) {   // the reference takes min() / max() of the edges (rubix/telescope/utils.py:170-174)
+    elo = ehi = e[0];
+    for (int s = 1; s < n_edges; ++s) { elo = fminf(elo, e[s]); ehi = fmaxf(ehi, e[s]); }
   }
   float dmin = 3.0e38f, dmax = 0.f;
   int nvalid = 0;
@@ -79,7 +103,17 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     int i, j;
     bool inside;
     ssp_cell(p, met[q], age[q], i, j, inside);
-    int px = pixel[q];
+    int px;
+    if (coords) {
+      const float x = coords[3 * (size_t)q], y = coords[3 * (size_t)q + 1];
+      const int xi = min(max(ss_right(e, n_edges, x) - 1, 0), nb - 1);
+      const int yi = min(max(ss_right(e, n_edges, y) - 1, 0), nb - 1);
+      px = xi + nb * yi;
+      if (mark_outside && !((x >= elo) && (x <= ehi) && (y >= elo) && (y <= ehi))) px = -1;
+      if (pixel) pixel[q] = px;
+    } else {
+      px = pixel[q];
+    }
     float d = expf(vel[3 * (size_t)q + p.vel_comp] / kSpeedOfLight);
     bool valid = inside && (mass[q] != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
     uint32_t key = (uint32_t)nseg << cell_bits;  // invalid: sorts behind every valid key
@@ -112,7 +146,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
   }
   if ((threadIdx.x & 31) == 0 && nvalid > 0) {
-    atomicMin(ctrl + C_DMIN, __float_as_int(dmin));
+    atomicMax(ctrl + C_DMIN, kDminBias - __float_as_int(dmin));
     atomicMax(ctrl + C_DMAX, __float_as_int(dmax));
     atomicAdd(ctrl + C_NVALID, nvalid);
   }
@@ -209,7 +243,7 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     // SSP knot window for the Doppler factors actually present
     int ja = 0, jb = 0;
     if (tot[0] > 0) {
-      float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+      float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
       float lo_l = p.tmin / dmax, hi_l = p.tmax / dmin;
       // first knot that can reach the band / one past the last knot that can be in it
       int a = 0, hi_a = p.L;
@@ -451,7 +485,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
   if (!active) return;  // spare warps (no __syncthreads below this line)
 
   // ---- cell regions: the channel range each warp can reach for the Doppler factors present --------
-  const float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+  const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
   {
     float e;
     int klo = owner ? channel_of<AFFINE>(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e) : 0x7fffffff;
@@ -844,7 +878,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   const int ja = ctrl[C_JA], jb = ctrl[C_JB];
   const int n_items = ctrl[C_NITEMS];
   const int jbase = (ja - 1) & ~3;               // multiple of 4 (16-byte template loads); slot s <-> knot jbase + s
-  if (jb - jbase + 1 > kWarpSlots) {             // the knot window does not fit one warp: fail loudly (poison_kernel)
+  if (jb - jbase + 1 > kWarpSlots) {             // the knot window does not fit one warp: fail loudly (reduce_partials_kernel poisons the cube)
     if (tid == 0) atomicExch(ctrl + C_ERROR, 2);
     return;
   }
@@ -863,7 +897,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   // previous knot of slot 0 for the "total" difference; diff0's first element is 0 (rubix/spectra/ifu.py:84-102)
   const float lzprev = (j0 - 1 >= 0 && j0 - 1 < p.L) ? p.lamz[j0 - 1] : lz[0];
 
-  const float dmin = __int_as_float(ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+  const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
   // chunk lines are summed in registers: a lane's span [k_0, k_8) holds at most one chunk start, and over
   // the Doppler range present that start is chunk cA or cA + 1
   int cA = 0;
@@ -1146,11 +1180,18 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   }
 }
 
-// cube[s] = sum over the spaxel's partial rows, in sub-range order (deterministic two-level reduction)
+// cube[s] = sum over the spaxel's partial rows, in sub-range order (deterministic two-level reduction).
+// A configuration the kernels cannot hold (knot window too large) poisons the cube with NaN here rather than
+// returning a silently wrong result.
 __global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const float *__restrict__ partials, int Wp, int W,
                                        int nseg, const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate) {
-  if (ctrl[C_ERROR]) return;
+  const bool poison = ctrl[C_ERROR] != 0;
   for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+    if (poison) {
+      for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x)
+        cube[(size_t)s * W + w] = __int_as_float(0x7fc00000);
+      continue;
+    }
     const int i0 = slot_start[s], i1 = slot_start[s + 1];
     if (i1 - i0 < 2) continue;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
@@ -1159,14 +1200,6 @@ __global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const
       cube[(size_t)s * W + w] = acc;
     }
   }
-}
-
-// a configuration the kernel cannot hold (knot window too large) poisons the cube with NaN rather
-// than returning a silently wrong result
-__global__ void poison_kernel(const int *__restrict__ ctrl, float *__restrict__ cube, size_t total) {
-  if (!ctrl[C_ERROR]) return;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-    cube[i] = __int_as_float(0x7fc00000);
 }
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -1216,10 +1249,10 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
   ws.idx_in = (uint32_t *)take(sizeof(uint32_t) * n);
   ws.idx_out = (uint32_t *)take(sizeof(uint32_t) * n);
   ws.rec = (float *)take(sizeof(float) * n * ws.rec_stride);
-  ws.counts = (int *)take(sizeof(int) * (nseg + 1));
+  ws.counts = (int *)take(sizeof(int) * (nseg + 1 + C_COUNT));   // counts, then ctrl: zeroed by one memset
+  ws.ctrl = ws.counts + (nseg + 1);
   ws.seg_start = (int *)take(sizeof(int) * (nseg + 1));
   ws.item_start = (int *)take(sizeof(int) * (nseg + 1));
-  ws.ctrl = (int *)take(sizeof(int) * C_COUNT);
   ws.items = (Item *)take(sizeof(Item) * ws.max_items);
   ws.partials = (float *)take(sizeof(float) * (size_t)ws.max_split * ws.Wp);
   ws.cub_temp = take(ws.cub_bytes);
@@ -1435,15 +1468,28 @@ extern "C" size_t rbx_build_cube_workspace_bytes(const rbx_plan *plan, int64_t n
 extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
                               const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels,
                               float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
-  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, d_pixel, n, num_spaxels, d_cube, d_ws, ws_bytes,
-                              stream_, 0);
+  RBX_REQUIRE(n == 0 || d_pixel, "rbx_build_cube: null pointer");
+  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, const_cast<int32_t *>(d_pixel), n, num_spaxels, d_cube,
+                              d_ws, ws_bytes, stream_, 0, nullptr, nullptr, 0, 0);
 }
 
-// accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in chunks so that the
-// host-to-device copy of one chunk overlaps the kernels of the previous one)
+extern "C" int rbx_assign_build_cube(const rbx_plan *plan, const float *d_coords, const float *d_edges, int n_edges,
+                                     int apply_filter, const float *d_vel, const float *d_mass, const float *d_met,
+                                     const float *d_age, int64_t n, int num_spaxels, int32_t *d_pixel_out,
+                                     float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
+  RBX_REQUIRE(n_edges >= 2 && (n == 0 || (d_coords && d_edges)), "rbx_assign_build_cube: bad argument");
+  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, d_pixel_out, n, num_spaxels, d_cube, d_ws, ws_bytes,
+                              stream_, 0, d_coords, d_edges, n_edges, apply_filter ? 1 : 0);
+}
+
+// accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in ranges so that the
+// host-to-device copy of one range overlaps the kernels of the previous one).
+// d_coords != NULL: spaxel assignment (+ aperture filter as pixel -1) inside prep_kernel; d_pixel is then an
+// optional output.
 int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
-                         const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube,
-                         void *d_ws, size_t ws_bytes, void *stream_, int accumulate) {
+                         const float *d_age, int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube,
+                         void *d_ws, size_t ws_bytes, void *stream_, int accumulate, const float *d_coords,
+                         const float *d_edges, int n_edges, int mark_outside) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RBX_REQUIRE(plan && d_cube, "rbx_build_cube: null plan or cube");
   RBX_REQUIRE(n >= 0 && n < (1ll << 31) - 1, "rbx_build_cube: n out of range");
@@ -1453,7 +1499,7 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   const int nseg = num_spaxels * num_spaxels;
   if (!accumulate) RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)nseg * v.W, stream));
   if (n == 0) return RBX_OK;
-  RBX_REQUIRE(d_vel && d_mass && d_met && d_age && d_pixel && d_ws, "rbx_build_cube: null pointer");
+  RBX_REQUIRE(d_vel && d_mass && d_met && d_age && (d_pixel || d_coords) && d_ws, "rbx_build_cube: null pointer");
   FusedWs ws;
   size_t need = 0;
   uintptr_t base = ((uintptr_t)d_ws + 255) & ~(uintptr_t)255;
@@ -1462,25 +1508,24 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
     set_error("rbx_build_cube: workspace too small (see rbx_build_cube_workspace_bytes)");
     return RBX_ERR_WORKSPACE_TOO_SMALL;
   }
-  RBX_CUDA_OK(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (nseg + 1), stream));
-  int h_ctrl[C_COUNT] = {0};
-  // ctrl init: dmin = +big, dmax = 0 -- via memset then a tiny kernel-free trick: 0x7f7fffff pattern
-  RBX_CUDA_OK(cudaMemsetAsync(ws.ctrl, 0, sizeof(int) * C_COUNT, stream));
-  RBX_CUDA_OK(cudaMemsetAsync(ws.ctrl + C_DMIN, 0x7f, sizeof(int), stream));  // 0x7f7f7f7f ~ 3.4e38
-  (void)h_ctrl;
+  // counts and ctrl are adjacent; all-zero is their initial state (dmin is stored biased, dmax as bits)
+  RBX_CUDA_OK(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (nseg + 1 + C_COUNT), stream));
 
   const int threads = 256;
   int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
   {
     const size_t hist_bytes = sizeof(int) * (size_t)nseg;
     const int smem_hist = hist_bytes <= 160 * 1024 ? 1 : 0;
+    const int edges_smem = (d_coords && n_edges <= 4096) ? 1 : 0;
+    const size_t dyn = (smem_hist ? hist_bytes : 0) + sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? n_edges : 0));
     // the per-block histogram is flushed with one atomic per non-empty bin: fewer blocks for big cubes
     int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, nseg <= 4096 ? 148 * 8 : 148 * 2) : blocks;
-    if (smem_hist && hist_bytes > 48 * 1024)
-      RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-    prep_kernel<<<pblocks, threads, smem_hist ? hist_bytes : 0, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n,
-                                                                          nseg, ws.cell_bits, ws.cell_shift, ws.keys_in, ws.idx_in,
-                                                                          ws.counts, ws.ctrl, smem_hist, ws.rec, ws.rec_stride);
+    if (dyn > 48 * 1024)
+      RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    prep_kernel<<<pblocks, threads, dyn, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n, nseg, ws.cell_bits,
+                                                   ws.cell_shift, ws.keys_in, ws.idx_in, ws.counts, ws.ctrl, smem_hist,
+                                                   ws.rec, ws.rec_stride, d_coords, d_edges, n_edges, mark_outside,
+                                                   edges_smem);
   }
   count_launch();
   RBX_LAUNCH_OK();
@@ -1532,9 +1577,6 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
   reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube, accumulate);
-  count_launch();
-  RBX_LAUNCH_OK();
-  poison_kernel<<<148, 256, 0, stream>>>(ws.ctrl, d_cube, (size_t)nseg * v.W);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;

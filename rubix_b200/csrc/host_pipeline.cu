@@ -142,12 +142,10 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
       RBX_CUDA_OK(cudaEventRecord(lane->copied[c], cs));
       RBX_CUDA_OK(cudaStreamWaitEvent(stream, lane->copied[c], 0));
     }
-    if (apply_filter)  // particles outside the aperture get pixel -1 (same cube as zeroing their mass)
-      TRY(rbx_filter_and_assign(d_coords + 3 * lo, m, d_edges, n_edges, nullptr, nullptr, nullptr, d_pixel + lo, nullptr, stream));
-    else
-      TRY(rbx_spaxel_assign(d_coords + 3 * lo, m, d_edges, n_edges, d_pixel + lo, nullptr, stream));
-    TRY(build_cube_impl(plan, d_vel + 3 * lo, d_mass + lo, d_met + lo, d_age + lo, d_pixel + lo, m, num_spaxels, d_cube,
-                        d_ws, ws_bytes, stream, c > 0 ? 1 : 0));
+    // spaxel assignment + aperture filter (pixel -1: the same cube as zeroing the mass) inside the cube build's
+    // first kernel: the particle arrays are read once
+    TRY(build_cube_impl(plan, d_vel + 3 * lo, d_mass + lo, d_met + lo, d_age + lo, nullptr, m, num_spaxels, d_cube, d_ws,
+                        ws_bytes, stream, c > 0 ? 1 : 0, d_coords + 3 * lo, d_edges, n_edges, apply_filter ? 1 : 0));
   }
   float *result = d_cube;
   if (h_psf || h_lsf) {

@@ -225,6 +225,26 @@ def build_cube(plan: Plan, velocity, mass, metallicity, age, pixel, num_spaxels:
     return cube
 
 
+def assign_build_cube(plan: Plan, coords, edges, velocity, mass, metallicity, age, num_spaxels: int,
+                      apply_filter: bool = True, out: Optional[torch.Tensor] = None, return_pixel: bool = False):
+    """filter_particles + spaxel_assignment + the fused cube build in one call (``rbx_assign_build_cube``): the
+    spaxel index is computed inside the first kernel of the build, the particle arrays are read once."""
+    coords, edges, velocity = dev(coords), dev(edges), dev(velocity)
+    mass, metallicity, age = dev(mass).reshape(-1), dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    n = mass.numel()
+    if coords.shape != (n, 3) or velocity.shape != (n, 3) or metallicity.numel() != n or age.numel() != n:
+        raise ValueError("particle arrays disagree in length")
+    S = int(num_spaxels)
+    cube = out if out is not None else torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
+    pixel = torch.empty(n, dtype=torch.int32, device="cuda") if return_pixel else None
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_workspace_bytes(plan.handle, n, S))
+    _lib.check(L.rbx_assign_build_cube(plan.handle, _p(coords), _p(edges), edges.numel(), 1 if apply_filter else 0,
+                                       _p(velocity), _p(mass), _p(metallicity), _p(age), n, S, _p(pixel), _p(cube),
+                                       _p(ws), ws.numel(), _stream()))
+    return (cube, pixel) if return_pixel else cube
+
+
 def _host_taps(k):
     """float32 host copy of a kernel given as numpy / list (None for CUDA tensors: those stay on the device)."""
     if k is None or (isinstance(k, torch.Tensor) and k.is_cuda):

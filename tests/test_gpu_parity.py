@@ -474,6 +474,22 @@ def test_psf_lsf_wavelength_slabs(ops):
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("apply_filter", [True, False])
+def test_assign_build_cube_equals_two_calls(ops, plans, apply_filter):
+    """rbx_assign_build_cube computes the spaxel index inside the build's first kernel: same pixels (bit-exact
+    integer work) and a bit-identical cube compared with spaxel assignment followed by rbx_build_cube."""
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(25)
+    d = synthetic.bench_g(50000, seed=17, scale=1.6)   # ~1 % of the particles outside the aperture
+    pix = ops.filter_and_assign(d["coords"], edges) if apply_filter else ops.spaxel_assign(d["coords"], edges)
+    two = ops.build_cube(plans["linear"], d["velocity"], d["mass"], d["metallicity"], d["age"], pix, 25)
+    one, pix1 = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                      d["age"], 25, apply_filter=apply_filter, return_pixel=True)
+    assert torch.equal(pix1, pix)
+    assert (pix < 0).any() == apply_filter
+    assert torch.equal(one, two)
+
+
 def test_pipeline_host_particle_ranges(ops, plans, bc03, muse_wave, monkeypatch):
     """rbx_pipeline_host bins a galaxy in particle ranges (copy / compute overlap, accumulating cube build):
     1, 2 and 5 ranges give the same cube, equal to the oracle's."""
