@@ -918,26 +918,36 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
   const float hdelta = 0.5f * p.tdelta;
 
-  while (true) {
-    int item_id = 0;
-    if (lane == 0) item_id = atomicAdd(ctrl + C_WORK, 1);
-    item_id = __shfl_sync(0xffffffffu, item_id, 0);
-    if (item_id >= n_items) break;
-    const Item it = items[item_id];
+  // The next work item is popped, and its first record batch requested, BEFORE the current item's cells are
+  // expanded: the queue atomic and two dependent global loads hide behind the expansion.
+  float4 nrec[RS / 4];   // my record of the NEXT batch, in flight during the current one
+  auto fetch_rec = [&](const Item &w, int b0) {
+    if (b0 + lane < w.count) {
+      const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)__ldg(sidx + w.start + b0 + lane) * RS);
+#pragma unroll
+      for (int u = 0; u < RS / 4; ++u) nrec[u] = __ldg(src + u);
+    }
+  };
+  Item it_next;
+  it_next.start = 0; it_next.count = 0; it_next.spaxel = 0; it_next.slot = -1;
+  auto pop_item = [&]() -> bool {
+    int id = 0;
+    if (lane == 0) id = atomicAdd(ctrl + C_WORK, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= n_items) return false;
+    it_next = items[id];
+    fetch_rec(it_next, 0);
+    return true;
+  };
+  bool have = pop_item();
+
+  while (have) {
+    const Item it = it_next;
 
     // Software pipeline.  Records: a batch of 32 sorted records is loaded coalesced (lane l loads record l)
     // and parked in the warp's shared-memory slot, so every particle's record is a broadcast read away.
     // Template rows: the eight 16-byte vectors of the NEXT (particle, table) group are in flight while the
     // current group is folded in and, for the last table, during the whole knot arithmetic of the particle.
-    float4 nrec[RS / 4];   // my record of the NEXT batch, in flight during the current one
-    auto fetch_rec = [&](int b0) {
-      if (b0 + lane < it.count) {
-        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)__ldg(sidx + it.start + b0 + lane) * RS);
-#pragma unroll
-        for (int u = 0; u < RS / 4; ++u) nrec[u] = __ldg(src + u);
-      }
-    };
-    fetch_rec(0);
     for (int b0 = 0; b0 < it.count; b0 += 32) {
       const int nb = min(32, it.count - b0);
       __syncwarp();
@@ -947,7 +957,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         for (int u = 0; u < RS / 4; ++u) dst[u] = nrec[u];
       }
       __syncwarp();
-      if (b0 + 32 < it.count) fetch_rec(b0 + 32);
+      if (b0 + 32 < it.count) fetch_rec(it, b0 + 32);
       float4 nf[8];
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
         if (interior) {
@@ -1111,6 +1121,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       flush(cA + 1, accBv, accBm);
     }
     accAv = accAm = accBv = accBm = 0.f;
+    have = pop_item();
 
     // ---- expand the cells into the spaxel spectrum and store it ---------------------------------------
     // Per chunk: slope_k = scar + sum_{j<=k} B_j and value_k = vcar + sum_{j<=k} (slope_j dt_j + A_j)
