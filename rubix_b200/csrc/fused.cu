@@ -928,6 +928,8 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       for (int u = 0; u < RS / 4; ++u) nrec[u] = __ldg(src + u);
     }
   };
+  float4 nf[8];          // template vectors of the next (particle, table) group
+  int nf_row = -1;       // linear: the template row they were loaded for
   Item it_next;
   it_next.start = 0; it_next.count = 0; it_next.spaxel = 0; it_next.slot = -1;
   auto pop_item = [&]() -> bool {
@@ -958,10 +960,14 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       }
       __syncwarp();
       if (b0 + 32 < it.count) fetch_rec(it, b0 + 32);
-      float4 nf[8];
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
         if (interior) {
-          const float *f = tab[t] + (size_t)__float_as_int(s_rec[i * RS + 2]) * p.Lp + j0;
+          const int rw = __float_as_int(s_rec[i * RS + 2]);
+          // linear: particles are sorted by (spaxel, template cell), so runs of particles share their four rows;
+          // the vectors already in registers are kept (at 10^7 particles ~90 % of the row loads go away)
+          if (NT == 1 && rw == nf_row) return;
+          nf_row = rw;
+          const float *f = tab[t] + (size_t)rw * p.Lp + j0;
           // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
           const size_t o1 = METHOD == RBX_METHOD_LINEAR ? rowB : rowC, o2 = METHOD == RBX_METHOD_LINEAR ? rowC : rowB;
           nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
