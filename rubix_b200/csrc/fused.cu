@@ -23,7 +23,6 @@
 
 namespace rbx {
 
-constexpr uint32_t kInvalidCell = 0xFFFFFFFFu;
 #ifndef RBX_NB
 #define RBX_NB 4
 #endif
@@ -1062,6 +1061,14 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       int ka[WK];
 #pragma unroll
       for (int r = 0; r < WK; ++r) ka[r] = skewed(k[r], lay.skew);
+#ifdef RBX_RACECHECK
+      // Knots outside the band (k = 0 or k = W) of several lanes land in the two junk cells 0 and W, which are
+      // never read back: a benign write-write overlap that compute-sanitizer racecheck reports.  This build
+      // gives every lane its own junk cell so that racecheck can show there is no other hazard.
+#pragma unroll
+      for (int r = 0; r < WK; ++r)
+        if (k[r] <= 0 || k[r] >= p.W) ka[r] = lay.ncells + lane;
+#endif
 #pragma unroll
       for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
 #pragma unroll
@@ -1451,7 +1458,7 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
     lay.skew = (unsigned)std::llround(std::fmin(alpha, 0.25) * 4294967296.0);
     lay.ncells = v.W + 2 + (int)(((unsigned long long)(v.W + 2) * lay.skew) >> 32) + 1;
   }
-  lay.w_base = a128(8 * lay.ncells);
+  lay.w_base = a128(8 * (lay.ncells + 32));   // + one junk cell per lane (RBX_RACECHECK builds)
   lay.w_rec = lay.w_base + a128(8 * lay.nch);
   lay.warp_stride = lay.w_rec + a128(4 * 32 * (v.method == RBX_METHOD_LINEAR ? 8 : 20));
   int nw = std::min(8, (227 * 1024 - lay.off_warp) / lay.warp_stride);
