@@ -184,6 +184,21 @@ int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity, const floa
                       void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * apply_noise, the stage right after the path (rubix/core/noise.py:15-78 ->
+ * rubix/telescope/noise/noise.py:37-115): flux image, median of the non-zero flux (jnp.median propagates the
+ * NaN of a flux-less spaxel -> 0, reproduced), S2N map, cube += cube * N * S2N.  N restates
+ * jax.random.normal / uniform(PRNGKey(0)): threefry2x32 with the element index as counter (key0 = key1 = 0
+ * for PRNGKey(0)); distribution 0 = "normal", 1 = "uniform".  d_out may alias d_in.
+ * rbx_noise_samples exposes the raw sample stream (and its 32-bit words) for tests.
+ * ------------------------------------------------------------------------------------------- */
+size_t rbx_apply_noise_workspace_bytes(int ny, int nx);
+int rbx_apply_noise(const float *d_in, float *d_out, int ny, int nx, int W, float signal_to_noise,
+                    int distribution, uint32_t key0, uint32_t key1, void *d_workspace,
+                    size_t workspace_bytes, void *stream);
+int rbx_noise_samples(float *d_out, uint32_t *d_bits, int64_t n, int distribution, uint32_t key0,
+                      uint32_t key1, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience call: the whole path (filter -> spaxel -> fused cube -> PSF -> LSF) for
  * callers that hold numpy / host arrays.  Copies inputs H2D, runs the kernels, copies the cube
  * back; h_cube is (num_spaxels, num_spaxels, W).  h_psf (M,N) / h_lsf (K,) may be NULL to skip.

@@ -463,6 +463,85 @@ def rotate_galaxy(positions, velocities, masses, halfmass_radius, alpha, beta, g
     return pos, vel, R
 
 
+# ---- apply_noise: the stage after the path (rubix/telescope/noise/noise.py) ---------------------------
+def threefry2x32(key, x0, x1):
+    """Threefry-2x32, 20 rounds (Salmon et al. 2011; jax._src.prng.threefry2x32_p).  uint32 arrays."""
+    k0, k1 = np.uint32(key[0]), np.uint32(key[1])
+    ks = [k0, k1, np.uint32(k0 ^ k1 ^ np.uint32(0x1BD11BDA))]
+    R = [[13, 15, 26, 6], [17, 29, 16, 24]]
+    x0 = np.asarray(x0, dtype=np.uint32).copy()
+    x1 = np.asarray(x1, dtype=np.uint32).copy()
+    with np.errstate(over="ignore"):
+        x0 += ks[0]
+        x1 += ks[1]
+        for g in range(5):
+            for r in R[g & 1]:
+                x0 += x1
+                x1 = (x1 << np.uint32(r)) | (x1 >> np.uint32(32 - r))
+                x1 ^= x0
+            x0 += ks[(g + 1) % 3]
+            x1 += ks[(g + 2) % 3] + np.uint32(g + 1)
+    return x0, x1
+
+
+def random_bits(key, n):
+    """jax's partitionable threefry (default since jax 0.5): element i uses the counter (hi32(i), lo32(i)) and
+    bits = x0 ^ x1."""
+    i = np.arange(n, dtype=np.uint64)
+    a, b = threefry2x32(key, (i >> np.uint64(32)).astype(np.uint32), (i & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    return a ^ b
+
+
+def _erfinv_f32(x):
+    """XLA's float32 ErfInv (Giles 2010, single precision), evaluated in float64 here."""
+    x = np.asarray(x, dtype=np.float64)
+    w = -np.log1p(-x * x)
+    small = w < 5.0
+    ws = np.where(small, w - 2.5, np.sqrt(np.maximum(w, 5.0)) - 3.0)
+    cs = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503,
+          -0.00417768164, 0.246640727, 1.50140941]
+    cl = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613,
+          0.00943887047, 1.00167406, 2.83297682]
+    ps = np.zeros_like(ws) + cs[0]
+    pl = np.zeros_like(ws) + cl[0]
+    for c in cs[1:]:
+        ps = ps * ws + c
+    for c in cl[1:]:
+        pl = pl * ws + c
+    return np.where(small, ps, pl) * x
+
+
+def sample_noise(n, distribution="normal", key=(0, 0)):
+    """rubix/telescope/noise/noise.py:8-34 with key = jax.random.PRNGKey(0) = (0, 0): jax.random.uniform takes
+    the top 23 bits into [1, 2) - 1; jax.random.normal maps a uniform on (-1, 1) through sqrt(2) erfinv."""
+    bits = random_bits(key, n)
+    f = ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    if distribution == "uniform":
+        return f.astype(np.float64)
+    if distribution != "normal":
+        raise ValueError(f"Invalid noise type: {distribution}. Supported types: ['normal', 'uniform']")
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    u = np.maximum(lo, f * (np.float32(1.0) - lo) + lo)
+    return np.sqrt(2.0) * _erfinv_f32(u)
+
+
+def calculate_S2N(datacube, signal_to_noise):
+    """rubix/telescope/noise/noise.py:37-78.  jnp.median propagates NaN: one spaxel without flux -> median 0."""
+    flux = np.sum(np.asarray(datacube, dtype=np.float64), axis=-1)
+    mask = flux > 0
+    median = np.median(flux) if mask.all() and flux.size else 0.0
+    factor = np.sqrt(median) / signal_to_noise
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(mask, factor / np.sqrt(flux), 0.0)
+
+
+def apply_noise(datacube, signal_to_noise, distribution="normal"):
+    """rubix/core/noise.py:63-78 + noise.py:81-115: datacube + datacube * N * S2N[:, :, None]."""
+    cube = np.asarray(datacube, dtype=np.float64)
+    noise = sample_noise(cube.size, distribution).reshape(cube.shape) * calculate_S2N(cube, signal_to_noise)[:, :, None]
+    return cube + cube * noise
+
+
 def calculate_wave_seq(wave_range, wave_res, dtype=np.float32):
     """rubix/telescope/utils.py:53 (``jnp.arange`` in f32).  Pinned bit-exactly by the ``wave``
     dataset of the reference's notebooks/data/dummy_datacube.h5 (tests/golden/muse_wave.npy)."""

@@ -24,6 +24,7 @@ EXPORTED = [
     "rbx_gaussian_psf_kernel", "rbx_gaussian_lsf_kernel",
     "rbx_pipeline_host",
     "rbx_rotate_galaxy", "rbx_rotate_galaxy_workspace_bytes",
+    "rbx_apply_noise", "rbx_apply_noise_workspace_bytes", "rbx_noise_samples",
     "rbx_profile_enable", "rbx_profile_fused",
 ]
 
@@ -88,6 +89,10 @@ def lib() -> C.CDLL:
         "rbx_pipeline_host": [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, vp],
     }
     sigs["rbx_rotate_galaxy"] = [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp, sz, vp]
+    sigs["rbx_apply_noise"] = [vp, vp, i32, i32, i32, f32, i32, C.c_uint32, C.c_uint32, vp, sz, vp]
+    sigs["rbx_noise_samples"] = [vp, vp, i64, i32, C.c_uint32, C.c_uint32, vp]
+    L.rbx_apply_noise_workspace_bytes.argtypes = [i32, i32]
+    L.rbx_apply_noise_workspace_bytes.restype = sz
     L.rbx_rotate_galaxy_workspace_bytes.argtypes = []
     L.rbx_rotate_galaxy_workspace_bytes.restype = sz
     for name, args in sigs.items():

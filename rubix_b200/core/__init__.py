@@ -9,3 +9,4 @@ from .telescope import (get_filter_particles, get_spatial_bin_edges, get_spaxel_
                         get_telescope)
 from .pipeline import RubixPipeline  # noqa: F401
 from .rotation import get_galaxy_rotation  # noqa: F401
+from .noise import get_apply_noise  # noqa: F401

@@ -7,8 +7,8 @@ and composition for the stages this package implements (no jax.jit: every stage 
 kernels on the current stream, the only synchronisation is at the end of ``run``).
 
 ``rotate_galaxy`` (the stage right before the path) runs on the device when the
-config carries ``galaxy.rotation``; ``apply_noise`` (8(f) #3) has no CUDA implementation here and is
-skipped with a warning unless supplied through ``extra_functions``.
+config carries ``galaxy.rotation``, ``apply_noise`` (the stage right after it, 8(f) #3) when it carries
+``telescope.noise``; a stage whose config block is absent is skipped with a warning.
 """
 
 from __future__ import annotations
@@ -27,6 +27,7 @@ from .data import RubixData, get_reshape_data, make_rubix_data
 from .ifu import (get_calculate_datacube, get_calculate_spectra, get_doppler_shift_and_resampling,
                   get_scale_spectrum_by_mass)
 from .lsf import get_convolve_lsf
+from .noise import get_apply_noise
 from .psf import get_convolve_psf
 from .rotation import get_galaxy_rotation
 from .ssp import get_ssp
@@ -139,7 +140,8 @@ class RubixPipeline:
         self.logger.info("Setting up the pipeline...")
         c = self.user_config
         rot = [get_galaxy_rotation(c)] if "rotation" in c.get("galaxy", {}) else []
-        return rot + [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
+        noise = [get_apply_noise(c)] if "noise" in c.get("telescope", {}) else []
+        return rot + noise + [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
                 get_scale_spectrum_by_mass(c), get_doppler_shift_and_resampling(c), get_calculate_datacube(c),
                 get_convolve_psf(c), get_convolve_lsf(c)] + self.extra_functions
 
@@ -154,7 +156,7 @@ class RubixPipeline:
             if name in registry:
                 chain.append(copy.deepcopy(registry[name]))  # rubix/pipeline/transformer.py:18
             elif name in NOT_ON_PATH:
-                self.logger.warning(f"stage {name} is outside the B200 hot path and was not supplied: skipped")
+                self.logger.warning(f"stage {name} has no configuration block (galaxy.rotation / telescope.noise): skipped")
             else:
                 raise RuntimeError(f"Transformer {name} not found in the registered functions")
         return chain

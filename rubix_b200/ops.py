@@ -152,6 +152,33 @@ def rotate_galaxy(coords, velocity, mass, halfmass_radius: float, alpha: float, 
     return out_c, out_v, R.reshape(3, 3)
 
 
+NOISE_DISTRIBUTIONS = {"normal": 0, "uniform": 1}
+
+
+def apply_noise(cube, signal_to_noise: float, distribution: str = "normal", key=(0, 0)) -> torch.Tensor:
+    """rubix/core/noise.py:63-78: cube + cube * N * S2N (``key`` = the two words of jax.random.PRNGKey(0))."""
+    if distribution not in NOISE_DISTRIBUTIONS:
+        raise ValueError(f"Invalid noise type: {distribution}. Supported types: {list(NOISE_DISTRIBUTIONS)}")
+    cube = dev(cube)
+    ny, nx, W = cube.shape
+    out = torch.empty_like(cube)
+    L = _lib.lib()
+    ws = _workspace(L.rbx_apply_noise_workspace_bytes(ny, nx))
+    _lib.check(L.rbx_apply_noise(_p(cube), _p(out), ny, nx, W, float(signal_to_noise), NOISE_DISTRIBUTIONS[distribution],
+                                 int(key[0]), int(key[1]), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def noise_samples(n: int, distribution: str = "normal", key=(0, 0)):
+    """The raw sample stream of apply_noise and its 32-bit words (tests)."""
+    _require_cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    bits = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().rbx_noise_samples(_p(out), _p(bits), n, NOISE_DISTRIBUTIONS[distribution], int(key[0]),
+                                            int(key[1]), _stream()))
+    return out, bits
+
+
 def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
     n = metallicity.numel()

@@ -592,3 +592,33 @@ def test_rotate_then_bin(ops, plans, bc03, muse_wave):
     rows_face = (cubes["face"].sum(axis=1) > 0).sum() + (cubes["face"].sum(axis=0) > 0).sum()
     rows_edge = min((cubes["edge"].sum(axis=1) > 0).sum(), (cubes["edge"].sum(axis=0) > 0).sum())
     assert rows_edge <= 3 and rows_face >= 20
+
+
+# ---- apply_noise -----------------------------------------------------------------------
+def test_noise_stream_matches_oracle(ops):
+    """The counter-based random words are integer work: bit-exact against the oracle's threefry; the float
+    mapping (uniform, sqrt(2) erfinv) to 1e-6."""
+    n = 100003
+    for dist in ("normal", "uniform"):
+        smp, bits = ops.noise_samples(n, dist)
+        assert np.array_equal(bits.cpu().numpy().view(np.uint32), orc.random_bits((0, 0), n))
+        ref = orc.sample_noise(n, dist)
+        # float32 evaluation of w = -log1p(-u^2) and the erfinv polynomial against the oracle's float64 one: the
+        # cancellation in 1 - u^2 costs a few 1e-6 relative in the tails (|N| > 3)
+        assert (np.abs(smp.cpu().numpy() - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))).all()
+    smp7, bits7 = ops.noise_samples(1000, "normal", key=(7, 11))
+    assert np.array_equal(bits7.cpu().numpy().view(np.uint32), orc.random_bits((7, 11), 1000))
+
+
+@pytest.mark.parametrize("shape", [(25, 25, 3721), (7, 9, 130)])
+@pytest.mark.parametrize("dist", ["normal", "uniform"])
+def test_apply_noise_matches_oracle(ops, shape, dist):
+    rng = np.random.default_rng(31)
+    cube = (rng.random(shape) * 3 + 0.2).astype(np.float32)
+    out = ops.apply_noise(cube, 12.5, dist).cpu().numpy()
+    ref = orc.apply_noise(cube, 12.5, dist)
+    assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
+    assert np.abs(out - cube).max() > 0
+    # a spaxel without flux switches the noise off altogether (the reference's NaN-propagating median)
+    cube[1, 2] = 0.0
+    assert np.array_equal(ops.apply_noise(cube, 12.5, dist).cpu().numpy(), cube)

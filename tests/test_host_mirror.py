@@ -189,3 +189,21 @@ def test_rotation_factory_name():
     for rot in ({"type": "face-on"}, {"type": "edge-on"}, {"alpha": 10, "beta": 20, "gamma": 30}):
         fn = get_galaxy_rotation({"galaxy": {"rotation": rot}, "data": {"args": {"particle_type": ["stars"]}}})
         assert fn.__name__ == "rotate_galaxy"  # the YAML node name (pipeline_config.yml)
+
+
+# ---- rubix/core/noise.py ---------------------------------------------------------------------------
+@pytest.mark.parametrize("tel,msg", [
+    ({}, "Noise information not provided in telescope config"),
+    ({"noise": {"noise_distribution": "normal"}}, "Signal to noise information not provided in noise config"),
+    ({"noise": {"signal_to_noise": 1}}, "Noise distribution not provided in noise config"),
+])
+def test_noise_config_errors(tel, msg):
+    from rubix_b200.core import get_apply_noise
+    with pytest.raises(ValueError, match=msg):
+        get_apply_noise({"telescope": tel})
+
+
+def test_noise_factory_name():
+    from rubix_b200.core import get_apply_noise
+    fn = get_apply_noise({"telescope": {"noise": {"signal_to_noise": 1, "noise_distribution": "normal"}}})
+    assert fn.__name__ == "apply_noise"

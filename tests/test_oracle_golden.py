@@ -275,3 +275,31 @@ def test_inertia_tensor_padding_quirk():
     assert np.allclose(R.T @ R, np.eye(3), atol=1e-12)
     w = np.diag(R.T @ want @ R)
     assert np.all(np.diff(w) >= 0)
+
+
+# ---- apply_noise (the stage after the path) --------------------------------------------------------
+def test_threefry2x32_known_answers():
+    """Random123 / jax tests/random_test.py testThreefry2x32 vectors."""
+    kat = [((0x0, 0x0), (0x0, 0x0), (0x6b200159, 0x99ba4efe)),
+           ((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x1cb996fc, 0xbb002be7)),
+           ((0x13198a2e, 0x03707344), (0x243f6a88, 0x85a308d3), (0xc4923a9c, 0x483df7a0))]
+    for key, ctr, want in kat:
+        a, b = orc.threefry2x32(key, np.array([ctr[0]], np.uint32), np.array([ctr[1]], np.uint32))
+        assert (int(a[0]), int(b[0])) == want
+
+
+def test_noise_samples_and_s2n():
+    n = orc.sample_noise(200000)
+    assert abs(n.mean()) < 0.01 and abs(n.std() - 1.0) < 0.01 and np.isfinite(n).all()
+    u = orc.sample_noise(200000, "uniform")
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+    with pytest.raises(ValueError, match="Invalid noise type"):
+        orc.sample_noise(4, "poisson")
+    rng = np.random.default_rng(4)
+    cube = rng.random((6, 5, 40)) + 0.1
+    s2n = orc.calculate_S2N(cube, 10.0)
+    flux = cube.sum(-1)
+    assert np.allclose(s2n, np.sqrt(np.median(flux)) / 10.0 / np.sqrt(flux))
+    cube[2, 3] = 0.0   # one spaxel without flux: jnp.median returns NaN -> nan_to_num -> 0 -> no noise at all
+    assert np.array_equal(orc.calculate_S2N(cube, 10.0), np.zeros((6, 5)))
+    assert np.array_equal(orc.apply_noise(cube, 10.0), cube)
