@@ -980,6 +980,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         }
       };
       issue_rows(0, 0);
+      float S2[WK];              // cubic: spectrum of the second particle of a pair
+      bool pair_pending = false;
+#pragma unroll
+      for (int r = 0; r < WK; ++r) S2[r] = 0.f;
     for (int qi = 0; qi < nb; ++qi) {
       const float *rb = s_rec + qi * RS;
       const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, -
@@ -987,37 +991,70 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
 
       // ---- mass-weighted spectrum at my eight knots ------------------------------------------------
+      // Cubic (16 rows per particle, no room to keep them in registers): when the NEXT particle reads the same
+      // template cell, its spectrum S2 is accumulated from the same row vectors and it skips its own loads.
       float S[WK + 1];
+      const bool second = NT > 1 && pair_pending;
+      bool pair_next = false;
+      if (second) {
 #pragma unroll
-      for (int r = 0; r < WK; ++r) S[r] = 0.f;
+        for (int r = 0; r < WK; ++r) S[r] = S2[r];
+      } else {
+        if (NT > 1 && qi + 1 < nb) pair_next = __float_as_int(s_rec[(qi + 1) * RS + 2]) == __float_as_int(r0.z);
+        const float *rb2 = rb + RS;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-        if (interior) {
-          float4 cur[8];
+        for (int r = 0; r < WK; ++r) { S[r] = 0.f; S2[r] = 0.f; }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) cur[u] = nf[u];
-          if (t + 1 < NT) issue_rows(qi, t + 1);
-          else if (qi + 1 < nb) issue_rows(qi + 1, 0);
+        for (int t = 0; t < NT; ++t) {
+          const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+          float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pair_next) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
+          const float wv2[4] = {w2.x, w2.y, w2.z, w2.w};
+          if (interior) {
+            float4 cur[8];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
-            S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
-            S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
-            S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
-            S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
+            for (int u = 0; u < 8; ++u) cur[u] = nf[u];
+            if (t + 1 < NT) {
+              issue_rows(qi, t + 1);
+            } else {
+              const int nq = qi + (pair_next ? 2 : 1);
+              if (nq < nb) issue_rows(nq, 0);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
+              S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
+              S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
+              S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
+              S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
+            }
+            if (NT > 1 && pair_next) {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
+                S2[0] = fmaf(wv2[a], lo.x, S2[0]); S2[1] = fmaf(wv2[a], lo.y, S2[1]);
+                S2[2] = fmaf(wv2[a], lo.z, S2[2]); S2[3] = fmaf(wv2[a], lo.w, S2[3]);
+                S2[4] = fmaf(wv2[a], hi.x, S2[4]); S2[5] = fmaf(wv2[a], hi.y, S2[5]);
+                S2[6] = fmaf(wv2[a], hi.z, S2[6]); S2[7] = fmaf(wv2[a], hi.w, S2[7]);
+              }
+            }
+          } else {
+            // lanes at the ends of the SSP grid: clamped scalar loads (jnp.interp end values)
+            const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
+            const float *f = tab[t] + row;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int r = 0; r < WK; ++r) {
+                const float fv = __ldg(f + off[a] + jc[r]);
+                S[r] = fmaf(wv[a], fv, S[r]);
+                if (NT > 1) S2[r] = fmaf(wv2[a], fv, S2[r]);
+              }
           }
-        } else {
-          // lanes at the ends of the SSP grid: clamped scalar loads (jnp.interp end values)
-          const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
-          const float *f = tab[t] + row;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int r = 0; r < WK; ++r) S[r] = fmaf(wv[a], __ldg(f + off[a] + jc[r]), S[r]);
         }
       }
+      pair_pending = pair_next;
 
       // ---- shifted positions, first channel at or above each knot ------------------------------------
       float x[WK], e[WK + 1];
