@@ -92,6 +92,29 @@ int build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mas
                     size_t ws_bytes, void *stream, int accumulate, const float *d_coords, const float *d_edges,
                     int n_edges, int mark_outside);
 
+// ---- packed float32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot for two IEEE operations, each lane
+// an ordinary round-to-nearest op, so results are bit-identical to the scalar form -------------------------
+__device__ __forceinline__ void ffma2s(float &d0, float &d1, float a0, float a1, float b0, float b1) {  // d = a * b + d
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2o(float &d0, float &d1, float a0, float a1, float b0, float b1, float c0, float c1) {  // d = a * b + c
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fmul2s(float &d0, float &d1, float a0, float a1, float b0, float b1) {  // d = a * b
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fadd2s(float &d0, float &d1, float a0, float a1, float b0, float b1) {  // d = a + b
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rc, ra, rb;\nmov.b64 {%0, %1}, rc;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // ---- small device helpers ---------------------------------------------------------------------
 // searchsorted(a, v, side='right') on a sorted array: number of elements <= v (NaN v -> n, like numpy/XLA
 // where NaN sorts last).

@@ -1024,19 +1024,19 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
-              S[0] = fmaf(wv[a], lo.x, S[0]); S[1] = fmaf(wv[a], lo.y, S[1]);
-              S[2] = fmaf(wv[a], lo.z, S[2]); S[3] = fmaf(wv[a], lo.w, S[3]);
-              S[4] = fmaf(wv[a], hi.x, S[4]); S[5] = fmaf(wv[a], hi.y, S[5]);
-              S[6] = fmaf(wv[a], hi.z, S[6]); S[7] = fmaf(wv[a], hi.w, S[7]);
+              ffma2s(S[0], S[1], wv[a], wv[a], lo.x, lo.y);
+              ffma2s(S[2], S[3], wv[a], wv[a], lo.z, lo.w);
+              ffma2s(S[4], S[5], wv[a], wv[a], hi.x, hi.y);
+              ffma2s(S[6], S[7], wv[a], wv[a], hi.z, hi.w);
             }
             if (NT > 1 && pair_next) {
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
-                S2[0] = fmaf(wv2[a], lo.x, S2[0]); S2[1] = fmaf(wv2[a], lo.y, S2[1]);
-                S2[2] = fmaf(wv2[a], lo.z, S2[2]); S2[3] = fmaf(wv2[a], lo.w, S2[3]);
-                S2[4] = fmaf(wv2[a], hi.x, S2[4]); S2[5] = fmaf(wv2[a], hi.y, S2[5]);
-                S2[6] = fmaf(wv2[a], hi.z, S2[6]); S2[7] = fmaf(wv2[a], hi.w, S2[7]);
+                ffma2s(S2[0], S2[1], wv2[a], wv2[a], lo.x, lo.y);
+                ffma2s(S2[2], S2[3], wv2[a], wv2[a], lo.z, lo.w);
+                ffma2s(S2[4], S2[5], wv2[a], wv2[a], hi.x, hi.y);
+                ffma2s(S2[6], S2[7], wv2[a], wv2[a], hi.z, hi.w);
               }
             }
           } else {
@@ -1143,10 +1143,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
       }
 #pragma unroll
-      for (int r = 0; r < WK; ++r) {
-        cv[r].x = fmaf(sc, dmv[r] * gx[r], cv[r].x);
-        cv[r].y = fmaf(sc, dmv[r], cv[r].y);
-      }
+      for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, dmv[r] * gx[r], dmv[r]);
 #pragma unroll
       for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
       __syncwarp();
