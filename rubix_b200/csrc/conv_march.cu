@@ -331,12 +331,14 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
     if (c < TL) {
       float o[TX];
       if constexpr (TX % 2 == 0) {
+        // even TX: the tile is stored channel-major, [channel][column], so a column PAIR is one 64-bit load
+        // (a half-warp's 16 addresses, TX words apart, fall into 16 different bank pairs) feeding one FFMA2
+        const float2 *tile = reinterpret_cast<const float2 *>(&s_mid[b][0][0]);   // [NT][TX / 2]
 #pragma unroll
         for (int ox = 0; ox < TX; ox += 2) {
-          float2 acc = fmul2(tp.kl2[0], make_float2(s_mid[b][ox][c], s_mid[b][ox + 1][c]));
+          float2 acc = fmul2(tp.kl2[0], tile[c * (TX / 2) + ox / 2]);
 #pragma unroll
-          for (int t = 1; t < KE; ++t)
-            acc = ffma2(tp.kl2[t], make_float2(s_mid[b][ox][c + t], s_mid[b][ox + 1][c + t]), acc);
+          for (int t = 1; t < KE; ++t) acc = ffma2(tp.kl2[t], tile[(c + t) * (TX / 2) + ox / 2], acc);
           o[ox] = acc.x; o[ox + 1] = acc.y;
         }
       } else {
@@ -410,8 +412,14 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
       if (yy - 1 >= yfirst && yy - 1 + NST < ylast) issue_row(yy - 1 + NST);
     }
     if (j >= 0) {
+      if constexpr (TX % 2 == 0) {
+        float2 *tile = reinterpret_cast<float2 *>(&s_mid[j & 1][0][0]);   // [NT][TX / 2], see lsf_store
 #pragma unroll
-      for (int ox = 0; ox < TX; ++ox) s_mid[j & 1][ox][c] = e[ox];
+        for (int ox = 0; ox < TX; ox += 2) tile[c * (TX / 2) + ox / 2] = make_float2(e[ox], e[ox + 1]);
+      } else {
+#pragma unroll
+        for (int ox = 0; ox < TX; ++ox) s_mid[j & 1][ox][c] = e[ox];
+      }
       mbar_arrive(smem_addr(&s_bar[NST + (j & 1)]));
     }
   }
@@ -428,7 +436,7 @@ psf_lsf_march_kernel(const float *__restrict__ in, float *__restrict__ out, int 
                      int rows_per_seg, int use_bulk, const __grid_constant__ MarchTaps tp) {
   constexpr int TL = NT - (KE - 1);
   constexpr int HE = (KE - 1) / 2;
-  __shared__ float s_mid[2][TX][NT];
+  __shared__ __align__(16) float s_mid[2][TX][NT];
   __shared__ __align__(128) float s_in[kMarchStages][TX + P - 1][kMarchRowFloats];
   __shared__ __align__(8) uint64_t s_bar[kMarchStages + 2];
   const int tiles_x = (nx + TX - 1) / TX;
