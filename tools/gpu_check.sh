@@ -12,6 +12,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 timeout 600 python bench.py --method cubic --no-cpu > $OUT/bench_cubic.json 2>> $OUT/bench.err
 timeout 600 python bench.py --particles 10000000 --no-cpu --steps 5 > $OUT/bench_1e7.json 2>> $OUT/bench.err
 timeout 600 python bench.py --particles 10000000 --spaxels 150 --no-cpu --steps 5 > $OUT/bench_1e7_s150.json 2>> $OUT/bench.err
+timeout 600 python bench.py --galaxies 8 --no-cpu --steps 5 > $OUT/bench_survey8.json 2>> $OUT/bench.err
 timeout 600 python tools/bench_stages.py > $OUT/stages.json 2> $OUT/stages.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_cube -s 3 -c 1 -o $OUT/prof_fused -f python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_fused.log 2>&1
