@@ -15,7 +15,10 @@ ap.add_argument("--particles", type=int, default=1_000_000)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--conv-only", action="store_true")
 args = ap.parse_args()
-peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except (OSError, ValueError, KeyError, TypeError):
+    peak = 6650.0
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
 
