@@ -75,7 +75,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
                             const float *__restrict__ coords, const float *__restrict__ edges, int n_edges,
                             int mark_outside, int edges_smem) {
   extern __shared__ int s_dyn[];
-  int *s_hist = s_dyn;                                  // per-block spaxel histogram (when it fits)
+  int *s_hist = s_dyn;   // small cubes: per-block spaxel histogram; large cubes: count_runs_kernel after the sort
   float *s_axes = reinterpret_cast<float *>(s_dyn + (smem_hist ? nseg : 0));   // SSP metallicity and age axes
   float *s_edges = s_axes + p.nz + p.na;
   if (smem_hist)
@@ -119,7 +119,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     if (valid) {
       uint32_t cell = (uint32_t)((i - 1) * (p.na - 1) + (j - 1));
       key = ((uint32_t)px << cell_bits) | (cell >> cell_shift);
-      atomicAdd(smem_hist ? s_hist + px : counts + px, 1);
+      if (smem_hist) atomicAdd(s_hist + px, 1);
       dmin = fminf(dmin, d);
       dmax = fmaxf(dmax, d);
       ++nvalid;
@@ -155,6 +155,20 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
       const int c = s_hist[s];
       if (c) atomicAdd(counts + s, c);
     }
+  }
+}
+
+// Per-spaxel particle counts from the SORTED keys: a spaxel's particles are one run, counts = run length
+// (no histogram atomics in prep_kernel).  counts is zeroed beforehand; invalid keys sort behind every spaxel.
+__global__ void count_runs_kernel(const uint32_t *__restrict__ keys_sorted, int n, int nseg, int cell_bits,
+                                  int *__restrict__ counts) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const int s = (int)(keys_sorted[q] >> cell_bits);
+    if (s >= nseg) continue;
+    const int sp = q > 0 ? (int)(keys_sorted[q - 1] >> cell_bits) : -1;
+    const int sn = q + 1 < n ? (int)(keys_sorted[q + 1] >> cell_bits) : nseg;
+    if (sp != s) atomicSub(counts + s, q);      // run start:  counts[s] -= first index
+    if (sn != s) atomicAdd(counts + s, q + 1);  // run end:    counts[s] += one past the last index
   }
 }
 
@@ -1572,12 +1586,14 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   const int threads = 256;
   int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
   {
-    const size_t hist_bytes = sizeof(int) * (size_t)nseg;
-    const int smem_hist = hist_bytes <= 160 * 1024 ? 1 : 0;
     const int edges_smem = (d_coords && n_edges <= 4096) ? 1 : 0;
-    const size_t dyn = (smem_hist ? hist_bytes : 0) + sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? n_edges : 0));
-    // the per-block histogram is flushed with one atomic per non-empty bin: fewer blocks for big cubes
-    int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, nseg <= 4096 ? 148 * 8 : 148 * 2) : blocks;
+    // spaxel counts: a per-block shared-memory histogram for MUSE-size cubes (one launch less); for large cubes
+    // (150 x 150: 90 KB of histogram per block would halve the occupancy and cost 22500 flush atomics per block)
+    // the run lengths of the sorted keys
+    const int smem_hist = nseg <= 4096 ? 1 : 0;
+    const size_t dyn = (smem_hist ? sizeof(int) * (size_t)nseg : 0) +
+                       sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? n_edges : 0));
+    const int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, 148 * 8) : blocks;
     if (dyn > 48 * 1024)
       RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     prep_kernel<<<pblocks, threads, dyn, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n, nseg, ws.cell_bits,
@@ -1591,6 +1607,11 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, cb, ws.keys_in, ws.keys_out, ws.idx_in, ws.idx_out,
                                               (int)n, 0, ws.end_bit, stream));
   count_launch(3);
+  if (nseg > 4096) {
+    count_runs_kernel<<<blocks, threads, 0, stream>>>(ws.keys_out, (int)n, nseg, ws.cell_bits, ws.counts);
+    count_launch();
+    RBX_LAUNCH_OK();
+  }
   int small_shift = 2, tail_shift = 3;
   if (const char *e = getenv("RBX_SMALL_SHIFT")) small_shift = std::max(0, std::min(5, atoi(e)));
   if (const char *e = getenv("RBX_TAIL_SHIFT")) tail_shift = std::max(1, std::min(6, atoi(e)));
@@ -1633,7 +1654,7 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   count_launch();
   RBX_LAUNCH_OK();
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
-  dim3 rgrid((v.W + 255) / 256, std::min(nseg, 65535));
+  dim3 rgrid((v.W + 255) / 256, std::min(nseg, 1184));   // blocks loop over spaxels; most have nothing to add
   reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube, accumulate);
   count_launch();
   RBX_LAUNCH_OK();
