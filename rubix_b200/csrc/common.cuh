@@ -157,10 +157,19 @@ __device__ __forceinline__ void ssp_cell(const PlanView &p, float zq, float aq, 
   j = min(max(ss_right(p.agrid, p.na, aq), 1), p.na - 1);
 }
 
+__device__ inline void ssp_terms_at(const PlanView &p, float zq, float aq, float mass, int i, int j, bool inside,
+                                    SspTerms &o);
+
 __device__ inline void ssp_terms(const PlanView &p, float zq, float aq, float mass, SspTerms &o) {
   int i, j;
   bool inside;
   ssp_cell(p, zq, aq, i, j, inside);
+  ssp_terms_at(p, zq, aq, mass, i, j, inside, o);
+}
+
+// the same with the cell (i, j) of ssp_cell() already known
+__device__ inline void ssp_terms_at(const PlanView &p, float zq, float aq, float mass, int i, int j, bool inside,
+                                    SspTerms &o) {
   if (!inside) { o.n = 0; return; }
   float x0 = p.zgrid[i - 1], x1 = p.zgrid[i], y0 = p.agrid[j - 1], y1 = p.agrid[j];
   float dx = x1 - x0, dy = y1 - y0;

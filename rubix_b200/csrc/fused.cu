@@ -124,7 +124,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
       dmax = fmaxf(dmax, d);
       ++nvalid;
       SspTerms tm;
-      ssp_terms(p, met[q], age[q], mass[q], tm);
+      ssp_terms_at(p, met[q], age[q], mass[q], i, j, inside, tm);
       float4 *r = reinterpret_cast<float4 *>(rec + (size_t)q * stride);
       r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), 0.f);
       r[1] = make_float4(tm.w[0], tm.w[1], tm.w[2], tm.w[3]);
