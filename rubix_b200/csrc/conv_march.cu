@@ -95,7 +95,7 @@ struct Cols {
 template <int P, int KE, int TX, int NT, bool EDGE>
 __device__ __forceinline__ void march_body(const float *__restrict__ in, float *__restrict__ out, int ny, int nx, int W,
                                            int pin, int pout, int x0, int w0, int ya, int yb, const MarchTaps &tp,
-                                           float (&s_mid)[2][TX][NT]) {
+                                           float (&s_mid)[4][TX][NT]) {
   constexpr int TL = NT - (KE - 1);      // output channels per block
   constexpr int HE = (KE - 1) / 2;       // spectral halo on each side
   constexpr int C = (P - 1) / 2;         // jax "same": out[y] = sum_m K[m] in[y - m + C]
@@ -217,8 +217,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // y pass of step u (u = step mod P, a compile-time value so that the P partial rows stay in registers):
 // the x-convolved input row h feeds output rows through taps 0..P-1; tap P-1 is a row's first
 // contribution (it initialises the slot), tap 0 its last -- that row is finished and returned in e.
-template <int P, int TX, int U>
-__device__ __forceinline__ void y_pass(float (&A)[P][TX], const float (&h)[TX], const MarchTaps &tp, float (&e)[TX]) {
+template <int P, int TX, int NT, int U>
+__device__ __forceinline__ void y_pass(float (&A)[P][TX], const float (&h)[TX], const MarchTaps &tp, float *dst, int c) {
   if constexpr (TX % 2 == 0) {
 #pragma unroll
     for (int m = 0; m < P - 1; ++m)
@@ -241,30 +241,40 @@ __device__ __forceinline__ void y_pass(float (&A)[P][TX], const float (&h)[TX], 
 #pragma unroll
     for (int ox = 0; ox < TX; ++ox) A[(U + P - 1) % P][ox] = tp.ky[P - 1] * h[ox];
   }
+  // the finished row (slot U % P) goes straight to the LSF tile `dst` (NULL while the first rows fill up):
+  // even TX channel-major [NT][TX / 2] pairs, odd TX column-major [TX][NT]
+  if (dst) {
+    if constexpr (TX % 2 == 0) {
+      float2 *tile = reinterpret_cast<float2 *>(dst);
 #pragma unroll
-  for (int ox = 0; ox < TX; ++ox) e[ox] = A[U % P][ox];
+      for (int ox = 0; ox < TX; ox += 2) tile[c * (TX / 2) + ox / 2] = make_float2(A[U % P][ox], A[U % P][ox + 1]);
+    } else {
+#pragma unroll
+      for (int ox = 0; ox < TX; ++ox) dst[ox * NT + c] = A[U % P][ox];
+    }
+  }
 }
 
-template <int P, int TX>
+template <int P, int TX, int NT>
 __device__ __forceinline__ void y_pass_dyn(int u, float (&A)[P][TX], const float (&h)[TX], const MarchTaps &tp,
-                                           float (&e)[TX]) {
+                                           float *dst, int c) {
   switch (u) {
-    case 0: y_pass<P, TX, 0>(A, h, tp, e); break;
-    case 1: if constexpr (P > 1) y_pass<P, TX, 1>(A, h, tp, e); break;
-    case 2: if constexpr (P > 2) y_pass<P, TX, 2>(A, h, tp, e); break;
-    case 3: if constexpr (P > 3) y_pass<P, TX, 3>(A, h, tp, e); break;
-    case 4: if constexpr (P > 4) y_pass<P, TX, 4>(A, h, tp, e); break;
-    case 5: if constexpr (P > 5) y_pass<P, TX, 5>(A, h, tp, e); break;
-    default: if constexpr (P > 6) y_pass<P, TX, 6>(A, h, tp, e); break;
+    case 0: y_pass<P, TX, NT, 0>(A, h, tp, dst, c); break;
+    case 1: if constexpr (P > 1) y_pass<P, TX, NT, 1>(A, h, tp, dst, c); break;
+    case 2: if constexpr (P > 2) y_pass<P, TX, NT, 2>(A, h, tp, dst, c); break;
+    case 3: if constexpr (P > 3) y_pass<P, TX, NT, 3>(A, h, tp, dst, c); break;
+    case 4: if constexpr (P > 4) y_pass<P, TX, NT, 4>(A, h, tp, dst, c); break;
+    case 5: if constexpr (P > 5) y_pass<P, TX, NT, 5>(A, h, tp, dst, c); break;
+    default: if constexpr (P > 6) y_pass<P, TX, NT, 6>(A, h, tp, dst, c); break;
   }
 }
 
 template <int P, int KE, int TX, int NT>
 __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, float *__restrict__ out, int ny, int nx,
                                                 int W, int pin, int pout, int x0, int w0, int ya, int yb, const MarchTaps &tp,
-                                                float (&s_mid)[2][TX][NT],
+                                                float (&s_mid)[4][TX][NT],
                                                 float (&s_in)[kMarchStages][TX + P - 1][kMarchRowFloats],
-                                                uint64_t (&s_bar)[kMarchStages + 2]) {
+                                                uint64_t (&s_bar)[kMarchStages + 4]) {
   static_assert(NT == 128 && kMarchStages == 4, "row staging is sized for 128 channels, 4 warps, 4 stages");
   constexpr int NST = kMarchStages;
   constexpr int TL = NT - (KE - 1);
@@ -289,8 +299,9 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
   if (c == 0) {
 #pragma unroll
     for (int st = 0; st < NST; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[st])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[NST])), "r"(NT));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[NST + 1])), "r"(NT));
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&s_bar[NST + b])), "r"(NT));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // columns outside the cube are never copied: zero them once, the readers need no predicate
@@ -363,10 +374,11 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
     for (int b = 0; b < TX; ++b) A[a][b] = 0.f;
 
   // Step i folds input row yy = ya - H + i in and finishes output row yy - C (emit index j = i - (P-1)).
-  // Order inside a step: [row i: stage wait, x pass, y pass] -> [wait for row j-1 in s_mid, LSF, store] ->
-  // [row j to s_mid, arrive].  The PSF arithmetic of row i sits between a thread's arrive for row j-1 and
-  // its wait for it, so the block never stalls on its slowest warp; two s_mid buffers suffice because a
-  // thread arrives for row j-1 only after its LSF of row j-2 (the previous user of the buffer row j takes).
+  // Order inside a step: [row i: stage wait, x pass, y pass with the finished row j stored to s_mid, arrive j]
+  // -> [wait for row j-1 in s_mid, LSF, store].  A whole step of arithmetic sits between a thread's arrive
+  // for a row and its wait for it, so the block never stalls on its slowest warp.  Four s_mid buffers: a
+  // thread that stores row j has passed the wait for row j-2, i.e. every thread has finished step j-3 and
+  // with it the LSF of row j-4, the previous user of the buffer.
   int u = 0;
   for (int i = 0; i < nsteps; ++i) {
     const int yy = ya - H + i;
@@ -397,36 +409,25 @@ __device__ __forceinline__ void march_body_bulk(const float *__restrict__ in, fl
 #pragma unroll
       for (int ox = 0; ox < TX; ++ox) h[ox] = 0.f;
     }
-    float e[TX];
-    y_pass_dyn<P, TX>(u, A, h, tp, e);
-    u = (u + 1 == P) ? 0 : u + 1;
     const int j = i - (P - 1);            // emit index of this step's finished row (valid when >= 0)
+    y_pass_dyn<P, TX, NT>(u, A, h, tp, j >= 0 ? &s_mid[j & 3][0][0] : nullptr, c);
+    u = (u + 1 == P) ? 0 : u + 1;
+    if (j >= 0) mbar_arrive(smem_addr(&s_bar[NST + (j & 3)]));
     if (j >= 1) {
-      mbar_wait(smem_addr(&s_bar[NST + ((j - 1) & 1)]), (uint32_t)(((j - 1) >> 1) & 1));
+      mbar_wait(smem_addr(&s_bar[NST + ((j - 1) & 3)]), (uint32_t)(((j - 1) >> 2) & 1));
       // every thread has read the stage of input row yy - 1: refill it NST rows ahead
       if (yy - 1 >= yfirst && yy - 1 + NST < ylast) issue_row(yy - 1 + NST);
-      lsf_store(ya + j - 1, (j - 1) & 1);
+      lsf_store(ya + j - 1, (j - 1) & 3);
     } else if (i >= 1) {
       // no finished row yet: the stage hand-over still needs every thread past its reads of row yy - 1
       __syncthreads();
       if (yy - 1 >= yfirst && yy - 1 + NST < ylast) issue_row(yy - 1 + NST);
     }
-    if (j >= 0) {
-      if constexpr (TX % 2 == 0) {
-        float2 *tile = reinterpret_cast<float2 *>(&s_mid[j & 1][0][0]);   // [NT][TX / 2], see lsf_store
-#pragma unroll
-        for (int ox = 0; ox < TX; ox += 2) tile[c * (TX / 2) + ox / 2] = make_float2(e[ox], e[ox + 1]);
-      } else {
-#pragma unroll
-        for (int ox = 0; ox < TX; ++ox) s_mid[j & 1][ox][c] = e[ox];
-      }
-      mbar_arrive(smem_addr(&s_bar[NST + (j & 1)]));
-    }
   }
   {
     const int j = nsteps - P;             // last finished row
-    mbar_wait(smem_addr(&s_bar[NST + (j & 1)]), (uint32_t)((j >> 1) & 1));
-    lsf_store(ya + j, j & 1);
+    mbar_wait(smem_addr(&s_bar[NST + (j & 3)]), (uint32_t)((j >> 2) & 1));
+    lsf_store(ya + j, j & 3);
   }
 }
 
@@ -436,9 +437,14 @@ psf_lsf_march_kernel(const float *__restrict__ in, float *__restrict__ out, int 
                      int rows_per_seg, int use_bulk, const __grid_constant__ MarchTaps tp) {
   constexpr int TL = NT - (KE - 1);
   constexpr int HE = (KE - 1) / 2;
-  __shared__ __align__(16) float s_mid[2][TX][NT];
-  __shared__ __align__(128) float s_in[kMarchStages][TX + P - 1][kMarchRowFloats];
-  __shared__ __align__(8) uint64_t s_bar[kMarchStages + 2];
+  // dynamic shared memory (more than the 48 KB static limit): [s_in | s_mid | s_bar]
+  extern __shared__ __align__(128) unsigned char march_smem[];
+  using InT = float[kMarchStages][TX + P - 1][kMarchRowFloats];
+  using MidT = float[4][TX][NT];
+  using BarT = uint64_t[kMarchStages + 4];
+  InT &s_in = *reinterpret_cast<InT *>(march_smem);
+  MidT &s_mid = *reinterpret_cast<MidT *>(march_smem + sizeof(InT));
+  BarT &s_bar = *reinterpret_cast<BarT *>(march_smem + sizeof(InT) + sizeof(MidT));
   const int tiles_x = (nx + TX - 1) / TX;
   const int x0 = (blockIdx.x % tiles_x) * TX;
   const int w0 = (blockIdx.x / tiles_x) * TL;
@@ -485,13 +491,16 @@ int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, int pin
                  cudaStream_t stream) {
   auto kernel = psf_lsf_march_kernel<P, KE, TX, NT>;
   constexpr int TL = NT - (KE - 1);
+  constexpr size_t kSmem = sizeof(float) * ((size_t)kMarchStages * (TX + P - 1) * kMarchRowFloats + 4 * TX * NT) +
+                           sizeof(uint64_t) * (kMarchStages + 4);
   static int slots_cached[64] = {};
   int dev = 0;
   RBX_CUDA_OK(cudaGetDevice(&dev));
   int slots = (dev >= 0 && dev < 64) ? slots_cached[dev] : 0;
   if (!slots) {
     int per_sm = 0, sms = 0;
-    RBX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, 0));
+    RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    RBX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, kSmem));
     RBX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     slots = std::max(1, per_sm * sms);
     if (dev >= 0 && dev < 64) slots_cached[dev] = slots;
@@ -514,7 +523,7 @@ int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, int pin
   static const bool no_bulk = getenv("RBX_MARCH_NO_BULK") != nullptr;
   // (an unaligned slab start inside a wider cube is fine: the bytes before it belong to the same cube)
   const int use_bulk = ((((uintptr_t)d_in & 15u) == 0 || pin > W) && !no_bulk) ? 1 : 0;
-  kernel<<<grid, NT, 0, stream>>>(d_in, d_out, ny, nx, W, pin, pout, rows, use_bulk, taps);
+  kernel<<<grid, NT, kSmem, stream>>>(d_in, d_out, ny, nx, W, pin, pout, rows, use_bulk, taps);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;
