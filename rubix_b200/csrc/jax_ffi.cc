@@ -116,4 +116,52 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxPsfLsf, PsfLsfImpl,
                                   .Arg<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Attr<int32_t>("ext"));
+// a0 + a1..a5 in one call: coords (n,3), edges (e,), velocity (n,3), mass, metallicity, age (n,) -> cube, workspace
+// (spaxel assignment and aperture filter inside the first kernel of the build)
+static ffi::Error AssignBuildCubeImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> coords, ffi::Buffer<ffi::F32> edges,
+                                      ffi::Buffer<ffi::F32> velocity, ffi::Buffer<ffi::F32> mass,
+                                      ffi::Buffer<ffi::F32> metallicity, ffi::Buffer<ffi::F32> age,
+                                      ffi::ResultBuffer<ffi::F32> cube, ffi::ResultBuffer<ffi::U8> workspace,
+                                      int64_t plan, int32_t num_spaxels, int32_t apply_filter) {
+  const int64_t n = mass.element_count();
+  return status(rbx_assign_build_cube(reinterpret_cast<const rbx_plan *>(plan), coords.typed_data(), edges.typed_data(),
+                                      (int)edges.element_count(), apply_filter, velocity.typed_data(), mass.typed_data(),
+                                      metallicity.typed_data(), age.typed_data(), n, num_spaxels, nullptr,
+                                      cube->typed_data(), workspace->typed_data(), workspace->size_bytes(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxAssignBuildCube, AssignBuildCubeImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<int32_t>("num_spaxels")
+                                  .Attr<int32_t>("apply_filter"));
+
+// a6 + a7 with the taps as static attributes (they are config constants inside rubix's closures:
+// rubix/core/psf.py:52-60, rubix/core/lsf.py:50-55): the HBM-bound marching kernel
+static ffi::Error PsfLsfTapsImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> cube, ffi::ResultBuffer<ffi::F32> out,
+                                 ffi::Span<const float> psf, int32_t psf_size, ffi::Span<const float> lsf, int32_t ext) {
+  auto d = cube.dimensions();
+  int rc = rbx_psf_lsf_taps(cube.typed_data(), out->typed_data(), (int)d[0], (int)d[1], (int)d[2], psf.begin(), psf_size,
+                            psf_size, lsf.begin(), (int)lsf.size(), ext, stream);
+  if (rc == RBX_ERR_UNSUPPORTED)
+    return ffi::Error(ffi::ErrorCode::kUnimplemented, "rubix_b200: taps need the device-tap call rbx_psf_lsf");
+  return status(rc);
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxPsfLsfTaps, PsfLsfTapsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<ffi::Span<const float>>("psf")
+                                  .Attr<int32_t>("psf_size")
+                                  .Attr<ffi::Span<const float>>("lsf")
+                                  .Attr<int32_t>("ext"));
 #endif  // RBX_HAVE_XLA_FFI

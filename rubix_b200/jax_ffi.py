@@ -16,7 +16,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _TARGETS = {"rbx_spaxel_assign": "RbxSpaxelAssign", "rbx_build_cube": "RbxBuildCube",
             "rbx_ssp_lookup": "RbxSspLookup", "rbx_doppler_resample": "RbxDopplerResample",
-            "rbx_psf_lsf": "RbxPsfLsf"}
+            "rbx_psf_lsf": "RbxPsfLsf", "rbx_assign_build_cube": "RbxAssignBuildCube",
+            "rbx_psf_lsf_taps": "RbxPsfLsfTaps"}
 _registered = False
 
 
@@ -62,3 +63,29 @@ def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12):
     register()
     return jax.ffi.ffi_call("rbx_psf_lsf", jax.ShapeDtypeStruct(cube.shape, cube.dtype))(
         cube, psf_kernel, lsf_kernel, ext=np.int32(ext))
+
+
+def assign_build_cube(plan_handle: int, workspace_bytes: int, coords, edges, velocity, mass, metallicity, age,
+                      num_spaxels: int, n_wave: int, apply_filter: bool = True):
+    """filter_particles + spaxel_assignment + the four fused ``ifu`` stages as one custom call."""
+    import jax
+    import jax.numpy as jnp
+    import numpy as np
+    register()
+    outs = (jax.ShapeDtypeStruct((num_spaxels, num_spaxels, n_wave), jnp.float32),
+            jax.ShapeDtypeStruct((workspace_bytes,), jnp.uint8))
+    cube, _ = jax.ffi.ffi_call("rbx_assign_build_cube", outs)(
+        coords, edges, velocity, mass, metallicity, age, plan=np.int64(plan_handle),
+        num_spaxels=np.int32(num_spaxels), apply_filter=np.int32(1 if apply_filter else 0))
+    return cube
+
+
+def psf_lsf_taps(cube, psf_kernel, lsf_kernel, ext: int = 12):
+    """PSF + LSF with the (host, config-constant) taps passed as static attributes."""
+    import jax
+    import numpy as np
+    register()
+    pk = np.ascontiguousarray(psf_kernel, dtype=np.float32)
+    lk = np.ascontiguousarray(lsf_kernel, dtype=np.float32).reshape(-1)
+    return jax.ffi.ffi_call("rbx_psf_lsf_taps", jax.ShapeDtypeStruct(cube.shape, cube.dtype))(
+        cube, psf=pk.reshape(-1), psf_size=np.int32(pk.shape[0]), lsf=lk, ext=np.int32(ext))
