@@ -262,6 +262,27 @@ def test_fused_cube_non_affine_grid(ops, bc03):
     _cube_close(out, ref, "fused non-affine grid")
 
 
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+@pytest.mark.parametrize("z,w0,w1,dw", [(0.3, 5000.0, 9000.0, 2.0), (0.0, 3800.0, 7000.0, 0.8), (0.02, 4000.0, 9800.0, 5.0),
+                                        (0.1, 4700.15, 9351.4, 30.0)])
+def test_fused_cube_other_arange_grids(ops, bc03, method, z, w0, w1, dw):
+    """Other redshifts and arange telescope grids: a different knot window, other chunk sizes and cell skews, a
+    grid much finer than the SSP's (0.8 A), a coarse one (5 A) and one coarser than the SSP's 20 A spacing
+    (30 A: two knots of a lane can share a channel -> the group kernel's CAS mode)."""
+    from rubix_b200 import synthetic
+    wave = np.arange(w0, w1, dw, dtype=np.float32)
+    plan = ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], wave, z, method=method)
+    edges = synthetic.spatial_edges(7)
+    lamz = (np.float32(1.0 + z) * bc03["wavelength"]).astype(np.float32)
+    data = _well_conditioned(synthetic.bench_g(4000, seed=23), lamz, wave)
+    out = _run_fused(ops, plan, data, edges, 7)
+    ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
+                                     data["age"], edges, 7, bc03["metallicity"], bc03["age"], bc03["wavelength"],
+                                     bc03["flux"], wave, z, method=method, dtype=np.float64, n_threads=8)
+    assert ref.max() > 0
+    _cube_close(out, ref, f"fused arange grid z={z} [{w0}, {w1}) step {dw} {method}")
+
+
 def test_fused_cube_large_fov_150(ops, plans, bc03, muse_wave):
     """BASELINE config 4 geometry (150 x 150 spaxels x 3721 channels) at a particle count the oracle
     finishes in seconds: many small spaxel segments, 335 MB cube."""
