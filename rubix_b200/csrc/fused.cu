@@ -994,10 +994,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         }
       };
       issue_rows(0, 0);
-      float S2[WK];              // cubic: spectrum of the second particle of a pair
-      bool pair_pending = false;
+      float S2[WK], S3[WK];      // cubic: spectra of the followers in a run of particles of one template cell
+      int run_pending = 0, run_len = 1;
 #pragma unroll
-      for (int r = 0; r < WK; ++r) S2[r] = 0.f;
+      for (int r = 0; r < WK; ++r) { S2[r] = 0.f; S3[r] = 0.f; }
     for (int qi = 0; qi < nb; ++qi) {
       const float *rb = s_rec + qi * RS;
       const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, -
@@ -1005,26 +1005,38 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
 
       // ---- mass-weighted spectrum at my eight knots ------------------------------------------------
-      // Cubic (16 rows per particle, no room to keep them in registers): when the NEXT particle reads the same
-      // template cell, its spectrum S2 is accumulated from the same row vectors and it skips its own loads.
+      // Cubic (16 rows per particle, no room to keep them in registers): when the next one or two particles read
+      // the same template cell, their spectra (S2, S3) are accumulated from the same row vectors and they skip
+      // their own loads.
       float S[WK + 1];
-      const bool second = NT > 1 && pair_pending;
-      bool pair_next = false;
-      if (second) {
+      const int follower = NT > 1 ? run_pending : 0;   // 0: leads a run, 1 / 2: first / second follower
+      int run_next = 0;
+      if (follower == 1) {
 #pragma unroll
         for (int r = 0; r < WK; ++r) S[r] = S2[r];
-      } else {
-        if (NT > 1 && qi + 1 < nb) pair_next = __float_as_int(s_rec[(qi + 1) * RS + 2]) == __float_as_int(r0.z);
-        const float *rb2 = rb + RS;
+        run_next = run_len > 2 ? 2 : 0;
+      } else if (follower == 2) {
 #pragma unroll
-        for (int r = 0; r < WK; ++r) { S[r] = 0.f; S2[r] = 0.f; }
+        for (int r = 0; r < WK; ++r) S[r] = S3[r];
+      } else {
+        int nfol = 0;   // followers of this particle
+        if (NT > 1 && qi + 1 < nb && __float_as_int(s_rec[(qi + 1) * RS + 2]) == __float_as_int(r0.z)) {
+          nfol = 1;
+          if (qi + 2 < nb && __float_as_int(s_rec[(qi + 2) * RS + 2]) == __float_as_int(r0.z)) nfol = 2;
+        }
+        run_len = 1 + nfol;
+        run_next = nfol ? 1 : 0;
+        const float *rb2 = rb + RS, *rb3 = rb + 2 * RS;
+#pragma unroll
+        for (int r = 0; r < WK; ++r) { S[r] = 0.f; S2[r] = 0.f; S3[r] = 0.f; }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
           const float wv[4] = {w.x, w.y, w.z, w.w};
-          float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pair_next) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
-          const float wv2[4] = {w2.x, w2.y, w2.z, w2.w};
+          float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f), w3 = w2;
+          if (nfol >= 1) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
+          if (nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + 4 + 4 * t);
+          const float wv2[4] = {w2.x, w2.y, w2.z, w2.w}, wv3[4] = {w3.x, w3.y, w3.z, w3.w};
           if (interior) {
             float4 cur[8];
 #pragma unroll
@@ -1032,7 +1044,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
             if (t + 1 < NT) {
               issue_rows(qi, t + 1);
             } else {
-              const int nq = qi + (pair_next ? 2 : 1);
+              const int nq = qi + 1 + nfol;
               if (nq < nb) issue_rows(nq, 0);
             }
 #pragma unroll
@@ -1043,7 +1055,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
               ffma2s(S[4], S[5], wv[a], wv[a], hi.x, hi.y);
               ffma2s(S[6], S[7], wv[a], wv[a], hi.z, hi.w);
             }
-            if (NT > 1 && pair_next) {
+            if (NT > 1 && nfol >= 1) {
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
@@ -1051,6 +1063,16 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
                 ffma2s(S2[2], S2[3], wv2[a], wv2[a], lo.z, lo.w);
                 ffma2s(S2[4], S2[5], wv2[a], wv2[a], hi.x, hi.y);
                 ffma2s(S2[6], S2[7], wv2[a], wv2[a], hi.z, hi.w);
+              }
+            }
+            if (NT > 1 && nfol >= 2) {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
+                ffma2s(S3[0], S3[1], wv3[a], wv3[a], lo.x, lo.y);
+                ffma2s(S3[2], S3[3], wv3[a], wv3[a], lo.z, lo.w);
+                ffma2s(S3[4], S3[5], wv3[a], wv3[a], hi.x, hi.y);
+                ffma2s(S3[6], S3[7], wv3[a], wv3[a], hi.z, hi.w);
               }
             }
           } else {
@@ -1063,12 +1085,12 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
               for (int r = 0; r < WK; ++r) {
                 const float fv = __ldg(f + off[a] + jc[r]);
                 S[r] = fmaf(wv[a], fv, S[r]);
-                if (NT > 1) S2[r] = fmaf(wv2[a], fv, S2[r]);
+                if (NT > 1) { S2[r] = fmaf(wv2[a], fv, S2[r]); S3[r] = fmaf(wv3[a], fv, S3[r]); }
               }
           }
         }
       }
-      pair_pending = pair_next;
+      run_pending = run_next;
 
       // ---- shifted positions, first channel at or above each knot ------------------------------------
       float x[WK], e[WK + 1];
