@@ -1,14 +1,18 @@
 // Fused a1..a5: particles -> (S*S, W) cube without materialising (n, L) or (n, W).
 //
 // Pipeline (all on the caller's stream, no host synchronisation):
-//   prep_kernel      validity, template cell, sort key = spaxel * ncell + cell, per-spaxel histogram,
-//                    min/max Doppler factor, per-particle record {d, 1/d, template row, weights * mass}
+//   prep_kernel      (optional) spaxel assignment + aperture filter, validity, template cell, sort key =
+//                    spaxel * ncell + cell, spaxel histogram (MUSE-size cubes), min/max Doppler factor,
+//                    per-particle record {d, 1/d, template row, weights * mass}
 //   cub radix sort   (key, particle index) pairs -- stable, so the summation order is deterministic
-//   segment_kernel   one block: segment starts, work items (segments split into <= psub particles),
-//                    SSP knot window for the observed Doppler range
-//   fused_cube_kernel persistent CTAs (one per SM); warp groups pull work items; per item the spaxel's
-//                    spectrum is accumulated in shared memory (no global atomics) and written once
+//   count_runs_kernel  (large cubes) spaxel counts from the run lengths of the sorted keys
+//   segment_kernel   one block: segment starts, work items (bulk items of psub particles, quarter-size tail
+//                    items behind them in the queue), SSP knot window for the observed Doppler range
+//   fused_cube_warp_kernel  persistent CTAs (one per SM), one warp per work item and particle, the spaxel's
+//                    spectrum accumulated in the warp's own shared-memory cells (no atomics), written once;
+//                    fused_cube_kernel (warp groups) for non-arange grids / SSP grids finer than the telescope's
 //   reduce_partials_kernel  spaxels that were split over several items: fixed-order sum of partial rows
+//                    (and NaN poisoning of the cube when a configuration did not fit)
 //
 // The algorithm of fused_cube_kernel is described above the kernel.  In short: for one particle the
 // reference evaluates p_w = jnp.interp(t_w, lam' = lam_z * d, s) for every telescope channel and rescales
