@@ -199,6 +199,41 @@ int rbx_noise_samples(float *d_out, uint32_t *d_bits, int64_t n, int distributio
                       uint32_t key1, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dust extinction, the calc_dusty_ifu variant (rubix/core/dust.py:15-65 -> apply_spaxel_extinction,
+ * rubix/spectra/dust/dust_extinction.py:169-358).
+ *
+ * rbx_dust_av: A_V of every star from the gas cells of its spaxel.  Per cell: 12 + log10(O/H) from
+ *   d_gas_metals (n_gas, n_metals; hydrogen = column 0, oxygen = column 4), the dust-to-gas ratio
+ *   1 / 10^(a + alpha (8.69 - x)) with h_dust_to_gas = {a_high, alpha_high, a_low, alpha_low, x_transition}
+ *   (HOST, Remy-Ruyer 2014 table 1; the high pair applies for x > x_transition), times mass * ext_const /
+ *   spaxel_area (ext_const = 3 pi Msun_g / kpc_cm^2 / (0.4 ln10 lambda_V[cm] rho_grain), dust_extinction.py:96-166).
+ *   Cells are sorted by (pixel, z) (jnp.lexsort, :240-245), accumulated along z per spaxel (:318) and
+ *   interpolated at the star's z with jnp.interp(left="extrapolate") on the reference's table, in which the
+ *   cells of all other spaxels sit at z * 1e30 with value 0 (:313-336).  d_av (n_star,) in input order; stars
+ *   with a pixel outside [0, n_spaxels) get 0.  d_cell_av_out (n_gas,) may be NULL (per-cell A_V, input order).
+ * rbx_apply_extinction: d_out[q, w] = d_spectra[q, w] * 10^(-0.4 * d_axav[w] * d_av[q])
+ *   (BaseExtRvModel.extinguish, dust_baseclasses.py:126-164; dust_extinction.py:341-356); d_axav (W,) is the
+ *   configuration's A(lambda)/A(V) curve.  d_out may alias d_spectra.
+ * rbx_build_cube_dusty: Doppler shift + resampling (rubix/spectra/ifu.py:224-266) of already mass-scaled SSP
+ *   spectra d_spectra (n, L), times the extinction factor, summed per spaxel into d_cube (num_spaxels^2, W)
+ *   (calculate_cube, rubix/spectra/ifu.py:270-288) -- the three stages doppler_shift_and_resampling ->
+ *   calculate_extinction -> calculate_datacube without the (n, W) intermediate.  d_av / d_axav NULL = no dust.
+ * ------------------------------------------------------------------------------------------- */
+size_t rbx_dust_av_workspace_bytes(int64_t n_gas, int n_spaxels);
+int rbx_dust_av(const float *d_gas_coords, const int32_t *d_gas_pixel, const float *d_gas_mass,
+                const float *d_gas_metals, int n_metals, int64_t n_gas, const float *d_star_coords,
+                const int32_t *d_star_pixel, int64_t n_star, int n_spaxels, const float *h_dust_to_gas,
+                float ext_const, float spaxel_area, float *d_av, float *d_cell_av_out, void *d_workspace,
+                size_t workspace_bytes, void *stream);
+int rbx_apply_extinction(const float *d_spectra, const float *d_av, const float *d_axav, int64_t n, int W,
+                         float *d_out, void *stream);
+size_t rbx_build_cube_dusty_workspace_bytes(int64_t n);
+int rbx_build_cube_dusty(const rbx_plan *plan, const float *d_spectra, const float *d_velocity,
+                         const int32_t *d_pixel, const float *d_av, const float *d_axav, int64_t n,
+                         int num_spaxels, float *d_cube, void *d_workspace, size_t workspace_bytes,
+                         void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience call: the whole path (filter -> spaxel -> fused cube -> PSF -> LSF) for
  * callers that hold numpy / host arrays.  Copies inputs H2D, runs the kernels, copies the cube
  * back; h_cube is (num_spaxels, num_spaxels, W).  h_psf (M,N) / h_lsf (K,) may be NULL to skip.

@@ -404,6 +404,239 @@ def apply_lsf(datacube, lsf_sigma, wave_resolution, extend_factor=12):
 
 
 # --------------------------------------------------------------------------------------
+# f4  dust extinction (calc_dusty_ifu): rubix/core/dust.py:15-65,
+#     rubix/spectra/dust/dust_extinction.py:13-358, extinction_models.py, generic_models.py
+# --------------------------------------------------------------------------------------
+MSUN_TO_GRAMS = 1.989e33     # rubix/config/rubix_config.yml:7
+KPC_TO_CM = 3.08568e21       # rubix/config/rubix_config.yml:6
+DUST_EFFECTIVE_WAVELENGTH = 5448.0  # Johnson V, dust_extinction.py:103
+
+#: Remy-Ruyer et al. 2014 table 1 as coded in dust_extinction.py:41-91: (a_high, alpha_high, a_low,
+#: alpha_low, x_transition); the single power laws have one branch.
+DUST_TO_GAS = {
+    ("MW", "power law slope free"): (2.21, 1.62, 2.21, 1.62, -np.inf),
+    ("MW", "broken power law fit"): (2.21, 1.00, 0.68, 3.08, 7.96),
+    ("Z", "power law slope free"): (2.21, 2.02, 2.21, 2.02, -np.inf),
+    ("Z", "broken power law fit"): (2.21, 1.00, 0.96, 3.10, 8.10),
+}
+
+
+def calculate_dust_to_gas_ratio(gas_metallicity, model, Xco, dtype=np.float64):
+    """dust_extinction.py:13-93: ``1 / 10**(a + alpha*(8.69 - x))`` with the branch of Table 1."""
+    if model == "power law slope fixed":
+        raise NotImplementedError("power law slope fixed not implemented yet.")
+    a_h, al_h, a_l, al_l, xt = DUST_TO_GAS[(Xco, model)]
+    x = np.asarray(gas_metallicity, dtype=dtype)
+    x_sol = dtype(8.69)
+    with np.errstate(over="ignore", invalid="ignore"):
+        hi = dtype(10.0) ** (dtype(a_h) + dtype(al_h) * (x_sol - x))
+        lo = dtype(10.0) ** (dtype(a_l) + dtype(al_l) * (x_sol - x))
+        return (dtype(1.0) / np.where(x > xt, hi, lo)).astype(dtype)
+
+
+def dust_extinction_constant(dust_grain_density, effective_wavelength=DUST_EFFECTIVE_WAVELENGTH):
+    """dust_extinction.py:150-162: A_V per unit dust surface density (Msun / kpc^2), a host scalar."""
+    conv = MSUN_TO_GRAMS / KPC_TO_CM ** 2
+    return 3.0 * np.pi * conv / (0.4 * np.log(10.0) * effective_wavelength * 1e-8 * dust_grain_density)
+
+
+def calculate_extinction(dust_column_density, dust_grain_density, dtype=np.float64):
+    return (np.asarray(dust_column_density, dtype=dtype) * dtype(dust_extinction_constant(dust_grain_density))).astype(dtype)
+
+
+def cardelli89(wave, Rv=3.1):
+    """extinction_models.py:104-178, evaluated on ``wave`` exactly as the reference passes it.
+
+    NB the CCM89 polynomials are functions of the wavenumber x = 1/lambda [1/micron], but
+    apply_spaxel_extinction hands ``wavelength / 1e4`` (microns) to ``evaluate`` unconverted
+    (dust_extinction.py:343-345), so the MUSE band lands in the branch ``0.3 <= wave < 1.1``
+    (a = 0.574 wave^1.61, b = -0.527 wave^1.61).  Restated literally: parity is with the reference."""
+    w = np.asarray(wave, dtype=np.float64)
+    a = np.zeros_like(w)
+    b = np.zeros_like(w)
+    ir = (0.3 <= w) & (w < 1.1)
+    opt = (1.1 <= w) & (w < 3.3)
+    nuv = (3.3 <= w) & (w <= 8.0)
+    fnuv = (5.9 <= w) & (w <= 8.0)
+    fuv = (8.0 < w) & (w <= 10.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        a = np.where(ir, 0.574 * w ** 1.61, a)
+        b = np.where(ir, -0.527 * w ** 1.61, b)
+        y = w - 1.82
+        a = np.where(opt, 1 + 0.17699 * y - 0.50447 * y ** 2 - 0.02427 * y ** 3 + 0.72085 * y ** 4
+                     + 0.01979 * y ** 5 - 0.77530 * y ** 6 + 0.32999 * y ** 7, a)
+        b = np.where(opt, 1.41338 * y + 2.28305 * y ** 2 + 1.07233 * y ** 3 - 5.38434 * y ** 4
+                     - 0.62251 * y ** 5 + 5.30260 * y ** 6 - 2.09002 * y ** 7, b)
+        a = np.where(nuv, 1.752 - 0.316 * w - 0.104 / ((w - 4.67) ** 2 + 0.341), a)
+        b = np.where(nuv, -3.09 + 1.825 * w + 1.206 / ((w - 4.62) ** 2 + 0.263), b)
+        y = w - 5.9
+        a = np.where(fnuv, a + (-0.04473 * y ** 2 - 0.009779 * y ** 3), a)
+        b = np.where(fnuv, b + (0.2130 * y ** 2 + 0.1207 * y ** 3), b)
+        y = w - 8.0
+        a = np.where(fuv, -1.073 - 0.628 * y + 0.137 * y ** 2 - 0.070 * y ** 3, a)
+        b = np.where(fuv, 13.670 + 4.257 * y - 0.420 * y ** 2 + 0.374 * y ** 3, b)
+    return a + b / Rv
+
+
+def _smoothstep(x, x_min, x_max):
+    """helpers.py:_smoothstep with N = 1: 3x^2 - 2x^3 on the clipped, normalised argument."""
+    x = np.clip((x - x_min) / (x_max - x_min), 0, 1)
+    return (3.0 - 2.0 * x) * x ** 2
+
+
+def _drude1d(x, amplitude, x_0, fwhm):
+    return amplitude * ((fwhm / x_0) ** 2) / ((x / x_0 - x_0 / x) ** 2 + (fwhm / x_0) ** 2)
+
+
+def _modified_drude(x, scale, x_o, gamma_o, asym):
+    gamma = 2.0 * gamma_o / (1.0 + np.exp(asym * (x - x_o)))
+    return scale * ((gamma / x_o) ** 2) / ((x / x_o - x_o / x) ** 2 + (gamma / x_o) ** 2)
+
+
+def _fm90(x, C1, C2, C3, C4, xo, gamma):
+    e = C1 + C2 * x
+    x2 = x ** 2
+    e = e + C3 * (x2 / ((x2 - xo ** 2) ** 2 + x2 * gamma ** 2))
+    y = np.where(x >= 5.9, x - 5.9, 0.0)
+    return np.where(x >= 5.9, e + C4 * (0.5392 * y ** 2 + 0.05644 * y ** 3), e)
+
+
+def _g23_nirmir(wave, params):
+    (scale, alpha, alpha2, swave, swidth, s1a, s1c, s1f, s1y, s2a, s2c, s2f, s2y) = params
+    p1 = scale * wave ** (-alpha)
+    p2 = scale * (swave ** (-alpha) / swave ** (-alpha2)) * wave ** (-alpha2)
+    wgt = _smoothstep(wave, swave - swidth / 2, swave + swidth / 2)
+    return p1 * (1.0 - wgt) + p2 * wgt + _modified_drude(wave, s1a, s1c, s1f, s1y) + _modified_drude(wave, s2a, s2c, s2f, s2y)
+
+
+def gordon23(wave, Rv=3.1):
+    """extinction_models.py:262-389 (Gordon et al. 2023), ``wave`` in microns."""
+    w = np.asarray(wave, dtype=np.float64)
+    a = np.zeros_like(w)
+    b = np.zeros_like(w)
+    ir = (1.0 <= w) & (w < 35.0)
+    opt = (0.3 <= w) & (w < 1.1)
+    uv = (0.09 <= w) & (w <= 0.3)
+    optir = (w >= 0.9) & (w <= 1.1)
+    uvopt = (w >= 0.3) & (w <= 0.33)
+    ir_a = [0.38526, 1.68467, 0.78791, 4.30578, 4.78338, 0.06652, 9.8434, 2.21205, -0.24703,
+            0.0267, 19.58294, 17.0, -0.27]
+    opt_a = [-0.35848, 0.7122, 0.08746, -0.05403, 0.00674, 0.03893, 2.288, 0.243, 0.02965, 2.054, 0.179,
+             0.01747, 1.587, 0.243]
+    opt_b = [0.12354, -2.68335, 2.01901, -0.39299, 0.03355, 0.18453, 2.288, 0.243, 0.19728, 2.054, 0.179,
+             0.1713, 1.587, 0.243]
+
+    def poly_drude(x, p):
+        c = p[:5]
+        poly = c[0] + x * (c[1] + x * (c[2] + x * (c[3] + x * c[4])))
+        return poly + _drude1d(x, p[5], p[6], p[7]) + _drude1d(x, p[8], p[9], p[10]) + _drude1d(x, p[11], p[12], p[13])
+
+    def powerlaw_b(x):
+        return -1.01251 * x ** 1.06099   # PowerLaw1d(amplitude=-1.01251, x_0=1, alpha=-1.06099)
+
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        x = 1.0 / w
+        a = np.where(ir, _g23_nirmir(w, ir_a), a)
+        b = np.where(ir, powerlaw_b(w), b)
+        a = np.where(opt, poly_drude(x, opt_a), a)
+        b = np.where(opt, poly_drude(x, opt_b), b)
+        wgt = _smoothstep(w, 0.9, 1.1)
+        a = np.where(optir, (1.0 - wgt) * poly_drude(x, opt_a) + wgt * _g23_nirmir(w, ir_a), a)
+        b = np.where(optir, (1.0 - wgt) * poly_drude(x, opt_b) + wgt * powerlaw_b(w), b)
+        fa = _fm90(x, 0.81297, 0.2775, 1.06295, 0.11303, 4.60, 0.99)
+        fb = _fm90(x, -2.97868, 1.89808, 3.10334, 0.65484, 4.60, 0.99)
+        a = np.where(uv, fa, a)
+        b = np.where(uv, fb, b)
+        wgt = _smoothstep(w, 0.3, 0.33)
+        a = np.where(uvopt, (1.0 - wgt) * fa + wgt * poly_drude(x, opt_a), a)
+        b = np.where(uvopt, (1.0 - wgt) * fb + wgt * poly_drude(x, opt_b), b)
+    return a + b * (1.0 / Rv - 1.0 / 3.1)
+
+
+EXTINCTION_MODELS = {"Cardelli89": cardelli89, "Gordon23": gordon23}
+
+
+def jnp_interp_left_extrapolate(x, xp, fp):
+    """``jnp.interp(x, xp, fp, left="extrapolate")``: as :func:`jnp_interp` without the left clamp."""
+    x, xp, fp = np.asarray(x), np.asarray(xp), np.asarray(fp)
+    i = np.clip(np.searchsorted(xp, x, side="right"), 1, len(xp) - 1)
+    df = fp[i] - fp[i - 1]
+    dx = xp[i] - xp[i - 1]
+    delta = x - xp[i - 1]
+    eps = np.spacing(np.finfo(xp.dtype).eps)
+    dx0 = np.abs(dx) <= eps
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        f = np.where(dx0, fp[i - 1], fp[i - 1] + (delta / np.where(dx0, 1, dx)) * df)
+    return np.where(x > xp[-1], fp[-1], f).astype(fp.dtype)
+
+
+def dust_cell_extinction(gas_mass, gas_metals, dust_grain_density, spaxel_area, model="broken power law fit",
+                         Xco="Z", dtype=np.float64):
+    """dust_extinction.py:283-297: A_V contribution of every gas cell (input order)."""
+    m = np.asarray(gas_metals, dtype=dtype)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        log_OH = dtype(12.0) + np.log10(m[:, 4] / (dtype(16.0) * m[:, 0]))
+    dtg = calculate_dust_to_gas_ratio(log_OH, model, Xco, dtype=dtype)
+    dust_mass = np.asarray(gas_mass, dtype=dtype) * dtg
+    return (calculate_extinction(dust_mass, dust_grain_density, dtype=dtype) / dtype(spaxel_area)).astype(dtype)
+
+
+def stars_av(gas_z, gas_pixel, gas_cell_extinction, star_z, star_pixel, n_spaxels, dtype=np.float64):
+    """dust_extinction.py:240-337, the reference algorithm spaxel by spaxel: both particle sets are
+    lexsorted by (pixel, z); for every spaxel the gas cells outside it are pushed to z * 1e30 with
+    value 0, the cumulative extinction of the cells inside is interpolated at the stars' z
+    (``left="extrapolate"``, right end value) and masked to the spaxel's stars.  Returns A_V per star
+    in input order.  The 1e30 factor is applied in float32 like the reference (x64 is off)."""
+    gz = np.asarray(gas_z, dtype=np.float32)
+    gp = np.asarray(gas_pixel)
+    sz = np.asarray(star_z, dtype=np.float32)
+    sp = np.asarray(star_pixel)
+    g_idx = np.lexsort((gz, gp))
+    s_idx = np.lexsort((sz, sp))
+    gz_s, gp_s = gz[g_idx], gp[g_idx]
+    ext_s = np.asarray(gas_cell_extinction, dtype=dtype)[g_idx]
+    sz_s, sp_s = sz[s_idx], sp[s_idx]
+    ids = np.arange(n_spaxels)
+    gb = np.concatenate([np.searchsorted(gp_s, ids, side="left"), [len(g_idx)]])
+    sb = np.concatenate([np.searchsorted(sp_s, ids, side="left"), [len(s_idx)]])
+    av = np.zeros(len(sz), dtype=dtype)
+    ar_g = np.arange(len(g_idx))
+    for s in range(n_spaxels):
+        s0, s1 = sb[s], sb[s + 1]
+        if s1 <= s0:
+            continue   # star_mask is empty: the spaxel adds nothing
+        gmask = (ar_g >= gb[s]) & (ar_g < gb[s + 1])
+        cum = np.cumsum(ext_s * gmask) * gmask
+        with np.errstate(over="ignore"):
+            xp = (gz_s * np.where(gmask, np.float32(1), np.float32(1e30))).astype(np.float32)
+        order = np.argsort(xp, kind="stable")     # jax.lax.sort_key_val is stable
+        xp_o, fp_o = xp[order].astype(dtype), cum[order]
+        av[s0:s1] = jnp_interp_left_extrapolate(sz_s[s0:s1].astype(dtype), xp_o, fp_o)
+    out = np.zeros_like(av)
+    out[s_idx] = av                                   # extinction[undo_sort]
+    return out
+
+
+def extinguish(wave_angstrom, av, model="Cardelli89", Rv=3.1, dtype=np.float64):
+    """dust_baseclasses.py:126-164 vmapped over stars (dust_extinction.py:341-345):
+    ``10 ** (-0.4 * axav(wave / 1e4) * Av)`` -> (n_star, n_wave)."""
+    axav = EXTINCTION_MODELS[model](np.asarray(wave_angstrom, dtype=np.float32).astype(np.float64) / 1e4, Rv).astype(dtype)
+    return np.power(dtype(10.0), dtype(-0.4) * axav[None, :] * np.asarray(av, dtype=dtype)[:, None])
+
+
+def apply_spaxel_extinction(spectra, wave_angstrom, gas_z, gas_pixel, gas_mass, gas_metals, star_z, star_pixel,
+                            n_spaxels, spaxel_area, dust_cfg, dtype=np.float64):
+    """dust_extinction.py:169-358 end to end: (n_star, n_wave) spectra times the per-star extinction."""
+    model = dust_cfg["extinction_model"]
+    if model not in EXTINCTION_MODELS:
+        raise ValueError(f"Extinction model '{model}' is not available. Choose from {list(EXTINCTION_MODELS)}.")
+    cell = dust_cell_extinction(gas_mass, gas_metals, dust_cfg["dust_grain_density"], spaxel_area,
+                                dust_cfg.get("dust_to_gas_model", "broken power law fit"), dust_cfg.get("Xco", "Z"), dtype)
+    av = stars_av(gas_z, gas_pixel, cell, star_z, star_pixel, n_spaxels, dtype)
+    return np.asarray(spectra, dtype=dtype) * extinguish(wave_angstrom, av, model, dust_cfg["Rv"], dtype), av
+
+
+# --------------------------------------------------------------------------------------
 # grids
 # --------------------------------------------------------------------------------------
 

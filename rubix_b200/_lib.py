@@ -25,6 +25,8 @@ EXPORTED = [
     "rbx_pipeline_host",
     "rbx_rotate_galaxy", "rbx_rotate_galaxy_workspace_bytes",
     "rbx_apply_noise", "rbx_apply_noise_workspace_bytes", "rbx_noise_samples",
+    "rbx_dust_av", "rbx_dust_av_workspace_bytes", "rbx_apply_extinction",
+    "rbx_build_cube_dusty", "rbx_build_cube_dusty_workspace_bytes",
     "rbx_profile_enable", "rbx_profile_fused",
 ]
 
@@ -91,6 +93,13 @@ def lib() -> C.CDLL:
     sigs["rbx_rotate_galaxy"] = [vp, vp, vp, i64, f32, vp, vp, vp, vp, vp, sz, vp]
     sigs["rbx_apply_noise"] = [vp, vp, i32, i32, i32, f32, i32, C.c_uint32, C.c_uint32, vp, sz, vp]
     sigs["rbx_noise_samples"] = [vp, vp, i64, i32, C.c_uint32, C.c_uint32, vp]
+    sigs["rbx_dust_av"] = [vp, vp, vp, vp, i32, i64, vp, vp, i64, i32, vp, f32, f32, vp, vp, vp, sz, vp]
+    sigs["rbx_apply_extinction"] = [vp, vp, vp, i64, i32, vp, vp]
+    sigs["rbx_build_cube_dusty"] = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp]
+    L.rbx_dust_av_workspace_bytes.argtypes = [i64, i32]
+    L.rbx_dust_av_workspace_bytes.restype = sz
+    L.rbx_build_cube_dusty_workspace_bytes.argtypes = [i64]
+    L.rbx_build_cube_dusty_workspace_bytes.restype = sz
     L.rbx_apply_noise_workspace_bytes.argtypes = [i32, i32]
     L.rbx_apply_noise_workspace_bytes.restype = sz
     L.rbx_rotate_galaxy_workspace_bytes.argtypes = []

@@ -14,7 +14,14 @@ CONSTANTS = {
     "SPEED_OF_LIGHT": 299792.458,  # km/s
     "LSOL_TO_ERG": 3.828e33,
     "MPC_TO_CM": 3.086e24,
+    "KPC_TO_CM": 3.08568e21,       # rubix_config.yml:6
+    "MSUN_TO_GRAMS": 1.989e33,     # rubix_config.yml:7
+    "MASS_OF_PROTON": 1.67262e-24, # rubix_config.yml:18
 }
+
+#: rubix_config.yml:145-150 (``ssp.dust``): package-level defaults of the dust variant
+DUST = {"extinction_model": "Cardelli89", "Rv": 3.1, "dust_to_gas_model": "broken power law fit", "Xco": "Z",
+        "dust_grain_density": 3.5}
 
 #: rubix_config.yml:242-245
 IFU = {"doppler": {"velocity_direction": "z"}}
@@ -74,6 +81,12 @@ PIPELINES = {
     "calc_ifu": _chain(["rotate_galaxy", "filter_particles", "spaxel_assignment", "reshape_data",
                         "calculate_spectra", "scale_spectrum_by_mass", "doppler_shift_and_resampling",
                         "calculate_datacube", "convolve_psf", "convolve_lsf", "apply_noise"]),
+    # pipeline_config.yml:62-126
+    "calc_dusty_ifu": _chain(["rotate_galaxy", "filter_particles", "spaxel_assignment", "reshape_data",
+                              "calculate_spectra", "scale_spectrum_by_mass", "doppler_shift_and_resampling",
+                              "calculate_extinction", "calculate_datacube", "convolve_psf", "convolve_lsf",
+                              "apply_noise"]),
 }
 
+SSP["dust"] = DUST
 rubix_config = {"constants": CONSTANTS, "ifu": IFU, "ssp": SSP, "telescopes": TELESCOPES, "pipelines": PIPELINES}

@@ -10,3 +10,4 @@ from .telescope import (get_filter_particles, get_spatial_bin_edges, get_spaxel_
 from .pipeline import RubixPipeline  # noqa: F401
 from .rotation import get_galaxy_rotation  # noqa: F401
 from .noise import get_apply_noise  # noqa: F401
+from .dust import get_extinction  # noqa: F401

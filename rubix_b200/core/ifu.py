@@ -67,6 +67,7 @@ class DeferredSpectra:
         self._config, self._stars, self.n = config, stars, n
         self.scaled = False
         self.resampled = False
+        self.extinction = None   # (A_V per star, A(lambda)/A(V) per channel) once calculate_extinction has run
         self.dtype = np.float32
 
     @property
@@ -87,6 +88,8 @@ class DeferredSpectra:
             spec = ops.scale_by_mass(spec, st.mass.reshape(-1))
         if self.resampled:
             spec = ops.doppler_resample(plan, spec, st.velocity.reshape(-1, 3))
+        if self.extinction is not None:
+            spec = ops.apply_extinction(spec, *self.extinction, out=spec)
         return spec.unsqueeze(0)
 
     def __array__(self, dtype=None, copy=None):
@@ -177,6 +180,27 @@ def get_doppler_shift_and_resampling(config: dict) -> Callable:
     return doppler_shift_and_resampling
 
 
+#: particles per pass of the dusty cube (bounds the (n, L) SSP spectra held at once: 3.4 kB per particle)
+DUSTY_CHUNK = 1 << 20
+
+
+def _dusty_cube(plan, st, mass, pix, num_spaxels: int, extinction):
+    """calc_dusty_ifu with deferred spectra: SSP lookup and mass scaling per chunk of particles, then
+    resampling + extinction + per-spaxel sum in one kernel (rbx_build_cube_dusty)."""
+    from .. import ops
+    av, axav = extinction
+    met, age, vel = st.metallicity.reshape(-1), st.age.reshape(-1), st.velocity.reshape(-1, 3)
+    n = met.numel()
+    cube = None
+    for lo in range(0, max(n, 1), DUSTY_CHUNK):
+        hi = min(n, lo + DUSTY_CHUNK)
+        spec = ops.ssp_lookup(plan, met[lo:hi], age[lo:hi])
+        spec = ops.scale_by_mass(spec, mass[lo:hi])
+        part = ops.build_cube_dusty(plan, spec, vel[lo:hi], pix[lo:hi], num_spaxels, av[lo:hi], axav)
+        cube = part if cube is None else cube.add_(part)
+    return cube
+
+
 def get_calculate_datacube(config: dict) -> Callable:
     """rubix/core/ifu.py:299-341: per-spaxel sum of the resampled spectra -> ``stars.datacube``
     (S, S, W).  With ``torch.distributed`` initialised and ``config["b200"]["distributed"]`` true the
@@ -198,8 +222,11 @@ def get_calculate_datacube(config: dict) -> Callable:
                                  "(doppler_shift_and_resampling has not run)")
             plan = get_plan(config)
             mass = st.mass.reshape(-1) if d.scaled else __import__("torch").ones_like(st.metallicity.reshape(-1))
-            cube = ops.build_cube(plan, st.velocity.reshape(-1, 3), mass, st.metallicity.reshape(-1),
-                                  st.age.reshape(-1), pix, num_spaxels)
+            if d.extinction is not None:
+                cube = _dusty_cube(plan, st, mass, pix, num_spaxels, d.extinction)
+            else:
+                cube = ops.build_cube(plan, st.velocity.reshape(-1, 3), mass, st.metallicity.reshape(-1),
+                                      st.age.reshape(-1), pix, num_spaxels)
         else:
             spec = ops.dev(st.spectra)
             cube = ops.segment_sum(spec.reshape(-1, spec.shape[-1]), pix, num_spaxels * num_spaxels)

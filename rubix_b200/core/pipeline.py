@@ -24,6 +24,7 @@ from ..h5lite import H5File
 from ..logger import get_logger
 from ..utils import get_config, get_pipeline_config
 from .data import RubixData, get_reshape_data, make_rubix_data
+from .dust import get_extinction
 from .ifu import (get_calculate_datacube, get_calculate_spectra, get_doppler_shift_and_resampling,
                   get_scale_spectrum_by_mass)
 from .lsf import get_convolve_lsf
@@ -105,6 +106,14 @@ def prepare_input(config: dict) -> RubixData:
         arrays = {k: v[idx] for k, v in arrays.items()}
         logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for stars")
     rd = make_rubix_data(**arrays, device=False)
+    gas = raw["particle_data"].get("gas")
+    if gas is not None:   # rubix/core/data.py:541-600: every stored attribute, centred coordinates
+        logger.info("Centering gas particles")
+        for k, v in gas.items():
+            v = (v - center).astype(np.float32) if k == "coords" else np.ascontiguousarray(v, dtype=np.float32)
+            if sub.get("use_subset"):   # the reference draws the indices from the STAR count for gas too
+                v = v[idx]
+            setattr(rd.gas, k, v)
     rd.galaxy.redshift = raw["redshift"]
     rd.galaxy.center = center
     rd.galaxy.halfmassrad_stars = raw["subhalo_halfmassrad_stars"]
@@ -133,7 +142,8 @@ class RubixPipeline:
         self.logger.info("Getting rubix data...")
         rd = prepare_input(self.user_config)
         n = len(rd.stars.coords) if rd.stars.coords is not None else 0
-        self.logger.info(f"Data loaded with {n} star particles and 0 gas particles.")
+        ng = len(rd.gas.coords) if rd.gas.coords is not None else 0
+        self.logger.info(f"Data loaded with {n} star particles and {ng} gas particles.")
         return rd
 
     def _get_pipeline_functions(self) -> list:
@@ -141,7 +151,8 @@ class RubixPipeline:
         c = self.user_config
         rot = [get_galaxy_rotation(c)] if "rotation" in c.get("galaxy", {}) else []
         noise = [get_apply_noise(c)] if "noise" in c.get("telescope", {}) else []
-        return rot + noise + [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
+        dusty = [get_extinction(c)] if self.user_config["pipeline"]["name"] == "calc_dusty_ifu" else []
+        return rot + noise + dusty + [get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c), get_reshape_data(c),
                 get_scale_spectrum_by_mass(c), get_doppler_shift_and_resampling(c), get_calculate_datacube(c),
                 get_convolve_psf(c), get_convolve_lsf(c)] + self.extra_functions
 

@@ -88,6 +88,8 @@ def get_filter_particles(config: dict) -> Callable:
             for k, v in vars(part).items():
                 if k in ("coords", "velocity", "mask", "spectra", "datacube", "spatial_bin_edges") or k in hot:
                     continue
+                if name == "gas" and k == "metals":   # rubix/core/telescope.py:186: gas metals are not masked
+                    continue
                 if isinstance(v, torch.Tensor) and v.numel() and v.reshape(-1).shape[0] % n == 0 and v.shape[:1] == coords.shape[:1]:
                     m = mask.reshape(coords.shape[:-1])
                     while m.ndim < v.ndim:

@@ -179,6 +179,65 @@ def noise_samples(n: int, distribution: str = "normal", key=(0, 0)):
     return out, bits
 
 
+def dust_av(gas_coords, gas_pixel, gas_mass, gas_metals, star_coords, star_pixel, n_spaxels: int, dust_to_gas,
+            ext_const: float, spaxel_area: float, return_cells: bool = False):
+    """A_V of every star from the gas cells of its spaxel (rubix/spectra/dust/dust_extinction.py:240-337).
+    ``dust_to_gas`` = (a_high, alpha_high, a_low, alpha_low, x_transition), see rubix_b200.dust."""
+    gas_coords, star_coords = dev(gas_coords).reshape(-1, 3), dev(star_coords).reshape(-1, 3)
+    gas_pixel, star_pixel = dev(gas_pixel, torch.int32).reshape(-1), dev(star_pixel, torch.int32).reshape(-1)
+    gas_mass = dev(gas_mass).reshape(-1)
+    ng, ns = gas_coords.shape[0], star_coords.shape[0]
+    gas_metals = dev(gas_metals).reshape(ng, -1) if ng else dev(gas_metals).reshape(0, 5)
+    if gas_pixel.numel() != ng or gas_mass.numel() != ng or star_pixel.numel() != ns:
+        raise ValueError("dust_av: per-particle arrays of different lengths")
+    av = torch.empty(ns, dtype=torch.float32, device="cuda")
+    cells = torch.empty(ng, dtype=torch.float32, device="cuda") if return_cells else None
+    L = _lib.lib()
+    ws = _workspace(L.rbx_dust_av_workspace_bytes(ng, int(n_spaxels)))
+    dtg = np.ascontiguousarray(np.asarray(dust_to_gas, dtype=np.float32))
+    if dtg.shape != (5,):
+        raise ValueError("dust_to_gas must hold (a_high, alpha_high, a_low, alpha_low, x_transition)")
+    _lib.check(L.rbx_dust_av(_p(gas_coords), _p(gas_pixel), _p(gas_mass), _p(gas_metals), gas_metals.shape[1], ng,
+                             _p(star_coords), _p(star_pixel), ns, int(n_spaxels), dtg.ctypes.data_as(C.c_void_p),
+                             float(ext_const), float(spaxel_area), _p(av), _p(cells), _p(ws), ws.numel(), _stream()))
+    return (av, cells) if return_cells else av
+
+
+def apply_extinction(spectra, av, axav, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """spectra (n, W) * 10^(-0.4 * axav (W,) * av (n,))  (rubix/spectra/dust/dust_baseclasses.py:126-164)."""
+    spectra, av, axav = dev(spectra), dev(av).reshape(-1), dev(axav).reshape(-1)
+    W = spectra.shape[-1]
+    n = spectra.numel() // W if W else 0
+    if av.numel() != n or axav.numel() != W:
+        raise ValueError("apply_extinction: av needs one entry per spectrum, axav one per wavelength")
+    out = torch.empty_like(spectra) if out is None else out
+    _lib.check(_lib.lib().rbx_apply_extinction(_p(spectra), _p(av), _p(axav), n, W, _p(out), _stream()))
+    return out
+
+
+def build_cube_dusty(plan: Plan, spectra, velocity, pixel, num_spaxels: int, av=None, axav=None) -> torch.Tensor:
+    """doppler_shift_and_resampling -> calculate_extinction -> calculate_datacube in one kernel: mass-scaled SSP
+    spectra (n, L) -> cube (S, S, W) without the (n, W) intermediate.  ``av`` / ``axav`` None = no dust."""
+    spectra, velocity = dev(spectra), dev(velocity).reshape(-1, 3)
+    pixel = dev(pixel, torch.int32).reshape(-1)
+    n = velocity.shape[0]
+    spectra = spectra.reshape(n, plan.L) if n else spectra.reshape(0, plan.L)
+    if pixel.numel() != n:
+        raise ValueError("build_cube_dusty: per-particle arrays of different lengths")
+    if (av is None) != (axav is None):
+        raise ValueError("build_cube_dusty: av and axav go together")
+    if av is not None:
+        av, axav = dev(av).reshape(-1), dev(axav).reshape(-1)
+        if av.numel() != n or axav.numel() != plan.W:
+            raise ValueError("build_cube_dusty: av needs one entry per particle, axav one per channel")
+    cube = torch.empty((num_spaxels, num_spaxels, plan.W), dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_dusty_workspace_bytes(n))
+    _lib.check(L.rbx_build_cube_dusty(plan.handle, _p(spectra), _p(velocity), _p(pixel), _p(av), _p(axav), n,
+                                      int(num_spaxels), _p(cube), _p(ws), ws.numel(), _stream()))
+    return cube
+
+
 def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
     n = metallicity.numel()
