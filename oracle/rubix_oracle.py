@@ -787,11 +787,12 @@ def calculate_wave_seq(wave_range, wave_res, dtype=np.float32):
 def particles_to_cube(coords, velocity, mass, metallicity, age, spatial_bin_edges, num_spaxels,
                       ssp_metallicity, ssp_age, ssp_wavelength, ssp_flux, target_wavelength,
                       redshift, method="cubic", direction="z", dtype=np.float32,
-                      apply_filter=True, chunk=20000, acc_dtype=None):
+                      apply_filter=True, chunk=20000, acc_dtype=None, extinction=None):
     """filter_particles -> spaxel_assignment -> calculate_spectra -> scale_spectrum_by_mass ->
-    doppler_shift_and_resampling -> calculate_datacube, in the reference's order
-    (rubix/config/pipeline_config.yml:1-45), chunked over particles only to bound memory.
-    All inputs are float32 arrays; ``dtype`` selects the arithmetic precision."""
+    doppler_shift_and_resampling -> [calculate_extinction] -> calculate_datacube, in the reference's
+    order (rubix/config/pipeline_config.yml:1-45, :62-126), chunked over particles only to bound memory.
+    All inputs are float32 arrays; ``dtype`` selects the arithmetic precision.  ``extinction`` (n, W)
+    is the per-star factor of the dusty variant (:func:`extinguish`), applied to the resampled spectra."""
     coords = np.asarray(coords, dtype=np.float32)
     edges = np.asarray(spatial_bin_edges, dtype=np.float32)
     if apply_filter:
@@ -810,6 +811,8 @@ def particles_to_cube(coords, velocity, mass, metallicity, age, spatial_bin_edge
         spec = scale_spectrum_by_mass(spec, np.asarray(mass[s:e], dtype=dtype))
         lam = velocity_doppler_shift(lam_z, velocity[s:e], direction=direction, dtype=dtype)
         res = resample_spectra(spec, lam, t)
+        if extinction is not None:
+            res = res * np.asarray(extinction[s:e], dtype=dtype)   # dust_extinction.py:356
         cube += calculate_cube(res, idx[s:e], num_spaxels, acc_dtype=acc_dtype)
     return cube, idx
 

@@ -27,6 +27,7 @@ EXPORTED = [
     "rbx_apply_noise", "rbx_apply_noise_workspace_bytes", "rbx_noise_samples",
     "rbx_dust_av", "rbx_dust_av_workspace_bytes", "rbx_apply_extinction",
     "rbx_build_cube_dusty", "rbx_build_cube_dusty_workspace_bytes",
+    "rbx_dusty_moments", "rbx_dusty_bins", "rbx_dusty_combine",
     "rbx_profile_enable", "rbx_profile_fused",
 ]
 
@@ -96,6 +97,10 @@ def lib() -> C.CDLL:
     sigs["rbx_dust_av"] = [vp, vp, vp, vp, i32, i64, vp, vp, i64, i32, vp, f32, f32, vp, vp, vp, sz, vp]
     sigs["rbx_apply_extinction"] = [vp, vp, vp, i64, i32, vp, vp]
     sigs["rbx_build_cube_dusty"] = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp]
+    sigs["rbx_dusty_bins"] = [vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp]
+    sigs["rbx_dusty_combine"] = [vp, i64, i32, i32, f32, f32, vp, i32, vp, vp]
+    L.rbx_dusty_moments.argtypes = []
+    L.rbx_dusty_moments.restype = i32
     L.rbx_dust_av_workspace_bytes.argtypes = [i64, i32]
     L.rbx_dust_av_workspace_bytes.restype = sz
     L.rbx_build_cube_dusty_workspace_bytes.argtypes = [i64]

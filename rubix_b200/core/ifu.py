@@ -20,6 +20,8 @@ Two execution modes, chosen per call by ``config["b200"]["fused"]`` (True / Fals
 
 from __future__ import annotations
 
+import os
+
 from typing import Callable
 
 import numpy as np
@@ -191,6 +193,10 @@ def _dusty_cube(plan, st, mass, pix, num_spaxels: int, extinction):
     av, axav = extinction
     met, age, vel = st.metallicity.reshape(-1), st.age.reshape(-1), st.velocity.reshape(-1, 3)
     n = met.numel()
+    if os.environ.get("RBX_DUSTY_IMPL", "binned") == "binned":
+        cube = ops.build_cube_dusty_binned(plan, vel, mass, met, age, pix, num_spaxels, av, axav)
+        if cube is not None:
+            return cube
     cube = None
     for lo in range(0, max(n, 1), DUSTY_CHUNK):
         hi = min(n, lo + DUSTY_CHUNK)

@@ -238,6 +238,48 @@ def build_cube_dusty(plan: Plan, spectra, velocity, pixel, num_spaxels: int, av=
     return cube
 
 
+#: the binned-moment dusty cube holds moments x spaxels x bins x W floats; beyond this many bytes (or for A_V ranges
+#: that need more than DUSTY_MAX_BINS bins) callers use build_cube_dusty instead
+DUSTY_MOMENT_BYTES = 24 << 30
+DUSTY_MAX_BINS = 4096
+
+
+def build_cube_dusty_binned(plan: Plan, velocity, mass, metallicity, age, pixel, num_spaxels: int, av, axav,
+                            x_max: float = 0.1) -> Optional[torch.Tensor]:
+    """calculate_spectra .. calculate_extinction .. calculate_datacube through the knot-based cube kernel: stars
+    binned by A_V, the extinction factor expanded to third order inside a bin (include/rubix_b200.h,
+    rbx_dusty_bins / rbx_dusty_combine).  Returns None when the A_V range or the cube size rule it out (non-finite
+    A_V, too many bins, too much memory) -- the caller then takes build_cube_dusty."""
+    velocity, mass = dev(velocity).reshape(-1, 3), dev(mass).reshape(-1)
+    metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    pixel, av, axav = dev(pixel, torch.int32).reshape(-1), dev(av).reshape(-1), dev(axav).reshape(-1)
+    n, S = mass.numel(), int(num_spaxels)
+    nseg = S * S
+    if n == 0:
+        return torch.zeros((S, S, plan.W), dtype=torch.float32, device="cuda")
+    lo, hi = (float(v) for v in torch.aminmax(av))          # one device -> host read per cube
+    kmax = float(axav.abs().max())
+    if not (np.isfinite(lo) and np.isfinite(hi) and np.isfinite(kmax)):
+        return None
+    step = x_max / max(0.4 * np.log(10.0) * kmax, 1e-30)
+    n_bins = max(1, int(np.ceil((hi - lo) / step)))
+    L = _lib.lib()
+    M = L.rbx_dusty_moments()
+    Sv = int(np.ceil(np.sqrt(nseg * n_bins)))
+    if n_bins > DUSTY_MAX_BINS or M * Sv * Sv * plan.W * 4 > DUSTY_MOMENT_BYTES:
+        return None
+    vpix = torch.empty(n, dtype=torch.int32, device="cuda")
+    wmass = torch.empty((M, n), dtype=torch.float32, device="cuda")
+    _lib.check(L.rbx_dusty_bins(_p(av), _p(pixel), _p(mass), n, nseg, n_bins, lo, step, _p(vpix), _p(wmass), _stream()))
+    moments = torch.empty((M, Sv, Sv, plan.W), dtype=torch.float32, device="cuda")
+    for m in range(M):
+        build_cube(plan, velocity, wmass[m], metallicity, age, vpix, Sv, out=moments[m])
+    cube = torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
+    _lib.check(L.rbx_dusty_combine(_p(moments), Sv * Sv * plan.W, nseg, n_bins, lo, step, _p(axav), plan.W, _p(cube),
+                                   _stream()))
+    return cube
+
+
 def ssp_lookup(plan: Plan, metallicity, age) -> torch.Tensor:
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
     n = metallicity.numel()
