@@ -11,3 +11,4 @@ from .pipeline import RubixPipeline  # noqa: F401
 from .rotation import get_galaxy_rotation  # noqa: F401
 from .noise import get_apply_noise  # noqa: F401
 from .dust import get_extinction  # noqa: F401
+from .fits import load_fits, store_fits  # noqa: F401
