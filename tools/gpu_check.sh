@@ -19,3 +19,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:fuse
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_cube -s 3 -c 1 -o $OUT/prof_fused_cubic -f python bench.py --steps 2 --warmup 3 --no-cpu --method cubic > $OUT/ncu_fused_cubic.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:march -s 2 -c 1 -o $OUT/prof_march_s150 -f python tools/prof_conv.py > $OUT/ncu_march.log 2>&1
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; cat $OUT/bench.json
+timeout 300 python tools/bench_dusty.py > $OUT/dusty.json 2> $OUT/dusty.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_dusty.csv python tools/bench_dusty.py --particles 200000 --gas 200000 --staged 20000 --reps 1 > $OUT/dusty_under_ncu.log 2>&1
+cat $OUT/dusty.json
