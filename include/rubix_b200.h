@@ -228,16 +228,20 @@ int rbx_dust_av(const float *d_gas_coords, const int32_t *d_gas_pixel, const flo
 int rbx_apply_extinction(const float *d_spectra, const float *d_av, const float *d_axav, int64_t n, int W,
                          float *d_out, void *stream);
 /* The dusty cube through rbx_build_cube (the knot-based kernel): stars are binned by A_V (n_bins bins of width step
- * from av0), rbx_dusty_bins writes the virtual spaxel id pixel * n_bins + bin (-1 for dropped ids) and the
- * rbx_dusty_moments() weight arrays mass * (A_V - A_bin)^m, d_wmass (moments, n); the caller runs rbx_build_cube once
- * per moment on ceil(sqrt(nseg * n_bins))^2 virtual spaxels into d_moments (moments, moment_stride floats each) and
- * rbx_dusty_combine folds them: cube[s, w] = sum_b 10^(-0.4 axav_w A_b) sum_m (-0.4 ln10 axav_w)^m / m! C_m[s n_bins + b, w].
+ * from av0) and the factor is expanded to third order inside a bin.  rbx_dusty_bins writes every star
+ * M = rbx_dusty_moments() times: virtual particle m of star i (arrays of M * n entries, moment-major) carries the weight
+ * mass * (A_V - A_bin)^m, the star's velocity / metallicity / age, and the virtual spaxel id
+ * (pixel * n_bins + bin) * M + m (-1 for dropped ids).  The caller runs rbx_build_cube ONCE on the M * n virtual
+ * particles with ceil(sqrt(nseg * n_bins * M))^2 virtual spaxels, and rbx_dusty_combine folds the rows:
+ * cube[s, w] = sum_b 10^(-0.4 axav_w A_b) sum_m (-0.4 ln10 axav_w)^m / m! vcube[(s n_bins + b) M + m, w].
  * Truncation < 2.6e-7 relative when 0.4 ln10 max|axav| step <= 0.1. */
 int rbx_dusty_moments(void);
-int rbx_dusty_bins(const float *d_av, const int32_t *d_pixel, const float *d_mass, int64_t n, int nseg, int n_bins,
-                   float av0, float step, int32_t *d_vpixel, float *d_wmass, void *stream);
-int rbx_dusty_combine(const float *d_moments, int64_t moment_stride, int nseg, int n_bins, float av0, float step,
-                      const float *d_axav, int W, float *d_cube, void *stream);
+int rbx_dusty_bins(const float *d_av, const int32_t *d_pixel, const float *d_mass, const float *d_velocity,
+                   const float *d_metallicity, const float *d_age, int64_t n, int nseg, int n_bins, float av0,
+                   float step, int32_t *d_vpixel, float *d_wmass, float *d_vvelocity, float *d_vmetallicity,
+                   float *d_vage, void *stream);
+int rbx_dusty_combine(const float *d_vcube, int nseg, int n_bins, float av0, float step, const float *d_axav, int W,
+                      float *d_cube, void *stream);
 size_t rbx_build_cube_dusty_workspace_bytes(int64_t n);
 int rbx_build_cube_dusty(const rbx_plan *plan, const float *d_spectra, const float *d_velocity,
                          const int32_t *d_pixel, const float *d_av, const float *d_axav, int64_t n,

@@ -97,8 +97,8 @@ def lib() -> C.CDLL:
     sigs["rbx_dust_av"] = [vp, vp, vp, vp, i32, i64, vp, vp, i64, i32, vp, f32, f32, vp, vp, vp, sz, vp]
     sigs["rbx_apply_extinction"] = [vp, vp, vp, i64, i32, vp, vp]
     sigs["rbx_build_cube_dusty"] = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp]
-    sigs["rbx_dusty_bins"] = [vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp]
-    sigs["rbx_dusty_combine"] = [vp, i64, i32, i32, f32, f32, vp, i32, vp, vp]
+    sigs["rbx_dusty_bins"] = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]
+    sigs["rbx_dusty_combine"] = [vp, i32, i32, f32, f32, vp, i32, vp, vp]
     L.rbx_dusty_moments.argtypes = []
     L.rbx_dusty_moments.restype = i32
     L.rbx_dust_av_workspace_bytes.argtypes = [i64, i32]

@@ -352,40 +352,49 @@ __global__ void dusty_keys_kernel(const int32_t *__restrict__ pixel, int64_t n, 
 // so that x = ln10 * 0.4 * k_w * (A_V - A_b) stays below 0.05 in magnitude) and the factor is expanded inside a bin:
 //   10^(-0.4 k_w A_V) = 10^(-0.4 k_w A_b) * (1 - x + x^2/2 - x^3/6 + ...),   truncation x^4/24 < 2.6e-7 relative.
 // The cube of every (spaxel, bin) pair is then sum_m (a_w^m / m!) C_m with a_w = -0.4 ln10 k_w and C_m the ordinary
-// (dust-free) cube of the bin's stars weighted by mass * (A_V - A_b)^m -- four runs of rbx_build_cube on a virtual
-// grid of S^2 * n_bins "spaxels" -- and dusty_combine_kernel folds bins and moments into the (S^2, W) cube.
+// (dust-free) cube of the bin's stars weighted by mass * (A_V - A_b)^m.  dusty_bins_kernel writes every star four
+// times (one virtual particle per moment, weight mass * (A_V - A_b)^m, virtual spaxel (s * n_bins + b) * 4 + m), ONE run
+// of rbx_build_cube bins the 4 n virtual particles onto the S^2 * n_bins * 4 virtual spaxels, and
+// dusty_combine_kernel folds bins and moments into the (S^2, W) cube.
 constexpr int kDustMoments = 4;
 
 __global__ void dusty_bins_kernel(const float *__restrict__ av, const int32_t *__restrict__ pixel,
-                                  const float *__restrict__ mass, int64_t n, int nseg, int n_bins, float av0, float step,
-                                  int32_t *__restrict__ vpixel, float *__restrict__ wmass) {
+                                  const float *__restrict__ mass, const float *__restrict__ vel,
+                                  const float *__restrict__ met, const float *__restrict__ age, int64_t n, int nseg,
+                                  int n_bins, float av0, float step, int32_t *__restrict__ vpixel, float *__restrict__ wmass,
+                                  float *__restrict__ vel_out, float *__restrict__ met_out, float *__restrict__ age_out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float a = av[i], m = mass[i];
     const int32_t px = pixel[i];
     int b = (int)floorf((a - av0) / step);
     b = b < 0 ? 0 : (b >= n_bins ? n_bins - 1 : b);
     const float da = a - (av0 + ((float)b + 0.5f) * step);
-    vpixel[i] = (px < 0 || px >= nseg) ? -1 : px * n_bins + b;
+    const int32_t base = (px < 0 || px >= nseg) ? -1 : (px * n_bins + b) * kDustMoments;
+    const float v0 = vel[3 * i], v1 = vel[3 * i + 1], v2 = vel[3 * i + 2], z = met[i], t = age[i];
     float w = m;
 #pragma unroll
-    for (int k = 0; k < kDustMoments; ++k) {
-      wmass[(size_t)k * n + i] = w;
+    for (int k = 0; k < kDustMoments; ++k) {   // one virtual particle per moment, in its own virtual spaxel
+      const size_t o = (size_t)k * n + i;
+      vpixel[o] = base < 0 ? -1 : base + k;
+      wmass[o] = w;
+      vel_out[3 * o] = v0; vel_out[3 * o + 1] = v1; vel_out[3 * o + 2] = v2;
+      met_out[o] = z;
+      age_out[o] = t;
       w *= da;
     }
   }
 }
 
-__global__ void dusty_combine_kernel(const float *__restrict__ moments, size_t moment_stride, int n_bins, float av0,
-                                     float step, const float *__restrict__ axav, int W, float *__restrict__ cube) {
+__global__ void dusty_combine_kernel(const float *__restrict__ vcube, int n_bins, float av0, float step,
+                                     const float *__restrict__ axav, int W, float *__restrict__ cube) {
   const int s = blockIdx.x;
   for (int w = threadIdx.x; w < W; w += blockDim.x) {
     const float m04 = __fmul_rn(-0.4f, axav[w]);
     const float a = m04 * 2.302585093f;
     float acc = 0.f;
     for (int b = 0; b < n_bins; ++b) {
-      const size_t row = ((size_t)s * n_bins + b) * W + w;
-      const float c0 = moments[row], c1 = moments[moment_stride + row], c2 = moments[2 * moment_stride + row],
-                  c3 = moments[3 * moment_stride + row];
+      const float *r = vcube + ((size_t)s * n_bins + b) * kDustMoments * W + w;
+      const float c0 = r[0], c1 = r[W], c2 = r[2 * (size_t)W], c3 = r[3 * (size_t)W];
       const float poly = c0 + a * (c1 + a * (0.5f * c2 + a * (0.16666667f * c3)));
       if (poly != 0.f) acc += exp10f(m04 * (av0 + ((float)b + 0.5f) * step)) * poly;
     }
@@ -580,25 +589,28 @@ extern "C" int rbx_build_cube_dusty(const rbx_plan *plan, const float *d_spectra
 
 extern "C" int rbx_dusty_moments(void) { return kDustMoments; }
 
-extern "C" int rbx_dusty_bins(const float *d_av, const int32_t *d_pixel, const float *d_mass, int64_t n, int nseg,
-                              int n_bins, float av0, float step, int32_t *d_vpixel, float *d_wmass, void *stream) {
+extern "C" int rbx_dusty_bins(const float *d_av, const int32_t *d_pixel, const float *d_mass, const float *d_velocity,
+                              const float *d_metallicity, const float *d_age, int64_t n, int nseg, int n_bins, float av0,
+                              float step, int32_t *d_vpixel, float *d_wmass, float *d_vvelocity, float *d_vmetallicity,
+                              float *d_vage, void *stream) {
   RBX_REQUIRE(n >= 0 && nseg > 0 && n_bins > 0 && step > 0.f, "rbx_dusty_bins: bad argument");
-  RBX_REQUIRE((int64_t)nseg * n_bins < (int64_t)1 << 31, "rbx_dusty_bins: spaxels x bins beyond int32");
+  RBX_REQUIRE((int64_t)nseg * n_bins * kDustMoments < (int64_t)1 << 31, "rbx_dusty_bins: spaxels x bins beyond int32");
   if (n == 0) return RBX_OK;
-  RBX_REQUIRE(d_av && d_pixel && d_mass && d_vpixel && d_wmass, "rbx_dusty_bins: null pointer");
-  dusty_bins_kernel<<<grid1d(n, 256), 256, 0, (cudaStream_t)stream>>>(d_av, d_pixel, d_mass, n, nseg, n_bins, av0, step,
-                                                                      d_vpixel, d_wmass);
+  RBX_REQUIRE(d_av && d_pixel && d_mass && d_velocity && d_metallicity && d_age && d_vpixel && d_wmass && d_vvelocity &&
+                  d_vmetallicity && d_vage, "rbx_dusty_bins: null pointer");
+  dusty_bins_kernel<<<grid1d(n, 256), 256, 0, (cudaStream_t)stream>>>(d_av, d_pixel, d_mass, d_velocity, d_metallicity, d_age,
+                                                                      n, nseg, n_bins, av0, step, d_vpixel, d_wmass,
+                                                                      d_vvelocity, d_vmetallicity, d_vage);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;
 }
 
-extern "C" int rbx_dusty_combine(const float *d_moments, int64_t moment_stride, int nseg, int n_bins, float av0, float step,
-                                 const float *d_axav, int W, float *d_cube, void *stream) {
-  RBX_REQUIRE(d_moments && d_axav && d_cube, "rbx_dusty_combine: null pointer");
-  RBX_REQUIRE(nseg > 0 && n_bins > 0 && W > 0 && moment_stride >= (int64_t)nseg * n_bins * W, "rbx_dusty_combine: bad shape");
-  dusty_combine_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(d_moments, (size_t)moment_stride, n_bins, av0, step, d_axav, W,
-                                                               d_cube);
+extern "C" int rbx_dusty_combine(const float *d_vcube, int nseg, int n_bins, float av0, float step, const float *d_axav, int W,
+                                 float *d_cube, void *stream) {
+  RBX_REQUIRE(d_vcube && d_axav && d_cube, "rbx_dusty_combine: null pointer");
+  RBX_REQUIRE(nseg > 0 && n_bins > 0 && W > 0, "rbx_dusty_combine: bad shape");
+  dusty_combine_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(d_vcube, n_bins, av0, step, d_axav, W, d_cube);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;

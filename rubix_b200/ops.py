@@ -247,8 +247,8 @@ DUSTY_MAX_BINS = 4096
 def build_cube_dusty_binned(plan: Plan, velocity, mass, metallicity, age, pixel, num_spaxels: int, av, axav,
                             x_max: float = 0.1) -> Optional[torch.Tensor]:
     """calculate_spectra .. calculate_extinction .. calculate_datacube through the knot-based cube kernel: stars
-    binned by A_V, the extinction factor expanded to third order inside a bin (include/rubix_b200.h,
-    rbx_dusty_bins / rbx_dusty_combine).  Returns None when the A_V range or the cube size rule it out (non-finite
+    binned by A_V, the extinction factor expanded to third order inside a bin, one run of the cube kernel over four
+    weighted copies of every star (include/rubix_b200.h, rbx_dusty_bins / rbx_dusty_combine).  Returns None when the A_V range or the cube size rule it out (non-finite
     A_V, too many bins, too much memory) -- the caller then takes build_cube_dusty."""
     velocity, mass = dev(velocity).reshape(-1, 3), dev(mass).reshape(-1)
     metallicity, age = dev(metallicity).reshape(-1), dev(age).reshape(-1)
@@ -265,18 +265,18 @@ def build_cube_dusty_binned(plan: Plan, velocity, mass, metallicity, age, pixel,
     n_bins = max(1, int(np.ceil((hi - lo) / step)))
     L = _lib.lib()
     M = L.rbx_dusty_moments()
-    Sv = int(np.ceil(np.sqrt(nseg * n_bins)))
-    if n_bins > DUSTY_MAX_BINS or M * Sv * Sv * plan.W * 4 > DUSTY_MOMENT_BYTES:
+    Sv = int(np.ceil(np.sqrt(nseg * n_bins * M)))
+    if n_bins > DUSTY_MAX_BINS or Sv * Sv * plan.W * 4 > DUSTY_MOMENT_BYTES:
         return None
-    vpix = torch.empty(n, dtype=torch.int32, device="cuda")
-    wmass = torch.empty((M, n), dtype=torch.float32, device="cuda")
-    _lib.check(L.rbx_dusty_bins(_p(av), _p(pixel), _p(mass), n, nseg, n_bins, lo, step, _p(vpix), _p(wmass), _stream()))
-    moments = torch.empty((M, Sv, Sv, plan.W), dtype=torch.float32, device="cuda")
-    for m in range(M):
-        build_cube(plan, velocity, wmass[m], metallicity, age, vpix, Sv, out=moments[m])
+    vpix = torch.empty(M * n, dtype=torch.int32, device="cuda")
+    wmass = torch.empty(M * n, dtype=torch.float32, device="cuda")
+    vvel = torch.empty((M * n, 3), dtype=torch.float32, device="cuda")
+    vmet, vage = torch.empty_like(wmass), torch.empty_like(wmass)
+    _lib.check(L.rbx_dusty_bins(_p(av), _p(pixel), _p(mass), _p(velocity), _p(metallicity), _p(age), n, nseg, n_bins, lo,
+                                step, _p(vpix), _p(wmass), _p(vvel), _p(vmet), _p(vage), _stream()))
+    vcube = build_cube(plan, vvel, wmass, vmet, vage, vpix, Sv)
     cube = torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
-    _lib.check(L.rbx_dusty_combine(_p(moments), Sv * Sv * plan.W, nseg, n_bins, lo, step, _p(axav), plan.W, _p(cube),
-                                   _stream()))
+    _lib.check(L.rbx_dusty_combine(_p(vcube), nseg, n_bins, lo, step, _p(axav), plan.W, _p(cube), _stream()))
     return cube
 
 
