@@ -54,17 +54,16 @@ def get_extinction(config: dict) -> Callable:
         st, gas = rubixdata.stars, rubixdata.gas
         if gas.coords is None or gas.pixel_assignment is None or gas.metals is None or gas.mass is None:
             raise ValueError("calculate_extinction needs gas particles with coords, pixel_assignment, metals and mass")
-        # [0]: the first device shard, like the reference (dust_extinction.py:240-245)
-        g3 = lambda a: ops.dev(a)[0] if ops.dev(a).ndim == 3 else ops.dev(a)
-        g2 = lambda a, dt=None: (ops.dev(a) if dt is None else ops.dev(a, dt))
-        gas_coords, star_coords = g3(gas.coords), g3(st.coords)
-        gpix = g2(gas.pixel_assignment, __import__("torch").int32)
-        spix = g2(st.pixel_assignment, __import__("torch").int32)
-        gpix = gpix[0] if gpix.ndim == 2 else gpix
-        spix = spix[0] if spix.ndim == 2 else spix
-        gmass = ops.dev(gas.mass)
-        gmass = gmass[0] if gmass.ndim == 2 else gmass
-        metals = g3(gas.metals)
+        import torch
+
+        def shard0(a, trailing, dtype=torch.float32):
+            """First device shard, like the reference's ``[0]`` (dust_extinction.py:240-245, :283-291)."""
+            t = ops.dev(a, dtype)
+            return t[0] if t.ndim == trailing + 2 else t
+
+        gas_coords, star_coords = shard0(gas.coords, 1), shard0(st.coords, 1)
+        gpix, spix = shard0(gas.pixel_assignment, 0, torch.int32), shard0(st.pixel_assignment, 0, torch.int32)
+        gmass, metals = shard0(gas.mass, 0), shard0(gas.metals, 1)
         av = ops.dust_av(gas_coords, gpix, gmass, metals, star_coords, spix, n_spaxels, dtg, ext_const, spaxel_area)
         axav_d = ops.dev(axav)
         if isinstance(st.spectra, DeferredSpectra):
