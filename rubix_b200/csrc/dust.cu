@@ -231,25 +231,29 @@ __global__ void apply_extinction_kernel(const float *__restrict__ spec, const fl
 // The reference materialises (n, W) twice between these stages (rubix/spectra/ifu.py:224-266 -> dust_extinction.py:356
 // -> ifu.py:270-288).  Here a block walks a chunk of the spaxel-sorted particle list; every thread owns kk =
 // ceil(W / 256) CONSECUTIVE channels, so the interval search of jnp.interp is one binary search for the first channel
-// and a forward walk for the rest; the particle's resampled values stay in registers until total / new is known, are
-// scaled, multiplied by 10^(-0.4 axav Av) and added to the thread's per-channel accumulators, which are flushed into
-// the cube (RED.ADD.F32) when the spaxel changes or the chunk ends.  t, dt and -0.4 axav are staged in shared memory
-// once per block; (lambda', spectrum) of the current particle too.  Traffic: 4 L bytes per particle instead of 16 W.
+// and a forward walk for the rest; the slope of every knot interval is computed once per particle (one IEEE division
+// per interval, not per channel: f = fp[i-1] + delta * (df / dx) instead of fp[i-1] + (delta / dx) * df, an ulp-level
+// reordering); the particle's resampled values stay in registers until total / new is known, are scaled, multiplied
+// by 10^(-0.4 axav Av) = 2^(e_w Av) and added to the thread's per-channel accumulators, which are flushed into the cube
+// (RED.ADD.F32) when the spaxel changes or the chunk ends.  t, dt and e_w are staged in shared memory once per block;
+// (lambda', spectrum, slopes) of the current particle too.  Traffic: 4 L bytes per particle instead of 16 W.
 template <int KMAX>
-__global__ void __launch_bounds__(256) resample_dusty_cube_kernel(
+__global__ void __launch_bounds__(256, KMAX <= 16 ? 4 : 1) resample_dusty_cube_kernel(
     PlanView p, const float *__restrict__ spec, const float *__restrict__ vel, const int32_t *__restrict__ spaxel_sorted,
     const uint32_t *__restrict__ order, const float *__restrict__ av, const float *__restrict__ axav, int64_t n, int nseg,
     int chunk, float *__restrict__ cube) {
   extern __shared__ float sm[];
-  float *t_s = sm, *dt_s = sm + p.W, *m04_s = sm + 2 * p.W, *lam = sm + 3 * p.W, *s = lam + p.L;
+  // t, dt, -0.4 log2(10) axav per channel (once per block); lambda', spectrum and the interval slopes of the particle
+  float *t_s = sm, *dt_s = sm + p.W, *e_s = sm + 2 * p.W, *lam = sm + 3 * p.W, *s = lam + p.L, *slope = s + p.L;
   __shared__ float red[16];
   __shared__ float bc;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int kk = (p.W + 255) / 256, w0 = tid * kk;
+  const int cnt = max(0, min(kk, p.W - w0));   // this thread's channels: w0 .. w0 + cnt - 1
   for (int w = tid; w < p.W; w += 256) {
     t_s[w] = p.t[w];
     dt_s[w] = p.dt[w];
-    m04_s[w] = axav ? __fmul_rn(-0.4f, axav[w]) : 0.f;
+    e_s[w] = axav ? __fmul_rn(-0.4f, axav[w]) * 3.3219281f : 0.f;   // 10^(-0.4 k A) = 2^(e A)
   }
   float acc[KMAX];
   const int64_t nchunks = (n + chunk - 1) / chunk;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(256) resample_dusty_cube_kernel(
         if (cur >= 0) {
 #pragma unroll
           for (int k = 0; k < KMAX; ++k)
-            if (k < kk && w0 + k < p.W && acc[k] != 0.f) atomicAdd(cube + (size_t)cur * p.W + w0 + k, acc[k]);
+            if (k < cnt && acc[k] != 0.f) atomicAdd(cube + (size_t)cur * p.W + w0 + k, acc[k]);
         }
         cur = spx;
 #pragma unroll
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(256) resample_dusty_cube_kernel(
       }
       const int64_t q = order[pos];
       const float d = expf(vel[3 * q + p.vel_comp] / kSpeedOfLight);
-      __syncthreads();   // the previous particle's readers are done with lam / s / red
+      __syncthreads();   // the previous particle's readers are done with lam / s / slope / red
       const float *sp = spec + q * p.L;
       for (int l = tid; l < p.L; l += 256) {
         lam[l] = __fmul_rn(p.lamz[l], d);
@@ -279,36 +283,41 @@ __global__ void __launch_bounds__(256) resample_dusty_cube_kernel(
       }
       __syncthreads();
       float tot = 0.f, nws = 0.f;
+      // per knot interval (l-1, l): the in-band flux sum (ifu.py:241-247) and the slope df / dx of jnp.interp's
+      // fp[i-1] + (delta / dx) * df, one IEEE division per interval instead of one per channel; a zero-width
+      // interval returns fp[i-1] (slope 0)
       for (int l = tid + 1; l < p.L; l += 256) {
-        const float x = lam[l];
-        if (x >= p.tmin && x <= p.tmax) tot += s[l] * (x - lam[l - 1]);
+        const float x = lam[l], dx = x - lam[l - 1];
+        if (x >= p.tmin && x <= p.tmax) tot += s[l] * dx;
+        slope[l] = (fabsf(dx) <= 1.4210855e-14f) ? 0.f : __fdiv_rn(s[l] - s[l - 1], dx);
       }
+      __syncthreads();
       float pv[KMAX];
-      if (w0 < p.W) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) pv[k] = 0.f;
+      if (cnt > 0) {
         int i = min(max(ss_right(lam, p.L, t_s[w0]), 1), p.L - 1);
-        float x0 = lam[i - 1], x1 = lam[i], f0 = s[i - 1], f1 = s[i];
+        float x0 = lam[i - 1], x1 = lam[i], f0 = s[i - 1], m = slope[i];
         const float lam_lo = lam[0], lam_hi = lam[p.L - 1], s_lo = s[0], s_hi = s[p.L - 1];
+        const bool inside = t_s[w0] >= lam_lo && t_s[w0 + cnt - 1] <= lam_hi;   // no end-value clamp for this thread
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
-          pv[k] = 0.f;
-          if (k < kk && w0 + k < p.W) {
+          if (k < cnt) {
             const float x = t_s[w0 + k];
             while (i < p.L - 1 && !(x1 > x)) {   // i = clip(searchsorted(lam, x, 'right'), 1, L-1)
               ++i;
-              x0 = x1; f0 = f1;
-              x1 = lam[i]; f1 = s[i];
+              x0 = x1; f0 = s[i - 1];
+              x1 = lam[i]; m = slope[i];
             }
-            const float dx = x1 - x0, df = f1 - f0, delta = x - x0;
-            float f = (fabsf(dx) <= 1.4210855e-14f) ? f0 : f0 + __fdiv_rn(delta, dx) * df;
-            if (x < lam_lo) f = s_lo;
-            if (x > lam_hi) f = s_hi;
+            float f = __fmaf_rn(x - x0, m, f0);
+            if (!inside) {
+              if (x < lam_lo) f = s_lo;
+              if (x > lam_hi) f = s_hi;
+            }
             pv[k] = f;
-            nws += f * dt_s[w0 + k];
+            nws = __fmaf_rn(f, dt_s[w0 + k], nws);
           }
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) pv[k] = 0.f;
       }
       tot = warp_sum(tot);
       nws = warp_sum(nws);
@@ -324,16 +333,16 @@ __global__ void __launch_bounds__(256) resample_dusty_cube_kernel(
       const float a_v = av ? av[q] : 0.f;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < kk && w0 + k < p.W) {
-          float v = __fmul_rn(pv[k], scale);                                   // the resampled spectrum (ifu.py:257)
-          if (av) v = __fmul_rn(v, exp10f(__fmul_rn(m04_s[w0 + k], a_v)));     // * extinction (dust_extinction.py:356)
-          acc[k] += v;                                                         // segment_sum (ifu.py:286)
+        if (k < cnt) {
+          float v = __fmul_rn(pv[k], scale);                             // the resampled spectrum (ifu.py:257)
+          if (av) v = __fmul_rn(v, exp2f(e_s[w0 + k] * a_v));            // * extinction (dust_extinction.py:356)
+          acc[k] += v;                                                   // segment_sum (ifu.py:286)
         }
     }
     if (cur >= 0) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < kk && w0 + k < p.W && acc[k] != 0.f) atomicAdd(cube + (size_t)cur * p.W + w0 + k, acc[k]);
+        if (k < cnt && acc[k] != 0.f) atomicAdd(cube + (size_t)cur * p.W + w0 + k, acc[k]);
     }
   }
 }
@@ -558,7 +567,7 @@ extern "C" int rbx_build_cube_dusty(const rbx_plan *plan, const float *d_spectra
   RBX_REQUIRE((d_av == nullptr) == (d_axav == nullptr), "rbx_build_cube_dusty: d_av and d_axav go together");
   RBX_REQUIRE(workspace_bytes >= rbx_build_cube_dusty_workspace_bytes(n), "rbx_build_cube_dusty: workspace too small");
   const int kk = (v.W + 255) / 256;
-  const size_t smem = sizeof(float) * (3 * (size_t)v.W + 2 * (size_t)v.L);
+  const size_t smem = sizeof(float) * (3 * (size_t)v.W + 3 * (size_t)v.L);
   if (kk > 32 || smem > 200 * 1024) {
     set_error("rbx_build_cube_dusty: telescope grid beyond 8192 channels (or SSP grid too long for shared memory)");
     return RBX_ERR_UNSUPPORTED;
@@ -577,7 +586,7 @@ extern "C" int rbx_build_cube_dusty(const rbx_plan *plan, const float *d_spectra
   int chunk = (int)((n + 148 * 32 - 1) / (148 * 32));
   chunk = chunk < 8 ? 8 : (chunk > 64 ? 64 : chunk);
   const int64_t nchunks = (n + chunk - 1) / chunk;
-  const int grid = (int)(nchunks < 148 * 4 ? nchunks : 148 * 4);
+  const int grid = (int)(nchunks < 148 * 8 ? nchunks : 148 * 8);
   auto kern = kk <= 16 ? resample_dusty_cube_kernel<16> : resample_dusty_cube_kernel<32>;
   if (smem > 48 * 1024) RBX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, 256, smem, stream>>>(v, d_spectra, d_velocity, (const int32_t *)w.keys_out, w.vals_out, d_av, d_axav, n, nseg,
