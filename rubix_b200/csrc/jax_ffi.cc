@@ -164,4 +164,50 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxPsfLsfTaps, PsfLsfTapsImpl,
                                   .Attr<int32_t>("psf_size")
                                   .Attr<ffi::Span<const float>>("lsf")
                                   .Attr<int32_t>("ext"));
+// dust variant (calc_dusty_ifu): A_V per star from the gas cells of its spaxel, replaces the lexsort / lax.scan part of
+// rubix/spectra/dust/dust_extinction.py:240-337; the dust-to-gas fit, the A_V constant and the spaxel area are static
+static ffi::Error DustAvImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> gas_coords, ffi::Buffer<ffi::S32> gas_pixel,
+                             ffi::Buffer<ffi::F32> gas_mass, ffi::Buffer<ffi::F32> gas_metals,
+                             ffi::Buffer<ffi::F32> star_coords, ffi::Buffer<ffi::S32> star_pixel,
+                             ffi::ResultBuffer<ffi::F32> av, ffi::ResultBuffer<ffi::U8> workspace, int32_t n_spaxels,
+                             ffi::Span<const float> dust_to_gas, float ext_const, float spaxel_area) {
+  if (dust_to_gas.size() != 5)
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "rubix_b200: dust_to_gas needs 5 parameters");
+  const int64_t n_gas = gas_mass.element_count(), n_star = star_pixel.element_count();
+  const int n_metals = n_gas ? (int)(gas_metals.element_count() / n_gas) : 5;
+  return status(rbx_dust_av(gas_coords.typed_data(), gas_pixel.typed_data(), gas_mass.typed_data(), gas_metals.typed_data(),
+                            n_metals, n_gas, star_coords.typed_data(), star_pixel.typed_data(), n_star, n_spaxels,
+                            dust_to_gas.begin(), ext_const, spaxel_area, av->typed_data(), nullptr, workspace->typed_data(),
+                            workspace->size_bytes(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxDustAv, DustAvImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int32_t>("n_spaxels")
+                                  .Attr<ffi::Span<const float>>("dust_to_gas")
+                                  .Attr<float>("ext_const")
+                                  .Attr<float>("spaxel_area"));
+
+// spectra (n, W) * 10^(-0.4 axav (W,) av (n,)): replaces extinguish + the final product, dust_extinction.py:341-356
+static ffi::Error ApplyExtinctionImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> spectra, ffi::Buffer<ffi::F32> av,
+                                      ffi::Buffer<ffi::F32> axav, ffi::ResultBuffer<ffi::F32> out) {
+  const int W = (int)axav.element_count();
+  return status(rbx_apply_extinction(spectra.typed_data(), av.typed_data(), axav.typed_data(),
+                                     (int64_t)av.element_count(), W, out->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(RbxApplyExtinction, ApplyExtinctionImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
 #endif  // RBX_HAVE_XLA_FFI

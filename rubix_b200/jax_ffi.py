@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _TARGETS = {"rbx_spaxel_assign": "RbxSpaxelAssign", "rbx_build_cube": "RbxBuildCube",
             "rbx_ssp_lookup": "RbxSspLookup", "rbx_doppler_resample": "RbxDopplerResample",
             "rbx_psf_lsf": "RbxPsfLsf", "rbx_assign_build_cube": "RbxAssignBuildCube",
-            "rbx_psf_lsf_taps": "RbxPsfLsfTaps"}
+            "rbx_psf_lsf_taps": "RbxPsfLsfTaps", "rbx_dust_av": "RbxDustAv",
+            "rbx_apply_extinction": "RbxApplyExtinction"}
 _registered = False
 
 
@@ -89,3 +90,26 @@ def psf_lsf_taps(cube, psf_kernel, lsf_kernel, ext: int = 12):
     lk = np.ascontiguousarray(lsf_kernel, dtype=np.float32).reshape(-1)
     return jax.ffi.ffi_call("rbx_psf_lsf_taps", jax.ShapeDtypeStruct(cube.shape, cube.dtype))(
         cube, psf=pk.reshape(-1), psf_size=np.int32(pk.shape[0]), lsf=lk, ext=np.int32(ext))
+
+
+def dust_av(workspace_bytes: int, gas_coords, gas_pixel, gas_mass, gas_metals, star_coords, star_pixel, n_spaxels: int,
+            dust_to_gas, ext_const: float, spaxel_area: float):
+    """A_V per star for ``apply_spaxel_extinction`` (rubix/spectra/dust/dust_extinction.py:240-337) as one custom
+    call; ``workspace_bytes`` from ``rbx_dust_av_workspace_bytes(n_gas, n_spaxels)``."""
+    import jax
+    import jax.numpy as jnp
+    import numpy as np
+    register()
+    outs = (jax.ShapeDtypeStruct(star_pixel.shape, jnp.float32), jax.ShapeDtypeStruct((workspace_bytes,), jnp.uint8))
+    av, _ = jax.ffi.ffi_call("rbx_dust_av", outs)(
+        gas_coords, gas_pixel, gas_mass, gas_metals, star_coords, star_pixel, n_spaxels=np.int32(n_spaxels),
+        dust_to_gas=np.asarray(dust_to_gas, dtype=np.float32), ext_const=np.float32(ext_const),
+        spaxel_area=np.float32(spaxel_area))
+    return av
+
+
+def apply_extinction(spectra, av, axav):
+    """``spectra * 10**(-0.4 * axav * av[:, None])`` (dust_extinction.py:341-356) as one custom call."""
+    import jax
+    register()
+    return jax.ffi.ffi_call("rbx_apply_extinction", jax.ShapeDtypeStruct(spectra.shape, spectra.dtype))(spectra, av, axav)
