@@ -206,3 +206,30 @@ def test_dusty_pipeline_order():
 def test_unknown_extinction_model_message():
     with pytest.raises(ValueError, match="Extinction model 'Nope' is not available"):
         dust.extinction_curve("Nope", np.array([5000.0]), 3.1)
+
+
+def test_prepare_input_loads_and_centres_gas(monkeypatch, tmp_path):
+    """rubix/core/data.py:541-600: every stored gas attribute is loaded, coordinates are centred on the subhalo
+    centre, and the subset indices are drawn from the STAR count (seed 42) for gas too."""
+    from rubix_b200.core import pipeline as pl
+    rng = np.random.default_rng(0)
+    ns, ng = 50, 80
+    stars = dict(coords=rng.normal(10, 1, (ns, 3)).astype(np.float32), velocity=rng.normal(0, 1, (ns, 3)).astype(np.float32),
+                 mass=np.ones(ns, np.float32), metallicity=np.full(ns, 0.01, np.float32), age=np.full(ns, 5.0, np.float32))
+    gas = dict(coords=rng.normal(10, 1, (ng, 3)).astype(np.float32), velocity=np.zeros((ng, 3), np.float32),
+               mass=np.arange(ng, dtype=np.float32), metals=rng.uniform(0, 1, (ng, 9)).astype(np.float32),
+               density=np.ones(ng, np.float32))
+    raw = {"particle_data": {"stars": stars, "gas": gas}, "redshift": 0.1,
+           "subhalo_center": np.array([10.0, 10.0, 10.0], np.float32), "subhalo_halfmassrad_stars": 2.0}
+    monkeypatch.setattr(pl, "load_rubix_galaxy", lambda path, types: raw)
+    cfg = copy.deepcopy(CONFIG)
+    cfg["output_path"] = str(tmp_path)
+    cfg["data"] = {"args": {"particle_type": ["stars", "gas"]}, "subset": {"use_subset": False}}
+    rd = pl.prepare_input(cfg)
+    assert np.allclose(rd.gas.coords, gas["coords"] - 10.0) and rd.gas.metals.shape == (ng, 9)
+    assert np.array_equal(rd.gas.mass, gas["mass"]) and rd.gas.density is not None
+    cfg["data"]["subset"] = {"use_subset": True, "subset_size": 20}
+    rd = pl.prepare_input(cfg)
+    np.random.seed(42)
+    idx = np.random.choice(np.arange(ns), size=20, replace=False)
+    assert len(rd.stars.mass) == 20 and np.array_equal(rd.gas.mass, gas["mass"][idx])
