@@ -38,19 +38,25 @@ def get_extinction(config: dict) -> Callable:
                                                       dist_z=config["galaxy"]["dist_z"], cosmology=get_cosmology(config))
     spaxel_area = float(np.float32(spatial_bin_size) ** 2)
     package = _dust.package_defaults()   # dust_to_gas_model / Xco come from the package-level rubix_config (:288-290)
+    # per-configuration constants, evaluated once (the reference re-traces them inside its jit): the A(lambda)/A(V)
+    # curve on the telescope grid, the dust-to-gas fit, the A_V constant.  An unknown model raises when the stage
+    # runs, like the reference (dust_extinction.py:224-228).
+    dcfg = config["ssp"]["dust"]
+    ext_model = dcfg["extinction_model"]
+    consts = {}
+    if ext_model in _dust.RV_MODELS:
+        consts["axav"] = _dust.extinction_curve(ext_model, wavelength, dcfg["Rv"])
+        consts["dtg"] = _dust.dust_to_gas_parameters(package["dust_to_gas_model"], package["Xco"])
+        consts["ext_const"] = _dust.extinction_constant(dcfg["dust_grain_density"])
 
     def calculate_extinction(rubixdata: RubixData) -> RubixData:
         """Apply the dust extinction to the spaxel data."""
         from .. import ops
         from .ifu import DeferredSpectra
         logger.info("Applying dust extinction to the spaxel data...")
-        dcfg = config["ssp"]["dust"]
-        ext_model = dcfg["extinction_model"]
         if ext_model not in _dust.RV_MODELS:   # dust_extinction.py:224-228
             raise ValueError(f"Extinction model '{ext_model}' is not available. Choose from {_dust.RV_MODELS}.")
-        axav = _dust.extinction_curve(ext_model, wavelength, dcfg["Rv"])
-        dtg = _dust.dust_to_gas_parameters(package["dust_to_gas_model"], package["Xco"])
-        ext_const = _dust.extinction_constant(dcfg["dust_grain_density"])
+        axav, dtg, ext_const = consts["axav"], consts["dtg"], consts["ext_const"]
         st, gas = rubixdata.stars, rubixdata.gas
         if gas.coords is None or gas.pixel_assignment is None or gas.metals is None or gas.mass is None:
             raise ValueError("calculate_extinction needs gas particles with coords, pixel_assignment, metals and mass")
@@ -65,7 +71,9 @@ def get_extinction(config: dict) -> Callable:
         gpix, spix = shard0(gas.pixel_assignment, 0, torch.int32), shard0(st.pixel_assignment, 0, torch.int32)
         gmass, metals = shard0(gas.mass, 0), shard0(gas.metals, 1)
         av = ops.dust_av(gas_coords, gpix, gmass, metals, star_coords, spix, n_spaxels, dtg, ext_const, spaxel_area)
-        axav_d = ops.dev(axav)
+        if "axav_d" not in consts or consts["axav_d"].device != av.device:
+            consts["axav_d"] = ops.dev(axav)
+        axav_d = consts["axav_d"]
         if isinstance(st.spectra, DeferredSpectra):
             if not st.spectra.resampled:
                 raise ValueError("calculate_extinction: spectra are not on the telescope wavelength grid "
