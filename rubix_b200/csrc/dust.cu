@@ -75,7 +75,7 @@ __device__ __forceinline__ void far_candidates(float z, int32_t pixel, unsigned 
 
 __global__ void dust_cell_kernel(const float *__restrict__ coords, const int32_t *__restrict__ pixel,
                                  const float *__restrict__ mass, const float *__restrict__ metals, int n_metals,
-                                 int64_t n, DustParams p, float *__restrict__ cell_av,
+                                 int64_t n, int n_spaxels, DustParams p, float *__restrict__ cell_av,
                                  unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals,
                                  unsigned long long *__restrict__ far) {
   unsigned long long bl = kNoLeft, br = kNoRight;
@@ -89,7 +89,10 @@ __global__ void dust_cell_kernel(const float *__restrict__ coords, const int32_t
     cell_av[i] = __fdiv_rn(__fmul_rn(dust_mass, p.ext_const), p.spaxel_area);
     const float z = coords[3 * i + 2];
     const int32_t px = pixel[i];
-    keys[i] = ((unsigned long long)((uint32_t)px ^ 0x80000000u) << 32) | f32_orderable(z);   // lexsort((z, pixel))
+    // lexsort((z, pixel)); ids below 0 / at or above n_spaxels (the assignment never produces them) collapse to one
+    // slot in front of / behind every spaxel, which keeps the key at 32 + log2(n_spaxels + 2) bits
+    const uint32_t slot = (uint32_t)(min(max(px, -1), n_spaxels) + 1);
+    keys[i] = ((unsigned long long)slot << 32) | f32_orderable(z);
     vals[i] = (uint32_t)i;
     unsigned long long l, r;
     far_candidates(z, px, l, r);
@@ -133,7 +136,7 @@ __global__ void dust_bounds_kernel(const unsigned long long *__restrict__ keys, 
   if (t <= n_spaxels) {
     int64_t lo = 0, hi = n;
     if (t == n_spaxels) lo = n;   // jnp.array([len(sorted)])
-    const unsigned long long want = (unsigned long long)((uint32_t)t ^ 0x80000000u) << 32;
+    const unsigned long long want = (unsigned long long)((uint32_t)t + 1u) << 32;
     while (lo < hi) {
       const int64_t mid = (lo + hi) >> 1;
       if (keys[mid] < want) lo = mid + 1; else hi = mid;
@@ -486,15 +489,17 @@ extern "C" int rbx_dust_av(const float *d_gas_coords, const int32_t *d_gas_pixel
   RBX_CUDA_OK(cudaMemsetAsync(w.far, 0x00, 2 * sizeof(unsigned long long), stream));        // kNoLeft
   RBX_CUDA_OK(cudaMemsetAsync(w.far + 2, 0xFF, 2 * sizeof(unsigned long long), stream));    // kNoRight
   dust_cell_kernel<<<grid1d(n_gas, 256), 256, 0, stream>>>(d_gas_coords, d_gas_pixel, d_gas_mass, d_gas_metals, n_metals,
-                                                            n_gas, p, w.cell_av, w.keys, w.vals, w.far);
+                                                            n_gas, n_spaxels, p, w.cell_av, w.keys, w.vals, w.far);
   count_launch();
   RBX_LAUNCH_OK();
   dust_far2_kernel<<<grid1d(n_gas, 256), 256, 0, stream>>>(d_gas_coords, d_gas_pixel, n_gas, w.far);
   count_launch();
   RBX_LAUNCH_OK();
   size_t cub_bytes = w.cub_bytes;
+  int key_bits = 33;
+  while ((1ll << (key_bits - 32)) < (long long)n_spaxels + 2) ++key_bits;
   RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_temp, cub_bytes, (const unsigned long long *)w.keys, w.keys_out,
-                                              (const uint32_t *)w.vals, w.vals_out, n_gas, 0, 64, stream));
+                                              (const uint32_t *)w.vals, w.vals_out, n_gas, 0, key_bits, stream));
   count_launch(3);
   int bgrid = grid1d(n_gas, 256);
   if (bgrid < (n_spaxels + 1 + 255) / 256) bgrid = (n_spaxels + 1 + 255) / 256;
