@@ -73,3 +73,68 @@ def test_two_rank_shard_reduce_and_slab_convolution(tmp_path, bc03):
     conv = orc.apply_lsf(orc.apply_psf(ref, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
     # slab-wise LSF with a 12-channel halo is exact (the kernel reaches +-12 channels)
     assert np.abs(got["conv"] - conv).max() <= 1e-12 * conv.max()
+
+
+def _dusty_inputs():
+    from rubix_b200 import synthetic
+    d = synthetic.bench_g(601, seed=42)
+    rng = np.random.default_rng(7)
+    ng = 900
+    gas = dict(coords=np.stack([rng.normal(0, 1.5, ng), rng.normal(0, 1.5, ng), rng.normal(0, 1.0, ng)], 1).astype(np.float32),
+               mass=(rng.uniform(0.5, 2, ng) * 2e5).astype(np.float32),
+               metals=rng.uniform(1e-4, 1e-2, (ng, 9)).astype(np.float32))
+    gas["metals"][:, 0] = 0.74
+    return d, gas
+
+
+def _dusty_cube(orc, stars, gas, tpl, wave, edges, S):
+    """calc_dusty_ifu on the oracle for one set of stars and ALL the gas cells."""
+    spix = orc.square_spaxel_assignment(stars["coords"], edges)
+    gpix = orc.square_spaxel_assignment(gas["coords"], edges)
+    cell = orc.dust_cell_extinction(gas["mass"], gas["metals"], 3.5, 0.145, "broken power law fit", "Z")
+    av = orc.stars_av(gas["coords"][:, 2], gpix, cell, stars["coords"][:, 2], spix, S * S)
+    ext = orc.extinguish(wave, av, "Cardelli89", 3.1)
+    cube, _ = orc.particles_to_cube(stars["coords"], stars["velocity"], stars["mass"], stars["metallicity"], stars["age"],
+                                    edges, S, tpl["metallicity"], tpl["age"], tpl["wavelength"], tpl["flux"], wave, 0.1,
+                                    method="linear", dtype=np.float64, extinction=ext)
+    return cube, av
+
+
+def _dusty_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import rubix_oracle as orc
+        from rubix_b200 import parallel, synthetic
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        tpl = np.load(os.path.join(root, "tests", "golden", "bc03lr_f32.npz"))
+        wave = synthetic.muse_wave()[:300]
+        edges = synthetic.spatial_edges(5)
+        stars, gas = _dusty_inputs()
+        mine = parallel.shard_particles(stars, rank, world)   # stars shard by rank, the gas cells are replicated
+        cube, av = _dusty_cube(orc, mine, gas, tpl, wave, edges, 5)
+        t = torch.from_numpy(np.ascontiguousarray(cube))
+        parallel.allreduce_cube(t)
+        parts = [None] * world
+        dist.all_gather_object(parts, (rank, av))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "dusty.npz"), cube=t.numpy(),
+                     av=np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_dusty_variant_shards_stars_and_replicates_gas(tmp_path, bc03):
+    """The dusty variant on two ranks: a star's A_V needs all the gas cells of its spaxel, so stars are sharded and
+    the gas is replicated; the partial cubes add up to the single-process cube with no further exchange."""
+    world = 2
+    mp.spawn(_dusty_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "dusty.npz")
+    from oracle import rubix_oracle as orc
+    from rubix_b200 import synthetic
+    stars, gas = _dusty_inputs()
+    ref, av = _dusty_cube(orc, stars, gas, bc03, synthetic.muse_wave()[:300], synthetic.spatial_edges(5), 5)
+    assert av.max() > 0.1 and ref.max() > 0
+    assert np.array_equal(got["av"], av)                       # per-star A_V does not depend on the star sharding
+    assert np.abs(got["cube"] - ref).max() <= 1e-12 * ref.max()
