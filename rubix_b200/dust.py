@@ -183,3 +183,47 @@ def extinction_curve(model: str, wave_angstrom, Rv: float) -> np.ndarray:
 def package_defaults() -> dict:
     """rubix_config.yml:145-150 (``ssp.dust`` of the package-level configuration)."""
     return dict(DUST)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's class interface (rubix/spectra/dust/dust_baseclasses.py, extinction_models.py), host / numpy:
+# ``Cardelli89(Rv=3.1)(wave)``, ``.evaluate(wave)``, ``.extinguish(wave, Av=..., Ebv=...)``
+# ---------------------------------------------------------------------------------------------
+class BaseExtRvModel:
+    """dust_baseclasses.py:72-164: an R(V)-dependent extinction curve A(lambda)/A(V)."""
+
+    _curve = None
+    wave_range_l = wave_range_h = Rv_range_l = Rv_range_h = None
+
+    def __init__(self, Rv: float = 3.1):
+        self.Rv = float(Rv)
+
+    def evaluate(self, wave) -> np.ndarray:
+        return type(self)._curve(wave, self.Rv)
+
+    def __call__(self, wave) -> np.ndarray:
+        return self.evaluate(wave)
+
+    def extinguish(self, wave, Av=None, Ebv=None) -> np.ndarray:
+        """dust_baseclasses.py:126-164: the fractional extinction ``10 ** (-0.4 * axav * Av)``."""
+        axav = self(wave)
+        if (Av is None) and (Ebv is None):
+            raise ValueError("neither Av or Ebv passed, one of them is required!")
+        if Av is None:
+            Av = self.Rv * Ebv
+        return np.power(F(10.0), F(-0.4) * axav * F(Av)).astype(F)
+
+
+class Cardelli89(BaseExtRvModel):
+    """extinction_models.py:22-178."""
+    _curve = staticmethod(cardelli89)
+    wave_range_l, wave_range_h, Rv_range_l, Rv_range_h = 0.3, 10.0, 2.0, 6.0
+
+
+class Gordon23(BaseExtRvModel):
+    """extinction_models.py:181-431."""
+    _curve = staticmethod(gordon23)
+    wave_range_l, wave_range_h, Rv_range_l, Rv_range_h = 0.0912, 32.0, 2.3, 5.6
+
+
+Rv_model_classes = {"Cardelli89": Cardelli89, "Gordon23": Gordon23}

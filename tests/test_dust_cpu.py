@@ -233,3 +233,22 @@ def test_prepare_input_loads_and_centres_gas(monkeypatch, tmp_path):
     np.random.seed(42)
     idx = np.random.choice(np.arange(ns), size=20, replace=False)
     assert len(rd.stars.mass) == 20 and np.array_equal(rd.gas.mass, gas["mass"][idx])
+
+
+# ---- the reference's class interface (tests/test_dust_classes.py:112-166) ---------------------------------------
+def test_extinction_model_classes():
+    wave = np.array([0.5, 1.0, 2.0, 3.0, 5.0, 8.0, 10.0], dtype=np.float32)
+    model = dust.Cardelli89(Rv=3.1)
+    r = model.evaluate(wave)
+    assert r.shape == wave.shape and np.all(r >= 0) and np.all(r <= 10)          # :112-123
+    assert np.array_equal(model(wave), r)
+    with pytest.raises(ValueError, match="neither Av or Ebv passed, one of them is required!"):   # :126-133
+        model.extinguish(wave)
+    got = model.extinguish(wave, Ebv=1.0)                                        # :136-151: Av = Rv * Ebv
+    assert np.allclose(got, np.power(10.0, -0.4 * r.astype(np.float64) * 3.1), rtol=2e-6)
+    assert np.allclose(model.extinguish(wave, Av=3.1), got)
+    g = dust.Gordon23(Rv=3.1)
+    wave = np.array([0.1, 0.3, 0.5, 1.0, 2.0, 5.0, 10.0, 20.0, 30.0], dtype=np.float32)
+    r = g.evaluate(wave)
+    assert r.shape == wave.shape and np.all(r >= 0) and np.all(r <= 10)          # :154-166
+    assert set(dust.Rv_model_classes) == set(dust.RV_MODELS)
