@@ -276,3 +276,34 @@ def test_dusty_pipeline_fused_equals_staged_and_oracle(bc03, muse_wave, tng_subs
     ref = orc.apply_lsf(orc.apply_psf(raw, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
     cube_close(outs[True], ref, "dusty pipeline vs oracle", rtol_max=2e-5)
     assert np.abs(outs[True].astype(np.float64) - ref).max() <= 1e-5 * np.abs(ref).sum()
+
+
+def test_dusty_cube_properties_at_full_size(ops, bc03, muse_wave):
+    """BASELINE config 2 size (10^6 particles, full MUSE grid), where the oracle is too slow: properties that do not
+    depend on size -- A_V = 0 reproduces the dust-free cube, extinction only removes flux, star shards add up, and
+    the binned-moment form agrees with the one-pass kernel."""
+    from rubix_b200 import synthetic
+    n = 1_000_000
+    p = synthetic.bench_g(n)
+    edges = synthetic.spatial_edges(25)
+    plan = ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1, method="linear")
+    pix = ops.spaxel_assign(p["coords"], edges)
+    vel, mass, met, age = (ops.dev(p[k]) for k in ("velocity", "mass", "metallicity", "age"))
+    axav = ops.dev(hdust.extinction_curve("Gordon23", muse_wave, 3.1))
+    av = ops.dev(np.random.default_rng(42).uniform(0.0, 3.0, n).astype(np.float32))
+    clean = ops.build_cube(plan, vel, mass, met, age, pix, 25)
+    mx = float(clean.max())
+    zero = ops.build_cube_dusty_binned(plan, vel, mass, met, age, pix, 25, torch.zeros_like(av), axav)
+    assert float((zero - clean).abs().max()) <= 2e-6 * mx
+    dusty = ops.build_cube_dusty_binned(plan, vel, mass, met, age, pix, 25, av, axav)
+    assert torch.isfinite(dusty).all() and float(dusty.min()) >= 0.0
+    assert bool((dusty <= clean * (1 + 1e-5) + 1e-6 * mx).all()) and float(dusty.sum()) < 0.9 * float(clean.sum())
+    h = n // 2
+    parts = sum(ops.build_cube_dusty_binned(plan, vel[s], mass[s], met[s], age[s], pix[s], 25, av[s], axav)
+                for s in (slice(0, h), slice(h, n)))
+    assert float((parts - dusty).abs().max()) <= 5e-6 * float(dusty.max())
+    m = 200_000   # the one-pass kernel on a subset (it needs the (m, L) SSP spectra)
+    spec = ops.scale_by_mass(ops.ssp_lookup(plan, met[:m], age[:m]), mass[:m])
+    one = ops.build_cube_dusty(plan, spec, vel[:m], pix[:m], 25, av[:m], axav)
+    binned = ops.build_cube_dusty_binned(plan, vel[:m], mass[:m], met[:m], age[:m], pix[:m], 25, av[:m], axav)
+    assert float((one - binned).abs().max()) <= 5e-6 * float(one.max())
