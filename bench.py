@@ -138,6 +138,13 @@ def cpu_arm(data, tpl, wave, edges, S, method, pk, lk, sample, threads):
     return time.perf_counter() - t0, cube
 
 
+def one_core_rate(data, tpl, wave, edges, S, method, pk, lk, sample):
+    """The same pass on ONE host thread over a smaller sample (1 core and all cores are both reported)."""
+    m = max(1, min(sample, 40000))
+    t, _ = cpu_arm(data, tpl, wave, edges, S, method, pk, lk, m, 1)
+    return {"value": m / t, "unit": "particles/s", "cores": 1, "sample": f"first {m} particles, one pass, one thread"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,7 +171,8 @@ def run_reference(args):
                    "note": "C restatement of rubix@dbb4487 (oracle/rubix_oracle.c), not jax: the reference is "
                            "pure Python/JAX and cannot be installed in this image"},
         "cpu_baseline": {"value": val, "unit": "particles/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} bench-G particles per step, all {threads} host threads (OpenMP)"},
+                         "sample": f"{sample} bench-G particles per step, all {threads} host threads (OpenMP)",
+                         "one_core": one_core_rate(data, tpl, wave, edges, S, args.method, pk, lk, sample)},
         "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -422,7 +430,9 @@ def main():
             ct, _ = cpu_arm(data, tpl, wave, edges_h, S, args.method, pk_h, lk_h, sample, threads)
             line["cpu_baseline"] = {"value": sample / ct, "unit": "particles/s", "cores": threads, "kind": "port",
                                     "sample": f"first {sample} particles of the same workload, one pass, "
-                                              f"oracle/rubix_oracle.c float32 on {threads} host threads"}
+                                              f"oracle/rubix_oracle.c float32 on {threads} host threads",
+                                    "one_core": one_core_rate(data, tpl, wave, edges_h, S, args.method, pk_h, lk_h,
+                                                              sample)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
