@@ -252,3 +252,20 @@ def test_extinction_model_classes():
     r = g.evaluate(wave)
     assert r.shape == wave.shape and np.all(r >= 0) and np.all(r <= 10)          # :154-166
     assert set(dust.Rv_model_classes) == set(dust.RV_MODELS)
+
+
+def test_get_extinction_errors_on_the_reference_minimal_configs():   # tests/test_dust_extinction.py:209-227
+    from rubix_b200.core import get_extinction
+    with pytest.raises(ValueError, match="Dust configuration not found in config file."):
+        get_extinction({"ssp": {}, "galaxy": {"dist_z": 0.1}})
+    with pytest.raises(ValueError, match="Extinction model not found in dust configuration."):
+        get_extinction({"ssp": {"dust": {}}, "galaxy": {"dist_z": 0.1}})
+
+
+def test_unknown_model_raises_when_the_stage_runs():   # tests/test_dust_extinction.py:192-206
+    from rubix_b200.core import RubixData, get_extinction
+    cfg = copy.deepcopy(CONFIG)
+    cfg["ssp"]["dust"]["extinction_model"] = "InvalidModel"
+    fn = get_extinction(cfg)   # the factory accepts it, like the reference's
+    with pytest.raises(ValueError, match="Extinction model 'InvalidModel' is not available. Choose from"):
+        fn(RubixData())
