@@ -34,7 +34,8 @@ typedef enum {
   RBX_ERR_CUDA = -2,
   RBX_ERR_WORKSPACE_TOO_SMALL = -3,
   RBX_ERR_UNSUPPORTED = -4, /* configuration outside the fused kernel's limits: use the stage calls */
-  RBX_ERR_NO_DEVICE = -5
+  RBX_ERR_NO_DEVICE = -5,
+  RBX_ERR_NCCL = -6
 } rbx_status;
 
 /* rubix/core/ssp.py:57-62: `ssp.method`; rubix's default when the key is absent is "cubic". */
@@ -46,6 +47,13 @@ const char *rbx_last_error(void);
 int rbx_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t rbx_launch_count(void);
+
+/* Tuning / test switches: "psub", "sort_bits", "fused_force_lut", "fused_force_cas", "fused_impl" (1 = group kernel),
+ * "fused_chs", "fused_no_skew", "fused_warps", "prep_blocks", "small_shift", "tail_shift", "host_chunks",
+ * "march_no_bulk", "sort_impl" (1 = cub), "fused_variant".  value < 0 restores the library's own choice.  The
+ * environment (RBX_<NAME>) seeds them ONCE when the library is loaded; no launch path calls getenv(). */
+int rbx_set_option(const char *name, int64_t value);
+int rbx_get_option(const char *name, int64_t *value);
 
 /* Optional CUDA-event timing of the dominant kernel (fused_cube_kernel) on its launch stream, for
  * bench.py's roofline line.  Not thread-safe; off by default. */
@@ -134,6 +142,56 @@ int rbx_assign_build_cube(const rbx_plan *plan, const float *d_coords, const flo
                           int32_t *d_pixel_out, float *d_cube, void *d_workspace, size_t workspace_bytes,
                           void *stream);
 
+/* The same with structure-of-arrays particles: x, y and the line-of-sight velocity (the component
+ * ifu.doppler.velocity_direction selects) as arrays of their own -- the 24 bytes per particle this path reads
+ * instead of the 40 of the (n, 3) arrays. */
+int rbx_assign_build_cube_packed(const rbx_plan *plan, const float *d_x, const float *d_y, const float *d_edges,
+                                 int n_edges, int apply_filter, const float *d_vlos, const float *d_mass,
+                                 const float *d_metallicity, const float *d_age, int64_t n, int num_spaxels,
+                                 int32_t *d_pixel_out, float *d_cube, void *d_workspace, size_t workspace_bytes,
+                                 void *stream);
+
+/* What the last build on this workspace did (synchronises `stream`).  *h_error: 0 ok; 1 work-item tables too small,
+ * 2 SSP knot window wider than the kernels hold, 3 Doppler range too wide for the chunk geometry -- for != 0 the
+ * cube was filled with NaN rather than left silently wrong.  *h_impl: 0 = fused_cube_warp_kernel ran, 1 = the
+ * general fused_cube_kernel (chosen on the device from the knot window and Doppler range actually present). */
+int rbx_build_cube_status(const rbx_plan *plan, int64_t n, int num_spaxels, const void *d_workspace, int *h_error,
+                          int *h_impl, void *stream);
+
+/* Slab-major partial cube for the multi-GPU exchange: the cube is stored as nslab wavelength slabs of
+ * wslab = ceil(W / nslab) channels, slab r an (S*S, ws) block with ws = wslab + 2 halo: its own channels plus `halo`
+ * channels of each neighbour (zeros beyond [0, W): the zero padding of the reference's 'same' convolutions).
+ * d_slabs holds nslab * S*S * ws floats.  One rbx_reduce_scatter_cube then leaves rank r with its summed slab
+ * including the LSF halo, ready for rbx_psf_lsf_taps_pitched (rubix/core/ifu.py:324-333 -> core/psf.py, core/lsf.py). */
+int rbx_slab_geometry(int W, int nslab, int halo, int *wslab, int *ws);
+int rbx_assign_build_cube_slabs(const rbx_plan *plan, const float *d_coords, const float *d_edges, int n_edges,
+                                int apply_filter, const float *d_velocity, const float *d_mass,
+                                const float *d_metallicity, const float *d_age, int64_t n, int num_spaxels, int nslab,
+                                int halo, float *d_slabs, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The exchange step: rubix sums the per-device cubes with jnp.sum(ifu_cubes, axis=0) after its pmap
+ * (rubix/core/ifu.py:324-333).  Here: one process per GPU, NCCL over NVLink, bound at run time (dlopen of
+ * libnccl.so.2 -- the copy the host process already loaded, if any).  rbx_comm_unique_id on one rank, its 128
+ * bytes handed to every rank by the host (any out-of-band channel), rbx_comm_init on every rank with its CUDA
+ * device current.  Collectives are asynchronous on `stream`; float32 sums.
+ *   rbx_reduce_cube          d_recv (root only) = sum over ranks of d_send[count]
+ *   rbx_allreduce_cube       every rank gets the sum
+ *   rbx_reduce_scatter_cube  d_send holds world * recv_count floats; rank r receives the sum of block r
+ *   rbx_allgather_cube       d_recv[world * send_count] = the blocks of all ranks in rank order
+ * ------------------------------------------------------------------------------------------- */
+#define RBX_COMM_ID_BYTES 128
+typedef struct rbx_comm rbx_comm;
+int rbx_comm_unique_id(void *id);
+int rbx_comm_init(rbx_comm **comm, const void *id, int rank, int world);
+int rbx_comm_destroy(rbx_comm *comm);
+int rbx_comm_info(const rbx_comm *comm, int *rank, int *world, int *nccl_version);
+int rbx_reduce_cube(rbx_comm *comm, const float *d_send, float *d_recv, int64_t count, int root, void *stream);
+int rbx_allreduce_cube(rbx_comm *comm, const float *d_send, float *d_recv, int64_t count, void *stream);
+int rbx_reduce_scatter_cube(rbx_comm *comm, const float *d_send, float *d_recv, int64_t recv_count, void *stream);
+int rbx_allgather_cube(rbx_comm *comm, const float *d_send, float *d_recv, int64_t send_count, void *stream);
+int rbx_allreduce_f64(rbx_comm *comm, const double *d_send, double *d_recv, int64_t count, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a6 apply_psf (rubix/telescope/psf/psf.py:56-57): per wavelength slice
  *    convolve2d(slice, kernel, mode="same"); d_kernel is (M, N) row-major on the device.
@@ -182,6 +240,16 @@ int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity, const floa
                       float halfmass_radius, const float *h_euler, float *d_coords_out,
                       float *d_velocity_out, float *d_rotation, void *d_workspace, size_t workspace_bytes,
                       void *stream);
+/* The same in two steps for a galaxy whose particles are sharded over ranks (the reference computes ONE rotation from
+ * all particles before its reshape / pmap split, rubix/core/rotation.py:76-115): rbx_rotate_moments writes this
+ * shard's inertia sums, 12 doubles (six second moments, n_inside, n, and x, y, z, mass of the galaxy's particle 0
+ * from the rank with first_shard != 0 -- the reference's index-0 padding term); the host sums them over the ranks
+ * (rbx_allreduce_f64) and rbx_rotate_apply derives the rotation and rotates the shard.  Same workspace size. */
+int rbx_rotate_moments(const float *d_coords, const float *d_mass, int64_t n, float halfmass_radius,
+                       int first_shard, double *d_moments, void *d_workspace, size_t workspace_bytes, void *stream);
+int rbx_rotate_apply(const float *d_coords, const float *d_velocity, int64_t n, const double *d_moments,
+                     const float *h_euler, float *d_coords_out, float *d_velocity_out, float *d_rotation,
+                     void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * apply_noise, the stage right after the path (rubix/core/noise.py:15-78 ->
@@ -258,6 +326,14 @@ int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, const float *
                       const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
                       const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
                       float *h_cube, void *stream);
+
+/* The same call with structure-of-arrays host buffers (x, y, line-of-sight velocity: 24 bytes per particle over
+ * PCIe instead of 40). */
+int rbx_pipeline_host_packed(const rbx_plan *plan, const float *h_x, const float *h_y, const float *h_vlos,
+                             const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                             const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
+                             const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                             float *h_cube, void *stream);
 
 #ifdef __cplusplus
 }

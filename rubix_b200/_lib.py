@@ -29,6 +29,12 @@ EXPORTED = [
     "rbx_build_cube_dusty", "rbx_build_cube_dusty_workspace_bytes",
     "rbx_dusty_moments", "rbx_dusty_bins", "rbx_dusty_combine",
     "rbx_profile_enable", "rbx_profile_fused",
+    "rbx_set_option", "rbx_get_option",
+    "rbx_assign_build_cube_packed", "rbx_build_cube_status", "rbx_slab_geometry", "rbx_assign_build_cube_slabs",
+    "rbx_pipeline_host_packed",
+    "rbx_comm_unique_id", "rbx_comm_init", "rbx_comm_destroy", "rbx_comm_info",
+    "rbx_reduce_cube", "rbx_allreduce_cube", "rbx_reduce_scatter_cube", "rbx_allgather_cube", "rbx_allreduce_f64",
+    "rbx_rotate_moments", "rbx_rotate_apply",
 ]
 
 RBX_OK = 0
@@ -99,6 +105,25 @@ def lib() -> C.CDLL:
     sigs["rbx_build_cube_dusty"] = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, sz, vp]
     sigs["rbx_dusty_bins"] = [vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp]
     sigs["rbx_dusty_combine"] = [vp, i32, i32, f32, f32, vp, i32, vp, vp]
+    sigs["rbx_set_option"] = [C.c_char_p, i64]
+    sigs["rbx_get_option"] = [C.c_char_p, C.POINTER(i64)]
+    sigs["rbx_assign_build_cube_packed"] = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp]
+    sigs["rbx_build_cube_status"] = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
+    sigs["rbx_slab_geometry"] = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    sigs["rbx_assign_build_cube_slabs"] = [vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, sz, vp]
+    sigs["rbx_pipeline_host_packed"] = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32,
+                                        vp, vp]
+    sigs["rbx_comm_unique_id"] = [vp]
+    sigs["rbx_comm_init"] = [C.POINTER(vp), vp, i32, i32]
+    sigs["rbx_comm_destroy"] = [vp]
+    sigs["rbx_comm_info"] = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    sigs["rbx_reduce_cube"] = [vp, vp, vp, i64, i32, vp]
+    sigs["rbx_allreduce_cube"] = [vp, vp, vp, i64, vp]
+    sigs["rbx_reduce_scatter_cube"] = [vp, vp, vp, i64, vp]
+    sigs["rbx_allgather_cube"] = [vp, vp, vp, i64, vp]
+    sigs["rbx_allreduce_f64"] = [vp, vp, vp, i64, vp]
+    sigs["rbx_rotate_moments"] = [vp, vp, i64, f32, i32, vp, vp, sz, vp]
+    sigs["rbx_rotate_apply"] = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.rbx_dusty_moments.argtypes = []
     L.rbx_dusty_moments.restype = i32
     L.rbx_dust_av_workspace_bytes.argtypes = [i64, i32]
@@ -130,3 +155,14 @@ def check(code: int) -> None:
 
 def launch_count() -> int:
     return int(lib().rbx_launch_count())
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning / test switch of the library (include/rubix_b200.h: rbx_set_option); value < 0 = the library's own choice."""
+    check(lib().rbx_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int64()
+    check(lib().rbx_get_option(name.encode(), C.byref(v)))
+    return int(v.value)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_HERE)
 CONSTANTS = {
     "SPEED_OF_LIGHT": 299792.458,  # km/s
     "LSOL_TO_ERG": 3.828e33,
-    "MPC_TO_CM": 3.086e24,
+    "MPC_TO_CM": 3.08568e24,
     "KPC_TO_CM": 3.08568e21,       # rubix_config.yml:6
     "MSUN_TO_GRAMS": 1.989e33,     # rubix_config.yml:7
     "MASS_OF_PROTON": 1.67262e-24, # rubix_config.yml:18
@@ -63,10 +63,9 @@ SSP = {
     },
 }
 
-#: where SSP template files are looked for, in order: $RUBIX_B200_TEMPLATE_PATH, the package's
-#: templates/ directory, and the float32 fixture committed under tests/golden/.
-TEMPLATE_PATHS = [p for p in (os.environ.get("RUBIX_B200_TEMPLATE_PATH"), os.path.join(_HERE, "templates"),
-                              os.path.join(ROOT, "tests", "golden")) if p]
+#: where SSP template files are looked for, in order: $RUBIX_B200_TEMPLATE_PATH, then the package's templates/
+#: directory (BC03lr as the float32 arrays the reference's loader produces, tools/make_golden.py).
+TEMPLATE_PATHS = [p for p in (os.environ.get("RUBIX_B200_TEMPLATE_PATH"), os.path.join(_HERE, "templates")) if p]
 
 #: pipeline_config.yml:1-60 (calc_ifu): node name -> depends_on
 def _chain(names):

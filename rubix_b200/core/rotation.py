@@ -36,8 +36,14 @@ def get_galaxy_rotation(config: dict) -> Callable:
                 assert component.velocity is not None, f"Velocities not found for {particle_type}. "
                 assert component.mass is not None, f"Masses not found for {particle_type}. "
                 # the reference uses the STELLAR half-mass radius for both components (rotation.py:88)
+                # a galaxy sharded over ranks (b200.distributed) gets ONE rotation: the inertia sums are all-reduced
+                comm = None
+                if isinstance(config.get("b200"), dict) and config["b200"].get("distributed"):
+                    from ..parallel import get_comm
+                    comm = get_comm()
                 coords, velocity, _ = ops.rotate_galaxy(component.coords, component.velocity, component.mass,
-                                                        float(rubixdata.galaxy.halfmassrad_stars), alpha, beta, gamma)
+                                                        float(rubixdata.galaxy.halfmassrad_stars), alpha, beta, gamma,
+                                                        comm=comm)
                 component.coords, component.velocity = coords, velocity
         return rubixdata
 

@@ -41,6 +41,16 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     }                                                                                       \
   } while (0)
 
+// Tuning / test switches (options.cu).  -1 = unset (the library's own choice).  Seeded once from the environment
+// (RBX_<NAME>) when the library is loaded, changed with rbx_set_option(); the launch path only reads atomics.
+enum Opt {
+  OPT_PSUB = 0, OPT_SORT_BITS, OPT_FUSED_FORCE_LUT, OPT_FUSED_FORCE_CAS, OPT_FUSED_IMPL, OPT_FUSED_CHS,
+  OPT_FUSED_NO_SKEW, OPT_FUSED_WARPS, OPT_PREP_BLOCKS, OPT_SMALL_SHIFT, OPT_TAIL_SHIFT, OPT_HOST_CHUNKS,
+  OPT_MARCH_NO_BULK, OPT_SORT_IMPL, OPT_FUSED_VARIANT, OPT_COUNT
+};
+int64_t opt(Opt o);
+inline bool opt_on(Opt o) { return opt(o) > 0; }
+
 constexpr int kMaxLutBuckets = 8192;  // channel-lookup buckets the fused kernel keeps in shared memory
 constexpr float kSpeedOfLight = 299792.458f;  // rubix/config/rubix_config.yml:8
 
@@ -86,11 +96,22 @@ struct rbx_plan {
 
 namespace rbx {
 
-// rbx_build_cube with an accumulate switch and optional in-kernel spaxel assignment (fused.cu)
-int build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
-                    const float *d_age, int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube, void *d_ws,
-                    size_t ws_bytes, void *stream, int accumulate, const float *d_coords, const float *d_edges,
-                    int n_edges, int mark_outside);
+// Everything the rbx_*build_cube* entry points hand to build_cube_impl (fused.cu).
+struct CubeBuild {
+  const float *vel = nullptr;      // Doppler component of particle 0 ...
+  int vstride = 3;                 // ... and floats between particles ((n, 3) arrays: 3; a line-of-sight array: 1)
+  const float *mass = nullptr, *met = nullptr, *age = nullptr;
+  int32_t *pixel = nullptr;        // spaxel ids: input when cx == nullptr, else an optional output
+  const float *cx = nullptr, *cy = nullptr;   // x / y of particle 0 (spaxel assignment inside prep_kernel) or nullptr
+  int cstride = 3;
+  const float *edges = nullptr;    // spatial bin edges (with cx)
+  int n_edges = 0;
+  int mark_outside = 0;            // aperture filter: particles outside the edges get pixel -1
+  int accumulate = 0;              // cube += instead of cube =
+  int nslab = 1, halo = 0;         // slab-major cube (rbx_assign_build_cube_slabs)
+};
+int build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, int num_spaxels, float *d_cube, void *d_ws,
+                    size_t ws_bytes, void *stream);
 
 // ---- packed float32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot for two IEEE operations, each lane
 // an ordinary round-to-nearest op, so results are bit-identical to the scalar form -------------------------

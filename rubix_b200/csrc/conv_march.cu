@@ -520,7 +520,7 @@ int launch_march(const float *d_in, float *d_out, int ny, int nx, int W, int pin
   const int rows = (ny + best_seg - 1) / best_seg;
   dim3 grid(bx, (ny + rows - 1) / rows);
   // bulk copies need 16-byte aligned global addresses: the staging aligns down relative to d_in
-  static const bool no_bulk = getenv("RBX_MARCH_NO_BULK") != nullptr;
+  const bool no_bulk = opt_on(OPT_MARCH_NO_BULK);
   // (an unaligned slab start inside a wider cube is fine: the bytes before it belong to the same cube)
   const int use_bulk = ((((uintptr_t)d_in & 15u) == 0 || pin > W) && !no_bulk) ? 1 : 0;
   kernel<<<grid, NT, kSmem, stream>>>(d_in, d_out, ny, nx, W, pin, pout, rows, use_bulk, taps);

@@ -44,7 +44,45 @@ constexpr int kMaxKnots = KPL * OWN * kMaxGroupWarps - 3;  // widest knot window
 
 struct Item { int start, count, spaxel, slot; };
 
-enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_COUNT };
+enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_IMPL, C_CHS, C_GCHS, C_COUNT };
+// ctrl[C_IMPL]: which cube kernel runs, decided on the device by segment_kernel from the knot window and the
+// Doppler range actually present (both kernels are launched; the one not selected returns at once)
+enum Impl { IMPL_WARP = 0, IMPL_GROUP = 1 };
+// ctrl[C_CHS] / ctrl[C_GCHS]: log2(channels per chunk) of the warp / group kernel, the smallest value (not below the
+// host's choice from the grids) whose chunk geometry holds for the Doppler range present
+// ctrl[C_ERROR]: 0 ok, 1 work-item tables too small, 2 knot window wider than the group kernel holds,
+// 3 no chunk size fits the Doppler range present (rbx_build_cube_status reports it; the cube is NaN)
+
+// Where the cube rows go.  Standard: (nseg, W) row-major (nslab = 1, ws = W).  Slab-major (multi-GPU):
+// nslab wavelength slabs of wslab channels, each stored as its own (nseg, ws) block with `halo` extra channels on
+// both sides (ws = wslab + 2 halo), so that one reduce-scatter hands every rank its summed slab INCLUDING the LSF
+// halo.  A channel within `halo` of a slab border is stored twice (its own slab and the neighbour's halo);
+// channels outside [0, W) stay zero from the initial memset (the zero padding of the 'same' convolution).
+struct CubeLayout {
+  int nslab, wslab, halo, ws;
+  long long slab_stride;   // nseg * ws
+};
+
+__device__ __forceinline__ void cube_put(float *__restrict__ cube, const CubeLayout &cl, int spaxel, int ch, float v,
+                                         bool add) {
+  if (cl.nslab == 1) {
+    float *q = cube + (size_t)spaxel * cl.ws + ch;
+    *q = add ? *q + v : v;
+    return;
+  }
+  const int r = ch / cl.wslab, o = ch - r * cl.wslab;
+  float *row = cube + (size_t)r * cl.slab_stride + (size_t)spaxel * cl.ws;
+  float *q = row + cl.halo + o;
+  const float nv = add ? *q + v : v;
+  *q = nv;
+  if (o < cl.halo && r > 0) row[cl.halo + o - cl.slab_stride + cl.wslab] = nv;                   // right halo of slab r - 1
+  if (o >= cl.wslab - cl.halo && r + 1 < cl.nslab) row[cl.slab_stride + o - (cl.wslab - cl.halo)] = nv;   // left halo of slab r + 1
+}
+__device__ __forceinline__ float cube_get(const float *__restrict__ cube, const CubeLayout &cl, int spaxel, int ch) {
+  if (cl.nslab == 1) return cube[(size_t)spaxel * cl.ws + ch];
+  const int r = ch / cl.wslab, o = ch - r * cl.wslab;
+  return cube[(size_t)r * cl.slab_stride + (size_t)spaxel * cl.ws + cl.halo + o];
+}
 
 struct FusedWs {
   uint32_t *keys_in, *keys_out, *idx_in, *idx_out;
@@ -71,13 +109,16 @@ constexpr int kDminBias = 0x7f7fffff;   // ctrl[C_DMIN] holds kDminBias - bits(d
 // With `coords` the spaxel assignment (rubix/telescope/utils.py:138-151, same searches as
 // spaxel_assign_kernel: bit-exact) and the aperture filter (rubix/core/telescope.py:155-174, as pixel -1)
 // happen here, so the particle arrays are read once; `pixel` then is an optional output.
-__global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const float *__restrict__ mass,
+// `vel` points at the Doppler component of particle 0 and advances by `vstride` floats per particle ((n, 3)
+// arrays: vstride 3; a packed line-of-sight velocity array: 1); likewise cx / cy / cstride for the coordinates.
+__global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstride, const float *__restrict__ mass,
                             const float *__restrict__ met, const float *__restrict__ age,
                             int32_t *__restrict__ pixel, int n, int nseg, int cell_bits, int cell_shift,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
                             int *__restrict__ ctrl, int smem_hist, float *__restrict__ rec, int stride,
-                            const float *__restrict__ coords, const float *__restrict__ edges, int n_edges,
-                            int mark_outside, int edges_smem) {
+                            const float *__restrict__ cx, const float *__restrict__ cy, int cstride,
+                            const float *__restrict__ edges, int n_edges, int mark_outside, int edges_smem) {
+  const bool coords = cx != nullptr;
   extern __shared__ int s_dyn[];
   int *s_hist = s_dyn;   // small cubes: per-block spaxel histogram; large cubes: count_runs_kernel after the sort
   float *s_axes = reinterpret_cast<float *>(s_dyn + (smem_hist ? nseg : 0));   // SSP metallicity and age axes
@@ -108,7 +149,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     ssp_cell(p, met[q], age[q], i, j, inside);
     int px;
     if (coords) {
-      const float x = coords[3 * (size_t)q], y = coords[3 * (size_t)q + 1];
+      const float x = cx[(size_t)cstride * q], y = cy[(size_t)cstride * q];
       const int xi = min(max(ss_right(e, n_edges, x) - 1, 0), nb - 1);
       const int yi = min(max(ss_right(e, n_edges, y) - 1, 0), nb - 1);
       px = xi + nb * yi;
@@ -117,7 +158,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, const flo
     } else {
       px = pixel[q];
     }
-    float d = expf(vel[3 * (size_t)q + p.vel_comp] / kSpeedOfLight);
+    float d = expf(vel[(size_t)vstride * q] / kSpeedOfLight);
     bool valid = inside && (mass[q] != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
     uint32_t key = (uint32_t)nseg << cell_bits;  // invalid: sorts behind every valid key
     if (valid) {
@@ -174,6 +215,49 @@ __global__ void count_runs_kernel(const uint32_t *__restrict__ keys_sorted, int 
     if (sp != s) atomicSub(counts + s, q);      // run start:  counts[s] -= first index
     if (sn != s) atomicAdd(counts + s, q + 1);  // run end:    counts[s] += one past the last index
   }
+}
+
+// number of channels below x, and t[k-1] (t[0] for k = 0).
+// AFFINE grids: k = ceil((x - t0) / delta) in float32.  Within ~1e-3 A of a channel wavelength the
+// rounded quotient may pick the neighbouring cell; the kink is then booked one channel off with the
+// matching e, which changes that single channel by dm * (t_k - x) <= dm * 1e-3 A: p(t) is continuous.
+template <bool AFFINE>
+__device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsigned char *s_lut,
+                                          const float2 *s_tt, float &e) {
+  if (AFFINE) {
+    const float v = fminf(fmaxf((x - p.t0) * p.tinv, 0.f), (float)p.W);
+    const int k = __float2int_ru(v);
+    e = __fadd_rn(__fmul_rn((float)max(k - 1, 0), p.tdelta), p.t0);
+    return k;
+  }
+  const int off = bucket_offset(x, p.tmin, p.trange, p.lut_scale);
+  const int l = *reinterpret_cast<const uint16_t *>(s_lut + off);
+  const float2 t2 = s_tt[l];
+  const bool up = t2.y < x;
+  e = up ? t2.y : t2.x;
+  return l + (up ? 1 : 0);
+}
+
+// ---- warp kernel geometry shared by segment_kernel (which decides whether the warp kernel can run) and the
+// kernel itself ------------------------------------------------------------------------------------------
+constexpr int WK = 8;                 // knots per lane
+constexpr int kWarpSlots = WK * 32;   // knot slots of one warp
+
+// Chunk lines of the warp kernel are summed in registers: over the Doppler range present, the first chunk start
+// inside lane `lane`'s channel span must be chunk cA or cA + 1, and the span must hold at most one chunk start.
+// Returns false when that does not hold (Doppler range too wide for this kernel: the group kernel takes over).
+__device__ __forceinline__ bool warp_lane_chunks(const PlanView &p, int jbase, int lane, float dmin, float dmax, int chs,
+                                                 int &cA) {
+  const int CH = 1 << chs;
+  const int j0 = jbase + WK * lane, j1 = j0 + WK;
+  const float lz0 = j0 < 0 ? -1.0e30f : (j0 >= p.L ? 1.0e30f : p.lamz[j0]);
+  const float lz1 = j1 < 0 ? -1.0e30f : (j1 >= p.L ? 1.0e30f : p.lamz[j1]);
+  float e;
+  const int kmin0 = channel_of<true>(__fmul_rn(lz0, dmin), p, nullptr, nullptr, e);
+  const int kmax0 = channel_of<true>(__fmul_rn(lz0, dmax), p, nullptr, nullptr, e);
+  const int knext = lane == 31 ? kmax0 : channel_of<true>(__fmul_rn(lz1, dmax), p, nullptr, nullptr, e);
+  cA = (kmin0 + CH - 1) >> chs;
+  return !((((kmax0 + CH - 1) >> chs) > cA + 1) || (knext - kmax0 + 2 >= CH));
 }
 
 // ---- segments / items / knot window (one block) -----------------------------------------------
@@ -240,9 +324,12 @@ __device__ __forceinline__ Cut cut_spaxel(int c, int psub, int small_shift, int 
 __global__ void __launch_bounds__(1024)
 segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
-                               int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl) {
+                               int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl,
+                               int warp_ok, int warp_chs, int group_chs) {
   __shared__ int s_w[33 * 4];
-  __shared__ int s_err;
+  __shared__ int s_err, s_ja, s_jb;
+  __shared__ int s_bad_w[16], s_bad_g[16];   // [chs]: the chunk geometry fails for 2^chs channels per chunk
+  if (threadIdx.x < 16) { s_bad_w[threadIdx.x] = 0; s_bad_g[threadIdx.x] = 0; }
   const int T = blockDim.x, t = threadIdx.x;
   const int per = (nseg + T - 1) / T;
   const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
@@ -280,6 +367,60 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     seg_start[nseg] = tot[0];
     item_start[nseg] = tot[3];
     s_err = err;
+    s_ja = ja; s_jb = jb;
+  }
+  __syncthreads();
+  // Which cube kernel, and with which chunk size: the warp kernel when the host found the plan eligible (warp_ok),
+  // the knot window fits its 256 slots and some chunk size <= 2^10 channels makes every lane's chunk geometry hold
+  // for the Doppler range present; else the group kernel (chunks <= 2^8 channels).  Benign races: threads only
+  // ever store 1 into the flags.
+  if (tot[0] > 0) {
+    const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+    if (t < 32) {
+      const int jbase = (s_ja - 1) & ~3;
+      for (int chs = warp_chs; chs <= 10; ++chs) {
+        int cA;
+        if (!warp_lane_chunks(p, jbase, t, dmin, dmax, chs, cA)) s_bad_w[chs] = 1;
+      }
+    }
+    // group kernel: a lane's first knot is some even slot of the window; checked for every knot (conservative)
+    const int jbg = (s_ja - 1) & ~1;
+    for (int j = jbg + t; j <= s_jb; j += T) {
+      auto lam = [&](int q) { return q < 0 ? -1.0e30f : (q >= p.L ? 1.0e30f : p.lamz[q]); };
+      float e;
+      int kmin0, kmax0, knext;
+      if (p.affine) {
+        kmin0 = channel_of<true>(__fmul_rn(lam(j), dmin), p, nullptr, nullptr, e);
+        kmax0 = channel_of<true>(__fmul_rn(lam(j), dmax), p, nullptr, nullptr, e);
+        knext = channel_of<true>(__fmul_rn(lam(j + KPL), dmax), p, nullptr, nullptr, e);
+      } else {   // any monotone grid: searches on the channel wavelengths (as many channels below x as the kernel's lookup)
+        auto below = [&](float x) { int a = 0, b = p.W; while (a < b) { int m = (a + b) >> 1; if (p.t[m] < x) a = m + 1; else b = m; } return a; };
+        kmin0 = below(__fmul_rn(lam(j), dmin));
+        kmax0 = below(__fmul_rn(lam(j), dmax));
+        knext = below(__fmul_rn(lam(j + KPL), dmax));
+      }
+      for (int chs = group_chs; chs <= 8; ++chs) {
+        const int CH = 1 << chs;
+        const int cA = (kmin0 + CH - 1) >> chs;
+        if ((((kmax0 + CH - 1) >> chs) > cA + 1) || (knext - kmax0 + 2 >= CH)) s_bad_g[chs] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    int wchs = -1, gchs = -1;
+    for (int chs = 10; chs >= warp_chs; --chs) if (!s_bad_w[chs]) wchs = chs;
+    for (int chs = 8; chs >= group_chs; --chs) if (!s_bad_g[chs]) gchs = chs;
+    const int jbase = (s_ja - 1) & ~3;
+    const bool warp = warp_ok != 0 && wchs >= 0 && (s_jb - jbase + 1 <= kWarpSlots);
+    ctrl[C_IMPL] = warp ? IMPL_WARP : IMPL_GROUP;
+    ctrl[C_CHS] = max(wchs, warp_chs);
+    ctrl[C_GCHS] = max(gchs, group_chs);
+    if (!warp && gchs < 0 && s_err == 0) {   // the Doppler range present is too wide for either kernel
+      s_err = 3;
+      ctrl[C_ERROR] = 3;
+      ctrl[C_NITEMS] = 0;
+    }
   }
   __syncthreads();
   const bool err = s_err != 0;
@@ -356,27 +497,6 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// number of channels below x, and t[k-1] (t[0] for k = 0).
-// AFFINE grids: k = ceil((x - t0) / delta) in float32.  Within ~1e-3 A of a channel wavelength the
-// rounded quotient may pick the neighbouring cell; the kink is then booked one channel off with the
-// matching e, which changes that single channel by dm * (t_k - x) <= dm * 1e-3 A: p(t) is continuous.
-template <bool AFFINE>
-__device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsigned char *s_lut,
-                                          const float2 *s_tt, float &e) {
-  if (AFFINE) {
-    const float v = fminf(fmaxf((x - p.t0) * p.tinv, 0.f), (float)p.W);
-    const int k = __float2int_ru(v);
-    e = __fadd_rn(__fmul_rn((float)max(k - 1, 0), p.tdelta), p.t0);
-    return k;
-  }
-  const int off = bucket_offset(x, p.tmin, p.trange, p.lut_scale);
-  const int l = *reinterpret_cast<const uint16_t *>(s_lut + off);
-  const float2 t2 = s_tt[l];
-  const bool up = t2.y < x;
-  e = up ? t2.y : t2.x;
-  return l + (up ? 1 : 0);
-}
-
 template <bool CAS>
 __device__ __forceinline__ void cell_add(float2 *cell, float a, float b) {
   if (!CAS) {
@@ -412,11 +532,15 @@ template <int METHOD, bool AFFINE>
 __global__ void __launch_bounds__(kCtaThreads, 1)
 fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                   const Item *__restrict__ items, int *__restrict__ ctrl,
-                  float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay, int accumulate) {
+                  float *__restrict__ cube, float *__restrict__ partials, int Wp, FusedLayout lay, int accumulate,
+                  CubeLayout cl) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ctrl[C_IMPL] != IMPL_GROUP) return;   // segment_kernel selected the warp kernel
+  const int chs = ctrl[C_GCHS];                  // >= chs: chosen by segment_kernel for the Doppler range present
+  const int nch = (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
 
   // ---- stage the lookup tables (TMA bulk copies, one elected thread) -----------------------------
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + lay.off_mbar);
@@ -497,7 +621,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
                    : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
     }
   }
-  for (int c = tid; c < lay.nch; c += kCtaThreads) s_tc[c] = p.t[min(c << lay.chs, p.W - 1)];
+  for (int c = tid; c < nch; c += kCtaThreads) s_tc[c] = p.t[min(c << chs, p.W - 1)];
   __syncthreads();
   if (!active) return;  // spare warps (no __syncthreads below this line)
 
@@ -521,7 +645,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
     if (lane == 0) {
       s_misc[2 + wg] = klo;
       s_misc[12 + wg] = khi;
-      if (span >= (1 << lay.chs)) atomicExch(ctrl + C_ERROR, 3);
+      if (span >= (1 << chs)) atomicExch(ctrl + C_ERROR, 3);
     }
   }
   group_barrier(1 + grp, gthreads);
@@ -539,7 +663,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
   const int own = owner ? 1 : 0;
   float2 *my_cells = s_step + (owner ? (shared_mode ? 0 : my_off - my_klo) : lay.cap + wg * 32 + lane);
   float2 *my_base = s_base + (size_t)wg * nbase;
-  const int CH = 1 << lay.chs;
+  const int CH = 1 << chs;
   // chunk lines are summed in registers: over the Doppler range present a lane's first knot moves by
   // less than one chunk, so the chunk start inside its span is chunk cA or cA + 1
   int cA = 0;
@@ -547,8 +671,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
     float e;
     const int kmin0 = channel_of<AFFINE>(__fmul_rn(lz[0], dmin), p, s_lut, s_tt, e);
     const int kmax0 = channel_of<AFFINE>(__fmul_rn(lz[0], dmax), p, s_lut, s_tt, e);
-    cA = (kmin0 + CH - 1) >> lay.chs;
-    if (owner && ((kmax0 + CH - 1) >> lay.chs) > cA + 1) atomicExch(ctrl + C_ERROR, 3);
+    cA = (kmin0 + CH - 1) >> chs;
+    if (owner && ((kmax0 + CH - 1) >> chs) > cA + 1) atomicExch(ctrl + C_ERROR, 3);
   }
   float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
@@ -669,12 +793,12 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
         g1[b] = d1 * gx1;
         ka[b] = k0 * own; kb[b] = k1 * own;
         // chunk base: the line valid at the first chunk start inside [k0, k2)
-        const int c = (k0 + CH - 1) >> lay.chs;
-        const int chan = c << lay.chs;
+        const int c = (k0 + CH - 1) >> chs;
+        const int chan = c << chs;
         const bool has = owner && chan < k2 && chan < p.W;
         const bool second = chan >= k1;
         const float Sr = second ? S1 : S0, mr = second ? m1 : m0, xr = second ? x1 : x0;
-        const float tch = s_tc[min(c, lay.nch - 1)];
+        const float tch = s_tc[min(c, nch - 1)];
         cb[b] = has ? 1 + (c - cA) : 0;
         bv[b] = fmaf(mr, tch - xr, Sr);
         bm[b] = mr;
@@ -776,8 +900,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
     // flush the register chunk lines, one lane after the other (neighbouring lanes can share a chunk)
     for (int l = 1; l <= OWN; ++l) {
       if (lane == l) {
-        if (cA < lay.nch) cell_add<false>(my_base + cA, accAv, accAm);
-        if (cA + 1 < lay.nch) cell_add<false>(my_base + cA + 1, accBv, accBm);
+        if (cA < nch) cell_add<false>(my_base + cA, accAv, accAm);
+        if (cA + 1 < nch) cell_add<false>(my_base + cA + 1, accBv, accBm);
       }
       __syncwarp();
     }
@@ -785,8 +909,8 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
     group_barrier(1 + grp, gthreads);
 
     // ---- expand the cells into the spaxel spectrum and store it -----------------------------------
-    float *row = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
-    for (int c = wg; c < lay.nch; c += NWG) {
+    float *prow = partials + (size_t)max(it.slot, 0) * Wp;
+    for (int c = wg; c < nch; c += NWG) {
       float vcar = 0.f, scar = 0.f;
       for (int w = 0; w < NWG; ++w) {
         const float2 bs = s_base[(size_t)w * nbase + c];
@@ -795,7 +919,7 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
       __syncwarp();
       if (lane < NWG) s_base[(size_t)lane * nbase + c] = make_float2(0.f, 0.f);
       for (int h = 0; h < CH; h += 32) {
-        const int ch = (c << lay.chs) + h + lane;
+        const int ch = (c << chs) + h + lane;
         float A = 0.f, B = 0.f;
         if (ch <= p.W) {
           int off = 0;
@@ -831,7 +955,10 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
           if (lane >= o) inc += n;
         }
         const float v = vcar + inc;
-        if (valid) row[ch] = (accumulate && it.slot < 0) ? row[ch] + v : v;
+        if (valid) {
+          if (it.slot < 0) cube_put(cube, cl, it.spaxel, ch, v, accumulate != 0);
+          else prow[ch] = v;
+        }
         scar = __shfl_sync(0xffffffffu, s, 31);
         vcar = __shfl_sync(0xffffffffu, v, 31);
       }
@@ -850,8 +977,6 @@ fused_cube_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__r
 // above with its CAS mode covers everything else), hence the eight read-modify-writes of a particle are
 // issued as 8 loads, 16 FMAs, 8 stores: one shared-memory round trip per particle instead of one per
 // knot.  Affine (arange) telescope grids only.
-constexpr int WK = 8;
-constexpr int kWarpSlots = WK * 32;
 
 struct WarpLayout {
   int off_tc;        // [nch] wavelength of each chunk's first channel
@@ -875,30 +1000,30 @@ template <int METHOD>
 __global__ void __launch_bounds__(256, 1)
 fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                        const Item *__restrict__ items, int *__restrict__ ctrl,
-                       float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay, int accumulate) {
+                       float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay, int accumulate,
+                       CubeLayout cl) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ctrl[C_IMPL] != IMPL_WARP) return;   // segment_kernel selected the group kernel (knot window / Doppler range)
+  const int chs = ctrl[C_CHS];                   // >= chs: chosen by segment_kernel for the Doppler range present
+  const int nch = (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
   float *s_tc = reinterpret_cast<float *>(smem + lay.off_tc);
   float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride);
   float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_base);
   float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_rec);   // [32][RS]
-  const int CH = 1 << lay.chs;
+  const int CH = 1 << chs;
 
-  for (int c = tid; c < lay.nch; c += blockDim.x) s_tc[c] = p.t[min(c << lay.chs, p.W - 1)];
+  for (int c = tid; c < nch; c += blockDim.x) s_tc[c] = p.t[min(c << chs, p.W - 1)];
   for (int q = lane; q < lay.ncells; q += 32) cells[q] = make_float2(0.f, 0.f);
-  for (int q = lane; q < lay.nch; q += 32) base[q] = make_float2(0.f, 0.f);
+  for (int q = lane; q < nch; q += 32) base[q] = make_float2(0.f, 0.f);
   __syncthreads();
 
   // ---- per-lane knot constants -------------------------------------------------------------------
   const int ja = ctrl[C_JA], jb = ctrl[C_JB];
   const int n_items = ctrl[C_NITEMS];
   const int jbase = (ja - 1) & ~3;               // multiple of 4 (16-byte template loads); slot s <-> knot jbase + s
-  if (jb - jbase + 1 > kWarpSlots) {             // the knot window does not fit one warp: fail loudly (reduce_partials_kernel poisons the cube)
-    if (tid == 0) atomicExch(ctrl + C_ERROR, 2);
-    return;
-  }
   const int j0 = jbase + WK * lane;
   const bool interior = j0 >= 0 && j0 + WK <= p.L;   // all eight knots inside the SSP grid: two 16-byte loads per row
   float lz[WK], rdl[WK];
@@ -918,15 +1043,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   // chunk lines are summed in registers: a lane's span [k_0, k_8) holds at most one chunk start, and over
   // the Doppler range present that start is chunk cA or cA + 1
   int cA = 0;
-  {
-    float e;
-    const int kmin0 = channel_of<true>(__fmul_rn(lz[0], dmin), p, nullptr, nullptr, e);
-    const int kmax0 = channel_of<true>(__fmul_rn(lz[0], dmax), p, nullptr, nullptr, e);
-    const float lznext = __shfl_down_sync(0xffffffffu, lz[0], 1);
-    const int knext = lane == 31 ? kmax0 : channel_of<true>(__fmul_rn(lznext, dmax), p, nullptr, nullptr, e);
-    cA = (kmin0 + CH - 1) >> lay.chs;
-    if (((kmax0 + CH - 1) >> lay.chs) > cA + 1 || knext - kmax0 + 2 >= CH) atomicExch(ctrl + C_ERROR, 3);
-  }
+  warp_lane_chunks(p, jbase, lane, dmin, dmax, chs, cA);   // segment_kernel checked that this holds
   float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
   const float *tab[NT];
@@ -1154,8 +1271,8 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       float bv, mr;
       int sel;
       {
-        const int c = (k[0] + CH - 1) >> lay.chs;
-        const int chan = c << lay.chs;
+        const int c = (k[0] + CH - 1) >> chs;
+        const int chan = c << chs;
         const bool has = chan < k[WK] && chan < p.W;
         float Sr = S[0], xr = x[0];
         mr = m[0];
@@ -1164,7 +1281,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           const bool take = k[r] <= chan;
           Sr = take ? S[r] : Sr; mr = take ? m[r] : mr; xr = take ? x[r] : xr;
         }
-        const float tch = s_tc[min(c, lay.nch - 1)];
+        const float tch = s_tc[min(c, nch - 1)];
         bv = fmaf(mr, tch - xr, Sr);
         sel = has ? 1 + (c - cA) : 0;
       }
@@ -1201,7 +1318,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           if (lane >= o && kk == key) { v += vv; m += mm; }
         }
         const int knext = __shfl_down_sync(0xffffffffu, key, 1);
-        if ((lane == 31 || knext != key) && key < lay.nch) cell_add<false>(base + key, v, m);
+        if ((lane == 31 || knext != key) && key < nch) cell_add<false>(base + key, v, m);
         __syncwarp();
       };
       flush(cA, accAv, accAm);
@@ -1215,14 +1332,13 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
     //   = vcar + scar (t_k - t_ref) + sum_{j<=k} (sB_j dt_j + A_j)      (sum dt_j telescopes exactly)
     // so the two warp scans of a 32-channel group do not depend on the carries: four groups are scanned
     // at once (four independent shuffle chains) and the carries are applied afterwards.
-    float *rowp = it.slot < 0 ? cube + (size_t)it.spaxel * p.W : partials + (size_t)it.slot * Wp;
-    const bool add_to_row = accumulate && it.slot < 0;
-    for (int c = 0; c < lay.nch; ++c) {
+    float *prow = partials + (size_t)max(it.slot, 0) * Wp;
+    for (int c = 0; c < nch; ++c) {
       const float2 bs = base[c];
       float vcar = bs.x, scar = bs.y;
       __syncwarp();
       if (lane == 0) base[c] = make_float2(0.f, 0.f);
-      const int cstart = c << lay.chs;
+      const int cstart = c << chs;
       for (int h = 0; h < CH; h += 128) {
         if (cstart + h > p.W) break;
         float A[4], sB[4], dtc[4], tk[4], tref[4];
@@ -1268,7 +1384,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         for (int g = 0; g < 4; ++g) {
           const int ch = cstart + h + 32 * g + lane;
           const float v = vcar + fmaf(scar, tk[g] - tref[g], inc[g]);
-          if (valid[g]) rowp[ch] = add_to_row ? rowp[ch] + v : v;
+          if (valid[g]) {
+            if (it.slot < 0) cube_put(cube, cl, it.spaxel, ch, v, accumulate != 0);
+            else prow[ch] = v;
+          }
           scar += __shfl_sync(0xffffffffu, sB[g], 31);
           vcar = __shfl_sync(0xffffffffu, v, 31);
         }
@@ -1282,20 +1401,21 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 // A configuration the kernels cannot hold (knot window too large) poisons the cube with NaN here rather than
 // returning a silently wrong result.
 __global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const float *__restrict__ partials, int Wp, int W,
-                                       int nseg, const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate) {
+                                       int nseg, const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate,
+                                       CubeLayout cl) {
   const bool poison = ctrl[C_ERROR] != 0;
   for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
     if (poison) {
       for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x)
-        cube[(size_t)s * W + w] = __int_as_float(0x7fc00000);
+        cube_put(cube, cl, s, w, __int_as_float(0x7fc00000), false);
       continue;
     }
     const int i0 = slot_start[s], i1 = slot_start[s + 1];
     if (i1 - i0 < 2) continue;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
-      float acc = accumulate ? cube[(size_t)s * W + w] : 0.f;
+      float acc = accumulate ? cube_get(cube, cl, s, w) : 0.f;
       for (int k = i0; k < i1; ++k) acc += partials[(size_t)k * Wp + w];
-      cube[(size_t)s * W + w] = acc;
+      cube_put(cube, cl, s, w, acc, false);
     }
   }
 }
@@ -1306,7 +1426,7 @@ static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // costs a fixed ~10 us of expansion, so few large items win as long as the quarter-size tail items behind them
 // keep the end of the persistent kernel short: 512 at 10^6 particles, 2048 at 10^7.
 static int choose_psub(int64_t n) {
-  if (const char *e = getenv("RBX_PSUB")) return std::max(32, atoi(e));
+  if (opt(OPT_PSUB) > 0) return (int)std::max<int64_t>(32, opt(OPT_PSUB));
   int64_t t = n / 2048;
   int ps = 256;
   while (ps < t && ps < 2048) ps <<= 1;
@@ -1325,7 +1445,7 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
   while ((1ull << seg_bits) <= (uint64_t)nseg) ++seg_bits;
   while ((1 << ncell_bits) < ws.ncell) ++ncell_bits;
   int want = 31;
-  if (const char *e = getenv("RBX_SORT_BITS")) want = atoi(e);
+  if (opt(OPT_SORT_BITS) > 0) want = (int)opt(OPT_SORT_BITS);
   ws.cell_bits = std::min(ncell_bits, std::max(2, want - seg_bits));
   if (seg_bits + ws.cell_bits > 31) ws.cell_bits = std::max(0, 31 - seg_bits);
   ws.cell_shift = ncell_bits - ws.cell_bits;
@@ -1444,12 +1564,8 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
   lay.chs = chs;
   lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
   lay.collide = (min2 * 0.97 <= (double)plan->max_dt) ? 1 : 0;
-  {
-    const char *e = getenv("RBX_FUSED_FORCE_LUT");
-    lay.force_lut = (e && e[0] == '1') ? 1 : 0;
-    const char *c = getenv("RBX_FUSED_FORCE_CAS");
-    if (c && c[0] == '1') lay.collide = 1;
-  }
+  lay.force_lut = opt_on(OPT_FUSED_FORCE_LUT) ? 1 : 0;
+  if (opt_on(OPT_FUSED_FORCE_CAS)) lay.collide = 1;
   lay.cap = v.W + 1 + kMaxGroupWarps * kRegionSlack;
   auto a16 = [](int x) { return (x + 15) & ~15; };
   auto a128 = [](int x) { return (x + 127) & ~127; };
@@ -1484,11 +1600,7 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
 static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_bytes) {
   const PlanView &v = plan->v;
   if (!v.affine || v.W + 2 >= (1 << 20)) return false;
-  if (const char *e = getenv("RBX_FUSED_IMPL")) {
-    if (!strcmp(e, "group")) return false;
-  }
-  if (const char *e = getenv("RBX_FUSED_FORCE_LUT")) if (e[0] == '1') return false;
-  if (const char *e = getenv("RBX_FUSED_FORCE_CAS")) if (e[0] == '1') return false;
+  if (opt_on(OPT_FUSED_IMPL) || opt_on(OPT_FUSED_FORCE_LUT) || opt_on(OPT_FUSED_FORCE_CAS)) return false;
   // knots that can reach the band for |v| up to ~0.03 c
   const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
   int inband = 0;
@@ -1503,10 +1615,10 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
   if (inband + 16 > kWarpSlots) return false;
   if (!(min1 * 0.97 > (double)plan->max_dt)) return false;   // two knots of a lane could share a cell
   const double span = max8 * 1.03 / (double)plan->min_dt + 4.0;
-  int chs = 6;
+  int chs = 7;   // the expansion walks a chunk 128 channels at a time
   while (chs <= 10 && span >= (double)(1 << chs)) ++chs;
   if (chs > 10) return false;
-  if (const char *e = getenv("RBX_FUSED_CHS")) chs = std::max(chs, atoi(e));
+  if (opt(OPT_FUSED_CHS) > 0) chs = std::max(chs, (int)opt(OPT_FUSED_CHS));
   auto a128 = [](int x) { return (x + 127) & ~127; };
   lay.chs = chs;
   lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
@@ -1528,7 +1640,7 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
     double target = std::ceil(stride);
     if (((long long)target & 1) == 0) target += 1.0;
     double alpha = stride > 1.0 ? (target - stride) / stride : 0.0;
-    if (getenv("RBX_FUSED_NO_SKEW")) alpha = 0.0;
+    if (opt_on(OPT_FUSED_NO_SKEW)) alpha = 0.0;
     lay.skew = (unsigned)std::llround(std::fmin(alpha, 0.25) * 4294967296.0);
     lay.ncells = v.W + 2 + (int)(((unsigned long long)(v.W + 2) * lay.skew) >> 32) + 1;
   }
@@ -1536,7 +1648,7 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
   lay.w_rec = lay.w_base + a128(8 * lay.nch);
   lay.warp_stride = lay.w_rec + a128(4 * 32 * (v.method == RBX_METHOD_LINEAR ? 8 : 20));
   int nw = std::min(8, (227 * 1024 - lay.off_warp) / lay.warp_stride);
-  if (const char *e = getenv("RBX_FUSED_WARPS")) nw = std::min(nw, std::max(1, atoi(e)));
+  if (opt(OPT_FUSED_WARPS) > 0) nw = std::min(nw, (int)opt(OPT_FUSED_WARPS));
   if (nw < 4) return false;
   lay.nwarps = nw;
   smem_bytes = (size_t)lay.off_warp + (size_t)nw * lay.warp_stride;
@@ -1566,28 +1678,99 @@ extern "C" size_t rbx_build_cube_workspace_bytes(const rbx_plan *plan, int64_t n
 extern "C" int rbx_build_cube(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
                               const float *d_age, const int32_t *d_pixel, int64_t n, int num_spaxels,
                               float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
-  RBX_REQUIRE(n == 0 || d_pixel, "rbx_build_cube: null pointer");
-  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, const_cast<int32_t *>(d_pixel), n, num_spaxels, d_cube,
-                              d_ws, ws_bytes, stream_, 0, nullptr, nullptr, 0, 0);
+  RBX_REQUIRE(plan && (n == 0 || d_pixel), "rbx_build_cube: null pointer");
+  CubeBuild b;
+  b.vel = d_vel ? d_vel + plan->v.vel_comp : nullptr;
+  b.mass = d_mass; b.met = d_met; b.age = d_age;
+  b.pixel = const_cast<int32_t *>(d_pixel);
+  return rbx::build_cube_impl(plan, b, n, num_spaxels, d_cube, d_ws, ws_bytes, stream_);
 }
 
 extern "C" int rbx_assign_build_cube(const rbx_plan *plan, const float *d_coords, const float *d_edges, int n_edges,
                                      int apply_filter, const float *d_vel, const float *d_mass, const float *d_met,
                                      const float *d_age, int64_t n, int num_spaxels, int32_t *d_pixel_out,
                                      float *d_cube, void *d_ws, size_t ws_bytes, void *stream_) {
-  RBX_REQUIRE(n_edges >= 2 && (n == 0 || (d_coords && d_edges)), "rbx_assign_build_cube: bad argument");
-  return rbx::build_cube_impl(plan, d_vel, d_mass, d_met, d_age, d_pixel_out, n, num_spaxels, d_cube, d_ws, ws_bytes,
-                              stream_, 0, d_coords, d_edges, n_edges, apply_filter ? 1 : 0);
+  RBX_REQUIRE(plan && n_edges >= 2 && (n == 0 || (d_coords && d_edges)), "rbx_assign_build_cube: bad argument");
+  CubeBuild b;
+  b.vel = d_vel ? d_vel + plan->v.vel_comp : nullptr;
+  b.mass = d_mass; b.met = d_met; b.age = d_age;
+  b.pixel = d_pixel_out;
+  b.cx = d_coords; b.cy = d_coords ? d_coords + 1 : nullptr;
+  b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
+  return rbx::build_cube_impl(plan, b, n, num_spaxels, d_cube, d_ws, ws_bytes, stream_);
 }
 
-// accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in ranges so that the
+// Structure-of-arrays particles: x, y and the line-of-sight velocity as arrays of their own (24 bytes per particle
+// instead of the 40 of the reference's (n, 3) coords / velocity arrays, of which this path never reads 16).
+extern "C" int rbx_assign_build_cube_packed(const rbx_plan *plan, const float *d_x, const float *d_y, const float *d_edges,
+                                            int n_edges, int apply_filter, const float *d_vlos, const float *d_mass,
+                                            const float *d_met, const float *d_age, int64_t n, int num_spaxels,
+                                            int32_t *d_pixel_out, float *d_cube, void *d_ws, size_t ws_bytes,
+                                            void *stream_) {
+  RBX_REQUIRE(plan && n_edges >= 2 && (n == 0 || (d_x && d_y && d_edges)), "rbx_assign_build_cube_packed: bad argument");
+  CubeBuild b;
+  b.vel = d_vlos; b.vstride = 1;
+  b.mass = d_mass; b.met = d_met; b.age = d_age;
+  b.pixel = d_pixel_out;
+  b.cx = d_x; b.cy = d_y; b.cstride = 1;
+  b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
+  return rbx::build_cube_impl(plan, b, n, num_spaxels, d_cube, d_ws, ws_bytes, stream_);
+}
+
+// Slab-major partial cube for the multi-GPU exchange: nslab wavelength slabs, each an (S*S, ws) block
+// with `halo` channels of its neighbours on both sides, so one ncclReduceScatter hands rank r its summed slab
+// ready for the PSF + LSF pass.
+extern "C" int rbx_slab_geometry(int W, int nslab, int halo, int *wslab, int *ws) {
+  RBX_REQUIRE(W >= 1 && nslab >= 1 && halo >= 0, "rbx_slab_geometry: bad argument");
+  const int w = (W + nslab - 1) / nslab;
+  if (wslab) *wslab = w;
+  if (ws) *ws = w + 2 * halo;
+  return RBX_OK;
+}
+
+extern "C" int rbx_assign_build_cube_slabs(const rbx_plan *plan, const float *d_coords, const float *d_edges, int n_edges,
+                                           int apply_filter, const float *d_vel, const float *d_mass, const float *d_met,
+                                           const float *d_age, int64_t n, int num_spaxels, int nslab, int halo,
+                                           float *d_slabs, void *d_ws, size_t ws_bytes, void *stream_) {
+  RBX_REQUIRE(plan && n_edges >= 2 && (n == 0 || (d_coords && d_edges)), "rbx_assign_build_cube_slabs: bad argument");
+  RBX_REQUIRE(nslab >= 1 && halo >= 0, "rbx_assign_build_cube_slabs: bad slab geometry");
+  const int wslab = (plan->v.W + nslab - 1) / nslab;
+  RBX_REQUIRE(nslab == 1 || halo <= wslab, "rbx_assign_build_cube_slabs: halo wider than a slab");
+  CubeBuild b;
+  b.vel = d_vel ? d_vel + plan->v.vel_comp : nullptr;
+  b.mass = d_mass; b.met = d_met; b.age = d_age;
+  b.cx = d_coords; b.cy = d_coords ? d_coords + 1 : nullptr;
+  b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
+  b.nslab = nslab; b.halo = halo;
+  return rbx::build_cube_impl(plan, b, n, num_spaxels, d_slabs, d_ws, ws_bytes, stream_);
+}
+
+// What the last build on this workspace did: *h_error = ctrl[C_ERROR] (0 ok; != 0: the cube was poisoned with NaN),
+// *h_impl = the kernel segment_kernel selected (0 warp kernel, 1 group kernel).  Synchronises `stream`.
+extern "C" int rbx_build_cube_status(const rbx_plan *plan, int64_t n, int num_spaxels, const void *d_ws, int *h_error,
+                                     int *h_impl, void *stream_) {
+  RBX_REQUIRE(plan && d_ws && n >= 0 && num_spaxels >= 1, "rbx_build_cube_status: bad argument");
+  if (h_error) *h_error = 0;
+  if (h_impl) *h_impl = 0;
+  if (n == 0) return RBX_OK;
+  FusedWs ws;
+  size_t need = 0;
+  const uintptr_t base = ((uintptr_t)d_ws + 255) & ~(uintptr_t)255;
+  layout_workspace(plan, n, num_spaxels * num_spaxels, (void *)base, ws, need);
+  int h[C_COUNT];
+  RBX_CUDA_OK(cudaMemcpyAsync(h, ws.ctrl, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  RBX_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+  if (h_error) *h_error = h[C_ERROR];
+  if (h_impl) *h_impl = h[C_IMPL];
+  return RBX_OK;
+}
+
+// b.accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in ranges so that the
 // host-to-device copy of one range overlaps the kernels of the previous one).
-// d_coords != NULL: spaxel assignment (+ aperture filter as pixel -1) inside prep_kernel; d_pixel is then an
-// optional output.
-int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *d_mass, const float *d_met,
-                         const float *d_age, int32_t *d_pixel, int64_t n, int num_spaxels, float *d_cube,
-                         void *d_ws, size_t ws_bytes, void *stream_, int accumulate, const float *d_coords,
-                         const float *d_edges, int n_edges, int mark_outside) {
+// b.cx != NULL: spaxel assignment (+ aperture filter as pixel -1) inside prep_kernel; b.pixel is then an optional
+// output.
+int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, int num_spaxels, float *d_cube,
+                         void *d_ws, size_t ws_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RBX_REQUIRE(plan && d_cube, "rbx_build_cube: null plan or cube");
   RBX_REQUIRE(n >= 0 && n < (1ll << 31) - 1, "rbx_build_cube: n out of range");
@@ -1595,9 +1778,16 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   if (rc != RBX_OK) return rc;
   const PlanView &v = plan->v;
   const int nseg = num_spaxels * num_spaxels;
-  if (!accumulate) RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)nseg * v.W, stream));
+  CubeLayout cl;
+  cl.nslab = std::max(1, b.nslab);
+  cl.halo = cl.nslab > 1 ? b.halo : 0;
+  cl.wslab = cl.nslab > 1 ? (v.W + cl.nslab - 1) / cl.nslab : v.W;
+  cl.ws = cl.wslab + 2 * cl.halo;
+  cl.slab_stride = (long long)nseg * cl.ws;
+  if (!b.accumulate)
+    RBX_CUDA_OK(cudaMemsetAsync(d_cube, 0, sizeof(float) * (size_t)cl.nslab * (size_t)cl.slab_stride, stream));
   if (n == 0) return RBX_OK;
-  RBX_REQUIRE(d_vel && d_mass && d_met && d_age && (d_pixel || d_coords) && d_ws, "rbx_build_cube: null pointer");
+  RBX_REQUIRE(b.vel && b.mass && b.met && b.age && (b.pixel || b.cx) && d_ws, "rbx_build_cube: null pointer");
   FusedWs ws;
   size_t need = 0;
   uintptr_t base = ((uintptr_t)d_ws + 255) & ~(uintptr_t)255;
@@ -1612,23 +1802,23 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
   const int threads = 256;
   int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
   {
-    const int edges_smem = (d_coords && n_edges <= 4096) ? 1 : 0;
+    const int edges_smem = (b.cx && b.n_edges <= 4096) ? 1 : 0;
     // spaxel counts: a per-block shared-memory histogram for MUSE-size cubes (one launch less); for large cubes
     // (150 x 150: 90 KB of histogram per block would halve the occupancy and cost 22500 flush atomics per block)
     // the run lengths of the sorted keys
     const int smem_hist = nseg <= 4096 ? 1 : 0;
     const size_t dyn = (smem_hist ? sizeof(int) * (size_t)nseg : 0) +
-                       sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? n_edges : 0));
+                       sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? b.n_edges : 0));
     int pcap = 148 * 4;   // measured (B200, 10^6 particles): 148 blocks 98 us, 296: 55, 592: 38, 1184: 44, 2368: 54 -- every
                           // block flushes its histogram with one atomic per non-empty spaxel
-    if (const char *e = getenv("RBX_PREP_BLOCKS")) pcap = std::max(1, atoi(e));
+    if (opt(OPT_PREP_BLOCKS) > 0) pcap = (int)opt(OPT_PREP_BLOCKS);
     const int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, pcap) : blocks;
     if (dyn > 48 * 1024)
       RBX_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    prep_kernel<<<pblocks, threads, dyn, stream>>>(v, d_vel, d_mass, d_met, d_age, d_pixel, (int)n, nseg, ws.cell_bits,
-                                                   ws.cell_shift, ws.keys_in, ws.idx_in, ws.counts, ws.ctrl, smem_hist,
-                                                   ws.rec, ws.rec_stride, d_coords, d_edges, n_edges, mark_outside,
-                                                   edges_smem);
+    prep_kernel<<<pblocks, threads, dyn, stream>>>(v, b.vel, b.vstride, b.mass, b.met, b.age, b.pixel, (int)n, nseg,
+                                                   ws.cell_bits, ws.cell_shift, ws.keys_in, ws.idx_in, ws.counts, ws.ctrl,
+                                                   smem_hist, ws.rec, ws.rec_stride, b.cx, b.cy, b.cstride, b.edges,
+                                                   b.n_edges, b.mark_outside, edges_smem);
   }
   count_launch();
   RBX_LAUNCH_OK();
@@ -1642,49 +1832,61 @@ int rbx::build_cube_impl(const rbx_plan *plan, const float *d_vel, const float *
     RBX_LAUNCH_OK();
   }
   int small_shift = 2, tail_shift = 3;
-  if (const char *e = getenv("RBX_SMALL_SHIFT")) small_shift = std::max(0, std::min(5, atoi(e)));
-  if (const char *e = getenv("RBX_TAIL_SHIFT")) tail_shift = std::max(1, std::min(6, atoi(e)));
-  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts, ws.seg_start,
-                                          ws.item_start, ws.items, ws.ctrl);
-  count_launch();
-  RBX_LAUNCH_OK();
+  if (opt(OPT_SMALL_SHIFT) >= 0) small_shift = (int)std::max<int64_t>(0, std::min<int64_t>(5, opt(OPT_SMALL_SHIFT)));
+  if (opt(OPT_TAIL_SHIFT) >= 0) tail_shift = (int)std::max<int64_t>(1, std::min<int64_t>(6, opt(OPT_TAIL_SHIFT)));
   FusedLayout lay;
   size_t smem = 0;
   rc = fused_layout(plan, lay, smem);
   if (rc != RBX_OK) return rc;
+  WarpLayout wlay;
+  size_t wsmem = 0;
+  // The warp kernel runs when the plan allows it (host: grid geometry) AND the particles do (device, segment_kernel:
+  // knot window and chunk geometry for the Doppler range present); otherwise the group kernel takes the same work
+  // queue.  Both are launched; the one not selected returns at once.
+  const bool warp_ok = warp_layout(plan, wlay, wsmem);
+  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts,
+                                          ws.seg_start, ws.item_start, ws.items, ws.ctrl, warp_ok ? 1 : 0,
+                                          warp_ok ? wlay.chs : 7, lay.chs);
+  count_launch();
+  RBX_LAUNCH_OK();
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const bool prof = g_profile.load() != 0;
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
-  auto launch = [&](auto kernel) -> int {
-    RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay,
-                                               accumulate);
-    return RBX_OK;
-  };
-  const bool affine = v.affine != 0 && !lay.force_lut;
-  WarpLayout wlay;
-  size_t wsmem = 0;
-  if (warp_layout(plan, wlay, wsmem)) {
+  if (warp_ok) {
     auto wlaunch = [&](auto kernel) -> int {
       RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
       kernel<<<nsm, wlay.nwarps * 32, wsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp,
-                                                       wlay, accumulate);
+                                                       wlay, b.accumulate, cl);
       return RBX_OK;
     };
     rc = v.method == RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR>)
                                        : wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC>);
-  } else if (v.method == RBX_METHOD_LINEAR)
-    rc = affine ? launch(fused_cube_kernel<RBX_METHOD_LINEAR, true>) : launch(fused_cube_kernel<RBX_METHOD_LINEAR, false>);
-  else
-    rc = affine ? launch(fused_cube_kernel<RBX_METHOD_CUBIC, true>) : launch(fused_cube_kernel<RBX_METHOD_CUBIC, false>);
-  if (rc != RBX_OK) return rc;
-  count_launch();
-  RBX_LAUNCH_OK();
+    if (rc != RBX_OK) return rc;
+    count_launch();
+    RBX_LAUNCH_OK();
+  }
+  {
+    auto launch = [&](auto kernel) -> int {
+      RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<nsm, kCtaThreads, smem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp, lay,
+                                                 b.accumulate, cl);
+      return RBX_OK;
+    };
+    const bool affine = v.affine != 0 && !lay.force_lut;
+    if (v.method == RBX_METHOD_LINEAR)
+      rc = affine ? launch(fused_cube_kernel<RBX_METHOD_LINEAR, true>) : launch(fused_cube_kernel<RBX_METHOD_LINEAR, false>);
+    else
+      rc = affine ? launch(fused_cube_kernel<RBX_METHOD_CUBIC, true>) : launch(fused_cube_kernel<RBX_METHOD_CUBIC, false>);
+    if (rc != RBX_OK) return rc;
+    count_launch();
+    RBX_LAUNCH_OK();
+  }
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   dim3 rgrid((v.W + 255) / 256, std::min(nseg, 1184));   // blocks loop over spaxels; most have nothing to add
-  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube, accumulate);
+  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube,
+                                                    b.accumulate, cl);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;

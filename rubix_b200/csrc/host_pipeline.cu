@@ -85,24 +85,38 @@ struct Scratch {
 
 #define TRY(x) do { int _rc = (x); if (_rc != RBX_OK) return _rc; } while (0)
 
-extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity,
-                                 const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
-                                 const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
-                                 const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
-                                 float *h_cube, void *stream_) {
+namespace {
+// The particle arrays of one call: the reference's layout ((n, 3) coords and velocity: 40 bytes per particle) or
+// structure-of-arrays x, y, line-of-sight velocity (24 bytes per particle: what the path reads).
+struct HostParticles {
+  const float *coords = nullptr, *velocity = nullptr;        // (n, 3)
+  const float *x = nullptr, *y = nullptr, *vlos = nullptr;   // (n,) each
+  const float *mass = nullptr, *metallicity = nullptr, *age = nullptr;
+  bool packed = false;
+};
+
+int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n, const float *h_edges, int n_edges,
+                       int num_spaxels, int apply_filter, const float *h_psf, int M, int N, const float *h_lsf, int K,
+                       int ext, float *h_cube, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RBX_REQUIRE(plan && h_cube && h_edges, "rbx_pipeline_host: null argument");
   RBX_REQUIRE(n >= 0 && n_edges >= 2 && num_spaxels >= 1, "rbx_pipeline_host: bad sizes");
-  RBX_REQUIRE(n == 0 || (h_coords && h_velocity && h_mass && h_metallicity && h_age), "rbx_pipeline_host: null particle array");
+  RBX_REQUIRE(n == 0 || (hp.mass && hp.metallicity && hp.age &&
+                         (hp.packed ? (hp.x && hp.y && hp.vlos) : (hp.coords && hp.velocity))),
+              "rbx_pipeline_host: null particle array");
+  const float *h_mass = hp.mass, *h_metallicity = hp.metallicity, *h_age = hp.age;
+  const int nc = hp.packed ? 1 : 3;   // floats per particle in the coordinate / velocity arrays
   const int W = plan->v.W;
   const size_t cube_elems = (size_t)num_spaxels * num_spaxels * W;
   Scratch sc(stream);
-  float *d_coords, *d_vel, *d_mass, *d_met, *d_age, *d_edges, *d_cube, *d_cube2 = nullptr, *d_psf = nullptr, *d_lsf = nullptr;
+  float *d_coords, *d_y = nullptr, *d_vel, *d_mass, *d_met, *d_age, *d_edges, *d_cube, *d_cube2 = nullptr, *d_psf = nullptr,
+        *d_lsf = nullptr;
   int32_t *d_pixel;
   void *d_ws;
   const size_t np = n > 0 ? (size_t)n : 1;
-  TRY(sc.get(&d_coords, 3 * np));
-  TRY(sc.get(&d_vel, 3 * np));
+  TRY(sc.get(&d_coords, nc * np));
+  if (hp.packed) TRY(sc.get(&d_y, np));
+  TRY(sc.get(&d_vel, nc * np));
   TRY(sc.get(&d_mass, np));
   TRY(sc.get(&d_met, np));
   TRY(sc.get(&d_age, np));
@@ -118,7 +132,7 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
   // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges; at 10^6 the
   // per-range launch overhead eats the overlap, 2.13 -> 2.09 ms with 2)
   int chunks = n >= 3000000 ? 5 : (n >= 1500000 ? 2 : 1);
-  if (const char *e = getenv("RBX_HOST_CHUNKS")) chunks = std::max(1, std::min(16, atoi(e)));
+  if (opt(OPT_HOST_CHUNKS) > 0) chunks = (int)std::min<int64_t>(16, opt(OPT_HOST_CHUNKS));
   if (n == 0) chunks = 1;
   CopyLane *lane = nullptr;
   std::unique_lock<std::mutex> lane_lock;
@@ -133,8 +147,14 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
   for (int c = 0; c < chunks && n > 0; ++c) {
     const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, m = hi - lo;
     cudaStream_t cs = chunks > 1 ? lane->stream : stream;
-    RBX_CUDA_OK(cudaMemcpyAsync(d_coords + 3 * lo, h_coords + 3 * lo, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, cs));
-    RBX_CUDA_OK(cudaMemcpyAsync(d_vel + 3 * lo, h_velocity + 3 * lo, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, cs));
+    if (hp.packed) {
+      RBX_CUDA_OK(cudaMemcpyAsync(d_coords + lo, hp.x + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
+      RBX_CUDA_OK(cudaMemcpyAsync(d_y + lo, hp.y + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
+      RBX_CUDA_OK(cudaMemcpyAsync(d_vel + lo, hp.vlos + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
+    } else {
+      RBX_CUDA_OK(cudaMemcpyAsync(d_coords + 3 * lo, hp.coords + 3 * lo, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, cs));
+      RBX_CUDA_OK(cudaMemcpyAsync(d_vel + 3 * lo, hp.velocity + 3 * lo, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, cs));
+    }
     RBX_CUDA_OK(cudaMemcpyAsync(d_mass + lo, h_mass + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
     RBX_CUDA_OK(cudaMemcpyAsync(d_met + lo, h_metallicity + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
     RBX_CUDA_OK(cudaMemcpyAsync(d_age + lo, h_age + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
@@ -144,8 +164,16 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
     }
     // spaxel assignment + aperture filter (pixel -1: the same cube as zeroing the mass) inside the cube build's
     // first kernel: the particle arrays are read once
-    TRY(build_cube_impl(plan, d_vel + 3 * lo, d_mass + lo, d_met + lo, d_age + lo, nullptr, m, num_spaxels, d_cube, d_ws,
-                        ws_bytes, stream, c > 0 ? 1 : 0, d_coords + 3 * lo, d_edges, n_edges, apply_filter ? 1 : 0));
+    CubeBuild b;
+    b.vel = hp.packed ? d_vel + lo : d_vel + 3 * lo + plan->v.vel_comp;
+    b.vstride = nc;
+    b.mass = d_mass + lo; b.met = d_met + lo; b.age = d_age + lo;
+    b.cx = d_coords + nc * lo;
+    b.cy = hp.packed ? d_y + lo : d_coords + 3 * lo + 1;
+    b.cstride = nc;
+    b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
+    b.accumulate = c > 0 ? 1 : 0;
+    TRY(build_cube_impl(plan, b, m, num_spaxels, d_cube, d_ws, ws_bytes, stream));
   }
   float *result = d_cube;
   if (h_psf || h_lsf) {
@@ -187,4 +215,29 @@ extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, co
   RBX_CUDA_OK(cudaMemcpyAsync(h_cube, result, sizeof(float) * cube_elems, cudaMemcpyDeviceToHost, stream));
   RBX_CUDA_OK(cudaStreamSynchronize(stream));  // the caller reads h_cube right after this returns
   return RBX_OK;
+}
+}  // namespace
+
+extern "C" int rbx_pipeline_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity,
+                                 const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                                 const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
+                                 const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                                 float *h_cube, void *stream_) {
+  HostParticles hp;
+  hp.coords = h_coords; hp.velocity = h_velocity;
+  hp.mass = h_mass; hp.metallicity = h_metallicity; hp.age = h_age;
+  return pipeline_host_impl(plan, hp, n, h_edges, n_edges, num_spaxels, apply_filter, h_psf, M, N, h_lsf, K, ext, h_cube,
+                            stream_);
+}
+
+extern "C" int rbx_pipeline_host_packed(const rbx_plan *plan, const float *h_x, const float *h_y, const float *h_vlos,
+                                        const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                                        const float *h_edges, int n_edges, int num_spaxels, int apply_filter,
+                                        const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
+                                        float *h_cube, void *stream_) {
+  HostParticles hp;
+  hp.x = h_x; hp.y = h_y; hp.vlos = h_vlos; hp.packed = true;
+  hp.mass = h_mass; hp.metallicity = h_metallicity; hp.age = h_age;
+  return pipeline_host_impl(plan, hp, n, h_edges, n_edges, num_spaxels, apply_filter, h_psf, M, N, h_lsf, K, ext, h_cube,
+                            stream_);
 }

@@ -91,17 +91,33 @@ __device__ void jacobi3(double A[3][3], double V[3][3]) {
   }
 }
 
-__global__ void inertia_finish_kernel(const double *__restrict__ partial, int nblocks, const float *__restrict__ coords,
-                                      const float *__restrict__ mass, int64_t n, float *__restrict__ R,
-                                      double *__restrict__ tensor_out) {
+// moments[12]: the six second moments, n_inside, n, and (x, y, z, m) of the galaxy's particle 0 -- every entry a plain
+// sum over particle shards (only the shard holding particle 0 contributes the last four), so a sharded galaxy
+// all-reduces this vector and every rank derives the same rotation
+__global__ void inertia_moments_kernel(const double *__restrict__ partial, int nblocks, const float *__restrict__ coords,
+                                       const float *__restrict__ mass, int64_t n, int first_shard,
+                                       double *__restrict__ moments) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int b = 0; b < nblocks; ++b)
     for (int k = 0; k < 7; ++k) s[k] += partial[(size_t)b * 8 + k];
+  for (int k = 0; k < 7; ++k) moments[k] = s[k];
+  moments[7] = (double)n;
+  const bool has0 = first_shard && n > 0;
+  moments[8] = has0 ? coords[0] : 0.0; moments[9] = has0 ? coords[1] : 0.0; moments[10] = has0 ? coords[2] : 0.0;
+  moments[11] = has0 ? mass[0] : 0.0;
+}
+
+__global__ void inertia_finish_kernel(const double *__restrict__ moments, float *__restrict__ R,
+                                      double *__restrict__ tensor_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[7];
+  for (int k = 0; k < 7; ++k) s[k] = moments[k];
+  const double n = moments[7];
   // jnp.where(mask, size=N) pads with index 0: particle 0 enters (N - n_inside) more times
   if (n > 0) {
-    const double pad = (double)n - s[6];
-    const double x = coords[0], y = coords[1], z = coords[2], m = mass[0];
+    const double pad = n - s[6];
+    const double x = moments[8], y = moments[9], z = moments[10], m = moments[11];
     s[0] += pad * m * x * x; s[1] += pad * m * y * y; s[2] += pad * m * z * z;
     s[3] += pad * m * x * y; s[4] += pad * m * x * z; s[5] += pad * m * y * z;
   }
@@ -161,23 +177,38 @@ __global__ void rotate_apply_kernel(const float *__restrict__ coords, const floa
 
 using namespace rbx;
 
-extern "C" size_t rbx_rotate_galaxy_workspace_bytes(void) { return sizeof(double) * 8 * kRotBlocks + 256; }
+extern "C" size_t rbx_rotate_galaxy_workspace_bytes(void) { return sizeof(double) * (8 * kRotBlocks + 16) + 256; }
 
-extern "C" int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity, const float *d_mass, int64_t n,
-                                 float halfmass_radius, const float *h_euler, float *d_coords_out,
-                                 float *d_velocity_out, float *d_rotation, void *d_workspace, size_t workspace_bytes,
-                                 void *stream_) {
+// Step 1 of rotate_galaxy for a galaxy whose particles are sharded over ranks: this shard's contribution to the
+// inertia sums, d_moments[12] doubles (see inertia_moments_kernel).  first_shard != 0 on the rank that holds the
+// galaxy's particle 0.  The host sums d_moments over the ranks (rbx_allreduce_f64) before rbx_rotate_apply.
+extern "C" int rbx_rotate_moments(const float *d_coords, const float *d_mass, int64_t n, float halfmass_radius,
+                                  int first_shard, double *d_moments, void *d_workspace, size_t workspace_bytes,
+                                  void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  RBX_REQUIRE(n >= 0 && h_euler && d_rotation, "rbx_rotate_galaxy: bad argument");
-  RBX_REQUIRE(n == 0 || (d_coords && d_mass && d_coords_out && d_workspace), "rbx_rotate_galaxy: null pointer");
-  RBX_REQUIRE((d_velocity == nullptr) == (d_velocity_out == nullptr), "rbx_rotate_galaxy: velocity in/out must both be given or both NULL");
-  RBX_REQUIRE(workspace_bytes >= rbx_rotate_galaxy_workspace_bytes(), "rbx_rotate_galaxy: workspace too small");
+  RBX_REQUIRE(n >= 0 && d_moments && d_workspace, "rbx_rotate_moments: bad argument");
+  RBX_REQUIRE(n == 0 || (d_coords && d_mass), "rbx_rotate_moments: null pointer");
+  RBX_REQUIRE(workspace_bytes >= rbx_rotate_galaxy_workspace_bytes(), "rbx_rotate_moments: workspace too small");
   double *partial = reinterpret_cast<double *>(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kRotBlocks, (n + kRotThreads - 1) / kRotThreads));
   inertia_partial_kernel<<<blocks, kRotThreads, 0, stream>>>(d_coords, d_mass, n, halfmass_radius, partial);
   count_launch();
   RBX_LAUNCH_OK();
-  inertia_finish_kernel<<<1, 32, 0, stream>>>(partial, blocks, d_coords, d_mass, n, d_rotation, nullptr);
+  inertia_moments_kernel<<<1, 32, 0, stream>>>(partial, blocks, d_coords, d_mass, n, first_shard, d_moments);
+  count_launch();
+  RBX_LAUNCH_OK();
+  return RBX_OK;
+}
+
+// Step 2: rotation from the (summed) moments, then (p @ R) @ E on this shard's particles.
+extern "C" int rbx_rotate_apply(const float *d_coords, const float *d_velocity, int64_t n, const double *d_moments,
+                                const float *h_euler, float *d_coords_out, float *d_velocity_out, float *d_rotation,
+                                void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBX_REQUIRE(n >= 0 && h_euler && d_rotation && d_moments, "rbx_rotate_apply: bad argument");
+  RBX_REQUIRE(n == 0 || (d_coords && d_coords_out), "rbx_rotate_apply: null pointer");
+  RBX_REQUIRE((d_velocity == nullptr) == (d_velocity_out == nullptr), "rbx_rotate_apply: velocity in/out must both be given or both NULL");
+  inertia_finish_kernel<<<1, 32, 0, stream>>>(d_moments, d_rotation, nullptr);
   count_launch();
   RBX_LAUNCH_OK();
   if (n > 0) {
@@ -189,4 +220,18 @@ extern "C" int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity,
     RBX_LAUNCH_OK();
   }
   return RBX_OK;
+}
+
+extern "C" int rbx_rotate_galaxy(const float *d_coords, const float *d_velocity, const float *d_mass, int64_t n,
+                                 float halfmass_radius, const float *h_euler, float *d_coords_out,
+                                 float *d_velocity_out, float *d_rotation, void *d_workspace, size_t workspace_bytes,
+                                 void *stream_) {
+  RBX_REQUIRE(n >= 0 && h_euler && d_rotation, "rbx_rotate_galaxy: bad argument");
+  RBX_REQUIRE(n == 0 || (d_coords && d_mass && d_coords_out && d_workspace), "rbx_rotate_galaxy: null pointer");
+  RBX_REQUIRE((d_velocity == nullptr) == (d_velocity_out == nullptr), "rbx_rotate_galaxy: velocity in/out must both be given or both NULL");
+  RBX_REQUIRE(workspace_bytes >= rbx_rotate_galaxy_workspace_bytes(), "rbx_rotate_galaxy: workspace too small");
+  double *moments = reinterpret_cast<double *>(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255) + 8 * kRotBlocks;
+  int rc = rbx_rotate_moments(d_coords, d_mass, n, halfmass_radius, 1, moments, d_workspace, workspace_bytes, stream_);
+  if (rc != RBX_OK) return rc;
+  return rbx_rotate_apply(d_coords, d_velocity, n, moments, h_euler, d_coords_out, d_velocity_out, d_rotation, stream_);
 }

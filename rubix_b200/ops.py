@@ -132,9 +132,14 @@ def euler_rotation_matrix(alpha: float, beta: float, gamma: float) -> np.ndarray
     return np.ascontiguousarray(Rz @ Ry @ Rx, dtype=np.float32)
 
 
-def rotate_galaxy(coords, velocity, mass, halfmass_radius: float, alpha: float, beta: float, gamma: float):
+def rotate_galaxy(coords, velocity, mass, halfmass_radius: float, alpha: float, beta: float, gamma: float,
+                  comm=None):
     """rubix/galaxy/alignment.py:233-265 on the device: inertia tensor of the particles within the
-    half-mass radius, eigenvector alignment, Euler rotation.  Returns (coords, velocity, R)."""
+    half-mass radius, eigenvector alignment, Euler rotation.  Returns (coords, velocity, R).
+
+    ``comm`` (an ``ops.Comm``): the arrays are this rank's contiguous shard of ONE galaxy; the inertia sums are
+    all-reduced so that every rank applies the rotation of the whole galaxy, as the reference does before it
+    splits the particles over devices (rubix/core/rotation.py:76-115)."""
     coords, mass = dev(coords), dev(mass).reshape(-1)
     velocity = None if velocity is None else dev(velocity)
     n = coords.shape[0]
@@ -146,9 +151,17 @@ def rotate_galaxy(coords, velocity, mass, halfmass_radius: float, alpha: float, 
     L = _lib.lib()
     ws = _workspace(L.rbx_rotate_galaxy_workspace_bytes())
     E = euler_rotation_matrix(alpha, beta, gamma)
-    _lib.check(L.rbx_rotate_galaxy(_p(coords), _p(velocity), _p(mass), n, float(np.float32(halfmass_radius)),
-                                   E.ctypes.data_as(C.c_void_p), _p(out_c), _p(out_v), _p(R), _p(ws), ws.numel(),
-                                   _stream()))
+    radius = float(np.float32(halfmass_radius))
+    if comm is None or comm.world == 1:
+        _lib.check(L.rbx_rotate_galaxy(_p(coords), _p(velocity), _p(mass), n, radius, E.ctypes.data_as(C.c_void_p),
+                                       _p(out_c), _p(out_v), _p(R), _p(ws), ws.numel(), _stream()))
+    else:
+        mom = torch.empty(12, dtype=torch.float64, device="cuda")
+        _lib.check(L.rbx_rotate_moments(_p(coords), _p(mass), n, radius, 1 if comm.rank == 0 else 0, _p(mom), _p(ws),
+                                        ws.numel(), _stream()))
+        comm.allreduce_f64(mom)
+        _lib.check(L.rbx_rotate_apply(_p(coords), _p(velocity), n, _p(mom), E.ctypes.data_as(C.c_void_p), _p(out_c),
+                                      _p(out_v), _p(R), _stream()))
     return out_c, out_v, R.reshape(3, 3)
 
 
@@ -373,6 +386,148 @@ def assign_build_cube(plan: Plan, coords, edges, velocity, mass, metallicity, ag
     return (cube, pixel) if return_pixel else cube
 
 
+def assign_build_cube_packed(plan: Plan, x, y, edges, vlos, mass, metallicity, age, num_spaxels: int,
+                             apply_filter: bool = True, out: Optional[torch.Tensor] = None):
+    """``rbx_assign_build_cube_packed``: the same build from structure-of-arrays particles (x, y and the
+    line-of-sight velocity as arrays of their own: the 24 bytes per particle the path reads)."""
+    x, y, edges, vlos = dev(x).reshape(-1), dev(y).reshape(-1), dev(edges), dev(vlos).reshape(-1)
+    mass, metallicity, age = dev(mass).reshape(-1), dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    n = mass.numel()
+    if any(t.numel() != n for t in (x, y, vlos, metallicity, age)):
+        raise ValueError("particle arrays disagree in length")
+    S = int(num_spaxels)
+    cube = out if out is not None else torch.empty((S, S, plan.W), dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_workspace_bytes(plan.handle, n, S))
+    _lib.check(L.rbx_assign_build_cube_packed(plan.handle, _p(x), _p(y), _p(edges), edges.numel(),
+                                              1 if apply_filter else 0, _p(vlos), _p(mass), _p(metallicity), _p(age),
+                                              n, S, None, _p(cube), _p(ws), ws.numel(), _stream()))
+    return cube
+
+
+def build_cube_status(plan: Plan, n: int, num_spaxels: int):
+    """(error, impl) of the last cube build of ``n`` particles on this stream's workspace: error 0 = ok (otherwise
+    the cube was filled with NaN); impl 0 = the warp kernel ran, 1 = the general group kernel."""
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_workspace_bytes(plan.handle, int(n), int(num_spaxels)))
+    err, impl = C.c_int(), C.c_int()
+    _lib.check(L.rbx_build_cube_status(plan.handle, int(n), int(num_spaxels), _p(ws), C.byref(err), C.byref(impl),
+                                       _stream()))
+    return int(err.value), int(impl.value)
+
+
+def slab_geometry(W: int, nslab: int, halo: int = 12):
+    """(wslab, ws): channels per wavelength slab and its stored width including the halo on both sides."""
+    a, b = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().rbx_slab_geometry(int(W), int(nslab), int(halo), C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
+def assign_build_cube_slabs(plan: Plan, coords, edges, velocity, mass, metallicity, age, num_spaxels: int, nslab: int,
+                            halo: int = 12, apply_filter: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``rbx_assign_build_cube_slabs``: the partial cube stored slab-major, (nslab, S*S, wslab + 2 halo), every slab
+    with the halo channels of its neighbours, ready for one reduce-scatter over the ranks."""
+    coords, edges, velocity = dev(coords), dev(edges), dev(velocity)
+    mass, metallicity, age = dev(mass).reshape(-1), dev(metallicity).reshape(-1), dev(age).reshape(-1)
+    n = mass.numel()
+    if coords.shape != (n, 3) or velocity.shape != (n, 3) or metallicity.numel() != n or age.numel() != n:
+        raise ValueError("particle arrays disagree in length")
+    S = int(num_spaxels)
+    _, ws_ch = slab_geometry(plan.W, nslab, halo)
+    slabs = out if out is not None else torch.empty((nslab, S * S, ws_ch), dtype=torch.float32, device="cuda")
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_workspace_bytes(plan.handle, n, S))
+    _lib.check(L.rbx_assign_build_cube_slabs(plan.handle, _p(coords), _p(edges), edges.numel(), 1 if apply_filter else 0,
+                                             _p(velocity), _p(mass), _p(metallicity), _p(age), n, S, int(nslab),
+                                             int(halo), _p(slabs), _p(ws), ws.numel(), _stream()))
+    return slabs
+
+
+def psf_lsf_own_slab(slab, num_spaxels: int, W: int, rank: int, nslab: int, psf_kernel, lsf_kernel, halo: int = 12,
+                     ext: int = 12) -> torch.Tensor:
+    """PSF + LSF of one summed slab (S*S, wslab + 2 halo) as rbx_reduce_scatter_cube leaves it on rank ``rank``;
+    returns the (S, S, n_own) interior, n_own = the slab's channels inside [0, W)."""
+    S = int(num_spaxels)
+    wslab, ws_ch = slab_geometry(W, nslab, halo)
+    slab = dev(slab).reshape(S, S, ws_ch)
+    hp, hl = _host_taps(psf_kernel), _host_taps(lsf_kernel)
+    if hp is None or hl is None:
+        raise ValueError("psf_lsf_own_slab needs host (numpy) kernels")
+    out = torch.empty_like(slab)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = _lib.lib().rbx_psf_lsf_taps_pitched(_p(slab), ws_ch, _p(out), ws_ch, S, S, ws_ch, vp(hp), hp.shape[0],
+                                             hp.shape[1], vp(hl.reshape(-1)), hl.size, ext, _stream())
+    if rc == _lib.RBX_ERR_UNSUPPORTED:
+        out = psf_lsf(slab, psf_kernel, lsf_kernel, ext, host_taps=False)
+    else:
+        _lib.check(rc)
+    n_own = max(0, min(wslab, W - rank * wslab))
+    return out[:, :, halo:halo + n_own]
+
+
+class Comm:
+    """The exchange step behind the C ABI (``rbx_comm_*``, NCCL bound at run time).  ``unique_id()`` on one rank,
+    the 128 bytes handed to every rank by the host, then ``Comm(id, rank, world)`` on every rank."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.lib().rbx_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, uid: bytes, rank: int, world: int):
+        _require_cuda()
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _lib.check(_lib.lib().rbx_comm_init(C.byref(self._h), buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    @classmethod
+    def from_torch_distributed(cls):
+        """Bootstrap over an initialised torch.distributed group (any backend): rank 0's id is broadcast."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        obj = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        return cls(obj[0], rank, world)
+
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        _lib.check(_lib.lib().rbx_comm_info(self._h, None, None, C.byref(v)))
+        return int(v.value)
+
+    def reduce(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None, root: int = 0):
+        recv = send if recv is None else recv
+        _lib.check(_lib.lib().rbx_reduce_cube(self._h, _p(send), _p(recv), send.numel(), int(root), _stream()))
+        return recv
+
+    def allreduce(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None):
+        recv = send if recv is None else recv
+        _lib.check(_lib.lib().rbx_allreduce_cube(self._h, _p(send), _p(recv), send.numel(), _stream()))
+        return recv
+
+    def allreduce_f64(self, buf: torch.Tensor):
+        _lib.check(_lib.lib().rbx_allreduce_f64(self._h, _p(buf), _p(buf), buf.numel(), _stream()))
+        return buf
+
+    def reduce_scatter(self, send: torch.Tensor, recv: torch.Tensor):
+        if send.numel() != recv.numel() * self.world:
+            raise ValueError("reduce_scatter: send must hold world * recv elements")
+        _lib.check(_lib.lib().rbx_reduce_scatter_cube(self._h, _p(send), _p(recv), recv.numel(), _stream()))
+        return recv
+
+    def allgather(self, send: torch.Tensor, recv: torch.Tensor):
+        if recv.numel() != send.numel() * self.world:
+            raise ValueError("allgather: recv must hold world * send elements")
+        _lib.check(_lib.lib().rbx_allgather_cube(self._h, _p(send), _p(recv), send.numel(), _stream()))
+        return recv
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().rbx_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def _host_taps(k):
     """float32 host copy of a kernel given as numpy / list (None for CUDA tensors: those stay on the device)."""
     if k is None or (isinstance(k, torch.Tensor) and k.is_cuda):
@@ -463,6 +618,27 @@ def psf_lsf(cube, psf_kernel, lsf_kernel, ext: int = 12, host_taps: bool = True)
         return convolve_lsf(convolve_psf(cube, pk), lk, ext)
     _lib.check(rc)
     return out
+
+
+def pipeline_host_packed(plan: Plan, x, y, vlos, mass, metallicity, age, edges, num_spaxels: int,
+                         psf_kernel=None, lsf_kernel=None, ext: int = 12, apply_filter: bool = True,
+                         out: Optional[np.ndarray] = None) -> np.ndarray:
+    """``rbx_pipeline_host_packed``: the host-buffer call with structure-of-arrays particles (24 B each over PCIe)."""
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+    x, y, vlos, mass = f32(x), f32(y), f32(vlos), f32(mass)
+    metallicity, age, edges = f32(metallicity), f32(age), f32(edges)
+    n = x.shape[0]
+    S = int(num_spaxels)
+    cube = out if out is not None else np.empty((S, S, plan.W), dtype=np.float32)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    pk = None if psf_kernel is None else f32(psf_kernel)
+    lk = None if lsf_kernel is None else f32(lsf_kernel)
+    M, N = (pk.shape if pk is not None else (0, 0))
+    K = len(lk) if lk is not None else 0
+    _lib.check(_lib.lib().rbx_pipeline_host_packed(
+        plan.handle, vp(x), vp(y), vp(vlos), vp(mass), vp(metallicity), vp(age), n, vp(edges), len(edges), S,
+        1 if apply_filter else 0, vp(pk), M, N, vp(lk), K, ext, vp(cube), _stream()))
+    return cube
 
 
 def pipeline_host(plan: Plan, coords, velocity, mass, metallicity, age, edges, num_spaxels: int,

@@ -31,16 +31,51 @@ def wavelength_slab(W: int, rank: int, world: int) -> Tuple[int, int]:
     return shard_range(W, rank, world)
 
 
+_comm = None
+
+
+def get_comm():
+    """The process-wide ``ops.Comm`` (NCCL through the C ABI, ``rbx_comm_*``), bootstrapped once over the initialised
+    ``torch.distributed`` group (which only carries the 128-byte NCCL id).  None when the job has one rank."""
+    global _comm
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    if _comm is None:
+        from . import ops
+        _comm = ops.Comm.from_torch_distributed()
+    return _comm
+
+
+def close_comm():
+    global _comm
+    if _comm is not None:
+        _comm.close()
+        _comm = None
+
+
+def _on_cuda(t) -> bool:
+    return bool(getattr(t, "is_cuda", False))
+
+
 def allreduce_cube(cube):
-    """Sum the partial cubes of all ranks in place (NCCL all-reduce on CUDA tensors)."""
+    """Sum the partial cubes of all ranks in place: ``rbx_allreduce_cube`` for CUDA tensors; CPU tensors (the gloo
+    tests of the host logic) go through torch.distributed."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(cube, op=dist.ReduceOp.SUM)
+        if _on_cuda(cube):
+            get_comm().allreduce(cube)
+        else:
+            dist.all_reduce(cube, op=dist.ReduceOp.SUM)
     return cube
 
 
 def reduce_cube(cube, dst: int = 0):
+    """Sum the partial cubes onto rank ``dst`` in place (``rbx_reduce_cube``; other ranks' buffers are unchanged)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(cube, dst=dst, op=dist.ReduceOp.SUM)
+        if _on_cuda(cube):
+            get_comm().reduce(cube, root=dst)
+        else:
+            dist.reduce(cube, dst=dst, op=dist.ReduceOp.SUM)
     return cube

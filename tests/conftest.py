@@ -18,8 +18,8 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def bc03():
-    """BC03lr SSP template as float32 (tests/golden/bc03lr_f32.npz, made by tools/make_golden.py)."""
-    d = np.load(os.path.join(GOLDEN, "bc03lr_f32.npz"))
+    """BC03lr SSP template as float32 (rubix_b200/templates/bc03lr_f32.npz, made by tools/make_golden.py)."""
+    d = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
     return {k: d[k] for k in d.files}
 
 

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out_dir):
         from oracle import rubix_oracle as orc
         from rubix_b200 import parallel, synthetic
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        tpl = np.load(os.path.join(root, "tests", "golden", "bc03lr_f32.npz"))
+        tpl = np.load(os.path.join(root, "rubix_b200", "templates", "bc03lr_f32.npz"))
         wave = synthetic.muse_wave()[:400]
         edges = synthetic.spatial_edges(5)
         data = synthetic.bench_g(3001, seed=42)  # odd count: the last shard is shorter
@@ -107,7 +107,7 @@ def _dusty_worker(rank, world, port, out_dir):
         from oracle import rubix_oracle as orc
         from rubix_b200 import parallel, synthetic
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        tpl = np.load(os.path.join(root, "tests", "golden", "bc03lr_f32.npz"))
+        tpl = np.load(os.path.join(root, "rubix_b200", "templates", "bc03lr_f32.npz"))
         wave = synthetic.muse_wave()[:300]
         edges = synthetic.spatial_edges(5)
         stars, gas = _dusty_inputs()

@@ -225,21 +225,26 @@ def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
     _cube_close(out, ref, f"fused {gen} {method}")
 
 
-@pytest.mark.parametrize("env", ["RBX_FUSED_FORCE_LUT=1", "RBX_FUSED_FORCE_CAS=1", "RBX_FUSED_IMPL=group",
-                                 "RBX_PSUB=64", "RBX_SMALL_SHIFT=1", "RBX_FUSED_NO_SKEW=1"])
+@pytest.mark.parametrize("env", ["fused_force_lut=1", "fused_force_cas=1", "fused_impl=1",
+                                 "psub=64", "small_shift=1", "fused_no_skew=1", "fused_chs=9", "sort_impl=1"])
 @pytest.mark.parametrize("method", ["linear", "cubic"])
-def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env, monkeypatch):
-    """The general paths -- the group kernel (RBX_FUSED_IMPL=group), its lookup-table channel search for
+def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env):
+    """The general paths -- the group kernel (option fused_impl = 1), its lookup-table channel search for
     non-arange telescope grids and its shared cell region with CAS adds for SSP grids finer than the
     telescope's -- forced on the MUSE configuration (they are otherwise only taken by configurations the
-    oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew."""
-    from rubix_b200 import synthetic
+    oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew / larger chunks."""
+    from rubix_b200 import _lib, synthetic
     env, val = env.split("=")
-    monkeypatch.setenv(env, val)
     edges = synthetic.spatial_edges(25)
     data = _well_conditioned(synthetic.bench_g(20000, seed=5), np.float32(1.1) * bc03["wavelength"], muse_wave)
-    out = _run_fused(ops, plans[method], data, edges, 25)
-    monkeypatch.delenv(env)
+    _lib.set_option(env, int(val))
+    try:
+        out = _run_fused(ops, plans[method], data, edges, 25)
+        err, impl = ops.build_cube_status(plans[method], len(data["mass"]), 25)
+    finally:
+        _lib.set_option(env, -1)
+    assert err == 0
+    assert impl == (1 if env in ("fused_force_lut", "fused_force_cas", "fused_impl") else 0)
     ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
                                      data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
                                      bc03["flux"], muse_wave, 0.1, method=method, dtype=np.float64, n_threads=8)
@@ -511,7 +516,7 @@ def test_assign_build_cube_equals_two_calls(ops, plans, apply_filter):
     assert torch.equal(one, two)
 
 
-def test_pipeline_host_particle_ranges(ops, plans, bc03, muse_wave, monkeypatch):
+def test_pipeline_host_particle_ranges(ops, plans, bc03, muse_wave):
     """rbx_pipeline_host bins a galaxy in particle ranges (copy / compute overlap, accumulating cube build):
     1, 2 and 5 ranges give the same cube, equal to the oracle's."""
     from rubix_b200 import synthetic
@@ -519,11 +524,14 @@ def test_pipeline_host_particle_ranges(ops, plans, bc03, muse_wave, monkeypatch)
     d = _well_conditioned(synthetic.bench_g(30011, seed=9), np.float32(1.1) * bc03["wavelength"], muse_wave)
     pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
     outs = {}
-    for c in (1, 2, 5):
-        monkeypatch.setenv("RBX_HOST_CHUNKS", str(c))
-        outs[c] = ops.pipeline_host(plans["linear"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"],
-                                    edges, 25, pk, lk).copy()
-    monkeypatch.delenv("RBX_HOST_CHUNKS")
+    from rubix_b200 import _lib
+    try:
+        for c in (1, 2, 5):
+            _lib.set_option("host_chunks", c)
+            outs[c] = ops.pipeline_host(plans["linear"], d["coords"], d["velocity"], d["mass"], d["metallicity"],
+                                        d["age"], edges, 25, pk, lk).copy()
+    finally:
+        _lib.set_option("host_chunks", -1)
     ref = c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, 25,
                                      bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave,
                                      0.1, method="linear", dtype=np.float64, n_threads=8)

@@ -1,0 +1,254 @@
+"""GPU parity at BASELINE.json's sizes, on the hard particles, and across ranks.
+
+* 10^6 (linear and cubic) and 10^7 (linear) bench-G particles -- ALL of them, knife-edge particles included --
+  against the float64 C oracle, through both ``rbx_assign_build_cube`` and the host-buffer call
+  ``rbx_pipeline_host`` (which bins 10^7 particles in 5 ranges); 150 x 150 spaxels at 10^6.  These sizes are where
+  segment splitting, tail items, psub = 2048 and the template-row reuse engage.
+* Knife-edge particles, one per spaxel so that every particle is judged on its own: a Doppler-shifted SSP knot
+  within float32 rounding of a band edge (rubix/spectra/ifu.py:241-244 masks ``tmin <= lam' <= tmax``; the knot
+  flips in or out of ``total_lum``) or of a channel wavelength.  The CUDA result must equal the oracle evaluated
+  at the particle's velocity or at a velocity a few float32 ulps of lam' to either side -- i.e. ONE of the answers
+  the reference's own float32 arithmetic can give -- never something else.
+* Doppler ranges wider than the default chunk geometry: the device picks a larger chunk (or the group kernel) on its
+  own; ranges nothing can hold fail loudly (status != 0, NaN cube).
+* world_size 2 over NCCL through the C ABI (``rbx_comm_*``): particle shards -> ``rbx_reduce_cube`` -> PSF + LSF on
+  rank 0, and slab-major partial cubes -> ``rbx_reduce_scatter_cube`` -> PSF + LSF per wavelength slab, both against
+  the oracle on the unsharded input (skipped on a one-GPU box).
+"""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle  # noqa: E402
+from oracle import rubix_oracle as orc  # noqa: E402
+from helpers import cube_close as _cube_close  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+C_KMS = 299792.458
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rubix_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def plans(ops, bc03, muse_wave):
+    return {m: ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1,
+                        method=m, direction="z") for m in ("linear", "cubic")}
+
+
+def _oracle_cube(d, edges, S, bc03, wave, method, dtype=np.float64, threads=None):
+    return c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, S,
+                                      bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], wave, 0.1,
+                                      method=method, dtype=dtype, n_threads=threads or (os.cpu_count() or 8))
+
+
+# ---- BASELINE sizes ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_cube_1e6_vs_oracle(ops, plans, bc03, muse_wave, method):
+    """Config 2 (10^6 bench-G, MUSE 25 x 25 x 3721, PSF + LSF): device call and host-buffer call against the float64
+    oracle; the two CUDA entry points agree bit for bit (one range at this size)."""
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(25)
+    d = synthetic.bench_g(1_000_000, seed=42)
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    ref = _oracle_cube(d, edges, 25, bc03, muse_wave, method)
+    cube = ops.assign_build_cube(plans[method], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                 d["age"], 25)
+    assert ops.build_cube_status(plans[method], 1_000_000, 25) == (0, 0)
+    _cube_close(cube.cpu().numpy(), ref, f"1e6 {method} cube")
+    refc = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
+    conv = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+    _cube_close(conv, refc, f"1e6 {method} cube + PSF + LSF")
+    host = ops.pipeline_host(plans[method], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges,
+                             25, pk, lk)
+    _cube_close(host, refc, f"1e6 {method} rbx_pipeline_host")
+    assert np.array_equal(host, conv)
+    packed = ops.pipeline_host_packed(plans[method], d["coords"][:, 0].copy(), d["coords"][:, 1].copy(),
+                                      d["velocity"][:, 2].copy(), d["mass"], d["metallicity"], d["age"], edges, 25, pk, lk)
+    assert np.array_equal(packed, host)
+
+
+def test_cube_1e7_vs_oracle(ops, plans, bc03, muse_wave):
+    """Config 3's galaxy on one GPU: 10^7 bench-G particles (psub = 2048, row reuse, 5 host ranges)."""
+    from rubix_b200 import synthetic
+    edges = synthetic.spatial_edges(25)
+    d = synthetic.bench_g(10_000_000, seed=42)
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    ref = _oracle_cube(d, edges, 25, bc03, muse_wave, "linear")
+    cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                 d["age"], 25)
+    assert ops.build_cube_status(plans["linear"], 10_000_000, 25) == (0, 0)
+    _cube_close(cube.cpu().numpy(), ref, "1e7 linear cube")
+    refc = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
+    host = ops.pipeline_host(plans["linear"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges,
+                             25, pk, lk)
+    _cube_close(host, refc, "1e7 linear rbx_pipeline_host (5 ranges)")
+
+
+def test_cube_150_1e6_vs_oracle(ops, plans, bc03, muse_wave):
+    """Config 4's grid (150 x 150 spaxels: run-length counts instead of the shared-memory histogram) at 10^6
+    particles, standard and slab-major layouts."""
+    from rubix_b200 import synthetic
+    S = 150
+    edges = synthetic.spatial_edges(S)
+    d = synthetic.bench_g(1_000_000, seed=7)
+    d["coords"] *= np.float32(4.0)   # spread the galaxy over the 30" field
+    ref = _oracle_cube(d, edges, S, bc03, muse_wave, "linear")
+    cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                 d["age"], S).cpu().numpy()
+    _cube_close(cube, ref, "S=150 1e6 linear cube")
+    # slab-major: 8 slabs with a 12-channel halo; every slab equals the matching channel window of the cube
+    nslab, halo = 8, 12
+    wslab, ws = ops.slab_geometry(3721, nslab, halo)
+    slabs = ops.assign_build_cube_slabs(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                        d["age"], S, nslab, halo).cpu().numpy()
+    flat = cube.reshape(S * S, -1)
+    for r in range(nslab):
+        lo = r * wslab - halo
+        want = np.zeros((S * S, ws), dtype=np.float32)
+        a, b = max(lo, 0), min(lo + ws, 3721)
+        want[:, a - lo:b - lo] = flat[:, a:b]
+        assert np.array_equal(slabs[r], want), f"slab {r}"
+
+
+# ---- knife-edge particles -----------------------------------------------------------------------------
+def _one_per_spaxel(n, S, edges, rng):
+    """n <= S*S particles, particle i at the centre of spaxel i."""
+    centres = (0.5 * (edges[:-1] + edges[1:])).astype(np.float32)
+    ids = np.arange(n)
+    coords = np.zeros((n, 3), dtype=np.float32)
+    coords[:, 0] = centres[ids % S]
+    coords[:, 1] = centres[ids // S]
+    return coords
+
+
+def _knife_velocities(lamz, targets, rng, n):
+    """Velocities that put a Doppler-shifted SSP knot within a few float32 ulps of one of ``targets``."""
+    v = np.empty(n, dtype=np.float32)
+    for i in range(n):
+        t = float(targets[rng.integers(len(targets))])
+        # a knot that reaches t with |v| <= 450 km/s
+        cand = np.nonzero(np.abs(np.log(t / lamz.astype(np.float64))) * C_KMS <= 450.0)[0]
+        j = int(cand[rng.integers(len(cand))])
+        ulps = rng.integers(-3, 4)
+        x = np.float32(t)
+        for _ in range(abs(int(ulps))):
+            x = np.nextafter(x, np.float32(np.inf if ulps > 0 else -np.inf))
+        v[i] = np.float32(np.log(float(x) / float(lamz[j])) * C_KMS)
+    return v
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+@pytest.mark.parametrize("where", ["band_edge", "channel"])
+def test_knife_edge_particles_one_of_the_reference_answers(ops, plans, bc03, muse_wave, method, where):
+    from rubix_b200 import synthetic
+    S, n = 25, 600
+    rng = np.random.default_rng(11)
+    edges = synthetic.spatial_edges(S)
+    lamz = (np.float32(1.1) * bc03["wavelength"]).astype(np.float32)
+    base = synthetic.bench_g(n, seed=3)
+    base["coords"] = _one_per_spaxel(n, S, edges, rng)
+    base["metallicity"] = rng.uniform(2e-4, 0.04, n).astype(np.float32)
+    targets = np.array([muse_wave[0], muse_wave[-1]]) if where == "band_edge" else muse_wave[rng.integers(1, 3720, 64)]
+    base["velocity"][:, 2] = _knife_velocities(lamz, targets, rng, n)
+    out = ops.assign_build_cube(plans[method], base["coords"], edges, base["velocity"], base["mass"],
+                                base["metallicity"], base["age"], S).cpu().numpy().reshape(S * S, -1)[:n]
+    assert np.isfinite(out).all()
+    # the answers the reference can give: float32 and float64 evaluation at v, float64 at v -+ 0.25 km/s (lam' moves
+    # by ~4e-3 A = 8 float32 ulps, the flip resolved either way; the spectrum itself moves by < 1e-5 of its scale)
+    cands = []
+    for dv, dt in ((0.0, np.float32), (0.0, np.float64), (-0.25, np.float64), (0.25, np.float64)):
+        d = {k: v.copy() for k, v in base.items()}
+        d["velocity"][:, 2] += np.float32(dv)
+        cands.append(_oracle_cube(d, edges, S, bc03, muse_wave, method, dtype=dt, threads=8).reshape(S * S, -1)[:n])
+    scale = np.abs(cands[1]).max(axis=1) + 1e-300
+    errs = np.stack([np.abs(out - c.astype(np.float64)).max(axis=1) / scale for c in cands])
+    best = errs.min(axis=0)
+    spread = np.abs(cands[2].astype(np.float64) - cands[3]).max(axis=1) / scale   # how far apart the answers are
+    print(f"[knife {where} {method}] best-match err: max {best.max():.2e}, median {np.median(best):.2e}; "
+          f"answers differ by up to {spread.max():.2e}; matched f32@v {np.mean(errs.argmin(0) == 0):.2f}")
+    # a flip moves the whole spectrum by ~5e-3 (band edge); matching ONE answer means well below that
+    assert best.max() <= 4e-5, f"particle {int(best.argmax())}: {errs[:, best.argmax()]}"
+
+
+# ---- Doppler ranges beyond the default chunk geometry -------------------------------------------------------
+@pytest.mark.parametrize("vmax_c,expect_ok", [(0.01, True), (0.04, True), (0.08, False)])
+def test_wide_doppler_range(ops, plans, bc03, muse_wave, vmax_c, expect_ok):
+    """|v| up to 0.01 c / 0.04 c: the device picks a larger chunk for the warp kernel and the cube still equals the
+    oracle's.  0.08 c: the knot window and the chunk geometry exceed both kernels -- status 2 or 3 and a NaN cube,
+    never a silently wrong one."""
+    from rubix_b200 import synthetic
+    S = 25
+    edges = synthetic.spatial_edges(S)
+    rng = np.random.default_rng(5)
+    d = synthetic.bench_g(20000, seed=13)
+    d["velocity"][:, 2] = rng.uniform(-vmax_c, vmax_c, 20000).astype(np.float32) * np.float32(C_KMS)
+    cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                 d["age"], S).cpu().numpy()
+    err, impl = ops.build_cube_status(plans["linear"], 20000, S)
+    print(f"[wide doppler {vmax_c}] status error={err} impl={impl}")
+    if not expect_ok:
+        assert err in (2, 3) and np.isnan(cube).all()
+        return
+    assert err == 0
+    from helpers import well_conditioned
+    dw = well_conditioned(d, np.float32(1.1) * bc03["wavelength"], muse_wave)
+    cube = ops.assign_build_cube(plans["linear"], dw["coords"], edges, dw["velocity"], dw["mass"], dw["metallicity"],
+                                 dw["age"], S).cpu().numpy()
+    ref = _oracle_cube(dw, edges, S, bc03, muse_wave, "linear", threads=8)
+    _cube_close(cube, ref, f"wide doppler {vmax_c} c", rtol_max=1e-5)
+
+
+def test_group_kernel_takes_over_and_fails_loudly(ops, plans, bc03, muse_wave):
+    """Option fused_impl = 1 stands for a plan the warp kernel cannot take: at |v| <= 0.01 c the group kernel picks a
+    larger chunk than the host's and matches the oracle; at 0.04 c no chunk of its fits -> status 3, NaN cube."""
+    from rubix_b200 import _lib, synthetic
+    from helpers import well_conditioned
+    S = 25
+    edges = synthetic.spatial_edges(S)
+    rng = np.random.default_rng(6)
+    d = synthetic.bench_g(20000, seed=14)
+    _lib.set_option("fused_impl", 1)
+    try:
+        d["velocity"][:, 2] = rng.uniform(-0.01, 0.01, 20000).astype(np.float32) * np.float32(C_KMS)
+        dw = well_conditioned(d, np.float32(1.1) * bc03["wavelength"], muse_wave)
+        cube = ops.assign_build_cube(plans["linear"], dw["coords"], edges, dw["velocity"], dw["mass"],
+                                     dw["metallicity"], dw["age"], S).cpu().numpy()
+        assert ops.build_cube_status(plans["linear"], len(dw["mass"]), S) == (0, 1)
+        ref = _oracle_cube(dw, edges, S, bc03, muse_wave, "linear", threads=8)
+        _cube_close(cube, ref, "group kernel, 0.01 c", rtol_max=1e-5)
+        d["velocity"][:, 2] = rng.uniform(-0.04, 0.04, 20000).astype(np.float32) * np.float32(C_KMS)
+        cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                     d["age"], S).cpu().numpy()
+        err, impl = ops.build_cube_status(plans["linear"], 20000, S)
+        assert err == 3 and impl == 1 and np.isnan(cube).all()
+    finally:
+        _lib.set_option("fused_impl", -1)
+
+
+# ---- world_size 2 over NCCL through the C ABI ----------------------------------------------------------
+def test_two_ranks_nccl_against_oracle():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(ROOT, "tests", "mgpu_worker.py")],
+                         capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    print(res.stdout[-4000:])
+    print(res.stderr[-4000:])
+    assert res.returncode == 0
+    assert "MGPU OK" in res.stdout

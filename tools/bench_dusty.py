@@ -32,7 +32,7 @@ def timeit(fn, reps=args.reps):
     return float(np.median(ts))
 
 
-tpl = np.load(os.path.join(ROOT, "tests", "golden", "bc03lr_f32.npz"))
+tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
 wave = synthetic.muse_wave()
 edges = synthetic.spatial_edges(25)
 plan = ops.Plan(tpl["metallicity"], tpl["age"], tpl["wavelength"], tpl["flux"], wave, 0.1, method=args.method)

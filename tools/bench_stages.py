@@ -35,7 +35,7 @@ def timeit(fn, reps=args.reps):
 
 
 out = {}
-tpl = np.load(os.path.join(ROOT, "tests", "golden", "bc03lr_f32.npz"))
+tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
 wave = synthetic.muse_wave()
 pk = ops.dev(np.load(os.path.join(ROOT, "tests", "golden", "muse_wave.npy"))[:1])  # placeholder, replaced below
 from rubix_b200.telescope import gaussian_kernel_2d, lsf_kernel  # noqa: E402

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from oracle import c_oracle
 from rubix_b200 import ops, synthetic
 from helpers import well_conditioned
-tpl = np.load("tests/golden/bc03lr_f32.npz")
+tpl = np.load("rubix_b200/templates/bc03lr_f32.npz")
 wave = synthetic.muse_wave(); edges = synthetic.spatial_edges(25)
 gen = sys.argv[1] if len(sys.argv) > 1 else "bench_u"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 from rubix_b200 import ops, synthetic  # noqa: E402
 from rubix_b200.telescope import gaussian_kernel_2d, lsf_kernel  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-tpl = np.load(os.path.join(ROOT, "tests", "golden", "bc03lr_f32.npz"))
+tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
 wave = synthetic.muse_wave(); edges = synthetic.spatial_edges(25)
 d = synthetic.bench_g(n)
 plan = ops.Plan(tpl["metallicity"], tpl["age"], tpl["wavelength"], tpl["flux"], wave, 0.1, method="linear")

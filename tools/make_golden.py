@@ -6,7 +6,7 @@ Run in the build container only (``/root/reference`` does not exist on the GPU b
 
 Outputs
 -------
-tests/golden/bc03lr_f32.npz   The BC03lr SSP template exactly as the reference's loader hands it to
+rubix_b200/templates/bc03lr_f32.npz   The BC03lr SSP template exactly as the reference's loader hands it to
                               interp2d: every dataset cast to float32, no log transform, no unit
                               change (rubix/spectra/ssp/grid.py:323-331, rubix_config.yml:152-176).
 tests/golden/muse_wave.npy    The ``wave`` dataset of notebooks/data/dummy_datacube.h5: a cube the
@@ -37,7 +37,7 @@ def main():
 
     with H5File(f"{REF}/rubix/spectra/ssp/templates/BC03lr.h5") as f:
         tpl = {k: f[k].read().astype(np.float32) for k in ("age", "metallicity", "wavelength", "flux")}
-    np.savez_compressed(os.path.join(OUT, "bc03lr_f32.npz"), **tpl)
+    np.savez_compressed(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"), **tpl)
 
     with H5File(f"{REF}/notebooks/data/dummy_datacube.h5") as f:
         np.save(os.path.join(OUT, "muse_wave.npy"), f["wave"].read())

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rubix_b200 import dust, ops, synthetic  # noqa: E402
 
-tpl = np.load(os.path.join(ROOT, "tests", "golden", "bc03lr_f32.npz"))
+tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
 wave = synthetic.muse_wave()
 plan = ops.Plan(tpl["metallicity"], tpl["age"], tpl["wavelength"], tpl["flux"], wave, 0.1, method="linear")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
