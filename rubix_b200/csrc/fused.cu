@@ -102,7 +102,7 @@ struct FusedWs {
 __device__ __forceinline__ int rec_stride_for(int method) { return method == RBX_METHOD_LINEAR ? 8 : 20; }
 
 // ---- prep ---------------------------------------------------------------------------------------
-// record (floats, original particle order): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=unused
+// record (floats, original particle order): [0]=d  [1]=1/d  [2]=template row (int bits)  [3]=d - 1 (expm1)
 // [4..]=interpolation weights * mass.  The cube kernels fetch records through the sorted index.
 constexpr int kDminBias = 0x7f7fffff;   // ctrl[C_DMIN] holds kDminBias - bits(dmin): a zeroed ctrl means "no particle yet"
 
@@ -158,7 +158,8 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
     } else {
       px = pixel[q];
     }
-    float d = expf(vel[(size_t)vstride * q] / kSpeedOfLight);
+    const float voc = vel[(size_t)vstride * q] / kSpeedOfLight;
+    float d = expf(voc);
     bool valid = inside && (mass[q] != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
     uint32_t key = (uint32_t)nseg << cell_bits;  // invalid: sorts behind every valid key
     if (valid) {
@@ -171,7 +172,7 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
       SspTerms tm;
       ssp_terms_at(p, met[q], age[q], mass[q], i, j, inside, tm);
       float4 *r = reinterpret_cast<float4 *>(rec + (size_t)q * stride);
-      r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), 0.f);
+      r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), expm1f(voc));
       r[1] = make_float4(tm.w[0], tm.w[1], tm.w[2], tm.w[3]);
       if (p.method != RBX_METHOD_LINEAR) {
         r[2] = make_float4(tm.w[4], tm.w[5], tm.w[6], tm.w[7]);
@@ -243,22 +244,53 @@ __device__ __forceinline__ int channel_of(float x, const PlanView &p, const unsi
 constexpr int WK = 8;                 // knots per lane
 constexpr int kWarpSlots = WK * 32;   // knot slots of one warp
 
+// The warp kernel works in CHANNEL UNITS of the affine telescope grid t_w = t0 + w delta: a knot at lam_z sits at
+//   u' = (lam_z d - t0) / delta - 1/2 = a eps + b,   a = lam_z / delta,  b = (lam_z - t0) / delta - 1/2,  eps = d - 1
+// (a, b rounded once from double, eps = expm1(v / c): u' is good to ~2.5e-4 channels = 3e-4 A, better than the
+// reference's own float32 lam_z * d).  The number of channels below the knot is ceil(u' + 1/2), obtained WITHOUT a
+// float -> int conversion: fl(u' + 1.5 * 2^23) rounds u' to the nearest integer, which is ceil(u' + 1/2) - 1 (a
+// knot exactly on a channel may land in the neighbouring cell with the matching offset: p(t) is continuous, the
+// channel value does not change), and the integer sits in the mantissa.
+constexpr float kMagic = 12582912.f;           // 1.5 * 2^23: ulp 1 on [2^23, 2^24)
+constexpr int kMagicM1Bits = 0x4B3FFFFF;       // bits of kMagic - 1
+struct KnotAB { float a, b; };
+__device__ __forceinline__ KnotAB knot_ab(const PlanView &p, int j) {
+  KnotAB k;
+  if (j < 0) { k.a = 0.f; k.b = -1000.5f; return k; }                 // below every band
+  if (j >= p.L) { k.a = 0.f; k.b = (float)p.W + 1000.f; return k; }   // above every band
+  const double lz = (double)p.lamz[j], t0 = (double)p.t0, dl = (double)p.tdelta;
+  k.a = (float)(lz / dl);
+  k.b = (float)((lz - t0) / dl - 0.5);
+  return k;
+}
+// KA = kMagic - 1 + (number of channels below the knot, clamped to [0, W])
+__device__ __forceinline__ float knot_ka(float u, float kahi) {
+  return fminf(fmaxf(__fadd_rn(u, kMagic), kMagic - 1.f), kahi);
+}
+__device__ __forceinline__ int knot_cell(float ka) { return __float_as_int(ka) - kMagicM1Bits; }
+
 // Chunk lines of the warp kernel are summed in registers: over the Doppler range present, the first chunk start
 // inside lane `lane`'s channel span must be chunk cA or cA + 1, and the span must hold at most one chunk start.
-// Returns false when that does not hold (Doppler range too wide for this kernel: the group kernel takes over).
-__device__ __forceinline__ bool warp_lane_chunks(const PlanView &p, int jbase, int lane, float dmin, float dmax, int chs,
-                                                 int &cA) {
+// Returns false when that does not hold (Doppler range too wide for this chunk size).  eps_lo / eps_hi bound
+// d - 1 of every particle (segment_kernel widens the observed range by a few ulps), and u' is monotone in eps, so
+// every particle's first cell lies in [kmin0, kmax0].
+__device__ __forceinline__ bool warp_lane_chunks(const PlanView &p, int jbase, int lane, float eps_lo, float eps_hi,
+                                                 int chs, int &cA) {
   const int CH = 1 << chs;
   const int j0 = jbase + WK * lane, j1 = j0 + WK;
-  const float lz0 = j0 < 0 ? -1.0e30f : (j0 >= p.L ? 1.0e30f : p.lamz[j0]);
-  const float lz1 = j1 < 0 ? -1.0e30f : (j1 >= p.L ? 1.0e30f : p.lamz[j1]);
-  float e;
-  const int kmin0 = channel_of<true>(__fmul_rn(lz0, dmin), p, nullptr, nullptr, e);
-  const int kmax0 = channel_of<true>(__fmul_rn(lz0, dmax), p, nullptr, nullptr, e);
-  const int knext = lane == 31 ? kmax0 : channel_of<true>(__fmul_rn(lz1, dmax), p, nullptr, nullptr, e);
+  const KnotAB k0 = knot_ab(p, j0), k1 = knot_ab(p, j1);
+  const float kahi = kMagic + (float)(p.W - 1);
+  const int kmin0 = knot_cell(knot_ka(fmaf(k0.a, eps_lo, k0.b), kahi));
+  const int kmax0 = knot_cell(knot_ka(fmaf(k0.a, eps_hi, k0.b), kahi));
+  const int knext = lane == 31 ? kmax0 : knot_cell(knot_ka(fmaf(k1.a, eps_hi, k1.b), kahi));
   cA = (kmin0 + CH - 1) >> chs;
   return !((((kmax0 + CH - 1) >> chs) > cA + 1) || (knext - kmax0 + 2 >= CH));
 }
+
+// d - 1 of every particle lies in [eps_lo_of(dmin), eps_hi_of(dmax)]: d = fl(exp(x)) and eps = expm1f(x) differ
+// from the exact values by a few ulps of d
+__device__ __forceinline__ float eps_lo_of(float dmin) { return (dmin - 1.f) - 1.0e-6f; }
+__device__ __forceinline__ float eps_hi_of(float dmax) { return (dmax - 1.f) + 1.0e-6f; }
 
 // ---- segments / items / knot window (one block) -----------------------------------------------
 // exclusive block scan of NV ints per thread (1024 threads): warp shuffles + one shared hop
@@ -376,11 +408,11 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
   // ever store 1 into the flags.
   if (tot[0] > 0) {
     const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
-    if (t < 32) {
+    if (t < 32 && p.affine) {
       const int jbase = (s_ja - 1) & ~3;
       for (int chs = warp_chs; chs <= 10; ++chs) {
         int cA;
-        if (!warp_lane_chunks(p, jbase, t, dmin, dmax, chs, cA)) s_bad_w[chs] = 1;
+        if (!warp_lane_chunks(p, jbase, t, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA)) s_bad_w[chs] = 1;
       }
     }
     // group kernel: a lane's first knot is some even slot of the window; checked for every knot (conservative)
@@ -986,14 +1018,19 @@ struct WarpLayout {
   int w_rec;         // offset of the record batch [32][RS] inside a warp block
   int nch, chs;      // chunks per row, log2(channels per chunk)
   int nwarps;        // warps per CTA
-  unsigned skew;     // cell index = k + floor(k * skew / 2^32): makes the lane stride an odd number of cells
+  float skew;        // cell slot = k + floor(max(k - 1, 0) * skew): makes the lane stride an odd number of cells
   int ncells;        // cells per warp (W + 2 + skew of the last one)
 };
 
-__device__ __forceinline__ int skewed(int k, unsigned skew) {
-  unsigned r;
-  asm("mad.hi.u32 %0, %1, %2, %1;" : "=r"(r) : "r"((unsigned)k), "r"(skew));
-  return (int)r;
+// Shared-memory slot of cell k (bank skew): k + floor(max(k - 1, 0) * alpha), computed in the float domain where
+// the knot's cell already lives (KA = kMagic - 1 + k, kc = max(k - 1, 0)): one FFMA rounded down adds the skew to
+// the integer in KA's mantissa.
+__device__ __forceinline__ int cell_slot(float KA, float kc, float alpha) {
+  return __float_as_int(__fmaf_rd(kc, alpha, KA)) - kMagicM1Bits;
+}
+__device__ __forceinline__ int cell_slot_of(int k, float alpha) {   // the same from the integer cell index (expansion)
+  const float KA = (float)k + (kMagic - 1.f);
+  return cell_slot(KA, fmaxf(KA, kMagic) - kMagic, alpha);
 }
 
 template <int METHOD>
@@ -1015,7 +1052,9 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_rec);   // [32][RS]
   const int CH = 1 << chs;
 
-  for (int c = tid; c < nch; c += blockDim.x) s_tc[c] = p.t[min(c << chs, p.W - 1)];
+  // u' of every chunk's first channel, from the actual float32 channel wavelength
+  for (int c = tid; c < nch; c += blockDim.x)
+    s_tc[c] = (float)(((double)p.t[min(c << chs, p.W - 1)] - (double)p.t0) / (double)p.tdelta - 0.5);
   for (int q = lane; q < lay.ncells; q += 32) cells[q] = make_float2(0.f, 0.f);
   for (int q = lane; q < nch; q += 32) base[q] = make_float2(0.f, 0.f);
   __syncthreads();
@@ -1026,31 +1065,35 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   const int jbase = (ja - 1) & ~3;               // multiple of 4 (16-byte template loads); slot s <-> knot jbase + s
   const int j0 = jbase + WK * lane;
   const bool interior = j0 >= 0 && j0 + WK <= p.L;   // all eight knots inside the SSP grid: two 16-byte loads per row
-  float lz[WK], rdl[WK];
+  float au[WK], bu[WK];                           // u' = au * (d - 1) + bu: knot position in channel units (see knot_ab)
+  float rdlu[WK];                                 // delta / (lam_z[j+1] - lam_z[j]): slope per channel = dS * rdlu / d
+  float dl[WK];                                   // lam_z[j] - lam_z[j-1]: total_lum = d * sum S_j dl_j over the knots in band
   int jc[WK];                                     // clamped knot index (jnp.interp end values)
 #pragma unroll
   for (int r = 0; r < WK; ++r) {
     const int j = j0 + r;
     jc[r] = min(max(j, 0), p.L - 1);
-    lz[r] = j < 0 ? -1.0e30f : (j >= p.L ? 1.0e30f : p.lamz[j]);
-    rdl[r] = (j < 0 || j >= p.L - 1) ? 0.f : p.rdl[j];
+    const KnotAB ab = knot_ab(p, j);
+    au[r] = ab.a; bu[r] = ab.b;
+    rdlu[r] = (j < 0 || j >= p.L - 1) ? 0.f : p.rdl[j] * p.tdelta;
+    // diff0's first element is 0 (rubix/spectra/ifu.py:84-102)
+    dl[r] = (j >= 1 && j < p.L) ? p.lamz[j] - p.lamz[j - 1] : 0.f;
   }
-  if (lane == 31) rdl[WK - 1] = 0.f;              // the segment leaving the window (always beyond the band)
-  // previous knot of slot 0 for the "total" difference; diff0's first element is 0 (rubix/spectra/ifu.py:84-102)
-  const float lzprev = (j0 - 1 >= 0 && j0 - 1 < p.L) ? p.lamz[j0 - 1] : lz[0];
+  if (lane == 31) rdlu[WK - 1] = 0.f;             // the segment leaving the window (always beyond the band)
+  const float kahi = kMagic + (float)(p.W - 1);
+  const float kain = kMagic + (float)(p.W - 2);   // kMagic <= KA <= kain: the knot lies in the band (t_0, t_{W-1}]
 
   const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
   // chunk lines are summed in registers: a lane's span [k_0, k_8) holds at most one chunk start, and over
   // the Doppler range present that start is chunk cA or cA + 1
   int cA = 0;
-  warp_lane_chunks(p, jbase, lane, dmin, dmax, chs, cA);   // segment_kernel checked that this holds
+  warp_lane_chunks(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA);   // segment_kernel checked that this holds
   float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
   const float *tab[NT];
 #pragma unroll
   for (int t = 0; t < NT; ++t) tab[t] = p.tab[t];
   const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
-  const float hdelta = 0.5f * p.tdelta;
 
   // The next work item is popped, and its first record batch requested, BEFORE the current item's cells are
   // expanded: the queue atomic and two dependent global loads hide behind the expansion.
@@ -1121,8 +1164,8 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       for (int r = 0; r < WK; ++r) { S2[r] = 0.f; S3[r] = 0.f; }
     for (int qi = 0; qi < nb; ++qi) {
       const float *rb = s_rec + qi * RS;
-      const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, -
-      const float d = r0.x, rd = r0.y;
+      const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, d - 1
+      const float d = r0.x, rd = r0.y, eps = r0.w;
       const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
 
       // ---- mass-weighted spectrum at my eight knots ------------------------------------------------
@@ -1213,39 +1256,40 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       }
       run_pending = run_next;
 
-      // ---- shifted positions, first channel at or above each knot ------------------------------------
-      float x[WK], e[WK + 1];
-      int k[WK + 1];
+      // ---- knot positions in channel units, first channel at or above each knot ---------------------------
+      // KA = kMagic - 1 + (channels below the knot): the knot's cell, kept as a float (compares, skew and the
+      // shared-memory address all work on it; no float <-> int conversion anywhere)
+      float u[WK], KA[WK + 1], kc[WK + 1], g[WK];
 #pragma unroll
       for (int r = 0; r < WK; ++r) {
-        x[r] = __fmul_rn(lz[r], d);
-        k[r] = channel_of<true>(x[r], p, nullptr, nullptr, e[r]);
+        u[r] = fmaf(au[r], eps, bu[r]);
+        KA[r] = knot_ka(u[r], kahi);
       }
       S[WK] = __shfl_down_sync(0xffffffffu, S[0], 1);
-      k[WK] = __shfl_down_sync(0xffffffffu, k[0], 1);
-      e[WK] = __shfl_down_sync(0xffffffffu, e[0], 1);
-      if (lane == 31) { S[WK] = S[WK - 1]; k[WK] = k[WK - 1]; e[WK] = e[WK - 1]; }
+      KA[WK] = __shfl_down_sync(0xffffffffu, KA[0], 1);
+      if (lane == 31) { S[WK] = S[WK - 1]; KA[WK] = KA[WK - 1]; }
+#pragma unroll
+      for (int r = 0; r <= WK; ++r) kc[r] = fmaxf(KA[r], kMagic) - kMagic;   // last channel below the knot, 0 below the band
 
       // ---- slopes, the two normalisation sums (rubix/spectra/ifu.py:241-251) -------------------------
-      float m[WK], gx[WK];
+      //   total = sum S_j (x_j - x_{j-1}) [x_j in band] = d * sum S_j dl_j
+      //   new = sum_w p(t_w) dt_w = delta * sum_j D_j (S_j + mu_j (D_j / 2 + g_j)), over the channels [k_j, k_{j+1}):
+      //   D_j channels, mu_j the slope per channel and g_j = kc_j - u'_j = (t[k_j - 1] - x_j) / delta + 1/2
+      float mu[WK];
       float tot = 0.f, nw = 0.f;
 #pragma unroll
       for (int r = 0; r < WK; ++r) {
-        m[r] = (S[r + 1] - S[r]) * rdl[r] * rd;
-        const float xprev = r == 0 ? __fmul_rn(lzprev, d) : x[r - 1];
-        const float wd = (x[r] >= p.tmin && x[r] <= p.tmax) ? x[r] - xprev : 0.f;
-        tot = fmaf(S[r], wd, tot);
-        // sum_w p(t_w) dt_w over the channels [k_r, k_{r+1}): S D + m T, D = sum dt_w (telescopes exactly in
-        // float32), T = sum dt_w (t_w - x) in closed form on the arange grid
-        // (the old n delta^2 / 2 term: on an arange grid n delta = D to first order in the channel-width
-        // rounding, so T = D (D/2 + (t[k-1] - x) + delta/2) and S D + m T = D (S + m T'))
-        const float D = e[r + 1] - e[r];
-        gx[r] = e[r] - x[r];
-        const float Tp = fmaf(0.5f, D, gx[r] + hdelta);
-        nw = fmaf(D, fmaf(m[r], Tp, S[r]), nw);
+        mu[r] = (S[r + 1] - S[r]) * rdlu[r] * rd;
+        g[r] = kc[r] - u[r];
+        // knots in the band [t_0, t_{W-1}] (1 <= cell <= W - 1): a predicated FFMA
+        asm("{\n.reg .pred p, q;\nsetp.ge.f32 p, %1, %2;\nsetp.le.and.f32 q, %1, %3, p;\n@q fma.rn.f32 %0, %4, %5, %0;\n}"
+            : "+f"(tot) : "f"(KA[r]), "f"(kMagic), "f"(kain), "f"(S[r]), "f"(dl[r]));
+        const float D = kc[r + 1] - kc[r];
+        const float Tp = fmaf(0.5f, D, g[r]);
+        nw = fmaf(D, fmaf(mu[r], Tp, S[r]), nw);
       }
-      float mp = __shfl_up_sync(0xffffffffu, m[WK - 1], 1);
-      if (lane == 0) mp = m[0];   // slot 0 of the window lies below the band for every Doppler factor present
+      float mp = __shfl_up_sync(0xffffffffu, mu[WK - 1], 1);
+      if (lane == 0) mp = mu[0];   // slot 0 of the window lies below the band for every Doppler factor present
 
       // Everything that does not need the scale is issued BEFORE the reduction, so that the cell loads and
       // the chunk-line selection overlap the shuffle latency.
@@ -1254,53 +1298,61 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       float dmv[WK];
       int ka[WK];
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ka[r] = skewed(k[r], lay.skew);
+      for (int r = 0; r < WK; ++r) ka[r] = cell_slot(KA[r], kc[r], lay.skew);
 #ifdef RBX_RACECHECK
       // Knots outside the band (k = 0 or k = W) of several lanes land in the two junk cells 0 and W, which are
       // never read back: a benign write-write overlap that compute-sanitizer racecheck reports.  This build
       // gives every lane its own junk cell so that racecheck can show there is no other hazard.
 #pragma unroll
       for (int r = 0; r < WK; ++r)
-        if (k[r] <= 0 || k[r] >= p.W) ka[r] = lay.ncells + lane;
+        if (KA[r] < kMagic || KA[r] >= kahi) ka[r] = lay.ncells + lane;
 #endif
 #pragma unroll
       for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
 #pragma unroll
-      for (int r = 0; r < WK; ++r) dmv[r] = m[r] - (r == 0 ? mp : m[r - 1]);
+      for (int r = 0; r < WK; ++r) dmv[r] = mu[r] - (r == 0 ? mp : mu[r - 1]);
       // ---- chunk line: the segment valid at the first chunk start inside [k_0, k_8) ---------------------
       float bv, mr;
       int sel;
       {
-        const int c = (k[0] + CH - 1) >> chs;
+        const int c = (knot_cell(KA[0]) + CH - 1) >> chs;
         const int chan = c << chs;
-        const bool has = chan < k[WK] && chan < p.W;
-        float Sr = S[0], xr = x[0];
-        mr = m[0];
+        const float chanKA = (float)chan + (kMagic - 1.f);
+        const bool has = chanKA < KA[WK] && chan < p.W;
+        float Sr = S[0], ur = u[0];
+        mr = mu[0];
 #pragma unroll
         for (int r = 1; r < WK; ++r) {
-          const bool take = k[r] <= chan;
-          Sr = take ? S[r] : Sr; mr = take ? m[r] : mr; xr = take ? x[r] : xr;
+          const bool take = KA[r] <= chanKA;
+          Sr = take ? S[r] : Sr; mr = take ? mu[r] : mr; ur = take ? u[r] : ur;
         }
         const float tch = s_tc[min(c, nch - 1)];
-        bv = fmaf(mr, tch - xr, Sr);
+        bv = fmaf(mr, tch - ur, Sr);
         sel = has ? 1 + (c - cA) : 0;
       }
 
       // ---- total / new   (rubix/spectra/ifu.py:252-255) -----------------------------------------------
+      // both sums in one butterfly: after the first exchange the lower half-warp carries `total`, the upper `new`
+      {
+        const bool lowh = lane < 16;
+        float v = lowh ? tot : nw;
+        const float w = lowh ? nw : tot;
+        v += __shfl_xor_sync(0xffffffffu, w, 16);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        nw += __shfl_xor_sync(0xffffffffu, nw, o);
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        tot = __shfl_sync(0xffffffffu, v, 0);
+        nw = __shfl_sync(0xffffffffu, v, 16);
       }
-      const float sc = nan_to_num0(tot / nw);
+      const float sc = nan_to_num0((d * tot) * p.tinv / nw);
 
       {
         const float sA = sel == 1 ? sc : 0.f, sB = sel == 2 ? sc : 0.f;
         accAv = fmaf(sA, bv, accAv); accAm = fmaf(sA, mr, accAm);
         accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
       }
+      // cell k: (sum dmu (g + 1/2), sum dmu) in channel units; the expansion takes the 1/2 out again
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, dmv[r] * gx[r], dmv[r]);
+      for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, dmv[r] * g[r], dmv[r]);
 #pragma unroll
       for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
       __syncwarp();
@@ -1349,15 +1401,16 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           const int ch = gstart + lane;
           A[g] = 0.f; sB[g] = 0.f;
           if (ch <= p.W) {
-            const int ca = skewed(ch, lay.skew);
+            const int ca = cell_slot_of(ch, lay.skew);
             const float2 cvv = cells[ca];
-            A[g] = cvv.x; sB[g] = cvv.y;
+            A[g] = fmaf(-0.5f, cvv.y, cvv.x); sB[g] = cvv.y;   // kinks (offset in channels, slope per channel)
             cells[ca] = make_float2(0.f, 0.f);
           }
           valid[g] = ch < p.W;
           const bool start = ch == cstart;      // the chunk's first channel takes the base line itself
           if (start || !valid[g]) { A[g] = 0.f; sB[g] = 0.f; }
-          dtc[g] = (start || !valid[g]) ? 0.f : __ldg(p.dt + ch);
+          // channel widths / distances in units of delta, from the actual float32 channel wavelengths
+          dtc[g] = (start || !valid[g]) ? 0.f : __ldg(p.dt + ch) * p.tinv;
           tk[g] = __ldg(p.t + min(ch, p.W - 1));
           tref[g] = __ldg(p.t + min(max(gstart - 1, cstart), p.W - 1));
         }
@@ -1383,7 +1436,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int ch = cstart + h + 32 * g + lane;
-          const float v = vcar + fmaf(scar, tk[g] - tref[g], inc[g]);
+          const float v = vcar + fmaf(scar, (tk[g] - tref[g]) * p.tinv, inc[g]);
           if (valid[g]) {
             if (it.slot < 0) cube_put(cube, cl, it.spaxel, ch, v, accumulate != 0);
             else prow[ch] = v;
@@ -1641,8 +1694,8 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
     if (((long long)target & 1) == 0) target += 1.0;
     double alpha = stride > 1.0 ? (target - stride) / stride : 0.0;
     if (opt_on(OPT_FUSED_NO_SKEW)) alpha = 0.0;
-    lay.skew = (unsigned)std::llround(std::fmin(alpha, 0.25) * 4294967296.0);
-    lay.ncells = v.W + 2 + (int)(((unsigned long long)(v.W + 2) * lay.skew) >> 32) + 1;
+    lay.skew = (float)std::fmin(alpha, 0.25);
+    lay.ncells = v.W + 2 + (int)std::floor((double)(v.W + 2) * (double)lay.skew) + 2;
   }
   lay.w_base = a128(8 * (lay.ncells + 32));   // + one junk cell per lane (RBX_RACECHECK builds)
   lay.w_rec = lay.w_base + a128(8 * lay.nch);

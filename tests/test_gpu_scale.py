@@ -48,6 +48,14 @@ def plans(ops, bc03, muse_wave):
                         method=m, direction="z") for m in ("linear", "cubic")}
 
 
+# float32 accumulation: a crowded spaxel sums ~10^4 (10^6 particles) to ~10^5 (10^7) spectra; the running sum's ulp
+# is 6e-8 of the spaxel's flux, so the summed rounding grows like sqrt(n) ulps -- the reference's own float32
+# segment_sum has at least that much.  Tolerances relative to the cube maximum at these sizes (the north-star bound,
+# 1e-5 of the cube's TOTAL flux, is five orders of magnitude looser and is asserted as well):
+RTOL_1E6 = 2e-5
+RTOL_1E7 = 6e-5
+
+
 def _oracle_cube(d, edges, S, bc03, wave, method, dtype=np.float64, threads=None):
     return c_oracle.particles_to_cube(d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges, S,
                                       bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], wave, 0.1,
@@ -67,13 +75,13 @@ def test_cube_1e6_vs_oracle(ops, plans, bc03, muse_wave, method):
     cube = ops.assign_build_cube(plans[method], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
                                  d["age"], 25)
     assert ops.build_cube_status(plans[method], 1_000_000, 25) == (0, 0)
-    _cube_close(cube.cpu().numpy(), ref, f"1e6 {method} cube")
+    _cube_close(cube.cpu().numpy(), ref, f"1e6 {method} cube", rtol_max=RTOL_1E6)
     refc = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
     conv = ops.psf_lsf(cube, pk, lk).cpu().numpy()
-    _cube_close(conv, refc, f"1e6 {method} cube + PSF + LSF")
+    _cube_close(conv, refc, f"1e6 {method} cube + PSF + LSF", rtol_max=RTOL_1E6)
     host = ops.pipeline_host(plans[method], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges,
                              25, pk, lk)
-    _cube_close(host, refc, f"1e6 {method} rbx_pipeline_host")
+    _cube_close(host, refc, f"1e6 {method} rbx_pipeline_host", rtol_max=RTOL_1E6)
     assert np.array_equal(host, conv)
     packed = ops.pipeline_host_packed(plans[method], d["coords"][:, 0].copy(), d["coords"][:, 1].copy(),
                                       d["velocity"][:, 2].copy(), d["mass"], d["metallicity"], d["age"], edges, 25, pk, lk)
@@ -90,11 +98,11 @@ def test_cube_1e7_vs_oracle(ops, plans, bc03, muse_wave):
     cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
                                  d["age"], 25)
     assert ops.build_cube_status(plans["linear"], 10_000_000, 25) == (0, 0)
-    _cube_close(cube.cpu().numpy(), ref, "1e7 linear cube")
+    _cube_close(cube.cpu().numpy(), ref, "1e7 linear cube", rtol_max=RTOL_1E7)
     refc = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
     host = ops.pipeline_host(plans["linear"], d["coords"], d["velocity"], d["mass"], d["metallicity"], d["age"], edges,
                              25, pk, lk)
-    _cube_close(host, refc, "1e7 linear rbx_pipeline_host (5 ranges)")
+    _cube_close(host, refc, "1e7 linear rbx_pipeline_host (5 ranges)", rtol_max=RTOL_1E7)
 
 
 def test_cube_150_1e6_vs_oracle(ops, plans, bc03, muse_wave):
@@ -108,7 +116,7 @@ def test_cube_150_1e6_vs_oracle(ops, plans, bc03, muse_wave):
     ref = _oracle_cube(d, edges, S, bc03, muse_wave, "linear")
     cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
                                  d["age"], S).cpu().numpy()
-    _cube_close(cube, ref, "S=150 1e6 linear cube")
+    _cube_close(cube, ref, "S=150 1e6 linear cube", rtol_max=RTOL_1E6)
     # slab-major: 8 slabs with a 12-channel halo; every slab equals the matching channel window of the cube
     nslab, halo = 8, 12
     wslab, ws = ops.slab_geometry(3721, nslab, halo)

@@ -5,8 +5,7 @@
 //   tools/fma_peak > profiles/fp32_peak.json          (on the B200 box; ~1 s)
 //
 // Three dependent-chain-free loops, every SM filled (blocks = SMs x resident blocks), timed with CUDA events after
-// a warm-up, best of `reps`; the SM clock is derived from clock64() deltas against the event time, so the clock the
-// loop really ran at is recorded with the number:
+// a warm-up, best of `reps` (bench.py samples the SM clock under load through NVML):
 //   ffma    16 independent scalar FFMA chains per thread          -> 2 flop per lane per instruction
 //   ffma2   16 independent packed fma.rn.f32x2 chains per thread  -> 4 flop per lane per instruction
 //   issue   the ffma loop counted in warp instructions: the issue-slot ceiling of 4 schedulers per SM
@@ -124,17 +123,17 @@ int main(int argc, char **argv) {
   const double warp_inst_per_s = lanes / 32.0 * fma_per_lane / (res[0].ms * 1e-3);
   const double warp_inst2_per_s = lanes / 32.0 * fma_per_lane / (res[1].ms * 1e-3);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"blocks\": %d, \"threads\": %d, \"chains\": %d,\n"
-         " \"ffma_tflops\": %.2f, \"ffma_ms\": %.4f, \"ffma_sm_mhz\": %.0f,\n"
-         " \"ffma2_tflops\": %.2f, \"ffma2_ms\": %.4f, \"ffma2_sm_mhz\": %.0f,\n"
+         " \"ffma_tflops\": %.2f, \"ffma_ms\": %.4f,\n"
+         " \"ffma2_tflops\": %.2f, \"ffma2_ms\": %.4f,\n"
          " \"fp32_tflops\": %.2f,\n"
          " \"ffma_warp_inst_per_s\": %.4e, \"ffma2_warp_inst_per_s\": %.4e,\n"
-         " \"ffma_warp_inst_per_clk_per_sm\": %.3f, \"ffma2_warp_inst_per_clk_per_sm\": %.3f,\n"
          " \"nominal_tflops_at_max_clock\": %.2f, \"max_clock_mhz\": %.0f,\n"
+         " \"ffma_warp_inst_per_clk_per_sm_at_max_clock\": %.3f,\n"
          " \"how\": \"tools/fma_peak.cu: %d independent FMA chains per thread, %d x %d threads, best of %d after 3 warm-ups, "
-         "CUDA events; SM clock = median block clock64() delta / event time\"}\n",
-         prop.name, sms, blocks, threads, CHAINS, ffma_tflops, res[0].ms, res[0].mhz, ffma2_tflops, res[1].ms,
-         res[1].mhz, std::max(ffma_tflops, ffma2_tflops), warp_inst_per_s, warp_inst2_per_s,
-         warp_inst_per_s / (sms * res[0].mhz * 1e6), warp_inst2_per_s / (sms * res[1].mhz * 1e6),
-         2.0 * sms * 128 * prop.clockRate * 1e3 / 1e12, prop.clockRate / 1e3, CHAINS, blocks, threads, reps);
+         "CUDA events\"}\n",
+         prop.name, sms, blocks, threads, CHAINS, ffma_tflops, res[0].ms, ffma2_tflops, res[1].ms,
+         std::max(ffma_tflops, ffma2_tflops), warp_inst_per_s, warp_inst2_per_s,
+         2.0 * sms * 128 * prop.clockRate * 1e3 / 1e12, prop.clockRate / 1e3,
+         warp_inst_per_s / (sms * prop.clockRate * 1e3), CHAINS, blocks, threads, reps);
   return 0;
 }
