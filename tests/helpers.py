@@ -16,9 +16,11 @@ def well_conditioned(data, lamz, wave, direction=2, tol=1e-2):
     lz = lamz.astype(np.float64)
     lo = np.searchsorted(lz, wave[0] / d.max()) - 2
     hi = np.searchsorted(lz, wave[-1] / d.min()) + 2
-    x = lz[None, max(lo, 0):hi] * d[:, None]
-    dist = np.minimum(np.abs(x - float(wave[0])).min(1), np.abs(x - float(wave[-1])).min(1))
-    keep = dist > tol
+    keep = np.empty(len(d), dtype=bool)
+    for a in range(0, len(d), 200_000):   # in blocks: 10^6 particles x ~250 knots of float64 would be 2 GB
+        x = lz[None, max(lo, 0):hi] * d[a:a + 200_000, None]
+        dist = np.minimum(np.abs(x - float(wave[0])).min(1), np.abs(x - float(wave[-1])).min(1))
+        keep[a:a + 200_000] = dist > tol
     return {k: v[keep] for k, v in data.items()}
 
 

@@ -113,6 +113,10 @@ def test_cube_150_1e6_vs_oracle(ops, plans, bc03, muse_wave):
     edges = synthetic.spatial_edges(S)
     d = synthetic.bench_g(1_000_000, seed=7)
     d["coords"] *= np.float32(4.0)   # spread the galaxy over the 30" field
+    # ~50 particles per spaxel: ONE knife-edge particle (helpers.well_conditioned) is 1e-4 of its spaxel, so they are
+    # left out here; test_knife_edge_particles_* judges them one by one
+    from helpers import well_conditioned
+    d = well_conditioned(d, np.float32(1.1) * bc03["wavelength"], muse_wave)
     ref = _oracle_cube(d, edges, S, bc03, muse_wave, "linear")
     cube = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
                                  d["age"], S).cpu().numpy()
@@ -143,12 +147,12 @@ def _one_per_spaxel(n, S, edges, rng):
 
 
 def _knife_velocities(lamz, targets, rng, n):
-    """Velocities that put a Doppler-shifted SSP knot within a few float32 ulps of one of ``targets``."""
+    """Velocities (|v| <= 1000 km/s) that put a Doppler-shifted SSP knot within a few float32 ulps of one of ``targets``."""
     v = np.empty(n, dtype=np.float32)
     for i in range(n):
         t = float(targets[rng.integers(len(targets))])
         # a knot that reaches t with |v| <= 450 km/s
-        cand = np.nonzero(np.abs(np.log(t / lamz.astype(np.float64))) * C_KMS <= 450.0)[0]
+        cand = np.nonzero(np.abs(np.log(t / lamz.astype(np.float64))) * C_KMS <= 1000.0)[0]
         j = int(cand[rng.integers(len(cand))])
         ulps = rng.integers(-3, 4)
         x = np.float32(t)
@@ -174,10 +178,11 @@ def test_knife_edge_particles_one_of_the_reference_answers(ops, plans, bc03, mus
     out = ops.assign_build_cube(plans[method], base["coords"], edges, base["velocity"], base["mass"],
                                 base["metallicity"], base["age"], S).cpu().numpy().reshape(S * S, -1)[:n]
     assert np.isfinite(out).all()
-    # the answers the reference can give: float32 and float64 evaluation at v, float64 at v -+ 0.25 km/s (lam' moves
-    # by ~4e-3 A = 8 float32 ulps, the flip resolved either way; the spectrum itself moves by < 1e-5 of its scale)
+    # the answers the reference can give: float32 and float64 evaluation at v, float64 at v -+ 0.1 km/s (lam' moves
+    # by 1.6e-3 .. 3.1e-3 A = 3+ float32 ulps, the flip resolved either way; the spectrum itself moves by a few 1e-5
+    # of its scale on the steepest features)
     cands = []
-    for dv, dt in ((0.0, np.float32), (0.0, np.float64), (-0.25, np.float64), (0.25, np.float64)):
+    for dv, dt in ((0.0, np.float32), (0.0, np.float64), (-0.1, np.float64), (0.1, np.float64)):
         d = {k: v.copy() for k, v in base.items()}
         d["velocity"][:, 2] += np.float32(dv)
         cands.append(_oracle_cube(d, edges, S, bc03, muse_wave, method, dtype=dt, threads=8).reshape(S * S, -1)[:n])
@@ -187,8 +192,8 @@ def test_knife_edge_particles_one_of_the_reference_answers(ops, plans, bc03, mus
     spread = np.abs(cands[2].astype(np.float64) - cands[3]).max(axis=1) / scale   # how far apart the answers are
     print(f"[knife {where} {method}] best-match err: max {best.max():.2e}, median {np.median(best):.2e}; "
           f"answers differ by up to {spread.max():.2e}; matched f32@v {np.mean(errs.argmin(0) == 0):.2f}")
-    # a flip moves the whole spectrum by ~5e-3 (band edge); matching ONE answer means well below that
-    assert best.max() <= 4e-5, f"particle {int(best.argmax())}: {errs[:, best.argmax()]}"
+    # a flip moves the whole spectrum by 2e-3 .. 5e-2 (band edge); matching ONE answer means far below that
+    assert best.max() <= 6e-5, f"particle {int(best.argmax())}: {errs[:, best.argmax()]}"
 
 
 # ---- Doppler ranges beyond the default chunk geometry -------------------------------------------------------
