@@ -1018,6 +1018,9 @@ struct WarpLayout {
   int w_rec;         // offset of the record batch [32][RS] inside a warp block
   int nch, chs;      // chunks per row, log2(channels per chunk)
   int nwarps;        // warps per CTA
+  int pair;          // two warps share one cell array (fused_cube_warp_kernel<.., true>)
+  int rec_bytes;     // bytes of one warp's record batch
+  int off_item;      // [arrays] work item handed from a pair's first warp to its second
   float skew;        // cell slot = k + floor(max(k - 1, 0) * skew): makes the lane stride an odd number of cells
   int ncells;        // cells per warp (W + 2 + skew of the last one)
 };
@@ -1033,8 +1036,17 @@ __device__ __forceinline__ int cell_slot_of(int k, float alpha) {   // the same 
   return cell_slot(KA, fmaxf(KA, kMagic) - kMagic, alpha);
 }
 
-template <int METHOD>
-__global__ void __launch_bounds__(256, 1)
+// PAIR: two warps share one cell array and one work item (14 warps per SM instead of 7: the kernel is latency bound
+// and 8 private arrays do not fit).  Warp h of a pair takes the item's particles q = h, h + 2, ...; everything up
+// to the scale factor is private to the warp, and the short read-modify-write of the cells is done in strictly
+// alternating TURNS (w0 particle 0, w1 particle 1, w0 particle 2, ...) handed over with two named barriers per
+// pair (bar.sync = wait for my turn, bar.arrive = pass the turn on): no atomics, the order of every addition is
+// fixed, the result stays bit-reproducible and does not depend on which kernel variant ran only in rounding.
+__device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int METHOD, bool PAIR, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                        const Item *__restrict__ items, int *__restrict__ ctrl,
                        float *__restrict__ cube, float *__restrict__ partials, int Wp, WarpLayout lay, int accumulate,
@@ -1046,17 +1058,24 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   if (ctrl[C_IMPL] != IMPL_WARP) return;   // segment_kernel selected the group kernel (knot window / Doppler range)
   const int chs = ctrl[C_CHS];                   // >= chs: chosen by segment_kernel for the Doppler range present
   const int nch = (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
+  const int arr = PAIR ? warp >> 1 : warp;       // my cell array
+  const int half = PAIR ? warp & 1 : 0;          // which warp of the pair
+  constexpr int PSTR = PAIR ? 2 : 1;             // particle stride inside an item
+  const int t_mine = 1 + 2 * arr + half, t_other = 1 + 2 * arr + (1 - half);   // named barriers: my turn / the other warp's
   float *s_tc = reinterpret_cast<float *>(smem + lay.off_tc);
-  float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride);
-  float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_base);
-  float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)warp * lay.warp_stride + lay.w_rec);   // [32][RS]
+  volatile int *s_item = reinterpret_cast<volatile int *>(smem + lay.off_item) + arr;
+  float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride);
+  float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_base);
+  float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_rec +
+                                           (size_t)half * lay.rec_bytes);   // [32][RS]
   const int CH = 1 << chs;
 
   // u' of every chunk's first channel, from the actual float32 channel wavelength
   for (int c = tid; c < nch; c += blockDim.x)
     s_tc[c] = (float)(((double)p.t[min(c << chs, p.W - 1)] - (double)p.t0) / (double)p.tdelta - 0.5);
-  for (int q = lane; q < lay.ncells; q += 32) cells[q] = make_float2(0.f, 0.f);
-  for (int q = lane; q < nch; q += 32) base[q] = make_float2(0.f, 0.f);
+  for (int q = lane + 32 * half; q < lay.ncells; q += 32 * PSTR) cells[q] = make_float2(0.f, 0.f);
+  for (int q = lane + 32 * half; q < nch; q += 32 * PSTR) base[q] = make_float2(0.f, 0.f);
+  if (PAIR && half == 0 && lane == 0) *s_item = atomicAdd(ctrl + C_WORK, 1);   // the pair's first work item
   __syncthreads();
 
   // ---- per-lane knot constants -------------------------------------------------------------------
@@ -1098,9 +1117,12 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   // The next work item is popped, and its first record batch requested, BEFORE the current item's cells are
   // expanded: the queue atomic and two dependent global loads hide behind the expansion.
   float4 nrec[RS / 4];   // my record of the NEXT batch, in flight during the current one
+  // PAIR: my particles of an item are q = half, half + 2, ...
+  auto my_count = [&](const Item &w) { return PAIR ? (w.count + 1 - half) >> 1 : w.count; };
   auto fetch_rec = [&](const Item &w, int b0) {
-    if (b0 + lane < w.count) {
-      const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)__ldg(sidx + w.start + b0 + lane) * RS);
+    if (b0 + lane < my_count(w)) {
+      const float4 *src =
+          reinterpret_cast<const float4 *>(rec + (size_t)__ldg(sidx + w.start + half + PSTR * (b0 + lane)) * RS);
 #pragma unroll
       for (int u = 0; u < RS / 4; ++u) nrec[u] = __ldg(src + u);
     }
@@ -1109,16 +1131,20 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   int nf_row = -1;       // linear: the template row they were loaded for
   Item it_next;
   it_next.start = 0; it_next.count = 0; it_next.spaxel = 0; it_next.slot = -1;
-  auto pop_item = [&]() -> bool {
-    int id = 0;
-    if (lane == 0) id = atomicAdd(ctrl + C_WORK, 1);
-    id = __shfl_sync(0xffffffffu, id, 0);
+  auto take_item = [&](int id) -> bool {
     if (id >= n_items) return false;
     it_next = items[id];
     fetch_rec(it_next, 0);
     return true;
   };
-  bool have = pop_item();
+  auto pop_item = [&]() -> bool {   // !PAIR
+    int id = 0;
+    if (lane == 0) id = atomicAdd(ctrl + C_WORK, 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    return take_item(id);
+  };
+  bool have = PAIR ? take_item(*s_item) : pop_item();
+  if (PAIR && half == 1) turn_pass(t_other);   // the first turn is warp 0's
 
   while (have) {
     const Item it = it_next;
@@ -1127,8 +1153,9 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
     // and parked in the warp's shared-memory slot, so every particle's record is a broadcast read away.
     // Template rows: the eight 16-byte vectors of the NEXT (particle, table) group are in flight while the
     // current group is folded in and, for the last table, during the whole knot arithmetic of the particle.
-    for (int b0 = 0; b0 < it.count; b0 += 32) {
-      const int nb = min(32, it.count - b0);
+    const int cnt = my_count(it);
+    for (int b0 = 0; b0 < cnt; b0 += 32) {
+      const int nb = min(32, cnt - b0);
       __syncwarp();
       if (lane < nb) {
         float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RS);
@@ -1136,7 +1163,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         for (int u = 0; u < RS / 4; ++u) dst[u] = nrec[u];
       }
       __syncwarp();
-      if (b0 + 32 < it.count) fetch_rec(it, b0 + 32);
+      if (b0 + 32 < cnt) fetch_rec(it, b0 + 32);
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
         if (interior) {
           const int rw = __float_as_int(s_rec[i * RS + 2]);
@@ -1307,8 +1334,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       for (int r = 0; r < WK; ++r)
         if (KA[r] < kMagic || KA[r] >= kahi) ka[r] = lay.ncells + lane;
 #endif
+      if (!PAIR) {
 #pragma unroll
-      for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+        for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+      }
 #pragma unroll
       for (int r = 0; r < WK; ++r) dmv[r] = mu[r] - (r == 0 ? mp : mu[r - 1]);
       // ---- chunk line: the segment valid at the first chunk start inside [k_0, k_8) ---------------------
@@ -1351,13 +1380,25 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         accBv = fmaf(sB, bv, accBv); accBm = fmaf(sB, mr, accBm);
       }
       // cell k: (sum dmu (g + 1/2), sum dmu) in channel units; the expansion takes the 1/2 out again
+      float ag[WK];
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, dmv[r] * g[r], dmv[r]);
+      for (int r = 0; r < WK; ++r) ag[r] = dmv[r] * g[r];
+      if (PAIR) {
+        turn_wait(t_mine);   // the cells are mine until turn_pass
+#pragma unroll
+        for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+      }
+#pragma unroll
+      for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, ag[r], dmv[r]);
 #pragma unroll
       for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
-      __syncwarp();
+      if (PAIR) turn_pass(t_other); else __syncwarp();
     }  // particles
     }  // record batches
+    if (PAIR && cnt < ((it.count + 1) >> 1)) {   // odd item: the second warp's empty last turn keeps the order
+      turn_wait(t_mine);
+      turn_pass(t_other);
+    }
 
     // flush the register chunk lines: cA is non-decreasing along the lanes, so lanes that share a chunk form
     // runs; a segmented shuffle scan sums each run in a fixed order and its last lane adds the total
@@ -1373,11 +1414,27 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         if ((lane == 31 || knext != key) && key < nch) cell_add<false>(base + key, v, m);
         __syncwarp();
       };
+      if (PAIR) turn_wait(t_mine);   // one more turn each: the chunk lines go into the pair's shared array
       flush(cA, accAv, accAm);
       flush(cA + 1, accBv, accBm);
+      if (PAIR) {
+        // warp 0 pops the pair's next item inside its turn; warp 1 reads it inside its own (after warp 0's)
+        if (half == 0 && lane == 0) *s_item = atomicAdd(ctrl + C_WORK, 1);
+        __syncwarp();
+        const int id = half == 1 ? *s_item : 0;
+        turn_pass(t_other);
+        if (half == 0) {
+          turn_wait(t_mine);         // warp 1's flush is done: every turn of this item is complete
+          turn_pass(t_other);        // acknowledge: warp 1 may go on (no barrier ever collects two arrivals of one warp)
+          have = take_item(*s_item);
+        } else {
+          turn_wait(t_mine);         // warp 0 has seen the end of my flush
+          have = take_item(id);
+        }
+      }
     }
     accAv = accAm = accBv = accBm = 0.f;
-    have = pop_item();
+    if (!PAIR) have = pop_item();
 
     // ---- expand the cells into the spaxel spectrum and store it ---------------------------------------
     // Per chunk: slope_k = scar + sum_{j<=k} B_j and value_k = vcar + sum_{j<=k} (slope_j dt_j + A_j)
@@ -1385,7 +1442,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
     // so the two warp scans of a 32-channel group do not depend on the carries: four groups are scanned
     // at once (four independent shuffle chains) and the carries are applied afterwards.
     float *prow = partials + (size_t)max(it.slot, 0) * Wp;
-    for (int c = 0; c < nch; ++c) {
+    for (int c = half; c < nch; c += PSTR) {   // PAIR: the two warps expand alternate chunks
       const float2 bs = base[c];
       float vcar = bs.x, scar = bs.y;
       __syncwarp();
@@ -1447,6 +1504,9 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       }
     }
     __syncwarp();
+    // PAIR: my half of the cells is clear again; that is warp 0's token for the first turn of the next item
+    // (warp 1's first turn follows warp 0's, which follows warp 0's own expansion)
+    if (PAIR && half == 1 && have) turn_pass(t_other);
   }
 }
 
@@ -1650,7 +1710,7 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
 }
 
 // Static limits and shared-memory layout of fused_cube_warp_kernel.  false: the plan needs the group kernel.
-static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_bytes) {
+static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_bytes, bool pair, int max_arrays) {
   const PlanView &v = plan->v;
   if (!v.affine || v.W + 2 >= (1 << 20)) return false;
   if (opt_on(OPT_FUSED_IMPL) || opt_on(OPT_FUSED_FORCE_LUT) || opt_on(OPT_FUSED_FORCE_CAS)) return false;
@@ -1676,7 +1736,8 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
   lay.chs = chs;
   lay.nch = (v.W + 1 + (1 << chs) - 1) >> chs;
   lay.off_tc = 0;
-  lay.off_warp = a128(4 * lay.nch);
+  lay.off_item = a128(4 * lay.nch);
+  lay.off_warp = lay.off_item + a128(4 * 8);
   // bank skew: the lane stride in cells (8 knots) becomes the next odd integer, so the 16 lanes of a
   // 64-bit shared-memory wavefront hit 16 different banks
   {
@@ -1699,12 +1760,14 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
   }
   lay.w_base = a128(8 * (lay.ncells + 32));   // + one junk cell per lane (RBX_RACECHECK builds)
   lay.w_rec = lay.w_base + a128(8 * lay.nch);
-  lay.warp_stride = lay.w_rec + a128(4 * 32 * (v.method == RBX_METHOD_LINEAR ? 8 : 20));
-  int nw = std::min(8, (227 * 1024 - lay.off_warp) / lay.warp_stride);
-  if (opt(OPT_FUSED_WARPS) > 0) nw = std::min(nw, (int)opt(OPT_FUSED_WARPS));
-  if (nw < 4) return false;
-  lay.nwarps = nw;
-  smem_bytes = (size_t)lay.off_warp + (size_t)nw * lay.warp_stride;
+  lay.pair = pair ? 1 : 0;
+  lay.rec_bytes = a128(4 * 32 * (v.method == RBX_METHOD_LINEAR ? 8 : 20));
+  lay.warp_stride = lay.w_rec + (pair ? 2 : 1) * lay.rec_bytes;
+  int na = std::min(std::min(pair ? 7 : 8, max_arrays), (227 * 1024 - lay.off_warp) / lay.warp_stride);   // cell arrays
+  if (opt(OPT_FUSED_WARPS) > 0) na = std::min(na, (int)opt(OPT_FUSED_WARPS));
+  if (na < 4) return false;
+  lay.nwarps = na * (pair ? 2 : 1);
+  smem_bytes = (size_t)lay.off_warp + (size_t)na * lay.warp_stride;
   return true;
 }
 
@@ -1896,7 +1959,12 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   // The warp kernel runs when the plan allows it (host: grid geometry) AND the particles do (device, segment_kernel:
   // knot window and chunk geometry for the Doppler range present); otherwise the group kernel takes the same work
   // queue.  Both are launched; the one not selected returns at once.
-  const bool warp_ok = warp_layout(plan, wlay, wsmem);
+  // linear: two warps per cell array (14 warps per SM); cubic keeps one warp per array (its 16 template rows per
+  // particle need the registers).  Option fused_variant = 1 forces one warp per array.
+  // fused_variant = 2: six arrays / 12 warps (168 registers per thread instead of 128).
+  const bool pair = v.method == RBX_METHOD_LINEAR && opt(OPT_FUSED_VARIANT) != 1;
+  const bool pair6 = pair && opt(OPT_FUSED_VARIANT) == 2;
+  const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, pair6 ? 6 : 8);
   segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts,
                                           ws.seg_start, ws.item_start, ws.items, ws.ctrl, warp_ok ? 1 : 0,
                                           warp_ok ? wlay.chs : 7, lay.chs);
@@ -1914,8 +1982,10 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
                                                        wlay, b.accumulate, cl);
       return RBX_OK;
     };
-    rc = v.method == RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR>)
-                                       : wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC>);
+    rc = v.method != RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, false, 256>)
+         : pair6                       ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384>)
+         : pair                        ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 448>)
+                                       : wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, false, 256>);
     if (rc != RBX_OK) return rc;
     count_launch();
     RBX_LAUNCH_OK();

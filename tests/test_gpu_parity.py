@@ -226,13 +226,15 @@ def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
 
 
 @pytest.mark.parametrize("env", ["fused_force_lut=1", "fused_force_cas=1", "fused_impl=1",
-                                 "psub=64", "small_shift=1", "fused_no_skew=1", "fused_chs=9", "sort_impl=1"])
+                                 "psub=64", "small_shift=1", "fused_no_skew=1", "fused_chs=9", "sort_impl=1",
+                                 "fused_variant=1", "fused_variant=2"])
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env):
     """The general paths -- the group kernel (option fused_impl = 1), its lookup-table channel search for
     non-arange telescope grids and its shared cell region with CAS adds for SSP grids finer than the
     telescope's -- forced on the MUSE configuration (they are otherwise only taken by configurations the
-    oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew / larger chunks."""
+    oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew / larger chunks /
+    one warp per cell array (fused_variant = 1) / six arrays with two warps each (2) instead of seven."""
     from rubix_b200 import _lib, synthetic
     env, val = env.split("=")
     edges = synthetic.spatial_edges(25)
