@@ -1959,12 +1959,18 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   // The warp kernel runs when the plan allows it (host: grid geometry) AND the particles do (device, segment_kernel:
   // knot window and chunk geometry for the Doppler range present); otherwise the group kernel takes the same work
   // queue.  Both are launched; the one not selected returns at once.
-  // linear: two warps per cell array (14 warps per SM); cubic keeps one warp per array (its 16 template rows per
-  // particle need the registers).  Option fused_variant = 1 forces one warp per array.
-  // fused_variant = 2: six arrays / 12 warps (168 registers per thread instead of 128).
-  const bool pair = v.method == RBX_METHOD_LINEAR && opt(OPT_FUSED_VARIANT) != 1;
-  const bool pair6 = pair && opt(OPT_FUSED_VARIANT) == 2;
-  const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, pair6 ? 6 : 8);
+  // Cube-kernel variant (option fused_variant; A/B numbers in DESIGN.md section 5):
+  //   1  one warp per cell array (7 warps per SM)
+  //   2  two warps per array, 6 arrays (12 warps, 168 registers)      <- default for ssp.method linear
+  //   3  two warps per array, 7 arrays (14 warps, 128 registers: spills)
+  //   4  two warps per array, 5 arrays (10 warps, 168 registers, more L1)
+  // cubic keeps one warp per array: its 16 template rows per particle need 245 registers, and with 168 the pair
+  // variant spills and gains nothing (10^6 particles: 1.2127 against 1.2145 ms).
+  int variant = (int)opt(OPT_FUSED_VARIANT);
+  if (variant < 1 || variant > 4) variant = v.method == RBX_METHOD_LINEAR ? 2 : 1;
+  const bool pair = variant != 1;
+  const int max_arrays = variant == 1 ? 8 : variant == 2 ? 6 : variant == 3 ? 7 : 5;
+  const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, max_arrays);
   segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts,
                                           ws.seg_start, ws.item_start, ws.items, ws.ctrl, warp_ok ? 1 : 0,
                                           warp_ok ? wlay.chs : 7, lay.chs);
@@ -1982,10 +1988,16 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
                                                        wlay, b.accumulate, cl);
       return RBX_OK;
     };
-    rc = v.method != RBX_METHOD_LINEAR ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, false, 256>)
-         : pair6                       ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384>)
-         : pair                        ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 448>)
-                                       : wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, false, 256>);
+    if (v.method == RBX_METHOD_LINEAR)
+      rc = variant == 1   ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, false, 256>)
+           : variant == 2 ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384>)
+           : variant == 3 ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 448>)
+                          : wlaunch(fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 320>);
+    else
+      rc = variant == 1   ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, false, 256>)
+           : variant == 2 ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, true, 384>)
+           : variant == 3 ? wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, true, 448>)
+                          : wlaunch(fused_cube_warp_kernel<RBX_METHOD_CUBIC, true, 320>);
     if (rc != RBX_OK) return rc;
     count_launch();
     RBX_LAUNCH_OK();

@@ -1,12 +1,25 @@
 #!/bin/bash
-# multi-GPU check (gpurun --gpus N): default bench and the large-FOV slab-sharded configuration
-N=${1:-2}
-TAG=${2:-multi}
-mkdir -p gpurun_out/$TAG
-timeout 300 python -m pytest tests -m gpu -x -q -k "slab or psf or lsf" 2>&1 | tail -2
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N "${@:2}"; }
-timeout 300 bash -c "$(declare -f run); N=$N; run 29521 --steps 10 --warmup 3 --no-cpu" > gpurun_out/$TAG/bench_n$N.json 2> gpurun_out/$TAG/bench_n$N.err
-timeout 400 bash -c "$(declare -f run); N=$N; run 29522 --steps 5 --warmup 3 --no-cpu --spaxels 150 --particles 1250000" > gpurun_out/$TAG/bench_n${N}_s150.json 2> gpurun_out/$TAG/bench_n${N}_s150.err
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --spaxels 150 --particles 1250000 > gpurun_out/$TAG/bench_n1_s150.json 2> gpurun_out/$TAG/bench_n1_s150.err
-for f in bench_n$N bench_n${N}_s150 bench_n1_s150; do tail -2 gpurun_out/$TAG/$f.err | cut -c1-300; python -c "
-import json;d=json.loads(open('gpurun_out/$TAG/$f.json').read().strip().splitlines()[-1]);print('$f', 'n_gpus',d['n_gpus'],'step ms',round(d['ms_per_step'],4),'e2e ms',round(d['e2e']['ms_per_step'],3), 'value M/s', round(d['value']/1e6,1), d['config']['parallelism'][:60])"; done
+# Multi-GPU visit (gpurun --gpus N): the NCCL worker test, strong-scaling bench lines for config 3 (MUSE) and config 4
+# (150 x 150, reduce-scatter), optionally the survey batch.   Usage: bash tools/gpu_multi.sh TAG N [survey]
+TAG=${1:-multi}
+N=${2:-2}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=index,name --format=csv > $OUT/smi.txt
+timeout -s KILL 600 python -m pytest tests/test_gpu_scale.py -m gpu -q -x -k "two_ranks" -s > $OUT/pytest_mgpu.log 2>&1; echo "mgpu pytest rc=$?" | tee -a $OUT/pytest_mgpu.log
+tail -5 $OUT/pytest_mgpu.log
+run() {  # name, args...
+  name=$1; shift
+  timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N "$@" > $OUT/$name.json 2> $OUT/$name.err; echo "$name rc=$?"
+}
+run bench_n${N} --steps 10 --warmup 3
+run bench_n${N}_s150 --steps 5 --warmup 3 --spaxels 150 --no-cpu
+if [ -n "$3" ]; then run bench_n${N}_survey --steps 5 --warmup 3 --particles 1000000 --galaxies 8 --no-cpu; fi
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("$OUT/bench_n*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("/")[-1], "value %.4g ms/step %.4f kernel_ms %.4f parity %s e2e_ms %s" % (d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d.get("parity",{}).get("ok"), d.get("e2e",{}).get("ms_per_step")))
+    except Exception as e: print(f, "ERR", e)
+PY
