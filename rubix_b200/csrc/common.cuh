@@ -96,6 +96,18 @@ struct rbx_plan {
 
 namespace rbx {
 
+// Radix sort of (key, particle index) pairs (sort.cu).
+constexpr int kSortMaxBits = 8;     // digit width: at most 256 bins per pass
+constexpr int kSortMaxPasses = 4;   // keys have < 32 significant bits
+struct SortPlan {
+  int npass, ntiles;
+  int bits[kSortMaxPasses], shift[kSortMaxPasses];
+};
+SortPlan make_sort_plan(int64_t n, int end_bit);
+size_t sort_state_words(const SortPlan &sp);   // uint32 words of state: per pass [256 digit counts][256: ticket][ntiles][256]
+int radix_sort_pairs(const SortPlan &sp, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n,
+                     uint32_t *d_state, uint32_t **keys_sorted, uint32_t **vals_sorted, cudaStream_t stream);
+
 // Everything the rbx_*build_cube* entry points hand to build_cube_impl (fused.cu).
 struct CubeBuild {
   const float *vel = nullptr;      // Doppler component of particle 0 ...

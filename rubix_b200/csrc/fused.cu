@@ -95,6 +95,9 @@ struct FusedWs {
   float *partials;  // (max_split, Wp)
   void *cub_temp;
   size_t cub_bytes;
+  SortPlan sp;           // own radix sort (sort.cu)
+  uint32_t *sort_state;  // its digit histograms / tickets / tile states, zeroed together with counts and ctrl
+  size_t zero_bytes;     // counts + ctrl + sort state: one memset
   int rec_stride, max_items, max_split, Wp, psub, end_bit, ncell;
   int cell_bits, cell_shift;  // sort key = spaxel << cell_bits | (template cell >> cell_shift)
 };
@@ -117,12 +120,17 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
                             int *__restrict__ ctrl, int smem_hist, float *__restrict__ rec, int stride,
                             const float *__restrict__ cx, const float *__restrict__ cy, int cstride,
-                            const float *__restrict__ edges, int n_edges, int mark_outside, int edges_smem) {
+                            const float *__restrict__ edges, int n_edges, int mark_outside, int edges_smem,
+                            SortPlan sp, uint32_t *__restrict__ sort_state) {
   const bool coords = cx != nullptr;
   extern __shared__ int s_dyn[];
   int *s_hist = s_dyn;   // small cubes: per-block spaxel histogram; large cubes: count_runs_kernel after the sort
   float *s_axes = reinterpret_cast<float *>(s_dyn + (smem_hist ? nseg : 0));   // SSP metallicity and age axes
   float *s_edges = s_axes + p.nz + p.na;
+  // digit histograms of every radix pass of the sort that follows (sort.cu), gathered while the keys are made
+  int *s_dig = reinterpret_cast<int *>(s_edges + ((coords && edges_smem) ? n_edges : 0));
+  if (sort_state)
+    for (int s = threadIdx.x; s < sp.npass * 256; s += blockDim.x) s_dig[s] = 0;
   if (smem_hist)
     for (int s = threadIdx.x; s < nseg; s += blockDim.x) s_hist[s] = 0;
   for (int s = threadIdx.x; s < p.nz; s += blockDim.x) s_axes[s] = p.zgrid[s];
@@ -181,7 +189,13 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
       }
     }
     keys[q] = key;
-    idx[q] = (uint32_t)q;
+    if (sort_state) {
+#pragma unroll
+      for (int ps = 0; ps < kSortMaxPasses; ++ps)
+        if (ps < sp.npass) atomicAdd(s_dig + ps * 256 + ((key >> sp.shift[ps]) & ((1u << sp.bits[ps]) - 1u)), 1);
+    } else {
+      idx[q] = (uint32_t)q;   // cub sorts explicit (key, index) pairs; the own sort's first pass knows the indices
+    }
   }
   // positive floats order like their bit patterns
 #pragma unroll
@@ -195,11 +209,18 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
     atomicMax(ctrl + C_DMAX, __float_as_int(dmax));
     atomicAdd(ctrl + C_NVALID, nvalid);
   }
+  if (smem_hist || sort_state) __syncthreads();
   if (smem_hist) {
-    __syncthreads();
     for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
       const int c = s_hist[s];
       if (c) atomicAdd(counts + s, c);
+    }
+  }
+  if (sort_state) {
+    const size_t per_pass = ((size_t)sp.ntiles + 2) * 256;
+    for (int s = threadIdx.x; s < sp.npass * 256; s += blockDim.x) {
+      const int c = s_dig[s];
+      if (c) atomicAdd(sort_state + (size_t)(s >> 8) * per_pass + (s & 255), (uint32_t)c);
     }
   }
 }
@@ -1580,8 +1601,13 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
   ws.idx_in = (uint32_t *)take(sizeof(uint32_t) * n);
   ws.idx_out = (uint32_t *)take(sizeof(uint32_t) * n);
   ws.rec = (float *)take(sizeof(float) * n * ws.rec_stride);
-  ws.counts = (int *)take(sizeof(int) * (nseg + 1 + C_COUNT));   // counts, then ctrl: zeroed by one memset
+  // counts, ctrl and the sort's state are adjacent: zeroed by one memset
+  ws.sp = make_sort_plan(n, ws.end_bit);
+  const size_t cc_bytes = align_up(sizeof(int) * (nseg + 1 + C_COUNT));
+  ws.zero_bytes = cc_bytes + sizeof(uint32_t) * sort_state_words(ws.sp);
+  ws.counts = (int *)take(ws.zero_bytes);
   ws.ctrl = ws.counts + (nseg + 1);
+  ws.sort_state = (uint32_t *)((char *)ws.counts + cc_bytes);
   ws.seg_start = (int *)take(sizeof(int) * (nseg + 1));
   ws.item_start = (int *)take(sizeof(int) * (nseg + 1));
   ws.items = (Item *)take(sizeof(Item) * ws.max_items);
@@ -1913,7 +1939,9 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     return RBX_ERR_WORKSPACE_TOO_SMALL;
   }
   // counts and ctrl are adjacent; all-zero is their initial state (dmin is stored biased, dmax as bits)
-  RBX_CUDA_OK(cudaMemsetAsync(ws.counts, 0, sizeof(int) * (nseg + 1 + C_COUNT), stream));
+  // the library's own radix sort (sort.cu); option sort_impl = 1: cub::DeviceRadixSort (kept for A/B runs)
+  const bool own_sort = opt(OPT_SORT_IMPL) != 1 && n < (1ll << 30);
+  RBX_CUDA_OK(cudaMemsetAsync(ws.counts, 0, own_sort ? ws.zero_bytes : sizeof(int) * (nseg + 1 + C_COUNT), stream));
 
   const int threads = 256;
   int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
@@ -1924,7 +1952,8 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     // the run lengths of the sorted keys
     const int smem_hist = nseg <= 4096 ? 1 : 0;
     const size_t dyn = (smem_hist ? sizeof(int) * (size_t)nseg : 0) +
-                       sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? b.n_edges : 0));
+                       sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? b.n_edges : 0)) +
+                       (own_sort ? sizeof(int) * 256 * (size_t)ws.sp.npass : 0);
     int pcap = 148 * 4;   // measured (B200, 10^6 particles): 148 blocks 98 us, 296: 55, 592: 38, 1184: 44, 2368: 54 -- every
                           // block flushes its histogram with one atomic per non-empty spaxel
     if (opt(OPT_PREP_BLOCKS) > 0) pcap = (int)opt(OPT_PREP_BLOCKS);
@@ -1934,14 +1963,23 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     prep_kernel<<<pblocks, threads, dyn, stream>>>(v, b.vel, b.vstride, b.mass, b.met, b.age, b.pixel, (int)n, nseg,
                                                    ws.cell_bits, ws.cell_shift, ws.keys_in, ws.idx_in, ws.counts, ws.ctrl,
                                                    smem_hist, ws.rec, ws.rec_stride, b.cx, b.cy, b.cstride, b.edges,
-                                                   b.n_edges, b.mark_outside, edges_smem);
+                                                   b.n_edges, b.mark_outside, edges_smem, ws.sp,
+                                                   own_sort ? ws.sort_state : nullptr);
   }
   count_launch();
   RBX_LAUNCH_OK();
-  size_t cb = ws.cub_bytes;
-  RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, cb, ws.keys_in, ws.keys_out, ws.idx_in, ws.idx_out,
-                                              (int)n, 0, ws.end_bit, stream));
-  count_launch(3);
+  if (own_sort) {
+    uint32_t *ks = nullptr, *vs = nullptr;
+    rc = radix_sort_pairs(ws.sp, ws.keys_in, ws.idx_in, ws.keys_out, ws.idx_out, n, ws.sort_state, &ks, &vs, stream);
+    if (rc != RBX_OK) return rc;
+    ws.keys_out = ks;
+    ws.idx_out = vs;
+  } else {
+    size_t cb = ws.cub_bytes;
+    RBX_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, cb, ws.keys_in, ws.keys_out, ws.idx_in, ws.idx_out,
+                                                (int)n, 0, ws.end_bit, stream));
+    // cub's kernels are library code: not counted in rbx_launch_count
+  }
   if (nseg > 4096) {
     count_runs_kernel<<<blocks, threads, 0, stream>>>(ws.keys_out, (int)n, nseg, ws.cell_bits, ws.counts);
     count_launch();

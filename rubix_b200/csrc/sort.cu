@@ -1,0 +1,160 @@
+// Stable LSD radix sort of (key, particle index) pairs for the cube build -- the "device radix sort of particles by
+// spaxel index" of the north star, written for this key layout: key = spaxel << cell_bits | template cell, at most
+// ~26 significant bits, so 3 (MUSE) or 4 (150 x 150) passes of <= 8 bits.
+//
+// One kernel per pass, each key read once per pass (single-pass chained scan with decoupled look-back):
+//   * the digit histograms of ALL passes come for free from prep_kernel, which writes the keys (a shared-memory
+//     histogram per block, flushed with atomics): no histogram kernel, no scan kernel;
+//   * a block takes the next tile of 4096 keys (atomic ticket: a tile only ever waits for tiles that are already
+//     running), ranks its keys per digit -- inside a warp with __match_any_sync in index order, across warps by a
+//     scan of the per-warp counts, so equal digits keep their input order: the sort is STABLE and the result
+//     bit-reproducible -- publishes its per-digit counts, looks back over the preceding tiles' counts / inclusive
+//     prefixes and scatters straight to the final positions.
+//   * pass 0 takes the values to be the particle indices 0 .. n-1 (nothing is read for them).
+#include "common.cuh"
+
+namespace rbx {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // keys per tile
+constexpr uint32_t kFlagAgg = 0x40000000u, kFlagPrefix = 0x80000000u, kCountMask = 0x3fffffffu;
+
+SortPlan make_sort_plan(int64_t n, int end_bit) {
+  SortPlan sp;
+  sp.npass = std::max(1, (end_bit + kSortMaxBits - 1) / kSortMaxBits);
+  const int per = (end_bit + sp.npass - 1) / sp.npass;
+  int shift = 0;
+  for (int i = 0; i < kSortMaxPasses; ++i) {
+    sp.shift[i] = shift;
+    sp.bits[i] = i < sp.npass ? std::max(1, std::min(per, end_bit - shift)) : 0;
+    shift += sp.bits[i];
+  }
+  sp.ntiles = (int)((n + kSortTile - 1) / kSortTile);
+  return sp;
+}
+
+size_t sort_state_words(const SortPlan &sp) {
+  // per pass: global digit histogram [256], ticket [1 (+ padding to 256)], tile states [ntiles][256]
+  return (size_t)sp.npass * ((size_t)sp.ntiles + 2) * 256;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
+                  uint32_t *__restrict__ vout, int n, int shift, int bits, uint32_t *__restrict__ pass_state) {
+  // pass_state: [0, 256) global digit histogram (from prep_kernel), [256] ticket, [512 + 256 tile, +256) tile states
+  __shared__ uint32_t s_whist[kSortThreads / 32][256];
+  __shared__ uint32_t s_base[256];
+  __shared__ uint32_t s_scan[256];
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = 1 << bits;
+  const uint32_t dmask = (uint32_t)nb - 1u;
+  if (tid == 0) s_tile = (int)atomicAdd(pass_state + 256, 1u);
+  for (int q = tid; q < (kSortThreads / 32) * 256; q += kSortThreads) (&s_whist[0][0])[q] = 0u;
+  __syncthreads();
+  const int tile = s_tile;
+  volatile uint32_t *state = pass_state + 512;
+  const int tbase = tile * kSortTile + warp * (32 * kSortItems);
+
+  // ---- rank my keys: inside the warp in index order (match-any groups), item by item --------------------------
+  uint32_t key[kSortItems];
+  int rank[kSortItems];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int idx = tbase + i * 32 + lane;
+    const bool valid = idx < n;
+    key[i] = valid ? kin[idx] : 0u;
+    const uint32_t d = (key[i] >> shift) & dmask;
+    const unsigned m = __match_any_sync(0xffffffffu, valid ? d : 0x10000u + (uint32_t)lane);
+    const int leader = __ffs(m) - 1;
+    uint32_t c = 0;
+    if (lane == leader && valid) {
+      c = s_whist[warp][d];
+      s_whist[warp][d] = c + (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    c = __shfl_sync(0xffffffffu, c, leader);
+    rank[i] = (int)c + __popc(m & lt);
+  }
+  __syncthreads();
+
+  // ---- per digit: exclusive prefix over the warps, tile total, look-back over the preceding tiles ----------------
+  if (tid < nb) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      const uint32_t t = s_whist[w][tid];
+      s_whist[w][tid] = tot;
+      tot += t;
+    }
+    uint32_t excl = 0;
+    if (tile == 0) {
+      state[tid] = tot | kFlagPrefix;
+    } else {
+      state[(size_t)tile * 256 + tid] = tot | kFlagAgg;
+      int t = tile - 1;
+      while (true) {
+        const uint32_t v = state[(size_t)t * 256 + tid];
+        if (v & kFlagPrefix) { excl += v & kCountMask; break; }
+        if (v & kFlagAgg) { excl += v & kCountMask; --t; }
+      }
+      state[(size_t)tile * 256 + tid] = (excl + tot) | kFlagPrefix;
+    }
+    s_base[tid] = excl;
+    s_scan[tid] = pass_state[tid];   // global count of this digit
+  }
+  __syncthreads();
+  // exclusive scan of the global digit histogram (<= 256 bins: one warp, 8 bins per lane)
+  if (warp == 0) {
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int b = lane * 8 + q; v[q] = b < nb ? s_scan[b] : 0u; sum += v[q]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int b = lane * 8 + q; if (b < nb) s_base[b] += run; run += v[q]; }
+  }
+  __syncthreads();
+
+  // ---- scatter to the final positions of this pass ---------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int idx = tbase + i * 32 + lane;
+    if (idx < n) {
+      const uint32_t d = (key[i] >> shift) & dmask;
+      const uint32_t pos = s_base[d] + s_whist[warp][d] + (uint32_t)rank[i];
+      kout[pos] = key[i];
+      vout[pos] = vin ? vin[idx] : (uint32_t)idx;
+    }
+  }
+}
+
+// Sorts n (key, index) pairs by the low end_bit bits of the key; the values of the first pass are 0 .. n-1.
+// buf_a holds the keys on entry; the result lands in *keys_sorted / *vals_sorted (one of the two buffer pairs).
+// d_state (sort_state_words() words) must hold the digit histograms written by prep_kernel and be zero elsewhere.
+int radix_sort_pairs(const SortPlan &sp, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, int64_t n,
+                     uint32_t *d_state, uint32_t **keys_sorted, uint32_t **vals_sorted, cudaStream_t stream) {
+  uint32_t *kin = keys_a, *vin = nullptr, *kout = keys_b, *vout = vals_b;
+  const size_t per_pass = ((size_t)sp.ntiles + 2) * 256;
+  for (int p = 0; p < sp.npass; ++p) {
+    radix_pass_kernel<<<sp.ntiles, kSortThreads, 0, stream>>>(kin, vin, kout, vout, (int)n, sp.shift[p], sp.bits[p],
+                                                               d_state + (size_t)p * per_pass);
+    count_launch();
+    RBX_LAUNCH_OK();
+    // ping-pong: the pair just written becomes the input (pass 0 wrote (keys_b, vals_b) without reading values)
+    uint32_t *nk = kout, *nv = vout;
+    kout = (nk == keys_b) ? keys_a : keys_b;
+    vout = (nv == vals_b) ? vals_a : vals_b;
+    kin = nk;
+    vin = nv;
+  }
+  *keys_sorted = kin;
+  *vals_sorted = vin;
+  return RBX_OK;
+}
+
+}  // namespace rbx

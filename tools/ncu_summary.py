@@ -63,3 +63,37 @@ ws, wi = sum(f(r, "L1 Wavefronts Shared") for r in sh), sum(f(r, "L1 Wavefronts 
 print(f"-- shared-memory wavefronts: {ws / 1e6:.1f} M, ideal {wi / 1e6:.1f} M --")
 for r in sh[:12]:
     print(f"  {r[ix['Source']].strip()[:40]:40s} exec {f(r, 'Instructions Executed') / 1e6:6.2f} M  wavefronts {f(r, 'L1 Wavefronts Shared') / 1e6:7.2f} M  ideal {f(r, 'L1 Wavefronts Shared Ideal') / 1e6:6.2f} M")
+
+# ---- optional: merge the per-particle counts into profiles/fused_ncu.json (bench.py's roofline reads them) ---------
+#   python tools/ncu_summary.py REP N_PARTICLES KEY [TXT_NAME]     e.g. KEY = linear_10000000  (method_particles[_spaxels])
+if len(sys.argv) > 3 and npart:
+    import json
+    import os
+    # FP32 flops per warp instruction and lane (arithmetic only: compares, selects, min/max and conversions count 0)
+    FLOPS = {"FFMA": 2, "FFMA2": 4, "FADD": 1, "FMUL": 1, "FADD2": 2, "FMUL2": 2, "MUFU": 1}
+    lanes = float(m.get("smsp__thread_inst_executed_per_inst_executed.ratio", ("", "32"))[1])
+    _bytes = lambda k: float(m[k][1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m[k][0]]
+    flops = sum(v * FLOPS.get(k, 0) for k, v in ops.items()) * lanes
+    rec = {
+        "warp_inst_per_particle": tot / npart,
+        "flop_per_particle": flops / npart,
+        "fp32_warp_inst_per_particle": sum(v for k, v in ops.items() if k in FLOPS) / npart,
+        "dram_bytes_per_launch": int(_bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")),
+        "kernel_ms_under_ncu": float(m["gpu__time_duration.sum"][1]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[m["gpu__time_duration.sum"][0]],
+        "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][1]),
+        "lsu_wavefront_pipe_pct": float(m["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][1]),
+        "smem_wavefronts_per_particle": ws / npart, "smem_wavefronts_ideal_per_particle": wi / npart,
+        "registers": int(m["launch__registers_per_thread"][1]), "block_size": int(m["launch__block_size"][1]),
+        "kernel": m.get("Kernel Name", ("", ""))[1],
+        "flop_rule": "per lane: FFMA 2, FFMA2 4, FADD / FMUL / MUFU 1, FADD2 / FMUL2 2; everything else 0",
+        "capture": (sys.argv[4] if len(sys.argv) > 4 else os.path.basename(rep)) + " (ncu --set full --clock-control none)",
+    }
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "fused_ncu.json")
+    try:
+        table = json.load(open(path))
+    except (OSError, ValueError):
+        table = {}
+    table[sys.argv[3]] = rec
+    json.dump(table, open(path, "w"), indent=1)
+    print(f"-- profiles/fused_ncu.json[{sys.argv[3]}]: {rec['warp_inst_per_particle']:.1f} warp inst, "
+          f"{rec['flop_per_particle']:.0f} flop per particle")
