@@ -9,7 +9,8 @@
 //     running), ranks its keys per digit -- inside a warp with __match_any_sync in index order, across warps by a
 //     scan of the per-warp counts, so equal digits keep their input order: the sort is STABLE and the result
 //     bit-reproducible -- publishes its per-digit counts, looks back over the preceding tiles' counts / inclusive
-//     prefixes and scatters straight to the final positions.
+//     prefixes, puts the tile in digit order in shared memory and writes every digit's run to its final position
+//     (consecutive threads write consecutive elements: coalesced runs instead of 4-byte scatters).
 //   * pass 0 takes the values to be the particle indices 0 .. n-1 (nothing is read for them).
 #include "common.cuh"
 
@@ -39,13 +40,15 @@ size_t sort_state_words(const SortPlan &sp) {
   return (size_t)sp.npass * ((size_t)sp.ntiles + 2) * 256;
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
 radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
                   uint32_t *__restrict__ vout, int n, int shift, int bits, uint32_t *__restrict__ pass_state) {
   // pass_state: [0, 256) global digit histogram (from prep_kernel), [256] ticket, [512 + 256 tile, +256) tile states
   __shared__ uint32_t s_whist[kSortThreads / 32][256];
-  __shared__ uint32_t s_base[256];
+  __shared__ uint32_t s_base[256];   // global position of the tile's first element of each digit
   __shared__ uint32_t s_scan[256];
+  __shared__ uint32_t s_loc[256];    // position of each digit's run inside the tile
+  __shared__ uint32_t s_keys[kSortTile], s_vals[kSortTile];
   __shared__ int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = 1 << bits;
@@ -94,42 +97,72 @@ radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__
       state[tid] = tot | kFlagPrefix;
     } else {
       state[(size_t)tile * 256 + tid] = tot | kFlagAgg;
+      // look back eight tiles at a time (independent loads: the chain of dependent L2 round trips is what a
+      // tile waits for); tiles before tile 0 count as an empty inclusive prefix
       int t = tile - 1;
-      while (true) {
-        const uint32_t v = state[(size_t)t * 256 + tid];
-        if (v & kFlagPrefix) { excl += v & kCountMask; break; }
-        if (v & kFlagAgg) { excl += v & kCountMask; --t; }
+      bool done = false;
+      while (!done) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = t - q >= 0 ? (uint32_t)state[(size_t)(t - q) * 256 + tid] : 0x80000000u;
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (done || used != q) continue;            // stop at the first prefix / the first tile that is not ready
+          if (v[q] & (kFlagPrefix | kFlagAgg)) {
+            excl += v[q] & kCountMask;
+            ++used;
+            if (v[q] & kFlagPrefix) done = true;
+          }
+        }
+        t -= used;
       }
       state[(size_t)tile * 256 + tid] = (excl + tot) | kFlagPrefix;
     }
     s_base[tid] = excl;
     s_scan[tid] = pass_state[tid];   // global count of this digit
+    s_loc[tid] = tot;                // count of this digit in the tile
   }
   __syncthreads();
-  // exclusive scan of the global digit histogram (<= 256 bins: one warp, 8 bins per lane)
-  if (warp == 0) {
+  // exclusive scans over the digits (<= 256 bins: one warp each, 8 bins per lane): warp 0 the global digit histogram
+  // (-> global base), warp 1 the tile's digit counts (-> run start inside the tile)
+  if (warp < 2) {
+    uint32_t *arr = warp == 0 ? s_scan : s_loc;
     uint32_t v[8], sum = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { const int b = lane * 8 + q; v[q] = b < nb ? s_scan[b] : 0u; sum += v[q]; }
+    for (int q = 0; q < 8; ++q) { const int b = lane * 8 + q; v[q] = b < nb ? arr[b] : 0u; sum += v[q]; }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     uint32_t run = inc - sum;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { const int b = lane * 8 + q; if (b < nb) s_base[b] += run; run += v[q]; }
+    for (int q = 0; q < 8; ++q) {
+      const int b = lane * 8 + q;
+      if (b < nb) { if (warp == 0) s_base[b] += run; else s_loc[b] = run; }
+      run += v[q];
+    }
   }
   __syncthreads();
 
-  // ---- scatter to the final positions of this pass ---------------------------------------------------------------
+  // ---- the tile in digit order in shared memory, then every run to its final position ---------------------------
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const int idx = tbase + i * 32 + lane;
     if (idx < n) {
       const uint32_t d = (key[i] >> shift) & dmask;
-      const uint32_t pos = s_base[d] + s_whist[warp][d] + (uint32_t)rank[i];
-      kout[pos] = key[i];
-      vout[pos] = vin ? vin[idx] : (uint32_t)idx;
+      const uint32_t lp = s_loc[d] + s_whist[warp][d] + (uint32_t)rank[i];
+      s_keys[lp] = key[i];
+      s_vals[lp] = vin ? vin[idx] : (uint32_t)idx;
     }
+  }
+  __syncthreads();
+  const int cnt = min(kSortTile, n - tile * kSortTile);
+  for (int j = tid; j < cnt; j += kSortThreads) {
+    const uint32_t k = s_keys[j];
+    const uint32_t d = (k >> shift) & dmask;
+    const uint32_t pos = s_base[d] + ((uint32_t)j - s_loc[d]);
+    kout[pos] = k;
+    vout[pos] = s_vals[j];
   }
 }
 

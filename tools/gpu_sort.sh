@@ -5,7 +5,7 @@ mkdir -p $OUT
 timeout -s KILL 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "fused_cube_synthetic or alternate_code_paths or large_fov" > $OUT/pytest_first.log 2>&1; echo "first pytest rc=$?" | tee -a $OUT/pytest_first.log
 tail -3 $OUT/pytest_first.log
 if ! grep -q " passed" $OUT/pytest_first.log || grep -q "failed" $OUT/pytest_first.log; then echo "STOP: first tests not green"; tail -40 $OUT/pytest_first.log; exit 1; fi
-timeout -s KILL 900 python -m pytest tests -m gpu -q --durations=5 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+timeout -s KILL 900 python -m pytest tests -m gpu -q -k "${KEXPR:-fused or cube or pipeline_host or dust}" --durations=5 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
 grep -E "passed|failed" $OUT/pytest_gpu.log | tail -3
 for n in 1000000 10000000; do
   timeout -s KILL 200 python bench.py --particles $n --no-cpu --no-e2e > $OUT/bench_own_$n.json 2>> $OUT/bench.err
