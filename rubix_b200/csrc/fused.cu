@@ -1556,14 +1556,16 @@ __global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// Particles per bulk work item.  Measured on B200 (tools/gpu_sweep.sh, profiles/r01_item_sweep.txt): every item
-// costs a fixed ~10 us of expansion, so few large items win as long as the quarter-size tail items behind them
-// keep the end of the persistent kernel short: 512 at 10^6 particles, 2048 at 10^7.
+// Particles per bulk work item.  Measured on B200 with the 12-warp kernel (tools/gpu_psub.sh, profiles/r02_item_sweep.txt):
+// every item costs a fixed expansion (3721 channels, two warps), so few large items win as long as the queue still
+// holds several items per warp pair and the quarter-size tail items keep the end of the persistent kernel short:
+// 512 up to 2.5 10^6 particles, 1024 at 5 10^6, 2048 at 10^7 (about 4000 .. 5000 bulk items).
 static int choose_psub(int64_t n) {
   if (opt(OPT_PSUB) > 0) return (int)std::max<int64_t>(32, opt(OPT_PSUB));
-  int64_t t = n / 2048;
+  const int64_t t = n / 3500;
   int ps = 256;
-  while (ps < t && ps < 2048) ps <<= 1;
+  while (2 * ps <= t && ps < 2048) ps <<= 1;
+  if (n >= 600000) ps = std::max(ps, 512);
   return ps;
 }
 
@@ -2057,7 +2059,8 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     RBX_LAUNCH_OK();
   }
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
-  dim3 rgrid((v.W + 255) / 256, std::min(nseg, 1184));   // blocks loop over spaxels; most have nothing to add
+  // blocks loop over spaxels (most have nothing to add); large cubes hold few split spaxels: fewer, longer blocks
+  dim3 rgrid(nseg > 4096 ? 2 : (v.W + 255) / 256, std::min(nseg, 1184));
   reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube,
                                                     b.accumulate, cl);
   count_launch();
