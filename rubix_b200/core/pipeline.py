@@ -162,6 +162,11 @@ class RubixPipeline:
             if fn.__name__ in registry:  # rubix/pipeline/abstract_pipeline.py:80-82
                 raise ValueError("A transformer with this name is already present")
             registry[fn.__name__] = fn
+        nodes = set(order_by_depends_on(self.pipeline_config))
+        for fn in self.extra_functions:   # the reference drops these silently; say so
+            if fn.__name__ not in nodes:
+                self.logger.warning(f"extra function {fn.__name__!r} is not a node of the "
+                                    f"{self.user_config['pipeline']['name']!r} pipeline configuration: it will not run")
         chain = []
         for name in order_by_depends_on(self.pipeline_config):
             if name in registry:

@@ -63,6 +63,7 @@ def get_filter_particles(config: dict) -> Callable:
     spatial_bin_edges = get_spatial_bin_edges(config)
 
     def filter_particles(rubixdata: RubixData) -> RubixData:
+        import numpy as np
         import torch
         from .. import ops
         logger.info("Filtering particles outside the aperture...")
@@ -90,6 +91,10 @@ def get_filter_particles(config: dict) -> Callable:
                     continue
                 if name == "gas" and k == "metals":   # rubix/core/telescope.py:186: gas metals are not masked
                     continue
+                if isinstance(v, np.ndarray) and v.dtype.kind in "fiu" and v.size and v.shape[:1] == tuple(coords.shape[:1]):
+                    # prepare_input keeps the gas fields as numpy arrays: they follow the mask rule like every
+                    # other per-particle attribute (rubix/core/telescope.py:176-190)
+                    v = ops.dev(v, dtype=torch.float32 if v.dtype.kind == "f" else torch.int32)
                 if isinstance(v, torch.Tensor) and v.numel() and v.reshape(-1).shape[0] % n == 0 and v.shape[:1] == coords.shape[:1]:
                     m = mask.reshape(coords.shape[:-1])
                     while m.ndim < v.ndim:

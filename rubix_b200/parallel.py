@@ -31,6 +31,35 @@ def wavelength_slab(W: int, rank: int, world: int) -> Tuple[int, int]:
     return shard_range(W, rank, world)
 
 
+def slab_geometry(W: int, nslab: int, halo: int = 12) -> Tuple[int, int]:
+    """(wslab, ws) of the slab-major partial cube (``rbx_slab_geometry``): ceil(W / nslab) channels per slab, stored
+    with ``halo`` channels of each neighbour."""
+    wslab = (W + nslab - 1) // nslab
+    return wslab, wslab + 2 * halo
+
+
+def slab_pack(cube: np.ndarray, nslab: int, halo: int = 12) -> np.ndarray:
+    """Host restatement of the layout ``rbx_assign_build_cube_slabs`` writes: (nseg, W) -> (nslab, nseg, ws); slab r
+    holds channels [r wslab - halo, (r + 1) wslab + halo), zeros outside [0, W).  One reduce-scatter over the first
+    axis then leaves rank r with its summed slab and the halo the LSF needs."""
+    nseg, W = cube.shape
+    wslab, ws = slab_geometry(W, nslab, halo)
+    out = np.zeros((nslab, nseg, ws), dtype=cube.dtype)
+    for r in range(nslab):
+        lo = r * wslab - halo
+        a, b = max(lo, 0), min(lo + ws, W)
+        if b > a:
+            out[r, :, a - lo:b - lo] = cube[:, a:b]
+    return out
+
+
+def slab_interior(slab: np.ndarray, W: int, rank: int, nslab: int, halo: int = 12) -> np.ndarray:
+    """The channels rank ``rank`` owns, cut out of its (.., ws) slab after the PSF / LSF pass."""
+    wslab, _ = slab_geometry(W, nslab, halo)
+    n_own = max(0, min(wslab, W - rank * wslab))
+    return slab[..., halo:halo + n_own]
+
+
 _comm = None
 
 

@@ -63,6 +63,18 @@ def circular_aperture(n: int) -> np.ndarray:
     return (((x - c) ** 2 + (y - c) ** 2) <= (n / 2.0) ** 2).astype(np.float32).ravel()
 
 
+def hexagonal_aperture(n: int) -> np.ndarray:
+    """rubix/telescope/apertures.py:12-40 (HEXAGONAL_APERTURE): a flat-topped hexagon inscribed in the n x n grid,
+    pixel centres at 1 .. n relative to the centre n / 2 + 1 / 2; same strict / inclusive comparisons."""
+    c = n / 2 + 0.5
+    idx = np.arange(1, n + 1, dtype=np.float64)
+    xx = idx[:, None] - c    # first array axis, as in the reference's ap_region[x - 1, y - 1]
+    yy = idx[None, :] - c
+    h = n * np.sqrt(3.0) / 4
+    rr = 2 * (n / 4) * h - (n / 4) * np.abs(yy) - h * np.abs(xx)
+    return ((rr >= 0) & (np.abs(xx) < n / 2) & (np.abs(yy) < h)).astype(np.float32).ravel()
+
+
 class TelescopeFactory:
     """rubix/telescope/factory.py:18-110: ``create_telescope(name)`` from the built-in table, a YAML
     path or a ``{name: {...}}`` dict (custom telescopes, e.g. the large-FOV MUSE variant)."""
@@ -83,8 +95,10 @@ class TelescopeFactory:
         ap = c.get("aperture_type", "square")
         if ap == "square":
             region = square_aperture(sbin)
-        elif ap in ("circular", "hexagonal"):
+        elif ap == "circular":
             region = circular_aperture(sbin)  # aperture masks are outside the particle->cube path
+        elif ap == "hexagonal":
+            region = hexagonal_aperture(sbin)
         else:
             raise ValueError(f"Unknown aperture type: {ap}")
         wave_seq = calculate_wave_seq(c["wave_range"], c["wave_res"])

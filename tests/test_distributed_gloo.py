@@ -47,9 +47,19 @@ def _worker(rank, world, port, out_dir):
         slab = orc.apply_lsf(orc.apply_psf(t.numpy()[:, :, hlo:hhi], pk), 0.5, 1.25)[:, :, lo - hlo:lo - hlo + hi - lo]
         parts = [None] * world
         dist.all_gather_object(parts, (lo, hi, slab))
+        # the large-FOV exchange: slab-major partial cubes with halos, summed, every rank keeps its own
+        # slab (gloo has no reduce-scatter: all-reduce + slice is the same sum), PSF + LSF on slab + halo
+        W = len(wave)
+        packed = torch.from_numpy(parallel.slab_pack(cube.reshape(25, W), world, 12))
+        dist.all_reduce(packed)
+        own = packed[rank].numpy().reshape(5, 5, -1)
+        own = parallel.slab_interior(orc.apply_lsf(orc.apply_psf(own, pk), 0.5, 1.25), W, rank, world, 12)
+        parts2 = [None] * world
+        dist.all_gather_object(parts2, (rank, own))
         if rank == 0:
             full = np.concatenate([p[2] for p in sorted(parts, key=lambda p: p[0])], axis=2)
-            np.savez(os.path.join(out_dir, "out.npz"), cube=t.numpy(), conv=full)
+            full2 = np.concatenate([p[1] for p in sorted(parts2, key=lambda p: p[0])], axis=2)
+            np.savez(os.path.join(out_dir, "out.npz"), cube=t.numpy(), conv=full, conv_slabs=full2)
     finally:
         dist.destroy_process_group()
 
@@ -73,6 +83,18 @@ def test_two_rank_shard_reduce_and_slab_convolution(tmp_path, bc03):
     conv = orc.apply_lsf(orc.apply_psf(ref, orc.gaussian_kernel_2d(5, 5, 0.6).astype(np.float64)), 0.5, 1.25)
     # slab-wise LSF with a 12-channel halo is exact (the kernel reaches +-12 channels)
     assert np.abs(got["conv"] - conv).max() <= 1e-12 * conv.max()
+    # the same through the slab-major layout (what rbx_assign_build_cube_slabs + rbx_reduce_scatter_cube carry)
+    assert got["conv_slabs"].shape == conv.shape
+    assert np.abs(got["conv_slabs"] - conv).max() <= 1e-12 * conv.max()
+
+
+def test_slab_geometry_matches_the_library():
+    import ctypes as C
+    from rubix_b200 import _lib, parallel
+    for W, g, h in ((3721, 8, 12), (3721, 2, 12), (400, 3, 5), (7, 8, 0)):
+        a, b = C.c_int(), C.c_int()
+        assert _lib.lib().rbx_slab_geometry(W, g, h, C.byref(a), C.byref(b)) == 0
+        assert (a.value, b.value) == parallel.slab_geometry(W, g, h)
 
 
 def _dusty_inputs():

@@ -207,3 +207,26 @@ def test_noise_factory_name():
     from rubix_b200.core import get_apply_noise
     fn = get_apply_noise({"telescope": {"noise": {"signal_to_noise": 1, "noise_distribution": "normal"}}})
     assert fn.__name__ == "apply_noise"
+
+
+def test_hexagonal_aperture_matches_the_reference_loop():
+    """rubix/telescope/apertures.py:12-40 restated as the reference writes it (a double loop with .at[].set)."""
+    import numpy as np
+    from rubix_b200.telescope import TelescopeFactory, hexagonal_aperture
+
+    def ref(sbin):
+        ap = np.zeros((sbin, sbin))
+        xc = yc = sbin / 2 + 0.5
+        for x in range(1, sbin + 1):
+            for y in range(1, sbin + 1):
+                xx, yy = x - xc, y - yc
+                rr = (2 * (sbin / 4) * (sbin * np.sqrt(3) / 4)) - ((sbin / 4) * abs(yy)) - ((sbin * np.sqrt(3) / 4) * abs(xx))
+                if rr >= 0 and abs(xx) < sbin / 2 and abs(yy) < sbin * np.sqrt(3) / 4:
+                    ap[x - 1, y - 1] = 1
+        return ap.flatten()
+
+    for n in (4, 5, 24, 25, 74):
+        assert np.array_equal(hexagonal_aperture(n), ref(n))
+    tel = TelescopeFactory({"HEX": dict(fov=5.0, spatial_res=0.2, wave_range=[4700.15, 9351.4], wave_res=1.25,
+                                         lsf_fwhm=2.51, aperture_type="hexagonal", pixel_type="square")}).create_telescope("HEX")
+    assert np.array_equal(np.asarray(tel.aperture_region), ref(25))

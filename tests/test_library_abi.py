@@ -51,3 +51,31 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_option_table(lib):
+    """rbx_set_option / rbx_get_option: the switches the launch path reads instead of getenv()."""
+    assert _lib.get_option("psub") == -1
+    _lib.set_option("psub", 64)
+    assert _lib.get_option("psub") == 64
+    _lib.set_option("psub", -5)          # any negative value = the library's own choice
+    assert _lib.get_option("psub") == -1
+    with pytest.raises(_lib.RubixB200Error, match="unknown option"):
+        _lib.set_option("no_such_switch", 1)
+    # nothing under csrc/ reads the environment on a launch path: getenv appears once, in the option seeding
+    csrc = os.path.join(ROOT, "rubix_b200", "csrc")
+    hits = [(f, i) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cc"))
+            for i, line in enumerate(open(os.path.join(csrc, f)), 1) if "getenv(" in line and not line.lstrip().startswith("//")]
+    assert [f for f, _ in hits] == ["options.cu"], hits
+
+
+def test_slab_geometry_and_comm_argument_checks(lib):
+    w, ws = C.c_int(), C.c_int()
+    assert lib.rbx_slab_geometry(3721, 8, 12, C.byref(w), C.byref(ws)) == 0
+    assert (w.value, ws.value) == (466, 490)             # ceil(3721 / 8), + 2 x 12 halo channels
+    assert lib.rbx_slab_geometry(3721, 0, 12, C.byref(w), C.byref(ws)) != 0
+    # the exchange entry points validate before touching NCCL or CUDA
+    assert lib.rbx_reduce_cube(None, None, None, 0, 0, None) != 0
+    assert lib.rbx_reduce_scatter_cube(None, None, None, 0, None) != 0
+    assert lib.rbx_comm_init(None, None, 0, 1) != 0
+    assert lib.rbx_build_cube_status(None, 0, 25, None, None, None, None) != 0
