@@ -38,6 +38,7 @@ def _worker(rank, world, port, out_dir):
         cube = c_oracle.particles_to_cube(mine["coords"], mine["velocity"], mine["mass"], mine["metallicity"],
                                           mine["age"], edges, 5, tpl["metallicity"], tpl["age"], tpl["wavelength"],
                                           tpl["flux"], wave, 0.1, method="linear", dtype=np.float64, n_threads=1)
+        partial = cube.copy()                       # t shares cube's memory and is summed in place
         t = torch.from_numpy(np.ascontiguousarray(cube))
         parallel.allreduce_cube(t)
         # PSF + LSF sharded by wavelength slab with a +-12 channel halo, then gathered
@@ -50,7 +51,7 @@ def _worker(rank, world, port, out_dir):
         # the large-FOV exchange: slab-major partial cubes with halos, summed, every rank keeps its own
         # slab (gloo has no reduce-scatter: all-reduce + slice is the same sum), PSF + LSF on slab + halo
         W = len(wave)
-        packed = torch.from_numpy(parallel.slab_pack(cube.reshape(25, W), world, 12))
+        packed = torch.from_numpy(parallel.slab_pack(partial.reshape(25, W), world, 12))
         dist.all_reduce(packed)
         own = packed[rank].numpy().reshape(5, 5, -1)
         own = parallel.slab_interior(orc.apply_lsf(orc.apply_psf(own, pk), 0.5, 1.25), W, rank, world, 12)
