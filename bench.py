@@ -454,46 +454,8 @@ def main():
     value = total / (ms_per_step * 1e-3)
     err_impl = ops.build_cube_status(plan, n, S)
 
-    # ---- parity: the same step on a bounded sample against the float64 oracle -----------------------------------
-    parity = None
-    if not args.no_parity:
-        P = max(world, min(args.parity_sample, total if G == 1 else n))
-        if G > 1:
-            g0 = gal[0]
-            c, v, _ = ops.rotate_galaxy(g0["coords"][:P], g0["velocity"][:P], g0["mass"][:P], 1.5, *g0["angles"])
-            ops.assign_build_cube(plan, c, edges, v, g0["mass"][:P], g0["metallicity"][:P], g0["age"][:P], S, out=cube)
-            got = ops.psf_lsf(cube, pk_h, lk_h).cpu().numpy()
-            pdata = dict(coords=c.cpu().numpy(), velocity=v.cpu().numpy(), mass=g0["host"]["mass"][:P],
-                         metallicity=g0["host"]["metallicity"][:P], age=g0["host"]["age"][:P])
-            what = f"first {P} particles of galaxy 0 (rotated on the device), cube + PSF + LSF vs the float64 oracle"
-        else:
-            pdata = galaxy(args, P, seed=42)            # a P-particle galaxy drawn like the workload's
-            mine = parallel.shard_particles(pdata, rank, world)
-            out = device_step(ops.dev(mine["coords"]), ops.dev(mine["velocity"]), ops.dev(mine["mass"]),
-                              ops.dev(mine["metallicity"]), ops.dev(mine["age"]))
-            if slab_mode:   # gather the slabs (padded to wslab channels)
-                pad = torch.zeros((S, S, wslab), dtype=torch.float32, device="cuda")
-                pad[:, :, :out.shape[2]] = out
-                parts = [torch.empty_like(pad) for _ in range(world)]
-                dist.all_gather(parts, pad)
-                got = torch.cat(parts, dim=2)[:, :, :W].cpu().numpy() if rank == 0 else None
-            else:
-                got = out.cpu().numpy() if rank == 0 else None
-            what = (f"a {P}-particle bench-G galaxy sharded over {world} rank(s) like the timed step, reduced cube + "
-                    "PSF + LSF vs the float64 oracle on the unsharded particles")
-        if rank == 0:
-            _, ref = cpu_arm(pdata, tpl, wave, edges_h, S, args.method, pk_h, lk_h, P, os.cpu_count() or 1, dtype=np.float64)
-            err = float(np.abs(got.astype(np.float64) - ref).max())
-            mx, tot = float(np.abs(ref).max()), float(np.abs(ref).sum())
-            parity = {"max_abs_err_over_max": err / mx, "over_total": err / tot, "n": int(P),
-                      "ok": bool(np.isfinite(got).all() and err <= 1e-5 * tot and err <= 2e-5 * mx),
-                      "tolerance": "max|d| <= 1e-5 * sum|cube| (BASELINE north star) and <= 2e-5 * max|cube| (a sparse "
-                                   "cube shows single knife-edge particles, tests/test_gpu_scale.py; dense cubes sit "
-                                   "near 1e-6)",
-                      "what": what}
-        del pdata
-
-    # ---- e2e: host buffers through the C ABI ----------------------------------------------------------------------
+    # ---- e2e: host buffers through the C ABI (right after the timed loop: the GPU and the PCIe link are still in
+    # their active power state; the oracle of the parity leg below keeps the GPU idle for a second or two) ---------
     e2e = None
     if not args.no_e2e:
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -554,7 +516,7 @@ def main():
             h2d = sum(v.numel() * 4 for v in hp.values())
 
         def time_e2e(fn):
-            for _ in range(2):
+            for _ in range(4):
                 fn()
             barrier()
             e_steps = max(3, min(args.steps, 10))
@@ -589,6 +551,45 @@ def main():
                              "h2d_bytes_per_step": int(24 * n + edges_h.nbytes + pk_h.nbytes + lk_h.nbytes),
                              "api": "rbx_pipeline_host_packed (x, y, line-of-sight velocity, mass, Z, age as separate "
                                     "host arrays: the 24 B / particle the path reads)"}
+
+    # ---- parity: the same step on a bounded sample against the float64 oracle -----------------------------------
+    parity = None
+    if not args.no_parity:
+        P = max(world, min(args.parity_sample, total if G == 1 else n))
+        if G > 1:
+            g0 = gal[0]
+            c, v, _ = ops.rotate_galaxy(g0["coords"][:P], g0["velocity"][:P], g0["mass"][:P], 1.5, *g0["angles"])
+            ops.assign_build_cube(plan, c, edges, v, g0["mass"][:P], g0["metallicity"][:P], g0["age"][:P], S, out=cube)
+            got = ops.psf_lsf(cube, pk_h, lk_h).cpu().numpy()
+            pdata = dict(coords=c.cpu().numpy(), velocity=v.cpu().numpy(), mass=g0["host"]["mass"][:P],
+                         metallicity=g0["host"]["metallicity"][:P], age=g0["host"]["age"][:P])
+            what = f"first {P} particles of galaxy 0 (rotated on the device), cube + PSF + LSF vs the float64 oracle"
+        else:
+            pdata = galaxy(args, P, seed=42)            # a P-particle galaxy drawn like the workload's
+            mine = parallel.shard_particles(pdata, rank, world)
+            out = device_step(ops.dev(mine["coords"]), ops.dev(mine["velocity"]), ops.dev(mine["mass"]),
+                              ops.dev(mine["metallicity"]), ops.dev(mine["age"]))
+            if slab_mode:   # gather the slabs (padded to wslab channels)
+                pad = torch.zeros((S, S, wslab), dtype=torch.float32, device="cuda")
+                pad[:, :, :out.shape[2]] = out
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                got = torch.cat(parts, dim=2)[:, :, :W].cpu().numpy() if rank == 0 else None
+            else:
+                got = out.cpu().numpy() if rank == 0 else None
+            what = (f"a {P}-particle bench-G galaxy sharded over {world} rank(s) like the timed step, reduced cube + "
+                    "PSF + LSF vs the float64 oracle on the unsharded particles")
+        if rank == 0:
+            _, ref = cpu_arm(pdata, tpl, wave, edges_h, S, args.method, pk_h, lk_h, P, os.cpu_count() or 1, dtype=np.float64)
+            err = float(np.abs(got.astype(np.float64) - ref).max())
+            mx, tot = float(np.abs(ref).max()), float(np.abs(ref).sum())
+            parity = {"max_abs_err_over_max": err / mx, "over_total": err / tot, "n": int(P),
+                      "ok": bool(np.isfinite(got).all() and err <= 1e-5 * tot and err <= 2e-5 * mx),
+                      "tolerance": "max|d| <= 1e-5 * sum|cube| (BASELINE north star) and <= 2e-5 * max|cube| (a sparse "
+                                   "cube shows single knife-edge particles, tests/test_gpu_scale.py; dense cubes sit "
+                                   "near 1e-6)",
+                      "what": what}
+        del pdata
 
     if rank == 0:
         (hbm_peak, hbm_src), fp32 = measured_peaks()
