@@ -50,7 +50,7 @@ int64_t rbx_launch_count(void);
 
 /* Tuning / test switches: "psub", "sort_bits", "fused_force_lut", "fused_force_cas", "fused_impl" (1 = group kernel),
  * "fused_chs", "fused_no_skew", "fused_warps", "prep_blocks", "small_shift", "tail_shift", "host_chunks",
- * "march_no_bulk", "sort_impl" (1 = cub), "fused_variant".  value < 0 restores the library's own choice.  The
+ * "march_no_bulk", "sort_impl" (1 = cub), "fused_variant", "host_ratio" (percent).  value < 0 restores the library's own choice.  The
  * environment (RBX_<NAME>) seeds them ONCE when the library is loaded; no launch path calls getenv(). */
 int rbx_set_option(const char *name, int64_t value);
 int rbx_get_option(const char *name, int64_t *value);

@@ -129,11 +129,27 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
   // The galaxy is binned in `chunks` contiguous particle ranges: the host-to-device copies of range c+1 run
   // on a second stream while the kernels of range c execute, and every range adds into the same cube
   // (fixed ranges, fixed order: the result stays deterministic).
-  // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges; at 10^6 the
-  // per-range launch overhead eats the overlap, 2.13 -> 2.09 ms with 2)
-  int chunks = n >= 3000000 ? 5 : (n >= 1500000 ? 2 : 1);
-  if (opt(OPT_HOST_CHUNKS) > 0) chunks = (int)std::min<int64_t>(16, opt(OPT_HOST_CHUNKS));
+  // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges.)
+  // The copies are the longer leg ((n, 3) layout: 36 B per particle at ~49 GB/s = 0.73 ns against ~0.58 ns of
+  // kernels), so what stays exposed is the first range's copy and the LAST range's kernels: the ranges shrink
+  // geometrically (each 0.8 of the one before: its kernels still finish under the next copy) and the last one is small.
+  int chunks = n >= 3000000 ? 8 : (n >= 700000 ? 2 : 1);
+  double ratio = 0.8;
+  if (opt(OPT_HOST_CHUNKS) > 0) { chunks = (int)std::min<int64_t>(16, opt(OPT_HOST_CHUNKS)); ratio = 1.0; }
+  if (opt(OPT_HOST_RATIO) > 0) ratio = std::min(1.0, std::max(0.3, (double)opt(OPT_HOST_RATIO) / 100.0));
   if (n == 0) chunks = 1;
+  int64_t bnd[17];
+  {
+    double wsum = 0.0, w = 1.0, acc = 0.0;
+    for (int c = 0; c < chunks; ++c) { wsum += w; w *= ratio; }
+    w = 1.0;
+    bnd[0] = 0;
+    for (int c = 0; c < chunks; ++c) {
+      acc += w / wsum;
+      w *= ratio;
+      bnd[c + 1] = c + 1 == chunks ? n : std::min<int64_t>(n, (int64_t)(acc * (double)n));
+    }
+  }
   CopyLane *lane = nullptr;
   std::unique_lock<std::mutex> lane_lock;
   if (chunks > 1) {
@@ -144,8 +160,10 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
     RBX_CUDA_OK(cudaStreamWaitEvent(lane->stream, lane->ready, 0));
   }
   if (n == 0) TRY(rbx_build_cube(plan, d_vel, d_mass, d_met, d_age, d_pixel, 0, num_spaxels, d_cube, d_ws, ws_bytes, stream));
+  bool first_range = true;
   for (int c = 0; c < chunks && n > 0; ++c) {
-    const int64_t lo = n * c / chunks, hi = n * (c + 1) / chunks, m = hi - lo;
+    const int64_t lo = bnd[c], hi = bnd[c + 1], m = hi - lo;
+    if (m <= 0) continue;
     cudaStream_t cs = chunks > 1 ? lane->stream : stream;
     if (hp.packed) {
       RBX_CUDA_OK(cudaMemcpyAsync(d_coords + lo, hp.x + lo, sizeof(float) * m, cudaMemcpyHostToDevice, cs));
@@ -172,7 +190,8 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
     b.cy = hp.packed ? d_y + lo : d_coords + 3 * lo + 1;
     b.cstride = nc;
     b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
-    b.accumulate = c > 0 ? 1 : 0;
+    b.accumulate = first_range ? 0 : 1;
+    first_range = false;
     TRY(build_cube_impl(plan, b, m, num_spaxels, d_cube, d_ws, ws_bytes, stream));
   }
   float *result = d_cube;
