@@ -129,12 +129,13 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
   // The galaxy is binned in `chunks` contiguous particle ranges: the host-to-device copies of range c+1 run
   // on a second stream while the kernels of range c execute, and every range adds into the same cube
   // (fixed ranges, fixed order: the result stays deterministic).
-  // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges.)
-  // The copies are the longer leg ((n, 3) layout: 36 B per particle at ~49 GB/s = 0.73 ns against ~0.58 ns of
-  // kernels), so what stays exposed is the first range's copy and the LAST range's kernels: the ranges shrink
-  // geometrically (each 0.8 of the one before: its kernels still finish under the next copy) and the last one is small.
-  int chunks = n >= 3000000 ? 8 : (n >= 700000 ? 2 : 1);
-  double ratio = 0.8;
+  // (measured on B200, profiles/r01_e2e_chunks.txt: 10^7 particles 16.4 -> 12.1 ms with 4-6 ranges; at 10^6 the
+  // per-range cost -- every range expands all spaxels and runs the whole launch sequence -- eats the overlap.
+  // Round 2 tried 8 geometrically shrinking ranges (ratio 0.7 / 0.8 / 0.9, so that only a small last range's kernels
+  // stay exposed): 10.5 / 10.2 / 9.7 ms against 8.7 ms with 5 equal ranges on the same workload -- the per-range
+  // cost outweighs the shorter tail, so the ranges stay equal; option host_ratio keeps the experiment reachable.)
+  int chunks = n >= 3000000 ? 5 : (n >= 1500000 ? 2 : 1);
+  double ratio = 1.0;
   if (opt(OPT_HOST_CHUNKS) > 0) { chunks = (int)std::min<int64_t>(16, opt(OPT_HOST_CHUNKS)); ratio = 1.0; }
   if (opt(OPT_HOST_RATIO) > 0) ratio = std::min(1.0, std::max(0.3, (double)opt(OPT_HOST_RATIO) / 100.0));
   if (n == 0) chunks = 1;
