@@ -1307,35 +1307,50 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       // ---- knot positions in channel units, first channel at or above each knot ---------------------------
       // KA = kMagic - 1 + (channels below the knot): the knot's cell, kept as a float (compares, skew and the
       // shared-memory address all work on it; no float <-> int conversion anywhere)
+      // The float arithmetic of two neighbouring knots goes through the packed f32x2 forms (one issue slot for two
+      // IEEE operations; each half is an ordinary round-to-nearest op, so the results are those of the scalar form).
       float u[WK], KA[WK + 1], kc[WK + 1], g[WK];
 #pragma unroll
-      for (int r = 0; r < WK; ++r) {
-        u[r] = fmaf(au[r], eps, bu[r]);
-        KA[r] = knot_ka(u[r], kahi);
+      for (int r = 0; r < WK; r += 2) {
+        ffma2o(u[r], u[r + 1], au[r], au[r + 1], eps, eps, bu[r], bu[r + 1]);
+        float kb0, kb1;
+        fadd2s(kb0, kb1, u[r], u[r + 1], kMagic, kMagic);
+        KA[r] = fminf(fmaxf(kb0, kMagic - 1.f), kahi);
+        KA[r + 1] = fminf(fmaxf(kb1, kMagic - 1.f), kahi);
       }
       S[WK] = __shfl_down_sync(0xffffffffu, S[0], 1);
       KA[WK] = __shfl_down_sync(0xffffffffu, KA[0], 1);
       if (lane == 31) { S[WK] = S[WK - 1]; KA[WK] = KA[WK - 1]; }
 #pragma unroll
-      for (int r = 0; r <= WK; ++r) kc[r] = fmaxf(KA[r], kMagic) - kMagic;   // last channel below the knot, 0 below the band
+      for (int r = 0; r < WK; r += 2)   // last channel below the knot, 0 below the band
+        fadd2s(kc[r], kc[r + 1], fmaxf(KA[r], kMagic), fmaxf(KA[r + 1], kMagic), -kMagic, -kMagic);
+      kc[WK] = fmaxf(KA[WK], kMagic) - kMagic;
 
       // ---- slopes, the two normalisation sums (rubix/spectra/ifu.py:241-251) -------------------------
       //   total = sum S_j (x_j - x_{j-1}) [x_j in band] = d * sum S_j dl_j
       //   new = sum_w p(t_w) dt_w = delta * sum_j D_j (S_j + mu_j (D_j / 2 + g_j)), over the channels [k_j, k_{j+1}):
       //   D_j channels, mu_j the slope per channel and g_j = kc_j - u'_j = (t[k_j - 1] - x_j) / delta + 1/2
       float mu[WK];
-      float tot = 0.f, nw = 0.f;
+      float tot = 0.f, nw = 0.f, nw1 = 0.f;
 #pragma unroll
-      for (int r = 0; r < WK; ++r) {
-        mu[r] = (S[r + 1] - S[r]) * rdlu[r] * rd;
-        g[r] = kc[r] - u[r];
+      for (int r = 0; r < WK; r += 2) {
+        const float dS0 = S[r + 1] - S[r], dS1 = S[r + 2] - S[r + 1];
+        float t0, t1;
+        fmul2s(t0, t1, dS0, dS1, rdlu[r], rdlu[r + 1]);
+        fmul2s(mu[r], mu[r + 1], t0, t1, rd, rd);
+        ffma2o(g[r], g[r + 1], u[r], u[r + 1], -1.f, -1.f, kc[r], kc[r + 1]);
         // knots in the band [t_0, t_{W-1}] (1 <= cell <= W - 1): a predicated FFMA
-        asm("{\n.reg .pred p, q;\nsetp.ge.f32 p, %1, %2;\nsetp.le.and.f32 q, %1, %3, p;\n@q fma.rn.f32 %0, %4, %5, %0;\n}"
-            : "+f"(tot) : "f"(KA[r]), "f"(kMagic), "f"(kain), "f"(S[r]), "f"(dl[r]));
-        const float D = kc[r + 1] - kc[r];
-        const float Tp = fmaf(0.5f, D, g[r]);
-        nw = fmaf(D, fmaf(mu[r], Tp, S[r]), nw);
+#pragma unroll
+        for (int q = r; q < r + 2; ++q)
+          asm("{\n.reg .pred p, q;\nsetp.ge.f32 p, %1, %2;\nsetp.le.and.f32 q, %1, %3, p;\n@q fma.rn.f32 %0, %4, %5, %0;\n}"
+              : "+f"(tot) : "f"(KA[q]), "f"(kMagic), "f"(kain), "f"(S[q]), "f"(dl[q]));
+        const float D0 = kc[r + 1] - kc[r], D1 = kc[r + 2] - kc[r + 1];
+        float Tp0, Tp1, in0, in1;
+        ffma2o(Tp0, Tp1, D0, D1, 0.5f, 0.5f, g[r], g[r + 1]);
+        ffma2o(in0, in1, mu[r], mu[r + 1], Tp0, Tp1, S[r], S[r + 1]);
+        ffma2s(nw, nw1, D0, D1, in0, in1);       // even and odd knots in two accumulators
       }
+      nw += nw1;
       float mp = __shfl_up_sync(0xffffffffu, mu[WK - 1], 1);
       if (lane == 0) mp = mu[0];   // slot 0 of the window lies below the band for every Doppler factor present
 
@@ -1403,7 +1418,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       // cell k: (sum dmu (g + 1/2), sum dmu) in channel units; the expansion takes the 1/2 out again
       float ag[WK];
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ag[r] = dmv[r] * g[r];
+      for (int r = 0; r < WK; r += 2) fmul2s(ag[r], ag[r + 1], dmv[r], dmv[r + 1], g[r], g[r + 1]);
       if (PAIR) {
         turn_wait(t_mine);   // the cells are mine until turn_pass
 #pragma unroll
