@@ -378,7 +378,14 @@ __global__ void __launch_bounds__(1024)
 segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl,
-                               int warp_ok, int warp_chs, int group_chs) {
+                               int warp_ok, int warp_chs, int group_chs, int lamz_smem) {
+  // the knot-window searches and the chunk geometry below are chains of dependent reads of lam_z by single threads:
+  // from shared memory they cost a few hundred cycles instead of ~10 us
+  extern __shared__ float s_lamz[];
+  if (lamz_smem) {
+    for (int q = threadIdx.x; q < p.L; q += blockDim.x) s_lamz[q] = p.lamz[q];
+    p.lamz = s_lamz;   // visible after the __syncthreads inside block_scan
+  }
   __shared__ int s_w[33 * 4];
   __shared__ int s_err, s_ja, s_jb;
   __shared__ int s_bad_w[16], s_bad_g[16];   // [chs]: the chunk geometry fails for 2^chs channels per chunk
@@ -2026,9 +2033,10 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   const bool pair = variant != 1;
   const int max_arrays = variant == 1 ? 8 : variant == 2 ? 6 : variant == 3 ? 7 : 5;
   const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, max_arrays);
-  segment_kernel<<<1, 1024, 0, stream>>>(v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts,
-                                          ws.seg_start, ws.item_start, ws.items, ws.ctrl, warp_ok ? 1 : 0,
-                                          warp_ok ? wlay.chs : 7, lay.chs);
+  const int lamz_smem = v.L <= 10000 ? 1 : 0;
+  segment_kernel<<<1, 1024, lamz_smem ? sizeof(float) * v.L : 0, stream>>>(
+      v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts, ws.seg_start, ws.item_start,
+      ws.items, ws.ctrl, warp_ok ? 1 : 0, warp_ok ? wlay.chs : 7, lay.chs, lamz_smem);
   count_launch();
   RBX_LAUNCH_OK();
   int dev = 0, nsm = 148;
