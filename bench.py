@@ -316,6 +316,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle comparison")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage", action="store_true", help="skip the timing of the HBM-bound PSF+LSF kernel on a 150x150 cube")
     ap.add_argument("--galaxies", type=int, default=1,
                     help="survey batch (config 5): galaxies per GPU and step, each with its own inclination "
                          "(rotate_galaxy on the device); replicas only, no collective")
@@ -591,6 +592,23 @@ def main():
                       "what": what}
         del pdata
 
+    # ---- the HBM-bound stage of the path on its large configuration: PSF + LSF of a 150 x 150 x 3721 cube ---------
+    stage = None
+    if rank == 0 and world == 1 and G == 1 and not args.no_stage:
+        big = torch.rand((150, 150, W), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            ops.psf_lsf(big, pk_h, lk_h)
+        ts = []
+        for _ in range(10):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.psf_lsf(big, pk_h, lk_h); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        stage = {"kernel": "psf_lsf_march_kernel", "cube": "150x150x3721 float32 (config 4), read once + written once",
+                 "ms_median": float(np.median(ts)), "ms_min": float(np.min(ts)), "algorithmic_bytes": int(8 * big.numel())}
+        del big
+
     if rank == 0:
         (hbm_peak, hbm_src), fp32 = measured_peaks()
         nz, na, L = tpl["flux"].shape
@@ -640,6 +658,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
+        if stage is not None:
+            gbs = stage["algorithmic_bytes"] / (stage["ms_median"] * 1e-3) / 1e9
+            stage.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                          "peak_source": hbm_src})
+            line["roofline_psf_lsf"] = stage
         if parity is not None:
             line["parity"] = parity
         if e2e is not None:
