@@ -297,3 +297,36 @@ def test_two_ranks_nccl_against_oracle():
     print(res.stderr[-4000:])
     assert res.returncode == 0
     assert "MGPU OK" in res.stdout
+
+
+# ---- config 5: one rotated galaxy through the whole chain ----------------------------------------------------
+def test_rotated_galaxy_chain_vs_oracle(ops, plans, bc03, muse_wave):
+    """rotate_galaxy -> filter / spaxel assignment -> fused cube -> PSF + LSF on 10^5 particles of a flattened disc
+    (one galaxy of the survey batch, rubix/galaxy/alignment.py:233-265 in front of the path).  The rotation itself is
+    compared with the float64 oracle; spaxel ids computed from the two sets of coordinates may differ only for particles
+    within rounding of a spaxel edge; the cube is compared with the oracle fed the SAME float32 coordinates."""
+    from rubix_b200 import synthetic
+    S, n = 25, 100_000
+    edges = synthetic.spatial_edges(S)
+    d = synthetic.bench_g(n, seed=77)
+    d["coords"][:, 2] *= np.float32(0.2)
+    angles = (35.0, 60.0, 110.0)
+    c, v, R = ops.rotate_galaxy(d["coords"], d["velocity"], d["mass"], 1.5, *angles)
+    cref, vref, Rref = orc.rotate_galaxy(d["coords"], d["velocity"], d["mass"], 1.5, *angles)
+    assert np.abs(R.cpu().numpy() - Rref).max() <= 2e-6
+    ch, vh = c.cpu().numpy(), v.cpu().numpy()
+    assert np.abs(ch - cref).max() <= 1e-5 * np.abs(cref).max() and np.abs(vh - vref).max() <= 1e-5 * np.abs(vref).max()
+    pix_cuda = orc.square_spaxel_assignment(ch, edges)
+    pix_ref = orc.square_spaxel_assignment(cref.astype(np.float32), edges)
+    moved = np.nonzero(pix_cuda != pix_ref)[0]
+    assert len(moved) <= 1e-3 * n
+    if len(moved):   # only particles sitting on a spaxel edge to within the rotation's rounding
+        dist = np.minimum(np.abs(ch[moved, 0, None] - edges[None]).min(1), np.abs(ch[moved, 1, None] - edges[None]).min(1))
+        assert dist.max() <= 1e-4
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    cube = ops.assign_build_cube(plans["linear"], c, edges, v, d["mass"], d["metallicity"], d["age"], S)
+    out = ops.psf_lsf(cube, pk, lk).cpu().numpy()
+    rot = dict(d, coords=ch, velocity=vh)
+    ref = _oracle_cube(rot, edges, S, bc03, muse_wave, "linear", threads=8)
+    refc = orc.apply_lsf(orc.apply_psf(ref, pk.astype(np.float64)), 0.5, 1.25)
+    _cube_close(out, refc, "rotated galaxy: cube + PSF + LSF", rtol_max=1e-5)
