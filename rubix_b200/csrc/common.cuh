@@ -65,6 +65,11 @@ struct PlanView {
   float t0, tdelta, tinv;      // affine grid parameters (tinv = 1 / tdelta)
   const float *zgrid, *agrid;  // SSP metallicity / age axes
   const float *tab[4];         // f, fx, fy, fxy: (nz*na, Lp) float32, rows 16-byte aligned
+  const float *wt[4];          // window tables of the warp cube kernel (plan.cu: window_table_kernel) or nullptr:
+                               // (nz*na, 256) float32, the knots wt_jbase .. wt_jbase + 255 of every row (clamped to
+                               // the SSP grid like jnp.interp's end values), laid out so that the two 16-byte loads
+                               // of a lane (its knots 8l .. 8l+3 and 8l+4 .. 8l+7) are each contiguous across the warp
+  int wt_jbase;                // first knot of the window (a multiple of 4, may be negative)
   const float *lamz;           // (L)  (1+z)*wavelength                       rubix/spectra/ifu.py:80
   const float *rdl;            // (L)  1/(lamz[j+1]-lamz[j]); 0 for the last knot or zero width
   const float *t;              // (W)  telescope wave_seq

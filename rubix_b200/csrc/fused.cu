@@ -151,50 +151,75 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
   }
   float dmin = 3.0e38f, dmax = 0.f;
   int nvalid = 0;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-    int i, j;
-    bool inside;
-    ssp_cell(p, met[q], age[q], i, j, inside);
-    int px;
-    if (coords) {
-      const float x = cx[(size_t)cstride * q], y = cy[(size_t)cstride * q];
-      const int xi = min(max(ss_right(e, n_edges, x) - 1, 0), nb - 1);
-      const int yi = min(max(ss_right(e, n_edges, y) - 1, 0), nb - 1);
-      px = xi + nb * yi;
-      if (mark_outside && !((x >= elo) && (x <= ehi) && (y >= elo) && (y <= ehi))) px = -1;
-      if (pixel) pixel[q] = px;
-    } else {
-      px = pixel[q];
-    }
-    const float voc = vel[(size_t)vstride * q] / kSpeedOfLight;
-    float d = expf(voc);
-    bool valid = inside && (mass[q] != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
-    uint32_t key = (uint32_t)nseg << cell_bits;  // invalid: sorts behind every valid key
-    if (valid) {
-      uint32_t cell = (uint32_t)((i - 1) * (p.na - 1) + (j - 1));
-      key = ((uint32_t)px << cell_bits) | (cell >> cell_shift);
-      if (smem_hist) atomicAdd(s_hist + px, 1);
-      dmin = fminf(dmin, d);
-      dmax = fmaxf(dmax, d);
-      ++nvalid;
-      SspTerms tm;
-      ssp_terms_at(p, met[q], age[q], mass[q], i, j, inside, tm);
-      float4 *r = reinterpret_cast<float4 *>(rec + (size_t)q * stride);
-      r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), expm1f(voc));
-      r[1] = make_float4(tm.w[0], tm.w[1], tm.w[2], tm.w[3]);
-      if (p.method != RBX_METHOD_LINEAR) {
-        r[2] = make_float4(tm.w[4], tm.w[5], tm.w[6], tm.w[7]);
-        r[3] = make_float4(tm.w[8], tm.w[9], tm.w[10], tm.w[11]);
-        r[4] = make_float4(tm.w[12], tm.w[13], tm.w[14], tm.w[15]);
+  // Latency bound (one particle's loads at a time leave the memory system idle): every thread first requests the
+  // inputs of U particles, then processes them.
+  constexpr int U = 4;
+  const int gstride = gridDim.x * blockDim.x;
+  for (int q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n; q0 += U * gstride) {
+    float in_x[U], in_y[U], in_v[U], in_m[U], in_z[U], in_a[U];
+    int in_px[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int q = q0 + k * gstride;
+      in_x[k] = in_y[k] = in_v[k] = in_m[k] = in_z[k] = in_a[k] = 0.f;
+      in_px[k] = -1;
+      if (q < n) {
+        in_z[k] = met[q]; in_a[k] = age[q]; in_m[k] = mass[q];
+        in_v[k] = vel[(size_t)vstride * q];
+        if (coords) { in_x[k] = cx[(size_t)cstride * q]; in_y[k] = cy[(size_t)cstride * q]; }
+        else in_px[k] = pixel[q];
       }
     }
-    keys[q] = key;
-    if (sort_state) {
 #pragma unroll
-      for (int ps = 0; ps < kSortMaxPasses; ++ps)
-        if (ps < sp.npass) atomicAdd(s_dig + ps * 256 + ((key >> sp.shift[ps]) & ((1u << sp.bits[ps]) - 1u)), 1);
-    } else {
-      idx[q] = (uint32_t)q;   // cub sorts explicit (key, index) pairs; the own sort's first pass knows the indices
+    for (int k = 0; k < U; ++k) {
+      const int q = q0 + k * gstride;
+      if (q >= n) break;
+      const float zq = in_z[k], aq = in_a[k], mq = in_m[k];
+      int i, j;
+      bool inside;
+      ssp_cell(p, zq, aq, i, j, inside);
+      int px;
+      if (coords) {
+        const float x = in_x[k], y = in_y[k];
+        const int xi = min(max(ss_right(e, n_edges, x) - 1, 0), nb - 1);
+        const int yi = min(max(ss_right(e, n_edges, y) - 1, 0), nb - 1);
+        px = xi + nb * yi;
+        if (mark_outside && !((x >= elo) && (x <= ehi) && (y >= elo) && (y <= ehi))) px = -1;
+        if (pixel) pixel[q] = px;
+      } else {
+        px = in_px[k];
+      }
+      const float voc = in_v[k] / kSpeedOfLight;
+      float d = expf(voc);
+      bool valid = inside && (mq != 0.f) && px >= 0 && px < nseg && (d > 0.f) && (d < 3.0e38f);
+      uint32_t key = (uint32_t)nseg << cell_bits;  // invalid: sorts behind every valid key
+      if (valid) {
+        uint32_t cell = (uint32_t)((i - 1) * (p.na - 1) + (j - 1));
+        key = ((uint32_t)px << cell_bits) | (cell >> cell_shift);
+        if (smem_hist) atomicAdd(s_hist + px, 1);
+        dmin = fminf(dmin, d);
+        dmax = fmaxf(dmax, d);
+        ++nvalid;
+        SspTerms tm;
+        ssp_terms_at(p, zq, aq, mq, i, j, inside, tm);
+        float4 *r = reinterpret_cast<float4 *>(rec + (size_t)q * stride);
+        r[0] = make_float4(d, 1.f / d, __int_as_float(tm.row[0]), expm1f(voc));
+        r[1] = make_float4(tm.w[0], tm.w[1], tm.w[2], tm.w[3]);
+        if (p.method != RBX_METHOD_LINEAR) {
+          r[2] = make_float4(tm.w[4], tm.w[5], tm.w[6], tm.w[7]);
+          r[3] = make_float4(tm.w[8], tm.w[9], tm.w[10], tm.w[11]);
+          r[4] = make_float4(tm.w[12], tm.w[13], tm.w[14], tm.w[15]);
+        }
+      }
+      keys[q] = key;
+      if (sort_state) {
+  #pragma unroll
+        for (int ps = 0; ps < kSortMaxPasses; ++ps)
+          if (ps < sp.npass) atomicAdd(s_dig + ps * 256 + ((key >> sp.shift[ps]) & ((1u << sp.bits[ps]) - 1u)), 1);
+      } else {
+        idx[q] = (uint32_t)q;   // cub sorts explicit (key, index) pairs; the own sort's first pass knows the indices
+      }
+    
     }
   }
   // positive floats order like their bit patterns
@@ -437,7 +462,7 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
   if (tot[0] > 0) {
     const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
     if (t < 32 && p.affine) {
-      const int jbase = (s_ja - 1) & ~3;
+      const int jbase = p.wt_jbase;   // the warp kernel's knot window is fixed per plan (window tables, plan.cu)
       for (int chs = warp_chs; chs <= 10; ++chs) {
         int cA;
         if (!warp_lane_chunks(p, jbase, t, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA)) s_bad_w[chs] = 1;
@@ -471,8 +496,9 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     int wchs = -1, gchs = -1;
     for (int chs = 10; chs >= warp_chs; --chs) if (!s_bad_w[chs]) wchs = chs;
     for (int chs = 8; chs >= group_chs; --chs) if (!s_bad_g[chs]) gchs = chs;
-    const int jbase = (s_ja - 1) & ~3;
-    const bool warp = warp_ok != 0 && wchs >= 0 && (s_jb - jbase + 1 <= kWarpSlots);
+    // slot 0 must lie below the band and the last slot beyond it for every Doppler factor present
+    const int jbase = p.wt_jbase;
+    const bool warp = warp_ok != 0 && wchs >= 0 && jbase <= s_ja - 1 && (s_jb - jbase + 1 <= kWarpSlots);
     ctrl[C_IMPL] = warp ? IMPL_WARP : IMPL_GROUP;
     ctrl[C_CHS] = max(wchs, warp_chs);
     ctrl[C_GCHS] = max(gchs, group_chs);
@@ -1109,17 +1135,14 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   // ---- per-lane knot constants -------------------------------------------------------------------
   const int ja = ctrl[C_JA], jb = ctrl[C_JB];
   const int n_items = ctrl[C_NITEMS];
-  const int jbase = (ja - 1) & ~3;               // multiple of 4 (16-byte template loads); slot s <-> knot jbase + s
+  const int jbase = p.wt_jbase;                  // slot s <-> knot jbase + s: the plan's window tables (plan.cu)
   const int j0 = jbase + WK * lane;
-  const bool interior = j0 >= 0 && j0 + WK <= p.L;   // all eight knots inside the SSP grid: two 16-byte loads per row
   float au[WK], bu[WK];                           // u' = au * (d - 1) + bu: knot position in channel units (see knot_ab)
   float rdlu[WK];                                 // delta / (lam_z[j+1] - lam_z[j]): slope per channel = dS * rdlu / d
   float dl[WK];                                   // lam_z[j] - lam_z[j-1]: total_lum = d * sum S_j dl_j over the knots in band
-  int jc[WK];                                     // clamped knot index (jnp.interp end values)
 #pragma unroll
   for (int r = 0; r < WK; ++r) {
     const int j = j0 + r;
-    jc[r] = min(max(j, 0), p.L - 1);
     const KnotAB ab = knot_ab(p, j);
     au[r] = ab.a; bu[r] = ab.b;
     rdlu[r] = (j < 0 || j >= p.L - 1) ? 0.f : p.rdl[j] * p.tdelta;
@@ -1139,8 +1162,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 
   const float *tab[NT];
 #pragma unroll
-  for (int t = 0; t < NT; ++t) tab[t] = p.tab[t];
-  const size_t rowB = (size_t)p.Lp, rowC = (size_t)p.na * p.Lp, rowD = (size_t)(p.na + 1) * p.Lp;
+  for (int t = 0; t < NT; ++t) tab[t] = p.wt[t] + 4 * lane;
+  // window tables: a row is 256 floats (knots clamped to the SSP grid: jnp.interp's end values); my knots 0..3 sit at
+  // float 4 * lane, my knots 4..7 at 128 + 4 * lane, so every warp-wide 16-byte load is one contiguous 512-byte block
+  const size_t rowB = (size_t)kWarpSlots, rowC = (size_t)p.na * kWarpSlots, rowD = (size_t)(p.na + 1) * kWarpSlots;
 
   // The next work item is popped, and its first record batch requested, BEFORE the current item's cells are
   // expanded: the queue atomic and two dependent global loads hide behind the expansion.
@@ -1193,24 +1218,22 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       __syncwarp();
       if (b0 + 32 < cnt) fetch_rec(it, b0 + 32);
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
-        if (interior) {
-          const int rw = __float_as_int(s_rec[i * RS + 2]);
-          // linear: particles are sorted by (spaxel, template cell), so runs of particles share their four rows;
-          // the vectors already in registers are kept (at 10^7 particles ~90 % of the row loads go away)
-          if (NT == 1 && rw == nf_row) return;
-          nf_row = rw;
-          const float *f = tab[t] + (size_t)rw * p.Lp + j0;
-          // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
-          const size_t o1 = METHOD == RBX_METHOD_LINEAR ? rowB : rowC, o2 = METHOD == RBX_METHOD_LINEAR ? rowC : rowB;
-          nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
-          nf[1] = __ldg(reinterpret_cast<const float4 *>(f + 4));
-          nf[2] = __ldg(reinterpret_cast<const float4 *>(f + o1));
-          nf[3] = __ldg(reinterpret_cast<const float4 *>(f + o1 + 4));
-          nf[4] = __ldg(reinterpret_cast<const float4 *>(f + o2));
-          nf[5] = __ldg(reinterpret_cast<const float4 *>(f + o2 + 4));
-          nf[6] = __ldg(reinterpret_cast<const float4 *>(f + rowD));
-          nf[7] = __ldg(reinterpret_cast<const float4 *>(f + rowD + 4));
-        }
+        const int rw = __float_as_int(s_rec[i * RS + 2]);
+        // linear: particles are sorted by (spaxel, template cell), so runs of particles share their four rows;
+        // the vectors already in registers are kept (at 10^7 particles ~90 % of the row loads go away)
+        if (NT == 1 && rw == nf_row) return;
+        nf_row = rw;
+        const float *f = tab[t] + (size_t)rw * kWarpSlots;
+        // linear weights are ordered rows (+0, +1, +na, +na+1); cubic (jj, ii): rows (+0, +na, +1, +na+1)
+        const size_t o1 = METHOD == RBX_METHOD_LINEAR ? rowB : rowC, o2 = METHOD == RBX_METHOD_LINEAR ? rowC : rowB;
+        nf[0] = __ldg(reinterpret_cast<const float4 *>(f));
+        nf[1] = __ldg(reinterpret_cast<const float4 *>(f + 128));
+        nf[2] = __ldg(reinterpret_cast<const float4 *>(f + o1));
+        nf[3] = __ldg(reinterpret_cast<const float4 *>(f + o1 + 128));
+        nf[4] = __ldg(reinterpret_cast<const float4 *>(f + o2));
+        nf[5] = __ldg(reinterpret_cast<const float4 *>(f + o2 + 128));
+        nf[6] = __ldg(reinterpret_cast<const float4 *>(f + rowD));
+        nf[7] = __ldg(reinterpret_cast<const float4 *>(f + rowD + 128));
       };
       issue_rows(0, 0);
       float S2[WK], S3[WK];      // cubic: spectra of the followers in a run of particles of one template cell
@@ -1221,7 +1244,6 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       const float *rb = s_rec + qi * RS;
       const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, d - 1
       const float d = r0.x, rd = r0.y, eps = r0.w;
-      const size_t row = (size_t)__float_as_int(r0.z) * p.Lp;
 
       // ---- mass-weighted spectrum at my eight knots ------------------------------------------------
       // Cubic (16 rows per particle, no room to keep them in registers): when the next one or two particles read
@@ -1256,7 +1278,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           if (nfol >= 1) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
           if (nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + 4 + 4 * t);
           const float wv2[4] = {w2.x, w2.y, w2.z, w2.w}, wv3[4] = {w3.x, w3.y, w3.z, w3.w};
-          if (interior) {
+          {
             float4 cur[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) cur[u] = nf[u];
@@ -1294,18 +1316,6 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
                 ffma2s(S3[6], S3[7], wv3[a], wv3[a], hi.z, hi.w);
               }
             }
-          } else {
-            // lanes at the ends of the SSP grid: clamped scalar loads (jnp.interp end values)
-            const size_t off[4] = {0, METHOD == RBX_METHOD_LINEAR ? rowB : rowC, METHOD == RBX_METHOD_LINEAR ? rowC : rowB, rowD};
-            const float *f = tab[t] + row;
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-              for (int r = 0; r < WK; ++r) {
-                const float fv = __ldg(f + off[a] + jc[r]);
-                S[r] = fmaf(wv[a], fv, S[r]);
-                if (NT > 1) { S2[r] = fmaf(wv2[a], fv, S2[r]); S3[r] = fmaf(wv3[a], fv, S3[r]); }
-              }
           }
         }
       }
@@ -1762,7 +1772,7 @@ static int fused_layout(const rbx_plan *plan, FusedLayout &lay, size_t &smem_byt
 // Static limits and shared-memory layout of fused_cube_warp_kernel.  false: the plan needs the group kernel.
 static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_bytes, bool pair, int max_arrays) {
   const PlanView &v = plan->v;
-  if (!v.affine || v.W + 2 >= (1 << 20)) return false;
+  if (!v.affine || !v.wt[0] || v.W + 2 >= (1 << 20)) return false;
   if (opt_on(OPT_FUSED_IMPL) || opt_on(OPT_FUSED_FORCE_LUT) || opt_on(OPT_FUSED_FORCE_CAS)) return false;
   // knots that can reach the band for |v| up to ~0.03 c
   const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
@@ -1980,6 +1990,8 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
                        (own_sort ? sizeof(int) * 256 * (size_t)ws.sp.npass : 0);
     int pcap = 148 * 4;   // measured (B200, 10^6 particles): 148 blocks 98 us, 296: 55, 592: 38, 1184: 44, 2368: 54 -- every
                           // block flushes its histogram with one atomic per non-empty spaxel
+    // large inputs: the flush is amortised over many particles per block, so fill the SMs (8 blocks each) instead
+    pcap = (int)std::min<int64_t>(148 * 16, std::max<int64_t>(pcap, n / 4096));
     if (opt(OPT_PREP_BLOCKS) > 0) pcap = (int)opt(OPT_PREP_BLOCKS);
     const int pblocks = smem_hist ? (int)std::min<int64_t>(blocks, pcap) : blocks;
     if (dyn > 48 * 1024)

@@ -1,5 +1,6 @@
 // Plan creation: per-configuration device tables (SSP template + derivative tables, redshifted
 // SSP wavelengths, telescope grid and its chunk-local helper tables).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -73,6 +74,19 @@ __global__ void lut_fill_kernel(const int *__restrict__ bucket, int W, int nb, u
     if (bucket[mid] < b) lo = mid + 1; else hi = mid;
   }
   lut[b] = (uint16_t)lo;
+}
+
+// Window table of the warp cube kernel: out[row][perm(s)] = tab[row][clamp(jbase + s, 0, L - 1)] for the 256 knot
+// slots s of the kernel's window.  Lane l owns the slots 8l .. 8l+7 and fetches them with two 16-byte loads; perm puts
+// the first halves of all 32 lanes into one contiguous 512-byte block and the second halves into the next, so each
+// warp-wide load touches 4 cache lines instead of 8-9 (rows of the plain table: 32-byte lane stride).
+__global__ void window_table_kernel(const float *__restrict__ tab, float *__restrict__ out, int rows, int L, int Lp,
+                                    int jbase) {
+  const int row = blockIdx.x, s = threadIdx.x;   // 256 threads
+  if (row >= rows) return;
+  const int l = s >> 3, r = s & 7;
+  const int dst = r < 4 ? 4 * l + r : 128 + 4 * l + (r - 4);
+  out[(size_t)row * 256 + dst] = tab[(size_t)row * Lp + min(max(jbase + s, 0), L - 1)];
 }
 
 }  // namespace rbx
@@ -228,6 +242,38 @@ extern "C" int rbx_plan_create(rbx_plan **out, const float *h_met, int nz, const
       cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, stream);
       if (cudaStreamSynchronize(stream) == cudaSuccess) pl->lut_ok = ok;
       v.lut = (const uint16_t *)d_lut;
+    }
+  }
+  // Window tables for the warp cube kernel (affine grids): the knot window is fixed per plan -- the knots that reach
+  // the band at rest (+3 either side, as segment_kernel counts them) with the spare slots split 1 : 2 between the blue
+  // and the red end (the red end moves twice as many knots per unit of Doppler shift).  segment_kernel checks that
+  // the Doppler range actually present stays inside it (BC03 on MUSE: |v| up to ~0.045 c) and hands wider ranges to the
+  // group kernel.
+  v.wt_jbase = 0;
+  for (int k = 0; k < 4; ++k) v.wt[k] = nullptr;
+  if (v.affine) {
+    int a0 = 0;
+    while (a0 < L && pl->h_lamz[a0] < tmin) ++a0;
+    int b0 = a0;
+    while (b0 < L && pl->h_lamz[b0] <= tmax) ++b0;
+    const int ja0 = std::max(0, a0 - 3), jb0 = std::min(L, b0 + 3);
+    const int need = jb0 - ja0 + 2;   // slots ja0 - 1 .. jb0
+    if (need <= 256) {
+      const int slack = 256 - need;
+      v.wt_jbase = ((ja0 - 1) - slack / 3) & ~3;
+      const int ntab = method == RBX_METHOD_CUBIC ? 4 : 1;
+      for (int k = 0; k < ntab; ++k) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, rows * 256 * sizeof(float)) != cudaSuccess) {
+          set_error("rbx_plan_create: cudaMalloc failed");
+          rbx_plan_destroy(pl);
+          return RBX_ERR_CUDA;
+        }
+        pl->allocs.push_back(p);
+        window_table_kernel<<<(int)rows, 256, 0, stream>>>(v.tab[k], (float *)p, (int)rows, L, v.Lp, v.wt_jbase);
+        count_launch();
+        v.wt[k] = (const float *)p;
+      }
     }
   }
 #undef TRY
