@@ -1107,6 +1107,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
                        CubeLayout cl) {
   constexpr int NT = METHOD == RBX_METHOD_LINEAR ? 1 : 4;   // tables
   constexpr int RS = METHOD == RBX_METHOD_LINEAR ? 8 : 20;  // record stride (floats)
+#ifndef RBX_PAIR_MAXFOL
+#define RBX_PAIR_MAXFOL 1
+#endif
+  constexpr int MAXFOL = PAIR ? RBX_PAIR_MAXFOL : 2;        // cubic: followers of a run leader (registers: 8 each)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (ctrl[C_IMPL] != IMPL_WARP) return;   // segment_kernel selected the group kernel (knot window / Doppler range)
@@ -1263,7 +1267,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         int nfol = 0;   // followers of this particle
         if (NT > 1 && qi + 1 < nb && __float_as_int(s_rec[(qi + 1) * RS + 2]) == __float_as_int(r0.z)) {
           nfol = 1;
-          if (qi + 2 < nb && __float_as_int(s_rec[(qi + 2) * RS + 2]) == __float_as_int(r0.z)) nfol = 2;
+          if (MAXFOL >= 2 && qi + 2 < nb && __float_as_int(s_rec[(qi + 2) * RS + 2]) == __float_as_int(r0.z)) nfol = 2;
         }
         run_len = 1 + nfol;
         run_next = nfol ? 1 : 0;
@@ -1276,18 +1280,27 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           const float wv[4] = {w.x, w.y, w.z, w.w};
           float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f), w3 = w2;
           if (nfol >= 1) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
-          if (nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + 4 + 4 * t);
+          if (MAXFOL >= 2 && nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + 4 + 4 * t);
           const float wv2[4] = {w2.x, w2.y, w2.z, w2.w}, wv3[4] = {w3.x, w3.y, w3.z, w3.w};
           {
+            // cubic pairs (168 registers): the vectors are consumed in place and the next table's are requested after
+            // the FMAs (the other warps of the SM cover the latency; a second register set would spill)
+#ifndef RBX_CUBIC_INPLACE
+#define RBX_CUBIC_INPLACE 1
+#endif
+            constexpr bool INPLACE = NT > 1 && PAIR && RBX_CUBIC_INPLACE;
             float4 cur[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) cur[u] = nf[u];
-            if (t + 1 < NT) {
-              issue_rows(qi, t + 1);
-            } else {
-              const int nq = qi + 1 + nfol;
-              if (nq < nb) issue_rows(nq, 0);
-            }
+            auto issue_next = [&]() {
+              if (t + 1 < NT) {
+                issue_rows(qi, t + 1);
+              } else {
+                const int nq = qi + 1 + nfol;
+                if (nq < nb) issue_rows(nq, 0);
+              }
+            };
+            if (!INPLACE) issue_next();
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
@@ -1306,7 +1319,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
                 ffma2s(S2[6], S2[7], wv2[a], wv2[a], hi.z, hi.w);
               }
             }
-            if (NT > 1 && nfol >= 2) {
+            if (NT > 1 && MAXFOL >= 2 && nfol >= 2) {
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const float4 lo = cur[2 * a], hi = cur[2 * a + 1];
@@ -1316,6 +1329,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
                 ffma2s(S3[6], S3[7], wv3[a], wv3[a], hi.z, hi.w);
               }
             }
+            if (INPLACE) issue_next();
           }
         }
       }
@@ -2038,10 +2052,11 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   //   2  two warps per array, 6 arrays (12 warps, 168 registers)      <- default for ssp.method linear
   //   3  two warps per array, 7 arrays (14 warps, 128 registers: spills)
   //   4  two warps per array, 5 arrays (10 warps, 168 registers, more L1)
-  // cubic keeps one warp per array: its 16 template rows per particle need 245 registers, and with 168 the pair
-  // variant spills and gains nothing (10^6 particles: 1.2127 against 1.2145 ms).
+  // cubic: with the plain template rows (32-byte lane stride, 8-9 cache lines per warp-wide load) the kernel was bound
+  // by the L1 data pipe and pairs gained nothing (10^6 particles: 1.2127 against 1.2145 ms); with the window tables
+  // it is latency bound and the pair variant wins: 10^6 1.10 -> 0.95 ms, 10^7 8.74 -> 7.40 ms.
   int variant = (int)opt(OPT_FUSED_VARIANT);
-  if (variant < 1 || variant > 4) variant = v.method == RBX_METHOD_LINEAR ? 2 : 1;
+  if (variant < 1 || variant > 4) variant = 2;
   const bool pair = variant != 1;
   const int max_arrays = variant == 1 ? 8 : variant == 2 ? 6 : variant == 3 ? 7 : 5;
   const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, max_arrays);
