@@ -64,6 +64,9 @@ struct PlanView {
   int affine;                  // t[w] == fadd(fmul(w, tdelta), t0) for every channel (numpy/jnp arange grids)
   float t0, tdelta, tinv;      // affine grid parameters (tinv = 1 / tdelta)
   const float *zgrid, *agrid;  // SSP metallicity / age axes
+  const uint16_t *alut;        // (alut_n) start index for the age-axis search of a query in bucket b (plan.cu)
+  int alut_n;
+  float alut_scale;            // bucket = (age - agrid[0]) * alut_scale
   const float *tab[4];         // f, fx, fy, fxy: (nz*na, Lp) float32, rows 16-byte aligned
   const float *wt[4];          // window tables of the warp cube kernel (plan.cu: window_table_kernel) or nullptr:
                                // (nz*na, 256) float32, the knots wt_jbase .. wt_jbase + 255 of every row (clamped to
@@ -163,6 +166,15 @@ __device__ __forceinline__ int ss_right(const float *__restrict__ a, int n, floa
     if (!(a[mid] > v)) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// The same count, found by walking from a guess k (any value; a good one costs one or two compares): exact.
+__device__ __forceinline__ int ss_right_from(const float *__restrict__ a, int n, float v, int k) {
+  if (v != v) return n;
+  k = min(max(k, 0), n);
+  while (k < n && !(a[k] > v)) ++k;
+  while (k > 0 && a[k - 1] > v) --k;
+  return k;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

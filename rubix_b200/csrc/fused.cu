@@ -114,7 +114,7 @@ constexpr int kDminBias = 0x7f7fffff;   // ctrl[C_DMIN] holds kDminBias - bits(d
 // happen here, so the particle arrays are read once; `pixel` then is an optional output.
 // `vel` points at the Doppler component of particle 0 and advances by `vstride` floats per particle ((n, 3)
 // arrays: vstride 3; a packed line-of-sight velocity array: 1); likewise cx / cy / cstride for the coordinates.
-__global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstride, const float *__restrict__ mass,
+__global__ void __launch_bounds__(256, 4) prep_kernel(PlanView p, const float *__restrict__ vel, int vstride, const float *__restrict__ mass,
                             const float *__restrict__ met, const float *__restrict__ age,
                             int32_t *__restrict__ pixel, int n, int nseg, int cell_bits, int cell_shift,
                             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx, int *__restrict__ counts,
@@ -129,6 +129,8 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
   float *s_edges = s_axes + p.nz + p.na;
   // digit histograms of every radix pass of the sort that follows (sort.cu), gathered while the keys are made
   int *s_dig = reinterpret_cast<int *>(s_edges + ((coords && edges_smem) ? n_edges : 0));
+  uint16_t *s_alut = reinterpret_cast<uint16_t *>(s_dig + (sort_state ? sp.npass * 256 : 0));
+  for (int s = threadIdx.x; s < p.alut_n; s += blockDim.x) s_alut[s] = p.alut[s];
   if (sort_state)
     for (int s = threadIdx.x; s < sp.npass * 256; s += blockDim.x) s_dig[s] = 0;
   if (smem_hist)
@@ -149,6 +151,14 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
     elo = ehi = e[0];
     for (int s = 1; s < n_edges; ++s) { elo = fminf(elo, e[s]); ehi = fmaxf(ehi, e[s]); }
   }
+  // The searches (two on the spaxel edges, one on each SSP axis) were 40 % of this kernel's instructions and of its
+  // stalls as bisections.  They now start from a guess -- the uniform-grid index for the edges, a bucket table for the
+  // age axis -- and walk to the exact searchsorted(side='right') answer on the GIVEN float32 values.
+  const float e0 = coords ? e[0] : 0.f;
+  const float einv = (coords && e[nb] > e[0]) ? (float)nb / (e[nb] - e[0]) : 0.f;
+  const float zlo = p.zgrid[0], zhi = p.zgrid[p.nz - 1], alo = p.agrid[0], ahi = p.agrid[p.na - 1];
+  const float abmax = (float)(p.alut_n - 1);
+  auto guess_of = [](float t, float hi) { return (int)fminf(fmaxf(t, 0.f), hi); };   // NaN -> 0
   float dmin = 3.0e38f, dmax = 0.f;
   int nvalid = 0;
   // Latency bound (one particle's loads at a time leave the memory system idle): every thread first requests the
@@ -175,14 +185,22 @@ __global__ void prep_kernel(PlanView p, const float *__restrict__ vel, int vstri
       const int q = q0 + k * gstride;
       if (q >= n) break;
       const float zq = in_z[k], aq = in_a[k], mq = in_m[k];
-      int i, j;
-      bool inside;
-      ssp_cell(p, zq, aq, i, j, inside);
+      // ssp_cell() with guided searches
+      const bool inside = (zq >= zlo) && (zq <= zhi) && (aq >= alo) && (aq <= ahi);
+      int zc = 0;
+      if (p.nz <= 16) {
+        for (int s = 0; s < p.nz; ++s) zc += !(p.zgrid[s] > zq) ? 1 : 0;   // sorted axis: the count of nodes <= zq (NaN: all)
+      } else {
+        zc = ss_right(p.zgrid, p.nz, zq);
+      }
+      const int i = min(max(zc, 1), p.nz - 1);
+      const int ag = s_alut[guess_of((aq - alo) * p.alut_scale, abmax)];
+      const int j = min(max(ss_right_from(p.agrid, p.na, aq, ag), 1), p.na - 1);
       int px;
       if (coords) {
         const float x = in_x[k], y = in_y[k];
-        const int xi = min(max(ss_right(e, n_edges, x) - 1, 0), nb - 1);
-        const int yi = min(max(ss_right(e, n_edges, y) - 1, 0), nb - 1);
+        const int xi = min(max(ss_right_from(e, n_edges, x, guess_of((x - e0) * einv, (float)nb) + 1) - 1, 0), nb - 1);
+        const int yi = min(max(ss_right_from(e, n_edges, y, guess_of((y - e0) * einv, (float)nb) + 1) - 1, 0), nb - 1);
         px = xi + nb * yi;
         if (mark_outside && !((x >= elo) && (x <= ehi) && (y >= elo) && (y <= ehi))) px = -1;
         if (pixel) pixel[q] = px;
@@ -1594,7 +1612,15 @@ __global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const
     if (i1 - i0 < 2) continue;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
       float acc = accumulate ? cube_get(cube, cl, s, w) : 0.f;
-      for (int k = i0; k < i1; ++k) acc += partials[(size_t)k * Wp + w];
+      // eight rows requested at once, added in row order (the kernel was bound by one dependent load per row)
+      for (int k = i0; k < i1; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = k + u < i1 ? __ldg(partials + (size_t)(k + u) * Wp + w) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (k + u < i1) acc += v[u];
+      }
       cube_put(cube, cl, s, w, acc, false);
     }
   }
@@ -2001,7 +2027,7 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     const int smem_hist = nseg <= 4096 ? 1 : 0;
     const size_t dyn = (smem_hist ? sizeof(int) * (size_t)nseg : 0) +
                        sizeof(float) * (size_t)(v.nz + v.na + (edges_smem ? b.n_edges : 0)) +
-                       (own_sort ? sizeof(int) * 256 * (size_t)ws.sp.npass : 0);
+                       (own_sort ? sizeof(int) * 256 * (size_t)ws.sp.npass : 0) + sizeof(uint16_t) * (size_t)v.alut_n;
     int pcap = 148 * 4;   // measured (B200, 10^6 particles): 148 blocks 98 us, 296: 55, 592: 38, 1184: 44, 2368: 54 -- every
                           // block flushes its histogram with one atomic per non-empty spaxel
     // large inputs: the flush is amortised over many particles per block, so fill the SMs (8 blocks each) instead

@@ -40,7 +40,7 @@ size_t sort_state_words(const SortPlan &sp) {
   return (size_t)sp.npass * ((size_t)sp.ntiles + 2) * 256;
 }
 
-__global__ void __launch_bounds__(kSortThreads, 4)
+__global__ void __launch_bounds__(kSortThreads, 3)
 radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
                   uint32_t *__restrict__ vout, int n, int shift, int bits, uint32_t *__restrict__ pass_state) {
   // pass_state: [0, 256) global digit histogram (from prep_kernel), [256] ticket, [512 + 256 tile, +256) tile states
@@ -61,26 +61,44 @@ radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__
   const int tbase = tile * kSortTile + warp * (32 * kSortItems);
 
   // ---- rank my keys: inside the warp in index order (match-any groups), item by item --------------------------
+  // Three sweeps so that nothing waits on its predecessor: (1) the 16 key loads and match-any votes are independent;
+  // (2) the leader of every group bumps the warp's digit counter with ONE shared-memory atomic -- atomics of a warp on
+  // one address are applied in issue order, so item i + 1 sees item i's count without a __syncwarp, and the 16
+  // atomics are in flight together (the former load / add / store per item was a chain of 16 shared-memory round
+  // trips); (3) the counter values are broadcast from the leaders.
   uint32_t key[kSortItems];
   int rank[kSortItems];
+  unsigned grp[kSortItems];
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const int idx = tbase + i * 32 + lane;
-    const bool valid = idx < n;
-    key[i] = valid ? kin[idx] : 0u;
-    const uint32_t d = (key[i] >> shift) & dmask;
-    const unsigned m = __match_any_sync(0xffffffffu, valid ? d : 0x10000u + (uint32_t)lane);
-    const int leader = __ffs(m) - 1;
-    uint32_t c = 0;
-    if (lane == leader && valid) {
-      c = s_whist[warp][d];
-      s_whist[warp][d] = c + (uint32_t)__popc(m);
-    }
-    __syncwarp();
-    c = __shfl_sync(0xffffffffu, c, leader);
-    rank[i] = (int)c + __popc(m & lt);
+    key[i] = idx < n ? kin[idx] : 0u;
   }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const bool valid = tbase + i * 32 + lane < n;
+    const uint32_t d = (key[i] >> shift) & dmask;
+    grp[i] = __match_any_sync(0xffffffffu, valid ? d : 0x10000u + (uint32_t)lane);
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const bool valid = tbase + i * 32 + lane < n;
+    const uint32_t d = (key[i] >> shift) & dmask;
+    rank[i] = 0;
+    if (lane == __ffs(grp[i]) - 1 && valid) rank[i] = (int)atomicAdd(&s_whist[warp][d], (uint32_t)__popc(grp[i]));
+    __syncwarp();   // orders the atomics of different lanes on one counter (it does not wait for their results)
+  }
+  // the values travel with the keys: requested here, they arrive while the tile waits for its look-back
+  uint32_t val[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int idx = tbase + i * 32 + lane;
+    val[i] = (vin && idx < n) ? vin[idx] : (uint32_t)idx;
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i)
+    rank[i] = __shfl_sync(0xffffffffu, rank[i], __ffs(grp[i]) - 1) + __popc(grp[i] & lt);
   __syncthreads();
 
   // ---- per digit: exclusive prefix over the warps, tile total, look-back over the preceding tiles ----------------
@@ -152,7 +170,7 @@ radix_pass_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__
       const uint32_t d = (key[i] >> shift) & dmask;
       const uint32_t lp = s_loc[d] + s_whist[warp][d] + (uint32_t)rank[i];
       s_keys[lp] = key[i];
-      s_vals[lp] = vin ? vin[idx] : (uint32_t)idx;
+      s_vals[lp] = val[i];
     }
   }
   __syncthreads();

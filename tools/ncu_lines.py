@@ -51,7 +51,7 @@ def main():
     rep, sym = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     lm = line_map(sym)
-    kern = re.sub(r"ILi\d+.*", "", sym).replace("_ZN3rbx", "")
+    kern = re.sub(r"^\d+", "", re.sub(r"ILi\d+.*", "", sym).replace("_ZN3rbx", ""))
     res = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f"::regex:{kern}:1"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(res)))
