@@ -75,6 +75,7 @@ struct PlanView {
   int wt_jbase;                // first knot of the window (a multiple of 4, may be negative)
   const float *lamz;           // (L)  (1+z)*wavelength                       rubix/spectra/ifu.py:80
   const float *rdl;            // (L)  1/(lamz[j+1]-lamz[j]); 0 for the last knot or zero width
+  const float *ka, *kb;        // (L)  knot position in channel units u' = ka * (d - 1) + kb (affine grids; fused.cu: knot_ab)
   const float *t;              // (W)  telescope wave_seq
   const float *dt;             // (W)  diff0(t): [0, t1-t0, ...]                rubix/spectra/ifu.py:84-102
   const uint16_t *lut;         // (nb)  number of channels whose bucket is smaller than b

@@ -322,9 +322,8 @@ __device__ __forceinline__ KnotAB knot_ab(const PlanView &p, int j) {
   KnotAB k;
   if (j < 0) { k.a = 0.f; k.b = -1000.5f; return k; }                 // below every band
   if (j >= p.L) { k.a = 0.f; k.b = (float)p.W + 1000.f; return k; }   // above every band
-  const double lz = (double)p.lamz[j], t0 = (double)p.t0, dl = (double)p.tdelta;
-  k.a = (float)(lz / dl);
-  k.b = (float)((lz - t0) / dl - 0.5);
+  k.a = p.ka[j];   // (float)(lam_z / delta) and (float)((lam_z - t0) / delta - 1/2), evaluated in double by rbx_plan_create
+  k.b = p.kb[j];
   return k;
 }
 // KA = kMagic - 1 + (number of channels below the knot, clamped to [0, W])
@@ -338,17 +337,25 @@ __device__ __forceinline__ int knot_cell(float ka) { return __float_as_int(ka) -
 // Returns false when that does not hold (Doppler range too wide for this chunk size).  eps_lo / eps_hi bound
 // d - 1 of every particle (segment_kernel widens the observed range by a few ulps), and u' is monotone in eps, so
 // every particle's first cell lies in [kmin0, kmax0].
-__device__ __forceinline__ bool warp_lane_chunks(const PlanView &p, int jbase, int lane, float eps_lo, float eps_hi,
-                                                 int chs, int &cA) {
-  const int CH = 1 << chs;
+struct LaneCells { int kmin0, kmax0, knext; };   // extreme first cells of a lane over the Doppler range, first cell of the next lane
+__device__ __forceinline__ LaneCells warp_lane_cells(const PlanView &p, int jbase, int lane, float eps_lo, float eps_hi) {
   const int j0 = jbase + WK * lane, j1 = j0 + WK;
   const KnotAB k0 = knot_ab(p, j0), k1 = knot_ab(p, j1);
   const float kahi = kMagic + (float)(p.W - 1);
-  const int kmin0 = knot_cell(knot_ka(fmaf(k0.a, eps_lo, k0.b), kahi));
-  const int kmax0 = knot_cell(knot_ka(fmaf(k0.a, eps_hi, k0.b), kahi));
-  const int knext = lane == 31 ? kmax0 : knot_cell(knot_ka(fmaf(k1.a, eps_hi, k1.b), kahi));
-  cA = (kmin0 + CH - 1) >> chs;
-  return !((((kmax0 + CH - 1) >> chs) > cA + 1) || (knext - kmax0 + 2 >= CH));
+  LaneCells c;
+  c.kmin0 = knot_cell(knot_ka(fmaf(k0.a, eps_lo, k0.b), kahi));
+  c.kmax0 = knot_cell(knot_ka(fmaf(k0.a, eps_hi, k0.b), kahi));
+  c.knext = lane == 31 ? c.kmax0 : knot_cell(knot_ka(fmaf(k1.a, eps_hi, k1.b), kahi));
+  return c;
+}
+__device__ __forceinline__ bool lane_chunks_ok(const LaneCells &c, int chs, int &cA) {
+  const int CH = 1 << chs;
+  cA = (c.kmin0 + CH - 1) >> chs;
+  return !((((c.kmax0 + CH - 1) >> chs) > cA + 1) || (c.knext - c.kmax0 + 2 >= CH));
+}
+__device__ __forceinline__ bool warp_lane_chunks(const PlanView &p, int jbase, int lane, float eps_lo, float eps_hi,
+                                                 int chs, int &cA) {
+  return lane_chunks_ok(warp_lane_cells(p, jbase, lane, eps_lo, eps_hi), chs, cA);
 }
 
 // d - 1 of every particle lies in [eps_lo_of(dmin), eps_hi_of(dmax)]: d = fl(exp(x)) and eps = expm1f(x) differ
@@ -481,9 +488,10 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
     if (t < 32 && p.affine) {
       const int jbase = p.wt_jbase;   // the warp kernel's knot window is fixed per plan (window tables, plan.cu)
+      const LaneCells lc = warp_lane_cells(p, jbase, t, eps_lo_of(dmin), eps_hi_of(dmax));
       for (int chs = warp_chs; chs <= 10; ++chs) {
         int cA;
-        if (!warp_lane_chunks(p, jbase, t, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA)) s_bad_w[chs] = 1;
+        if (!lane_chunks_ok(lc, chs, cA)) s_bad_w[chs] = 1;
       }
     }
     // group kernel: a lane's first knot is some even slot of the window; checked for every knot (conservative)
@@ -1411,6 +1419,11 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       int ka[WK];
 #pragma unroll
       for (int r = 0; r < WK; ++r) ka[r] = cell_slot(KA[r], kc[r], lay.skew);
+#ifdef RBX_FAKE_BANKS
+      // timing experiment only (wrong results): what would conflict-free cell updates be worth?
+#pragma unroll
+      for (int r = 0; r < WK; ++r) ka[r] = (ka[r] & ~31) + lane;
+#endif
 #ifdef RBX_RACECHECK
       // Knots outside the band (k = 0 or k = W) of several lanes land in the two junk cells 0 and W, which are
       // never read back: a benign write-write overlap that compute-sanitizer racecheck reports.  This build

@@ -258,6 +258,19 @@ extern "C" int rbx_plan_create(rbx_plan **out, const float *h_met, int nz, const
       v.lut = (const uint16_t *)d_lut;
     }
   }
+  {  // knot positions in channel units of the affine grid, rounded once from double (fused.cu: knot_ab)
+    std::vector<float> ka(L, 0.f), kb(L, 0.f);
+    if (v.affine) {
+      const double t0 = (double)v.t0, dl = (double)v.tdelta;
+      for (int l = 0; l < L; ++l) {
+        const double lz = (double)pl->h_lamz[l];
+        ka[l] = (float)(lz / dl);
+        kb[l] = (float)((lz - t0) / dl - 0.5);
+      }
+    }
+    TRY(upload(pl, ka.data(), (size_t)L, &v.ka, stream));
+    TRY(upload(pl, kb.data(), (size_t)L, &v.kb, stream));
+  }
   // Window tables for the warp cube kernel (affine grids): the knot window is fixed per plan -- the knots that reach
   // the band at rest (+3 either side, as segment_kernel counts them) with the spare slots split 1 : 2 between the blue
   // and the red end (the red end moves twice as many knots per unit of Doppler shift).  segment_kernel checks that
