@@ -44,7 +44,7 @@ constexpr int kMaxKnots = KPL * OWN * kMaxGroupWarps - 3;  // widest knot window
 
 struct Item { int start, count, spaxel, slot; };
 
-enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_IMPL, C_CHS, C_GCHS, C_COUNT };
+enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_IMPL, C_CHS, C_GCHS, C_NSPLITSEG, C_COUNT };
 // ctrl[C_IMPL]: which cube kernel runs, decided on the device by segment_kernel from the knot window and the
 // Doppler range actually present (both kernels are launched; the one not selected returns at once)
 enum Impl { IMPL_WARP = 0, IMPL_GROUP = 1 };
@@ -90,6 +90,7 @@ struct FusedWs {
   int *counts;      // (nseg + 1)
   int *seg_start;   // (nseg + 1)
   int *item_start;  // (nseg + 1)
+  int *split_list;  // (nseg) spaxels cut into several items, in spaxel order (reduce_partials_kernel walks this list)
   int *ctrl;        // C_COUNT
   Item *items;      // (max_items)
   float *partials;  // (max_split, Wp)
@@ -415,6 +416,10 @@ struct Cut { int bulk, tail, nb, ns, psmall; };
 __device__ __forceinline__ Cut cut_spaxel(int c, int psub, int small_shift, int tail_shift) {
   Cut k;
   k.psmall = max(32, psub >> small_shift);
+  if (c <= psub) {   // one item, no integer divisions (most spaxels of a large cube)
+    k.tail = 0; k.bulk = c; k.nb = c > 0 ? 1 : 0; k.ns = 0;
+    return k;
+  }
   k.tail = 0;
   if (c > psub) k.tail = min(c, ((c >> tail_shift) + k.psmall - 1) / k.psmall * k.psmall);
   k.bulk = c - k.tail;
@@ -428,7 +433,8 @@ __global__ void __launch_bounds__(1024)
 segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, int max_items, int max_split,
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl,
-                               int warp_ok, int warp_chs, int group_chs, int lamz_smem) {
+                               int warp_ok, int warp_chs, int group_chs, int lamz_smem, int counts_smem,
+                               int *__restrict__ split_list) {
   // the knot-window searches and the chunk geometry below are chains of dependent reads of lam_z by single threads:
   // from shared memory they cost a few hundred cycles instead of ~10 us
   extern __shared__ float s_lamz[];
@@ -436,21 +442,29 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     for (int q = threadIdx.x; q < p.L; q += blockDim.x) s_lamz[q] = p.lamz[q];
     p.lamz = s_lamz;   // visible after the __syncthreads inside block_scan
   }
-  __shared__ int s_w[33 * 4];
+  // a thread owns a contiguous range of spaxels (22 of them at 150 x 150): the counts are fetched coalesced into
+  // shared memory first, and the segment offsets leave through the same array
+  int *s_cnt = reinterpret_cast<int *>(s_lamz + (lamz_smem ? p.L : 0));
+  if (counts_smem) {
+    for (int q = threadIdx.x; q < nseg; q += blockDim.x) s_cnt[q] = counts[q];
+    __syncthreads();
+  }
+  const int *cnt = counts_smem ? s_cnt : counts;
+  __shared__ int s_w[33 * 5];
   __shared__ int s_err, s_ja, s_jb;
   __shared__ int s_bad_w[16], s_bad_g[16];   // [chs]: the chunk geometry fails for 2^chs channels per chunk
   if (threadIdx.x < 16) { s_bad_w[threadIdx.x] = 0; s_bad_g[threadIdx.x] = 0; }
   const int T = blockDim.x, t = threadIdx.x;
   const int per = (nseg + T - 1) / T;
   const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
-  int v[4] = {0, 0, 0, 0}, tot[4];  // particles, bulk items, small items, split rows
+  int v[5] = {0, 0, 0, 0, 0}, tot[5];  // particles, bulk items, small items, split rows, split spaxels
   for (int s = lo; s < hi; ++s) {
-    const int c = counts[s];
+    const int c = cnt[s];
     const Cut k = cut_spaxel(c, psub, small_shift, tail_shift);
     const int ni = k.nb + k.ns;
-    v[0] += c; v[1] += k.nb; v[2] += k.ns; v[3] += ni > 1 ? ni : 0;
+    v[0] += c; v[1] += k.nb; v[2] += k.ns; v[3] += ni > 1 ? ni : 0; v[4] += ni > 1 ? 1 : 0;
   }
-  block_scan<4>(v, tot, s_w);   // v: exclusive prefixes; tot: totals
+  block_scan<5>(v, tot, s_w);   // v: exclusive prefixes; tot: totals
   if (t == 0) {
     int err = 0;
     if (tot[1] + tot[2] > max_items || tot[3] > max_split) err = 1;
@@ -474,26 +488,29 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     ctrl[C_ERROR] = err;
     ctrl[C_WORK] = 0;
     ctrl[C_NSPLIT] = tot[3];
+    ctrl[C_NSPLITSEG] = err ? 0 : tot[4];
     seg_start[nseg] = tot[0];
     item_start[nseg] = tot[3];
     s_err = err;
     s_ja = ja; s_jb = jb;
   }
-  __syncthreads();
   // Which cube kernel, and with which chunk size: the warp kernel when the host found the plan eligible (warp_ok),
   // the knot window fits its 256 slots and some chunk size <= 2^10 channels makes every lane's chunk geometry hold
   // for the Doppler range present; else the group kernel (chunks <= 2^8 channels).  Benign races: threads only
   // ever store 1 into the flags.
+  // The warp kernel's window is fixed per plan, so its check (warp 1) runs beside thread 0's knot-window search.
+  if (tot[0] > 0 && t >= 32 && t < 64 && p.affine) {
+    const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
+    const int jbase = p.wt_jbase;   // the warp kernel's knot window is fixed per plan (window tables, plan.cu)
+    const LaneCells lc = warp_lane_cells(p, jbase, t - 32, eps_lo_of(dmin), eps_hi_of(dmax));
+    for (int chs = warp_chs; chs <= 10; ++chs) {
+      int cA;
+      if (!lane_chunks_ok(lc, chs, cA)) s_bad_w[chs] = 1;
+    }
+  }
+  __syncthreads();
   if (tot[0] > 0) {
     const float dmin = __int_as_float(kDminBias - ctrl[C_DMIN]), dmax = __int_as_float(ctrl[C_DMAX]);
-    if (t < 32 && p.affine) {
-      const int jbase = p.wt_jbase;   // the warp kernel's knot window is fixed per plan (window tables, plan.cu)
-      const LaneCells lc = warp_lane_cells(p, jbase, t, eps_lo_of(dmin), eps_hi_of(dmax));
-      for (int chs = warp_chs; chs <= 10; ++chs) {
-        int cA;
-        if (!lane_chunks_ok(lc, chs, cA)) s_bad_w[chs] = 1;
-      }
-    }
     // group kernel: a lane's first knot is some even slot of the window; checked for every knot (conservative)
     const int jbg = (s_ja - 1) & ~1;
     for (int j = jbg + t; j <= s_jb; j += T) {
@@ -536,13 +553,14 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
   }
   __syncthreads();
   const bool err = s_err != 0;
-  int ra = v[0], rb = v[1], rs = tot[1] + v[2], rc = v[3];
+  int ra = v[0], rb = v[1], rs = tot[1] + v[2], rc = v[3], rl = v[4];
   for (int s = lo; s < hi; ++s) {
-    const int c = counts[s];
+    const int c = cnt[s];
     const Cut k = cut_spaxel(c, psub, small_shift, tail_shift);
     const int ni = k.nb + k.ns;
-    seg_start[s] = ra;
+    if (counts_smem) s_cnt[s] = ra; else seg_start[s] = ra;   // my own range: nobody else reads these counts
     item_start[s] = rc;
+    if (ni > 1 && !err) split_list[rl++] = s;
     if (!err) {
       for (int q = 0; q < k.nb; ++q) {   // bulk items: front of the queue
         Item it;
@@ -562,6 +580,10 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
       }
     }
     ra += c; rb += k.nb; rs += k.ns; rc += ni > 1 ? ni : 0;
+  }
+  if (counts_smem) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < nseg; q += blockDim.x) seg_start[q] = s_cnt[q];
   }
 }
 
@@ -1163,7 +1185,6 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   __syncthreads();
 
   // ---- per-lane knot constants -------------------------------------------------------------------
-  const int ja = ctrl[C_JA], jb = ctrl[C_JB];
   const int n_items = ctrl[C_NITEMS];
   const int jbase = p.wt_jbase;                  // slot s <-> knot jbase + s: the plan's window tables (plan.cu)
   const int j0 = jbase + WK * lane;
@@ -1611,18 +1632,21 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 // cube[s] = sum over the spaxel's partial rows, in sub-range order (deterministic two-level reduction).
 // A configuration the kernels cannot hold (knot window too large) poisons the cube with NaN here rather than
 // returning a silently wrong result.
-__global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const float *__restrict__ partials, int Wp, int W,
-                                       int nseg, const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate,
-                                       CubeLayout cl) {
-  const bool poison = ctrl[C_ERROR] != 0;
-  for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
-    if (poison) {
+__global__ void reduce_partials_kernel(const int *__restrict__ slot_start, const int *__restrict__ split_list,
+                                       const float *__restrict__ partials, int Wp, int W, int nseg,
+                                       const int *__restrict__ ctrl, float *__restrict__ cube, int accumulate, CubeLayout cl) {
+  if (ctrl[C_ERROR] != 0) {   // poison
+    for (int s = blockIdx.y; s < nseg; s += gridDim.y)
       for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x)
         cube_put(cube, cl, s, w, __int_as_float(0x7fc00000), false);
-      continue;
-    }
+    return;
+  }
+  // only the spaxels that were cut into several items have rows to add (segment_kernel lists them: at 150 x 150
+  // a few hundred of 22500)
+  const int nsplit = ctrl[C_NSPLITSEG];
+  for (int e = blockIdx.y; e < nsplit; e += gridDim.y) {
+    const int s = split_list[e];
     const int i0 = slot_start[s], i1 = slot_start[s + 1];
-    if (i1 - i0 < 2) continue;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < W; w += gridDim.x * blockDim.x) {
       float acc = accumulate ? cube_get(cube, cl, s, w) : 0.f;
       // eight rows requested at once, added in row order (the kernel was bound by one dependent load per row)
@@ -1697,6 +1721,7 @@ static int layout_workspace(const rbx_plan *plan, int64_t n, int nseg, void *bas
   ws.sort_state = (uint32_t *)((char *)ws.counts + cc_bytes);
   ws.seg_start = (int *)take(sizeof(int) * (nseg + 1));
   ws.item_start = (int *)take(sizeof(int) * (nseg + 1));
+  ws.split_list = (int *)take(sizeof(int) * (nseg + 1));
   ws.items = (Item *)take(sizeof(Item) * ws.max_items);
   ws.partials = (float *)take(sizeof(float) * (size_t)ws.max_split * ws.Wp);
   ws.cub_temp = take(ws.cub_bytes);
@@ -2100,9 +2125,13 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   const int max_arrays = variant == 1 ? 8 : variant == 2 ? 6 : variant == 3 ? 7 : 5;
   const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, max_arrays);
   const int lamz_smem = v.L <= 10000 ? 1 : 0;
-  segment_kernel<<<1, 1024, lamz_smem ? sizeof(float) * v.L : 0, stream>>>(
+  const int counts_smem = nseg > 1024 && nseg <= 40000 ? 1 : 0;   // one spaxel per thread needs no staging
+  const size_t seg_dyn = (lamz_smem ? sizeof(float) * v.L : 0) + (counts_smem ? sizeof(int) * (size_t)nseg : 0);
+  if (seg_dyn > 48 * 1024)
+    RBX_CUDA_OK(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_dyn));
+  segment_kernel<<<1, 1024, seg_dyn, stream>>>(
       v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts, ws.seg_start, ws.item_start,
-      ws.items, ws.ctrl, warp_ok ? 1 : 0, warp_ok ? wlay.chs : 7, lay.chs, lamz_smem);
+      ws.items, ws.ctrl, warp_ok ? 1 : 0, warp_ok ? wlay.chs : 7, lay.chs, lamz_smem, counts_smem, ws.split_list);
   count_launch();
   RBX_LAUNCH_OK();
   int dev = 0, nsm = 148;
@@ -2149,9 +2178,9 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   }
   if (prof) { cudaEventRecord(g_ev[1], stream); g_ev_pending = true; }
   // blocks loop over spaxels (most have nothing to add); large cubes hold few split spaxels: fewer, longer blocks
-  dim3 rgrid(nseg > 4096 ? 2 : (v.W + 255) / 256, std::min(nseg, 1184));
-  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.partials, ws.Wp, v.W, nseg, ws.ctrl, d_cube,
-                                                    b.accumulate, cl);
+  dim3 rgrid((v.W + 255) / 256, std::min(nseg, 592));
+  reduce_partials_kernel<<<rgrid, 256, 0, stream>>>(ws.item_start, ws.split_list, ws.partials, ws.Wp, v.W, nseg, ws.ctrl,
+                                                    d_cube, b.accumulate, cl);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;
