@@ -46,7 +46,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 enum Opt {
   OPT_PSUB = 0, OPT_SORT_BITS, OPT_FUSED_FORCE_LUT, OPT_FUSED_FORCE_CAS, OPT_FUSED_IMPL, OPT_FUSED_CHS,
   OPT_FUSED_NO_SKEW, OPT_FUSED_WARPS, OPT_PREP_BLOCKS, OPT_SMALL_SHIFT, OPT_TAIL_SHIFT, OPT_HOST_CHUNKS,
-  OPT_MARCH_NO_BULK, OPT_SORT_IMPL, OPT_FUSED_VARIANT, OPT_HOST_RATIO, OPT_COUNT
+  OPT_MARCH_NO_BULK, OPT_SORT_IMPL, OPT_FUSED_VARIANT, OPT_HOST_RATIO, OPT_FUSED_TR, OPT_COUNT
 };
 int64_t opt(Opt o);
 inline bool opt_on(Opt o) { return opt(o) > 0; }

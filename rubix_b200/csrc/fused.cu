@@ -47,7 +47,7 @@ struct Item { int start, count, spaxel, slot; };
 enum Ctrl { C_NITEMS = 0, C_JA, C_JB, C_ERROR, C_WORK, C_NVALID, C_DMIN, C_DMAX, C_NSPLIT, C_IMPL, C_CHS, C_GCHS, C_NSPLITSEG, C_COUNT };
 // ctrl[C_IMPL]: which cube kernel runs, decided on the device by segment_kernel from the knot window and the
 // Doppler range actually present (both kernels are launched; the one not selected returns at once)
-enum Impl { IMPL_WARP = 0, IMPL_GROUP = 1 };
+enum Impl { IMPL_WARP = 0, IMPL_GROUP = 1, IMPL_WARP_TR = 2 };   // TR: the warp kernel with the transposed cell layout
 // ctrl[C_CHS] / ctrl[C_GCHS]: log2(channels per chunk) of the warp / group kernel, the smallest value (not below the
 // host's choice from the grids) whose chunk geometry holds for the Doppler range present
 // ctrl[C_ERROR]: 0 ok, 1 work-item tables too small, 2 knot window wider than the group kernel holds,
@@ -318,6 +318,7 @@ constexpr int kWarpSlots = WK * 32;   // knot slots of one warp
 // channel value does not change), and the integer sits in the mantissa.
 constexpr float kMagic = 12582912.f;           // 1.5 * 2^23: ulp 1 on [2^23, 2^24)
 constexpr int kMagicM1Bits = 0x4B3FFFFF;       // bits of kMagic - 1
+constexpr int kMagicBits = 0x4B400000;         // bits of kMagic
 struct KnotAB { float a, b; };
 __device__ __forceinline__ KnotAB knot_ab(const PlanView &p, int j) {
   KnotAB k;
@@ -434,7 +435,7 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
                                const int *__restrict__ counts, int *__restrict__ seg_start,
                                int *__restrict__ item_start, Item *__restrict__ items, int *__restrict__ ctrl,
                                int warp_ok, int warp_chs, int group_chs, int lamz_smem, int counts_smem,
-                               int *__restrict__ split_list) {
+                               int *__restrict__ split_list, int tr_B) {
   // the knot-window searches and the chunk geometry below are chains of dependent reads of lam_z by single threads:
   // from shared memory they cost a few hundred cycles instead of ~10 us
   extern __shared__ float s_lamz[];
@@ -453,7 +454,9 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
   __shared__ int s_w[33 * 5];
   __shared__ int s_err, s_ja, s_jb;
   __shared__ int s_bad_w[16], s_bad_g[16];   // [chs]: the chunk geometry fails for 2^chs channels per chunk
+  __shared__ int s_bad_tr;                   // ... and for the transposed layout's blocks of tr_B channels
   if (threadIdx.x < 16) { s_bad_w[threadIdx.x] = 0; s_bad_g[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) s_bad_tr = 0;
   const int T = blockDim.x, t = threadIdx.x;
   const int per = (nseg + T - 1) / T;
   const int lo = min(t * per, nseg), hi = min(lo + per, nseg);
@@ -507,6 +510,10 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
       int cA;
       if (!lane_chunks_ok(lc, chs, cA)) s_bad_w[chs] = 1;
     }
+    if (tr_B > 0) {   // at most one block start inside a lane's span, and it is block cA or cA + 1 for every particle
+      const int cA = (lc.kmin0 + tr_B - 1) / tr_B;
+      if ((lc.kmax0 + tr_B - 1) / tr_B > cA + 1 || lc.knext - lc.kmax0 + 1 > tr_B) s_bad_tr = 1;
+    }
   }
   __syncthreads();
   if (tot[0] > 0) {
@@ -542,7 +549,7 @@ segment_kernel(PlanView p, int nseg, int psub, int small_shift, int tail_shift, 
     // slot 0 must lie below the band and the last slot beyond it for every Doppler factor present
     const int jbase = p.wt_jbase;
     const bool warp = warp_ok != 0 && wchs >= 0 && jbase <= s_ja - 1 && (s_jb - jbase + 1 <= kWarpSlots);
-    ctrl[C_IMPL] = warp ? IMPL_WARP : IMPL_GROUP;
+    ctrl[C_IMPL] = warp ? ((tr_B > 0 && !s_bad_tr) ? IMPL_WARP_TR : IMPL_WARP) : IMPL_GROUP;
     ctrl[C_CHS] = max(wchs, warp_chs);
     ctrl[C_GCHS] = max(gchs, group_chs);
     if (!warp && gchs < 0 && s_err == 0) {   // the Doppler range present is too wide for either kernel
@@ -1125,6 +1132,11 @@ struct WarpLayout {
   int off_item;      // [arrays] work item handed from a pair's first warp to its second
   float skew;        // cell slot = k + floor(max(k - 1, 0) * skew): makes the lane stride an odd number of cells
   int ncells;        // cells per warp (W + 2 + skew of the last one)
+  // transposed layout (fused_cube_warp_kernel<.., TR = true>): cells in blocks of tr_B, stored [row][32 columns], so a
+  // cell's bank is its BLOCK and the 16 lanes of a half-warp (one lane stride <= tr_B cells apart) never share one
+  int tr_B, tr_ncols;   // cells per block (= channels per chunk), blocks in use (<= 26)
+  float tr_invB;        // (1 / tr_B) (1 + 2^-20)
+  int w_stage;          // offset of the expansion's staging tile [32][8] floats inside a warp block
 };
 
 // Shared-memory slot of cell k (bank skew): k + floor(max(k - 1, 0) * alpha), computed in the float domain where
@@ -1147,7 +1159,7 @@ __device__ __forceinline__ int cell_slot_of(int k, float alpha) {   // the same 
 __device__ __forceinline__ void turn_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void turn_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int METHOD, bool PAIR, int MAXT>
+template <int METHOD, bool PAIR, int MAXT, bool TR = false>
 __global__ void __launch_bounds__(MAXT, 1)
 fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t *__restrict__ sidx,
                        const Item *__restrict__ items, int *__restrict__ ctrl,
@@ -1161,9 +1173,12 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   constexpr int MAXFOL = PAIR ? RBX_PAIR_MAXFOL : 2;        // cubic: followers of a run leader (registers: 8 each)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (ctrl[C_IMPL] != IMPL_WARP) return;   // segment_kernel selected the group kernel (knot window / Doppler range)
+  static_assert(!TR || (PAIR && METHOD == RBX_METHOD_LINEAR), "the transposed layout is built for the linear pair kernel");
+  if (ctrl[C_IMPL] != (TR ? IMPL_WARP_TR : IMPL_WARP)) return;   // segment_kernel selected another kernel
   const int chs = ctrl[C_CHS];                   // >= chs: chosen by segment_kernel for the Doppler range present
-  const int nch = (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
+  const int nch = TR ? lay.tr_ncols : (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
+  const int TB = lay.tr_B;                       // TR: cells per block = channels per chunk
+  constexpr int RSS = TR ? 64 : RS;              // floats between parked records (TR: one per cell row, in the unused columns)
   const int arr = PAIR ? warp >> 1 : warp;       // my cell array
   const int half = PAIR ? warp & 1 : 0;          // which warp of the pair
   constexpr int PSTR = PAIR ? 2 : 1;             // particle stride inside an item
@@ -1172,13 +1187,16 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   volatile int *s_item = reinterpret_cast<volatile int *>(smem + lay.off_item) + arr;
   float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride);
   float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_base);
-  float *s_rec = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_rec +
-                                           (size_t)half * lay.rec_bytes);   // [32][RS]
-  const int CH = 1 << chs;
+  // TR: the cell array is [tr_B rows][32 columns] of which <= 26 columns hold blocks; a warp's 32 parked records
+  // (32 bytes each) sit in columns 26..29 of rows 32 * half .. 32 * half + 31, column 31 of the last row is the junk cell
+  float *s_rec = TR ? reinterpret_cast<float *>(cells + 32 * 32 * half + 26)
+                    : reinterpret_cast<float *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_rec +
+                                                (size_t)half * lay.rec_bytes);   // [32][RS]
+  const int CH = TR ? TB : 1 << chs;
 
   // u' of every chunk's first channel, from the actual float32 channel wavelength
   for (int c = tid; c < nch; c += blockDim.x)
-    s_tc[c] = (float)(((double)p.t[min(c << chs, p.W - 1)] - (double)p.t0) / (double)p.tdelta - 0.5);
+    s_tc[c] = (float)(((double)p.t[min(TR ? c * TB : c << chs, p.W - 1)] - (double)p.t0) / (double)p.tdelta - 0.5);
   for (int q = lane + 32 * half; q < lay.ncells; q += 32 * PSTR) cells[q] = make_float2(0.f, 0.f);
   for (int q = lane + 32 * half; q < nch; q += 32 * PSTR) base[q] = make_float2(0.f, 0.f);
   if (PAIR && half == 0 && lane == 0) *s_item = atomicAdd(ctrl + C_WORK, 1);   // the pair's first work item
@@ -1208,7 +1226,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   // chunk lines are summed in registers: a lane's span [k_0, k_8) holds at most one chunk start, and over
   // the Doppler range present that start is chunk cA or cA + 1
   int cA = 0;
-  warp_lane_chunks(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA);   // segment_kernel checked that this holds
+  if (TR) cA = (warp_lane_cells(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax)).kmin0 + TB - 1) / TB;
+  else warp_lane_chunks(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA);   // segment_kernel checked that this holds
+  // TR: slot of cell k = 32 k - blk (32 B - 1), blk = floor(k / B) from one rounded FMA
+  const float trHalf = -(kMagic - 1.f) - 0.5f * (float)TB;   // KA + trHalf = k - B / 2 (exact)
   float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
   const float *tab[NT];
@@ -1262,14 +1283,14 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       const int nb = min(32, cnt - b0);
       __syncwarp();
       if (lane < nb) {
-        float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RS);
+        float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RSS);
 #pragma unroll
         for (int u = 0; u < RS / 4; ++u) dst[u] = nrec[u];
       }
       __syncwarp();
       if (b0 + 32 < cnt) fetch_rec(it, b0 + 32);
       auto issue_rows = [&](int i, int t) {   // rows of particle i (in this batch), table t
-        const int rw = __float_as_int(s_rec[i * RS + 2]);
+        const int rw = __float_as_int(s_rec[i * RSS + 2]);
         // linear: particles are sorted by (spaxel, template cell), so runs of particles share their four rows;
         // the vectors already in registers are kept (at 10^7 particles ~90 % of the row loads go away)
         if (NT == 1 && rw == nf_row) return;
@@ -1292,7 +1313,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 #pragma unroll
       for (int r = 0; r < WK; ++r) { S2[r] = 0.f; S3[r] = 0.f; }
     for (int qi = 0; qi < nb; ++qi) {
-      const float *rb = s_rec + qi * RS;
+      const float *rb = s_rec + qi * RSS;
       const float4 r0 = *reinterpret_cast<const float4 *>(rb);   // d, 1/d, row, d - 1
       const float d = r0.x, rd = r0.y, eps = r0.w;
 
@@ -1312,13 +1333,13 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         for (int r = 0; r < WK; ++r) S[r] = S3[r];
       } else {
         int nfol = 0;   // followers of this particle
-        if (NT > 1 && qi + 1 < nb && __float_as_int(s_rec[(qi + 1) * RS + 2]) == __float_as_int(r0.z)) {
+        if (NT > 1 && qi + 1 < nb && __float_as_int(s_rec[(qi + 1) * RSS + 2]) == __float_as_int(r0.z)) {
           nfol = 1;
-          if (MAXFOL >= 2 && qi + 2 < nb && __float_as_int(s_rec[(qi + 2) * RS + 2]) == __float_as_int(r0.z)) nfol = 2;
+          if (MAXFOL >= 2 && qi + 2 < nb && __float_as_int(s_rec[(qi + 2) * RSS + 2]) == __float_as_int(r0.z)) nfol = 2;
         }
         run_len = 1 + nfol;
         run_next = nfol ? 1 : 0;
-        const float *rb2 = rb + RS, *rb3 = rb + 2 * RS;
+        const float *rb2 = rb + RSS, *rb3 = rb + 2 * RSS;
 #pragma unroll
         for (int r = 0; r < WK; ++r) { S[r] = 0.f; S2[r] = 0.f; S3[r] = 0.f; }
 #pragma unroll
@@ -1438,8 +1459,21 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       float2 cv[WK];
       float dmv[WK];
       int ka[WK];
+      if (TR) {
+        // slot = 32 (k mod B) + floor(k / B): the bank is the block.  floor(k / B) = RN((k - B / 2) / B) (the factor
+        // 1 + 2^-20 in tr_invB breaks the ties upwards); k = 0 (a knot below the band) gives block -1 = the junk slot
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ka[r] = cell_slot(KA[r], kc[r], lay.skew);
+        for (int r = 0; r < WK; r += 2) {
+          float h0, h1, b0, b1;
+          fadd2s(h0, h1, KA[r], KA[r + 1], trHalf, trHalf);
+          ffma2o(b0, b1, h0, h1, lay.tr_invB, lay.tr_invB, kMagic, kMagic);
+          ka[r] = 32 * (__float_as_int(KA[r]) - kMagicM1Bits) - (__float_as_int(b0) - kMagicBits) * (32 * TB - 1);
+          ka[r + 1] = 32 * (__float_as_int(KA[r + 1]) - kMagicM1Bits) - (__float_as_int(b1) - kMagicBits) * (32 * TB - 1);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < WK; ++r) ka[r] = cell_slot(KA[r], kc[r], lay.skew);
+      }
 #ifdef RBX_FAKE_BANKS
       // timing experiment only (wrong results): what would conflict-free cell updates be worth?
 #pragma unroll
@@ -1451,7 +1485,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       // gives every lane its own junk cell so that racecheck can show there is no other hazard.
 #pragma unroll
       for (int r = 0; r < WK; ++r)
-        if (KA[r] < kMagic || KA[r] >= kahi) ka[r] = lay.ncells + lane;
+        if (!TR && (KA[r] < kMagic || KA[r] >= kahi)) ka[r] = lay.ncells + lane;
 #endif
       if (!PAIR) {
 #pragma unroll
@@ -1463,10 +1497,20 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       float bv, mr;
       int sel;
       {
-        const int c = (knot_cell(KA[0]) + CH - 1) >> chs;
-        const int chan = c << chs;
-        const float chanKA = (float)chan + (kMagic - 1.f);
-        const bool has = chanKA < KA[WK] && chan < p.W;
+        int c;
+        float chanKA;
+        bool has;
+        if (TR) {   // c = ceil(k_0 / B) = RN((k_0 + B - 1 - B / 2) / B), in the float domain like the cell index
+          const float cf = fmaf(KA[0] + (trHalf + (float)(TB - 1)), lay.tr_invB, kMagic);
+          c = __float_as_int(cf) - kMagicBits;
+          chanKA = fmaf(cf - kMagic, (float)TB, kMagic - 1.f);
+          has = chanKA < KA[WK] && chanKA < (kMagic - 1.f) + (float)p.W;
+        } else {
+          c = (knot_cell(KA[0]) + CH - 1) >> chs;
+          const int chan = c << chs;
+          chanKA = (float)chan + (kMagic - 1.f);
+          has = chanKA < KA[WK] && chan < p.W;
+        }
         float Sr = S[0], ur = u[0];
         mr = mu[0];
 #pragma unroll
@@ -1561,6 +1605,55 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
     // so the two warp scans of a 32-channel group do not depend on the carries: four groups are scanned
     // at once (four independent shuffle chains) and the carries are applied afterwards.
     float *prow = partials + (size_t)max(it.slot, 0) * Wp;
+    if (TR) {
+      // Transposed layout: lane b walks block b = chunk b (channels b B .. b B + B - 1) row by row -- at every step the
+      // 32 lanes read 32 different banks -- starting from the chunk's line, so there are no carries between lanes and
+      // no scans: slope_k = slope_{k-1} + B_k, value_k = value_{k-1} + slope_k dt_k + A_k.  Eight rows at a time go
+      // through a staging tile so that the stores are runs of eight consecutive channels.  The pair's first warp does
+      // this alone (the second one has nothing to wait for but its next turn).
+      if (half == 0) {
+        float *stage = reinterpret_cast<float *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_stage);
+        const int blk = lane;
+        const bool active = blk < nch;
+        float v = 0.f, sl = 0.f;
+        if (active) { const float2 bs = base[blk]; v = bs.x; sl = bs.y; base[blk] = make_float2(0.f, 0.f); }
+        const int ch0 = blk * TB;
+        float tprev = 0.f;
+        for (int i0 = 0; i0 < TB; i0 += 8) {
+          float out[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int row = i0 + r, ch = ch0 + row;
+            float2 cv = make_float2(0.f, 0.f);
+            if (active) { cv = cells[32 * row + blk]; cells[32 * row + blk] = make_float2(0.f, 0.f); }
+            // t_w = fl(fl(w delta) + t0): what rbx_plan_create verified for this grid (PlanView::affine)
+            const float tk = __fadd_rn(__fmul_rn((float)ch, p.tdelta), p.t0);
+            const bool use = row > 0 && ch < p.W;   // the chunk's first channel takes the line itself
+            const float dtc = use ? __fmul_rn(__fsub_rn(tk, tprev), p.tinv) : 0.f;
+            const float A = use ? fmaf(-0.5f, cv.y, cv.x) : 0.f;   // kinks: offset in channels, slope per channel
+            sl += use ? cv.y : 0.f;
+            v = fmaf(sl, dtc, v + A);
+            tprev = tk;
+            out[r] = v;
+          }
+          __syncwarp();
+          float4 *st = reinterpret_cast<float4 *>(stage + lane * 8);
+          st[0] = make_float4(out[0], out[1], out[2], out[3]);
+          st[1] = make_float4(out[4], out[5], out[6], out[7]);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int run = q * 4 + (lane >> 3), e = lane & 7;
+            const int ch = run * TB + i0 + e;
+            const float val = stage[run * 8 + e];
+            if (run < nch && ch < p.W) {
+              if (it.slot < 0) cube_put(cube, cl, it.spaxel, ch, val, accumulate != 0);
+              else prow[ch] = val;
+            }
+          }
+        }
+      }
+    } else
     for (int c = half; c < nch; c += PSTR) {   // PAIR: the two warps expand alternate chunks
       const float2 bs = base[c];
       float vcar = bs.x, scar = bs.y;
@@ -1909,6 +2002,45 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
   return true;
 }
 
+// The transposed-cell variant of the linear pair kernel: blocks of B cells, B the first multiple
+// of 8 that holds a lane's span of 8 knots (+ 0.4 % Doppler stretch + 2), stored [B rows][32 columns]; at most 26
+// columns hold blocks (columns 26..29 of rows 0..63 park the two warps' records, column 31 of the last row is the junk
+// cell).  segment_kernel verifies the geometry for the Doppler range present and falls back to the linear layout.
+static bool warp_layout_tr(const rbx_plan *plan, const WarpLayout &base, WarpLayout &lay, size_t &smem_bytes, int max_arrays) {
+  const PlanView &v = plan->v;
+  if (v.method != RBX_METHOD_LINEAR || opt(OPT_FUSED_TR) == 0) return false;
+  const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
+  double max8 = 0.0;
+  for (int l = 0; l < v.L; ++l) {
+    const double x = plan->h_lamz[l];
+    if (x < lo || x > hi) continue;
+    max8 = std::fmax(max8, (double)plan->h_lamz[std::min(l + WK, v.L - 1)] - x);
+  }
+  const int B = ((int)std::ceil(max8 * 1.004 / (double)plan->min_dt) + 2 + 7) & ~7;
+  const int ncols = (v.W + 2 + B - 1) / B;
+  if (B < 64 || ncols > 26 || 32 * B > (1 << 15)) return false;
+  auto a128 = [](int x) { return (x + 127) & ~127; };
+  lay = base;
+  lay.tr_B = B;
+  lay.tr_ncols = ncols;
+  lay.tr_invB = (float)((1.0 / (double)B) * (1.0 + 1.0 / 1048576.0));
+  lay.nch = ncols;
+  lay.ncells = 32 * B;
+  lay.off_item = a128(4 * 32);
+  lay.off_warp = lay.off_item + a128(4 * 8);
+  lay.w_base = a128(8 * lay.ncells);
+  lay.w_stage = lay.w_base + a128(8 * ncols);
+  lay.w_rec = lay.w_stage;   // unused: the records are parked inside the cell array
+  lay.rec_bytes = 0;
+  lay.warp_stride = lay.w_stage + 1024;
+  int na = std::min(std::min(7, max_arrays), (227 * 1024 - lay.off_warp) / lay.warp_stride);
+  if (opt(OPT_FUSED_WARPS) > 0) na = std::min(na, (int)opt(OPT_FUSED_WARPS));
+  if (na < max_arrays) return false;   // fewer arrays than the linear layout holds: not worth it
+  lay.nwarps = na * 2;
+  smem_bytes = (size_t)lay.off_warp + (size_t)na * lay.warp_stride;
+  return true;
+}
+
 static int check_fused_config(const rbx_plan *plan, int num_spaxels) {
   FusedLayout lay;
   size_t smem = 0;
@@ -2015,7 +2147,7 @@ extern "C" int rbx_build_cube_status(const rbx_plan *plan, int64_t n, int num_sp
   RBX_CUDA_OK(cudaMemcpyAsync(h, ws.ctrl, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
   RBX_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
   if (h_error) *h_error = h[C_ERROR];
-  if (h_impl) *h_impl = h[C_IMPL];
+  if (h_impl) *h_impl = h[C_IMPL] == IMPL_WARP_TR ? IMPL_WARP : h[C_IMPL];   // both are the warp kernel
   return RBX_OK;
 }
 
@@ -2124,6 +2256,9 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   const bool pair = variant != 1;
   const int max_arrays = variant == 1 ? 8 : variant == 2 ? 6 : variant == 3 ? 7 : 5;
   const bool warp_ok = warp_layout(plan, wlay, wsmem, pair, max_arrays);
+  WarpLayout tlay;
+  size_t tsmem = 0;
+  const bool tr_ok = warp_ok && variant == 2 && warp_layout_tr(plan, wlay, tlay, tsmem, max_arrays);
   const int lamz_smem = v.L <= 10000 ? 1 : 0;
   const int counts_smem = nseg > 1024 && nseg <= 40000 ? 1 : 0;   // one spaxel per thread needs no staging
   const size_t seg_dyn = (lamz_smem ? sizeof(float) * v.L : 0) + (counts_smem ? sizeof(int) * (size_t)nseg : 0);
@@ -2131,7 +2266,8 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
     RBX_CUDA_OK(cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_dyn));
   segment_kernel<<<1, 1024, seg_dyn, stream>>>(
       v, nseg, ws.psub, small_shift, tail_shift, ws.max_items, ws.max_split, ws.counts, ws.seg_start, ws.item_start,
-      ws.items, ws.ctrl, warp_ok ? 1 : 0, warp_ok ? wlay.chs : 7, lay.chs, lamz_smem, counts_smem, ws.split_list);
+      ws.items, ws.ctrl, warp_ok ? 1 : 0, warp_ok ? wlay.chs : 7, lay.chs, lamz_smem, counts_smem, ws.split_list,
+      tr_ok ? tlay.tr_B : 0);
   count_launch();
   RBX_LAUNCH_OK();
   int dev = 0, nsm = 148;
@@ -2139,6 +2275,14 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const bool prof = g_profile.load() != 0;
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
+  if (tr_ok) {   // the transposed-cell variant; returns at once unless segment_kernel selected it
+    auto kernel = fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384, true>;
+    RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    kernel<<<nsm, tlay.nwarps * 32, tsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp,
+                                                     tlay, b.accumulate, cl);
+    count_launch();
+    RBX_LAUNCH_OK();
+  }
   if (warp_ok) {
     auto wlaunch = [&](auto kernel) -> int {
       RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));

@@ -12,7 +12,7 @@ namespace rbx {
 static const char *const kOptNames[OPT_COUNT] = {
     "psub", "sort_bits", "fused_force_lut", "fused_force_cas", "fused_impl", "fused_chs", "fused_no_skew",
     "fused_warps", "prep_blocks", "small_shift", "tail_shift", "host_chunks", "march_no_bulk", "sort_impl",
-    "fused_variant", "host_ratio"};
+    "fused_variant", "host_ratio", "fused_tr"};
 
 static std::atomic<int64_t> g_opts[OPT_COUNT];
 
