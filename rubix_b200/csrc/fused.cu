@@ -1230,6 +1230,23 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   else warp_lane_chunks(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax), chs, cA);   // segment_kernel checked that this holds
   // TR: slot of cell k = 32 k - blk (32 B - 1), blk = floor(k / B) from one rounded FMA
   const float trHalf = -(kMagic - 1.f) - 0.5f * (float)TB;   // KA + trHalf = k - B / 2 (exact)
+  // shared-memory byte address of cell k: 256 k - blk (256 B - 8) + cells = 256 bits(KA) - (256 B - 8) bits(blkf) + trC
+  const unsigned trM = 256u * (unsigned)TB - 8u;
+  const unsigned trC = smem_u32(cells) - 256u * (unsigned)kMagicM1Bits + trM * (unsigned)kMagicBits;
+  // Lanes whose knots lie above the band for every particle would all hit cell W, which shares its bank with the
+  // last block's real cells (a 2-way conflict in every instruction): they get junk slots of their own in the unused
+  // columns 26.. of the last row.  (Lanes below the band share the junk slot of block -1: column 31, a free bank.)
+  unsigned trAnd = 0xffffffffu, trOr = 0u;
+  if (TR) {
+    const LaneCells lc0 = warp_lane_cells(p, jbase, lane, eps_lo_of(dmin), eps_hi_of(dmax));
+    const bool dead_hi = lc0.kmin0 >= p.W;
+    const unsigned dm = __ballot_sync(0xffffffffu, dead_hi);
+    if (dead_hi) {
+      const int idx = min(lane - (__ffs(dm) - 1), 4);
+      trAnd = 0u;
+      trOr = smem_u32(cells) + 8u * (unsigned)(32 * (TB - 1) + 26 + idx);
+    }
+  }
   float accAv = 0.f, accAm = 0.f, accBv = 0.f, accBm = 0.f;
 
   const float *tab[NT];
@@ -1467,8 +1484,8 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
           float h0, h1, b0, b1;
           fadd2s(h0, h1, KA[r], KA[r + 1], trHalf, trHalf);
           ffma2o(b0, b1, h0, h1, lay.tr_invB, lay.tr_invB, kMagic, kMagic);
-          ka[r] = 32 * (__float_as_int(KA[r]) - kMagicM1Bits) - (__float_as_int(b0) - kMagicBits) * (32 * TB - 1);
-          ka[r + 1] = 32 * (__float_as_int(KA[r + 1]) - kMagicM1Bits) - (__float_as_int(b1) - kMagicBits) * (32 * TB - 1);
+          ka[r] = (int)(((256u * (unsigned)__float_as_int(KA[r]) - trM * (unsigned)__float_as_int(b0) + trC) & trAnd) | trOr);
+          ka[r + 1] = (int)(((256u * (unsigned)__float_as_int(KA[r + 1]) - trM * (unsigned)__float_as_int(b1) + trC) & trAnd) | trOr);
         }
       } else {
 #pragma unroll
@@ -1477,7 +1494,7 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
 #ifdef RBX_FAKE_BANKS
       // timing experiment only (wrong results): what would conflict-free cell updates be worth?
 #pragma unroll
-      for (int r = 0; r < WK; ++r) ka[r] = (ka[r] & ~31) + lane;
+      for (int r = 0; r < WK; ++r) if (!TR) ka[r] = (ka[r] & ~31) + lane;
 #endif
 #ifdef RBX_RACECHECK
       // Knots outside the band (k = 0 or k = W) of several lanes land in the two junk cells 0 and W, which are
@@ -1548,13 +1565,25 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       for (int r = 0; r < WK; r += 2) fmul2s(ag[r], ag[r + 1], dmv[r], dmv[r + 1], g[r], g[r + 1]);
       if (PAIR) {
         turn_wait(t_mine);   // the cells are mine until turn_pass
+        if (TR) {   // ka holds shared-memory byte addresses
 #pragma unroll
-        for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+          for (int r = 0; r < WK; ++r)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cv[r].x), "=f"(cv[r].y) : "r"(ka[r]) : "memory");
+        } else {
+#pragma unroll
+          for (int r = 0; r < WK; ++r) cv[r] = cells[ka[r]];
+        }
       }
 #pragma unroll
       for (int r = 0; r < WK; ++r) ffma2s(cv[r].x, cv[r].y, sc, sc, ag[r], dmv[r]);
+      if (TR) {
 #pragma unroll
-      for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
+        for (int r = 0; r < WK; ++r)
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(ka[r]), "f"(cv[r].x), "f"(cv[r].y) : "memory");
+      } else {
+#pragma unroll
+        for (int r = 0; r < WK; ++r) cells[ka[r]] = cv[r];
+      }
       if (PAIR) turn_pass(t_other); else __syncwarp();
     }  // particles
     }  // record batches
