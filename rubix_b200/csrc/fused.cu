@@ -1173,12 +1173,15 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   constexpr int MAXFOL = PAIR ? RBX_PAIR_MAXFOL : 2;        // cubic: followers of a run leader (registers: 8 each)
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  static_assert(!TR || (PAIR && METHOD == RBX_METHOD_LINEAR), "the transposed layout is built for the linear pair kernel");
+  static_assert(!TR || PAIR, "the transposed layout is built for the pair kernel");
   if (ctrl[C_IMPL] != (TR ? IMPL_WARP_TR : IMPL_WARP)) return;   // segment_kernel selected another kernel
   const int chs = ctrl[C_CHS];                   // >= chs: chosen by segment_kernel for the Doppler range present
   const int nch = TR ? lay.tr_ncols : (p.W + 1 + (1 << chs) - 1) >> chs;   // <= nch (the shared-memory layout)
   const int TB = lay.tr_B;                       // TR: cells per block = channels per chunk
-  constexpr int RSS = TR ? 64 : RS;              // floats between parked records (TR: one per cell row, in the unused columns)
+  // floats between parked records.  TR: a record sits in the unused columns 26.. of one cell row (linear: 32 bytes) or
+  // of two rows (cubic: 48 + 32 bytes); voff(u) = float offset of its u-th 16-byte vector
+  constexpr int RSS = TR ? (NT > 1 ? 128 : 64) : RS;
+  auto voff = [](int u) { return (TR && u >= 3) ? 64 + 4 * (u - 3) : 4 * u; };
   const int arr = PAIR ? warp >> 1 : warp;       // my cell array
   const int half = PAIR ? warp & 1 : 0;          // which warp of the pair
   constexpr int PSTR = PAIR ? 2 : 1;             // particle stride inside an item
@@ -1187,9 +1190,10 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
   volatile int *s_item = reinterpret_cast<volatile int *>(smem + lay.off_item) + arr;
   float2 *cells = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride);
   float2 *base = reinterpret_cast<float2 *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_base);
-  // TR: the cell array is [tr_B rows][32 columns] of which <= 26 columns hold blocks; a warp's 32 parked records
-  // (32 bytes each) sit in columns 26..29 of rows 32 * half .. 32 * half + 31, column 31 of the last row is the junk cell
-  float *s_rec = TR ? reinterpret_cast<float *>(cells + 32 * 32 * half + 26)
+  // TR: the cell array is [tr_B rows][32 columns] of which <= 26 columns hold blocks; a warp's 32 parked records sit in
+  // the columns 26.. of rows 32 * half .. (linear; cubic: two rows each, rows 64 * half ..); the last row's columns
+  // 26..31 are junk cells
+  float *s_rec = TR ? reinterpret_cast<float *>(cells + 32 * (32 * (RSS / 64)) * half + 26)
                     : reinterpret_cast<float *>(smem + lay.off_warp + (size_t)arr * lay.warp_stride + lay.w_rec +
                                                 (size_t)half * lay.rec_bytes);   // [32][RS]
   const int CH = TR ? TB : 1 << chs;
@@ -1300,9 +1304,8 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
       const int nb = min(32, cnt - b0);
       __syncwarp();
       if (lane < nb) {
-        float4 *dst = reinterpret_cast<float4 *>(s_rec + lane * RSS);
 #pragma unroll
-        for (int u = 0; u < RS / 4; ++u) dst[u] = nrec[u];
+        for (int u = 0; u < RS / 4; ++u) *reinterpret_cast<float4 *>(s_rec + lane * RSS + voff(u)) = nrec[u];
       }
       __syncwarp();
       if (b0 + 32 < cnt) fetch_rec(it, b0 + 32);
@@ -1361,11 +1364,11 @@ fused_cube_warp_kernel(PlanView p, const float *__restrict__ rec, const uint32_t
         for (int r = 0; r < WK; ++r) { S[r] = 0.f; S2[r] = 0.f; S3[r] = 0.f; }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const float4 w = *reinterpret_cast<const float4 *>(rb + 4 + 4 * t);
+          const float4 w = *reinterpret_cast<const float4 *>(rb + voff(1 + t));
           const float wv[4] = {w.x, w.y, w.z, w.w};
           float4 w2 = make_float4(0.f, 0.f, 0.f, 0.f), w3 = w2;
-          if (nfol >= 1) w2 = *reinterpret_cast<const float4 *>(rb2 + 4 + 4 * t);
-          if (MAXFOL >= 2 && nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + 4 + 4 * t);
+          if (nfol >= 1) w2 = *reinterpret_cast<const float4 *>(rb2 + voff(1 + t));
+          if (MAXFOL >= 2 && nfol >= 2) w3 = *reinterpret_cast<const float4 *>(rb3 + voff(1 + t));
           const float wv2[4] = {w2.x, w2.y, w2.z, w2.w}, wv3[4] = {w3.x, w3.y, w3.z, w3.w};
           {
             // cubic pairs (168 registers): the vectors are consumed in place and the next table's are requested after
@@ -2037,7 +2040,7 @@ static bool warp_layout(const rbx_plan *plan, WarpLayout &lay, size_t &smem_byte
 // cell).  segment_kernel verifies the geometry for the Doppler range present and falls back to the linear layout.
 static bool warp_layout_tr(const rbx_plan *plan, const WarpLayout &base, WarpLayout &lay, size_t &smem_bytes, int max_arrays) {
   const PlanView &v = plan->v;
-  if (v.method != RBX_METHOD_LINEAR || opt(OPT_FUSED_TR) == 0) return false;
+  if (opt(OPT_FUSED_TR) == 0) return false;
   const double lo = (double)v.tmin / 1.03, hi = (double)v.tmax * 1.03;
   double max8 = 0.0;
   for (int l = 0; l < v.L; ++l) {
@@ -2047,7 +2050,7 @@ static bool warp_layout_tr(const rbx_plan *plan, const WarpLayout &base, WarpLay
   }
   const int B = ((int)std::ceil(max8 * 1.004 / (double)plan->min_dt) + 2 + 7) & ~7;
   const int ncols = (v.W + 2 + B - 1) / B;
-  if (B < 64 || ncols > 26 || 32 * B > (1 << 15)) return false;
+  if (B < (v.method == RBX_METHOD_LINEAR ? 64 : 128) || ncols > 26 || 32 * B > (1 << 15)) return false;   // rows that park records
   auto a128 = [](int x) { return (x + 127) & ~127; };
   lay = base;
   lay.tr_B = B;
@@ -2305,7 +2308,8 @@ int rbx::build_cube_impl(const rbx_plan *plan, const CubeBuild &b, int64_t n, in
   const bool prof = g_profile.load() != 0;
   if (prof) { profile_collect(); cudaEventRecord(g_ev[0], stream); }
   if (tr_ok) {   // the transposed-cell variant; returns at once unless segment_kernel selected it
-    auto kernel = fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384, true>;
+    auto kernel = v.method == RBX_METHOD_LINEAR ? fused_cube_warp_kernel<RBX_METHOD_LINEAR, true, 384, true>
+                                                : fused_cube_warp_kernel<RBX_METHOD_CUBIC, true, 384, true>;
     RBX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     kernel<<<nsm, tlay.nwarps * 32, tsmem, stream>>>(v, ws.rec, ws.idx_out, ws.items, ws.ctrl, d_cube, ws.partials, ws.Wp,
                                                      tlay, b.accumulate, cl);

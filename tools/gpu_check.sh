@@ -23,6 +23,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_1e6.csv python bench.py --particles 1000000 --steps 2 --warmup 3 --no-cpu --no-parity --no-e2e > $OUT/bench_under_ncu_1e6.log 2>&1
 for cfg in "linear 10000000" "linear 5000000" "linear 2500000" "linear 1250000" "linear 1000000" "cubic 1000000"; do
   set -- $cfg
-  timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:fused_cube_warp -s 3 -c 1 -o $OUT/prof_fused_$1_$2 -f python bench.py --particles $2 --method $1 --steps 2 --warmup 3 --no-cpu --no-parity --no-e2e > $OUT/ncu_fused_$1_$2.log 2>&1
+  timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:fused_cube_warp -s 4 -c 2 -o $OUT/prof_fused_$1_$2 -f python bench.py --particles $2 --method $1 --steps 2 --warmup 3 --no-cpu --no-parity --no-e2e > $OUT/ncu_fused_$1_$2.log 2>&1
 done
 timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:march -s 2 -c 1 -o $OUT/prof_march_s150 -f python tools/prof_conv.py > $OUT/ncu_march.log 2>&1
