@@ -158,6 +158,13 @@ int rbx_assign_build_cube_packed(const rbx_plan *plan, const float *d_x, const f
 int rbx_build_cube_status(const rbx_plan *plan, int64_t n, int num_spaxels, const void *d_workspace, int *h_error,
                           int *h_impl, void *stream);
 
+/* Which shared-memory cell layout the warp kernel of the last build on this workspace used (synchronises `stream`):
+ * *h_transposed = 1 for the transposed block layout (a cell's bank is its block: DESIGN.md section 5), 0 for cells in
+ * channel order or when the general kernel ran.  Results agree to rounding; the choice is made on the device from the
+ * Doppler range present (option fused_tr = 0 switches the transposed layout off). */
+int rbx_build_cube_cell_layout(const rbx_plan *plan, int64_t n, int num_spaxels, const void *d_workspace,
+                               int *h_transposed, void *stream);
+
 /* Slab-major partial cube for the multi-GPU exchange: the cube is stored as nslab wavelength slabs of
  * wslab = ceil(W / nslab) channels, slab r an (S*S, ws) block with ws = wslab + 2 halo: its own channels plus `halo`
  * channels of each neighbour (zeros beyond [0, W): the zero padding of the reference's 'same' convolutions).

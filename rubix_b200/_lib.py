@@ -35,6 +35,7 @@ EXPORTED = [
     "rbx_comm_unique_id", "rbx_comm_init", "rbx_comm_destroy", "rbx_comm_info",
     "rbx_reduce_cube", "rbx_allreduce_cube", "rbx_reduce_scatter_cube", "rbx_allgather_cube", "rbx_allreduce_f64",
     "rbx_rotate_moments", "rbx_rotate_apply",
+    "rbx_build_cube_cell_layout",
 ]
 
 RBX_OK = 0
@@ -109,6 +110,7 @@ def lib() -> C.CDLL:
     sigs["rbx_get_option"] = [C.c_char_p, C.POINTER(i64)]
     sigs["rbx_assign_build_cube_packed"] = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp]
     sigs["rbx_build_cube_status"] = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
+    sigs["rbx_build_cube_cell_layout"] = [vp, i64, i32, vp, C.POINTER(i32), vp]
     sigs["rbx_slab_geometry"] = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     sigs["rbx_assign_build_cube_slabs"] = [vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, sz, vp]
     sigs["rbx_pipeline_host_packed"] = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32,

@@ -2183,6 +2183,22 @@ extern "C" int rbx_build_cube_status(const rbx_plan *plan, int64_t n, int num_sp
   return RBX_OK;
 }
 
+extern "C" int rbx_build_cube_cell_layout(const rbx_plan *plan, int64_t n, int num_spaxels, const void *d_ws,
+                                          int *h_transposed, void *stream_) {
+  RBX_REQUIRE(plan && d_ws && n >= 0 && num_spaxels >= 1, "rbx_build_cube_cell_layout: bad argument");
+  if (h_transposed) *h_transposed = 0;
+  if (n == 0) return RBX_OK;
+  FusedWs ws;
+  size_t need = 0;
+  const uintptr_t base = ((uintptr_t)d_ws + 255) & ~(uintptr_t)255;
+  layout_workspace(plan, n, num_spaxels * num_spaxels, (void *)base, ws, need);
+  int h[C_COUNT];
+  RBX_CUDA_OK(cudaMemcpyAsync(h, ws.ctrl, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  RBX_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+  if (h_transposed) *h_transposed = h[C_IMPL] == IMPL_WARP_TR ? 1 : 0;
+  return RBX_OK;
+}
+
 // b.accumulate != 0: d_cube += the cube of these particles (rbx_pipeline_host bins a galaxy in ranges so that the
 // host-to-device copy of one range overlaps the kernels of the previous one).
 // b.cx != NULL: spaxel assignment (+ aperture filter as pixel -1) inside prep_kernel; b.pixel is then an optional

@@ -416,6 +416,16 @@ def build_cube_status(plan: Plan, n: int, num_spaxels: int):
     return int(err.value), int(impl.value)
 
 
+def build_cube_cell_layout(plan: Plan, n: int, num_spaxels: int) -> bool:
+    """True when the warp kernel of the last cube build of ``n`` particles on this stream's workspace kept its cells in
+    the transposed block layout, False for cells in channel order / the group kernel."""
+    L = _lib.lib()
+    ws = _workspace(L.rbx_build_cube_workspace_bytes(plan.handle, int(n), int(num_spaxels)))
+    tr = C.c_int()
+    _lib.check(L.rbx_build_cube_cell_layout(plan.handle, int(n), int(num_spaxels), _p(ws), C.byref(tr), _stream()))
+    return bool(tr.value)
+
+
 def slab_geometry(W: int, nslab: int, halo: int = 12):
     """(wslab, ws): channels per wavelength slab and its stored width including the halo on both sides."""
     a, b = C.c_int(), C.c_int()

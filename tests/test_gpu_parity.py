@@ -227,14 +227,15 @@ def test_fused_cube_synthetic(ops, plans, bc03, muse_wave, method, gen):
 
 @pytest.mark.parametrize("env", ["fused_force_lut=1", "fused_force_cas=1", "fused_impl=1",
                                  "psub=64", "small_shift=1", "fused_no_skew=1", "fused_chs=9", "sort_impl=1",
-                                 "fused_variant=1", "fused_variant=2"])
+                                 "fused_variant=1", "fused_variant=2", "fused_tr=0"])
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, env):
     """The general paths -- the group kernel (option fused_impl = 1), its lookup-table channel search for
     non-arange telescope grids and its shared cell region with CAS adds for SSP grids finer than the
     telescope's -- forced on the MUSE configuration (they are otherwise only taken by configurations the
     oracle is slow on); and the warp kernel with other work-item cuts / without the bank skew / larger chunks /
-    one warp per cell array (fused_variant = 1) / six arrays with two warps each (2) instead of seven."""
+    one warp per cell array (fused_variant = 1) / six arrays with two warps each (2) instead of seven / cells in
+    channel order instead of the transposed block layout (fused_tr = 0)."""
     from rubix_b200 import _lib, synthetic
     env, val = env.split("=")
     edges = synthetic.spatial_edges(25)
@@ -247,6 +248,8 @@ def test_fused_cube_alternate_code_paths(ops, plans, bc03, muse_wave, method, en
         _lib.set_option(env, -1)
     assert err == 0
     assert impl == (1 if env in ("fused_force_lut", "fused_force_cas", "fused_impl") else 0)
+    if env in ("fused_tr", "fused_variant") and val in ("0", "1"):
+        assert not ops.build_cube_cell_layout(plans[method], len(data["mass"]), 25)
     ref = c_oracle.particles_to_cube(data["coords"], data["velocity"], data["mass"], data["metallicity"],
                                      data["age"], edges, 25, bc03["metallicity"], bc03["age"], bc03["wavelength"],
                                      bc03["flux"], muse_wave, 0.1, method=method, dtype=np.float64, n_threads=8)

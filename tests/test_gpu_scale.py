@@ -256,6 +256,42 @@ def test_wide_doppler_range(ops, plans, bc03, muse_wave, vmax_c, expect_ok):
     _cube_close(cube, ref, f"wide doppler {vmax_c} c", rtol_max=1e-5)
 
 
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_transposed_cell_layout_is_the_default_and_agrees(ops, plans, bc03, muse_wave, method):
+    """The default MUSE configuration runs the warp kernel with the transposed cell layout; option fused_tr = 0 gives
+    the channel-order layout.  Both match the oracle and each other to rounding (different summation trees in the
+    expansion), each is bit-reproducible, and a Doppler range beyond the block geometry (0.04 c) falls back to the
+    channel-order layout on the device."""
+    from rubix_b200 import _lib, synthetic
+    S = 25
+    edges = synthetic.spatial_edges(S)
+    d = synthetic.bench_g(200000, seed=21)
+    run = lambda: ops.assign_build_cube(plans[method], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"],
+                                        d["age"], S).cpu().numpy()
+    a = run()
+    assert ops.build_cube_status(plans[method], 200000, S) == (0, 0)
+    assert ops.build_cube_cell_layout(plans[method], 200000, S)
+    assert np.array_equal(a, run())
+    _lib.set_option("fused_tr", 0)
+    try:
+        b = run()
+        assert ops.build_cube_status(plans[method], 200000, S) == (0, 0)
+        assert not ops.build_cube_cell_layout(plans[method], 200000, S)
+    finally:
+        _lib.set_option("fused_tr", -1)
+    scale = np.abs(b).max()
+    print(f"[transposed vs channel order, {method}] max |diff| / max = {np.abs(a - b).max() / scale:.2e}")
+    assert np.abs(a - b).max() <= 5e-6 * scale
+    ref = _oracle_cube(d, edges, S, bc03, muse_wave, method, threads=8)
+    _cube_close(a, ref, f"transposed layout {method}", rtol_max=2e-5)
+    if method == "linear":
+        rng = np.random.default_rng(8)
+        d["velocity"][:, 2] = rng.uniform(-0.04, 0.04, 200000).astype(np.float32) * np.float32(C_KMS)
+        run()
+        assert ops.build_cube_status(plans[method], 200000, S) == (0, 0)
+        assert not ops.build_cube_cell_layout(plans[method], 200000, S)
+
+
 def test_group_kernel_takes_over_and_fails_loudly(ops, plans, bc03, muse_wave):
     """Option fused_impl = 1 stands for a plan the warp kernel cannot take: at |v| <= 0.01 c the group kernel picks a
     larger chunk than the host's and matches the oracle; at 0.04 c no chunk of its fits -> status 3, NaN cube."""
