@@ -493,15 +493,23 @@ def main():
         else:
             # N > 1: pinned host shard -> device (async copies), device path, NCCL through the C ABI, result to the host
             hp = {k: pin(v) for k, v in data.items()}
-            dbuf = {k: torch.empty_like(v) for k, v in dict(coords=coords, velocity=vel, mass=mass, metallicity=met,
-                                                             age=age).items()}
+            hnp = {k: v.numpy() for k, v in hp.items()}
             hslab = (torch.empty((S, S, max(0, min(wslab, W - rank * wslab))), dtype=torch.float32).pin_memory()
                      if slab_mode else None)
 
             def e2e_step():
-                for k in dbuf:
-                    dbuf[k].copy_(hp[k], non_blocking=True)
-                out = device_step(dbuf["coords"], dbuf["velocity"], dbuf["mass"], dbuf["metallicity"], dbuf["age"])
+                # rbx_build_cube_host: the shard goes to the device in ranges on a second stream while the kernels of
+                # the previous range run (what rbx_pipeline_host does on one GPU); exchange + PSF + LSF on the device
+                if slab_mode:
+                    ops.build_cube_host(plan, hnp["coords"], hnp["velocity"], hnp["mass"], hnp["metallicity"], hnp["age"],
+                                        edges_h, S, out=slabs, nslab=world, halo=HALO)
+                    comm.reduce_scatter(slabs, own)
+                    out = ops.psf_lsf_own_slab(own, S, W, rank, world, pk_h, lk_h, HALO)
+                else:
+                    ops.build_cube_host(plan, hnp["coords"], hnp["velocity"], hnp["mass"], hnp["metallicity"], hnp["age"],
+                                        edges_h, S, out=cube)
+                    comm.reduce(cube, root=0)
+                    out = ops.psf_lsf(cube, pk_h, lk_h) if rank == 0 else cube
                 if slab_mode:
                     hslab.copy_(out, non_blocking=True)
                     torch.cuda.synchronize()
@@ -510,9 +518,11 @@ def main():
                     hcube.copy_(out, non_blocking=True)
                 torch.cuda.synchronize()
                 return float(hcube[S // 2, S // 2, 100]) if rank == 0 else 0.0
-            e2e_api = ("pinned host shards -> device, device ops + rbx_reduce_scatter_cube through the C ABI, PSF+LSF per "
-                       "wavelength slab, each slab to its rank's host" if slab_mode else
-                       "pinned host shards -> device, device ops + rbx_reduce_cube through the C ABI, cube to rank 0's host")
+            e2e_api = ("rbx_build_cube_host (pinned host shard copied in ranges under the previous range's kernels) + "
+                       "rbx_reduce_scatter_cube through the C ABI, PSF+LSF per wavelength slab, each slab to its rank's "
+                       "host" if slab_mode else
+                       "rbx_build_cube_host (pinned host shard copied in ranges under the previous range's kernels) + "
+                       "rbx_reduce_cube through the C ABI, PSF+LSF on rank 0, cube to rank 0's host")
             d2h = (hslab.numel() if slab_mode else hcube.numel()) * 4
             h2d = sum(v.numel() * 4 for v in hp.values())
 

@@ -342,6 +342,17 @@ int rbx_pipeline_host_packed(const rbx_plan *plan, const float *h_x, const float
                              const float *h_psf, int M, int N, const float *h_lsf, int K, int ext,
                              float *h_cube, void *stream);
 
+/* A rank's host shard -> its PARTIAL cube on the device: the first half of rbx_pipeline_host for the multi-GPU path
+ * (rubix/core/ifu.py:299-333: every device bins its particle shard, then jnp.sum over devices -- here
+ * rbx_reduce_cube / rbx_reduce_scatter_cube follow on the device).  The shard is copied in contiguous ranges on a
+ * second stream while the kernels of the previous range run.  nslab > 1: slab-major cube with `halo` channels as
+ * rbx_assign_build_cube_slabs writes it (d_cube then holds nslab * S*S * ws floats), else (S, S, W).  Stream-ordered:
+ * returns without synchronising; the host arrays (pinned for the overlap) must stay valid until `stream` has passed
+ * this call. */
+int rbx_build_cube_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity, const float *h_mass,
+                        const float *h_metallicity, const float *h_age, int64_t n, const float *h_edges, int n_edges,
+                        int num_spaxels, int apply_filter, int nslab, int halo, float *d_cube, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

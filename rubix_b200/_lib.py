@@ -35,7 +35,7 @@ EXPORTED = [
     "rbx_comm_unique_id", "rbx_comm_init", "rbx_comm_destroy", "rbx_comm_info",
     "rbx_reduce_cube", "rbx_allreduce_cube", "rbx_reduce_scatter_cube", "rbx_allgather_cube", "rbx_allreduce_f64",
     "rbx_rotate_moments", "rbx_rotate_apply",
-    "rbx_build_cube_cell_layout",
+    "rbx_build_cube_cell_layout", "rbx_build_cube_host",
 ]
 
 RBX_OK = 0
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     sigs["rbx_assign_build_cube_slabs"] = [vp, vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, sz, vp]
     sigs["rbx_pipeline_host_packed"] = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32,
                                         vp, vp]
+    sigs["rbx_build_cube_host"] = [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, vp]
     sigs["rbx_comm_unique_id"] = [vp]
     sigs["rbx_comm_init"] = [C.POINTER(vp), vp, i32, i32]
     sigs["rbx_comm_destroy"] = [vp]

@@ -95,11 +95,14 @@ struct HostParticles {
   bool packed = false;
 };
 
+// d_cube_ext != nullptr: rbx_build_cube_host -- the cube (slab-major when nslab > 1) is left on the device in the
+// caller's buffer, no PSF / LSF, no device-to-host copy, no synchronisation (stream-ordered like cudaMemcpyAsync: the
+// host arrays must stay valid until `stream` has passed this call).
 int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n, const float *h_edges, int n_edges,
                        int num_spaxels, int apply_filter, const float *h_psf, int M, int N, const float *h_lsf, int K,
-                       int ext, float *h_cube, void *stream_) {
+                       int ext, float *h_cube, void *stream_, float *d_cube_ext = nullptr, int nslab = 1, int halo = 0) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  RBX_REQUIRE(plan && h_cube && h_edges, "rbx_pipeline_host: null argument");
+  RBX_REQUIRE(plan && (h_cube || d_cube_ext) && h_edges, "rbx_pipeline_host: null argument");
   RBX_REQUIRE(n >= 0 && n_edges >= 2 && num_spaxels >= 1, "rbx_pipeline_host: bad sizes");
   RBX_REQUIRE(n == 0 || (hp.mass && hp.metallicity && hp.age &&
                          (hp.packed ? (hp.x && hp.y && hp.vlos) : (hp.coords && hp.velocity))),
@@ -122,7 +125,8 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
   TRY(sc.get(&d_age, np));
   TRY(sc.get(&d_pixel, np));
   TRY(sc.get(&d_edges, (size_t)n_edges));
-  TRY(sc.get(&d_cube, cube_elems));
+  if (d_cube_ext) d_cube = d_cube_ext;
+  else TRY(sc.get(&d_cube, cube_elems));
   const size_t ws_bytes = rbx_build_cube_workspace_bytes(plan, n, num_spaxels);
   TRY(sc.get((char **)&d_ws, ws_bytes));
   RBX_CUDA_OK(cudaMemcpyAsync(d_edges, h_edges, sizeof(float) * n_edges, cudaMemcpyHostToDevice, stream));
@@ -135,6 +139,7 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
   // stay exposed): 10.5 / 10.2 / 9.7 ms against 8.7 ms with 5 equal ranges on the same workload -- the per-range
   // cost outweighs the shorter tail, so the ranges stay equal; option host_ratio keeps the experiment reachable.)
   int chunks = n >= 3000000 ? 5 : (n >= 1500000 ? 2 : 1);
+  if (d_cube_ext && n >= 700000 && n < 3000000) chunks = n >= 1500000 ? 3 : 2;   // a rank's shard: no PSF / copy-out tail
   double ratio = 1.0;
   if (opt(OPT_HOST_CHUNKS) > 0) { chunks = (int)std::min<int64_t>(16, opt(OPT_HOST_CHUNKS)); ratio = 1.0; }
   if (opt(OPT_HOST_RATIO) > 0) ratio = std::min(1.0, std::max(0.3, (double)opt(OPT_HOST_RATIO) / 100.0));
@@ -160,7 +165,11 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
     RBX_CUDA_OK(cudaEventRecord(lane->ready, stream));
     RBX_CUDA_OK(cudaStreamWaitEvent(lane->stream, lane->ready, 0));
   }
-  if (n == 0) TRY(rbx_build_cube(plan, d_vel, d_mass, d_met, d_age, d_pixel, 0, num_spaxels, d_cube, d_ws, ws_bytes, stream));
+  if (n == 0) {
+    CubeBuild b0;
+    b0.nslab = nslab; b0.halo = halo;
+    TRY(build_cube_impl(plan, b0, 0, num_spaxels, d_cube, d_ws, ws_bytes, stream));
+  }
   bool first_range = true;
   for (int c = 0; c < chunks && n > 0; ++c) {
     const int64_t lo = bnd[c], hi = bnd[c + 1], m = hi - lo;
@@ -192,9 +201,11 @@ int pipeline_host_impl(const rbx_plan *plan, const HostParticles &hp, int64_t n,
     b.cstride = nc;
     b.edges = d_edges; b.n_edges = n_edges; b.mark_outside = apply_filter ? 1 : 0;
     b.accumulate = first_range ? 0 : 1;
+    b.nslab = nslab; b.halo = halo;
     first_range = false;
     TRY(build_cube_impl(plan, b, m, num_spaxels, d_cube, d_ws, ws_bytes, stream));
   }
+  if (d_cube_ext) return RBX_OK;   // the scratch is released in stream order (Scratch's destructor)
   float *result = d_cube;
   if (h_psf || h_lsf) {
     TRY(sc.get(&d_cube2, cube_elems));
@@ -260,4 +271,22 @@ extern "C" int rbx_pipeline_host_packed(const rbx_plan *plan, const float *h_x, 
   hp.mass = h_mass; hp.metallicity = h_metallicity; hp.age = h_age;
   return pipeline_host_impl(plan, hp, n, h_edges, n_edges, num_spaxels, apply_filter, h_psf, M, N, h_lsf, K, ext, h_cube,
                             stream_);
+}
+
+// A rank's host shard -> its partial cube on the device (the first half of rbx_pipeline_host, for the multi-GPU
+// path: the exchange rbx_reduce_cube / rbx_reduce_scatter_cube and the PSF + LSF follow on the device).  The shard
+// is copied in contiguous ranges on a second stream while the kernels of the previous range run, like
+// rbx_pipeline_host does.  nslab > 1: slab-major cube (rbx_assign_build_cube_slabs).  Stream-ordered: returns
+// without synchronising; the host arrays must stay valid until `stream` has passed this call.
+extern "C" int rbx_build_cube_host(const rbx_plan *plan, const float *h_coords, const float *h_velocity,
+                                   const float *h_mass, const float *h_metallicity, const float *h_age, int64_t n,
+                                   const float *h_edges, int n_edges, int num_spaxels, int apply_filter, int nslab,
+                                   int halo, float *d_cube, void *stream_) {
+  RBX_REQUIRE(d_cube, "rbx_build_cube_host: null cube");
+  RBX_REQUIRE(nslab >= 1 && halo >= 0, "rbx_build_cube_host: bad slab geometry");
+  HostParticles hp;
+  hp.coords = h_coords; hp.velocity = h_velocity;
+  hp.mass = h_mass; hp.metallicity = h_metallicity; hp.age = h_age;
+  return pipeline_host_impl(plan, hp, n, h_edges, n_edges, num_spaxels, apply_filter, nullptr, 0, 0, nullptr, 0, 0, nullptr,
+                            stream_, d_cube, nslab, nslab > 1 ? halo : 0);
 }

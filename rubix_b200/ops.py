@@ -651,6 +651,24 @@ def pipeline_host_packed(plan: Plan, x, y, vlos, mass, metallicity, age, edges, 
     return cube
 
 
+def build_cube_host(plan: Plan, coords, velocity, mass, metallicity, age, edges, num_spaxels: int,
+                    out: torch.Tensor, nslab: int = 1, halo: int = 12, apply_filter: bool = True) -> torch.Tensor:
+    """``rbx_build_cube_host``: a rank's HOST shard (numpy arrays, pinned for the copy / compute overlap) -> its partial
+    cube in the device tensor ``out`` ((S, S, W), or the slab-major (nslab, S*S, ws) block for ``nslab > 1``).  Stream
+    ordered: the host arrays must stay alive until the stream has passed the call (the exchange and the PSF + LSF that
+    follow on the same stream are fine)."""
+    req = lambda a: a if (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous) else \
+        np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+    coords, velocity, mass = req(coords), req(velocity), req(mass)
+    metallicity, age, edges = req(metallicity), req(age), req(edges)
+    _require_cuda()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().rbx_build_cube_host(
+        plan.handle, vp(coords), vp(velocity), vp(mass), vp(metallicity), vp(age), coords.shape[0], vp(edges),
+        len(edges), int(num_spaxels), 1 if apply_filter else 0, int(nslab), int(halo), _p(out), _stream()))
+    return out
+
+
 def pipeline_host(plan: Plan, coords, velocity, mass, metallicity, age, edges, num_spaxels: int,
                   psf_kernel=None, lsf_kernel=None, ext: int = 12, apply_filter: bool = True,
                   out: Optional[np.ndarray] = None) -> np.ndarray:

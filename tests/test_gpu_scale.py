@@ -292,6 +292,40 @@ def test_transposed_cell_layout_is_the_default_and_agrees(ops, plans, bc03, muse
         assert not ops.build_cube_cell_layout(plans[method], 200000, S)
 
 
+def test_build_cube_host_matches_device_call(ops, plans, bc03, muse_wave):
+    """rbx_build_cube_host (a rank's host shard -> partial cube on the device, copied in ranges): one range is bit
+    identical to the device call on the same particles, three ranges agree to float32 accumulation, and the slab-major
+    form equals rbx_assign_build_cube_slabs."""
+    from rubix_b200 import _lib, synthetic
+    S, n = 25, 300000
+    edges = synthetic.spatial_edges(S)
+    d = synthetic.bench_g(n, seed=31)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h = {k: pin(v) for k, v in d.items()}
+    dev = ops.assign_build_cube(plans["linear"], d["coords"], edges, d["velocity"], d["mass"], d["metallicity"], d["age"],
+                                S).cpu().numpy()
+    out = torch.empty((S, S, len(muse_wave)), dtype=torch.float32, device="cuda")
+    one = ops.build_cube_host(plans["linear"], h["coords"], h["velocity"], h["mass"], h["metallicity"], h["age"], edges, S,
+                              out=out).cpu().numpy()
+    assert np.array_equal(one, dev)
+    _lib.set_option("host_chunks", 3)
+    try:
+        three = ops.build_cube_host(plans["linear"], h["coords"], h["velocity"], h["mass"], h["metallicity"], h["age"],
+                                    edges, S, out=out).cpu().numpy()
+    finally:
+        _lib.set_option("host_chunks", -1)
+    scale = np.abs(dev).max()
+    assert np.abs(three - dev).max() <= 2e-6 * scale
+    wslab, ws = ops.slab_geometry(len(muse_wave), 4, 12)
+    a = torch.empty((4, S * S, ws), dtype=torch.float32, device="cuda")
+    b = torch.empty_like(a)
+    ops.assign_build_cube_slabs(plans["linear"], ops.dev(d["coords"]), ops.dev(edges), ops.dev(d["velocity"]),
+                                ops.dev(d["mass"]), ops.dev(d["metallicity"]), ops.dev(d["age"]), S, 4, 12, out=a)
+    ops.build_cube_host(plans["linear"], h["coords"], h["velocity"], h["mass"], h["metallicity"], h["age"], edges, S,
+                        out=b, nslab=4, halo=12)
+    assert torch.equal(a, b)
+
+
 def test_group_kernel_takes_over_and_fails_loudly(ops, plans, bc03, muse_wave):
     """Option fused_impl = 1 stands for a plan the warp kernel cannot take: at |v| <= 0.01 c the group kernel picks a
     larger chunk than the host's and matches the oracle; at 0.04 c no chunk of its fits -> status 3, NaN cube."""
