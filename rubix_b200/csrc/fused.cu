@@ -2050,7 +2050,8 @@ static bool warp_layout_tr(const rbx_plan *plan, const WarpLayout &base, WarpLay
   }
   const int B = ((int)std::ceil(max8 * 1.004 / (double)plan->min_dt) + 2 + 7) & ~7;
   const int ncols = (v.W + 2 + B - 1) / B;
-  if (B < (v.method == RBX_METHOD_LINEAR ? 64 : 128) || ncols > 26 || 32 * B > (1 << 15)) return false;   // rows that park records
+  // rows 0..63 (linear) / 0..127 (cubic) park the records; the last row's spare columns are the junk cells
+  if (B < (v.method == RBX_METHOD_LINEAR ? 72 : 136) || ncols > 26 || 32 * B > (1 << 15)) return false;
   auto a128 = [](int x) { return (x + 127) & ~127; };
   lay = base;
   lay.tr_B = B;

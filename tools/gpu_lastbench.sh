@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-lb}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout -s KILL 200 python -m pytest tests -m gpu -q -x -k "transposed or alternate_code or fused_cube_synthetic or build_cube_host" > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $OUT/pytest.log
+timeout 300 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+python -c "
+import json;d=json.load(open('$OUT/bench.json'));r=d['roofline'];print(d['ms_per_step'],d['value'],r['frac'],r['issue_frac'],r['hbm_frac'],d['e2e']['ms_per_step'],d['parity']['ok'],d['cpu_baseline']['value'])"
