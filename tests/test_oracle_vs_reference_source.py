@@ -1,0 +1,152 @@
+"""The oracle against the REFERENCE'S OWN SOURCE (CPU, no GPU).
+
+tests/golden/ref_numpy_stages.npz and ref_numpy_cube.npz were produced by tools/make_ref_golden.py: the reference
+files rubix/spectra/ifu.py, rubix/telescope/utils.py, rubix/telescope/psf/{kernels,psf}.py, rubix/telescope/lsf/lsf.py,
+rubix/galaxy/alignment.py and rubix/telescope/noise/noise.py executed UNCHANGED with numpy standing in for jax.numpy
+(tools/refshim.py), on float64 arrays.  The oracle's float64 mode -- the "truth" every GPU parity test compares with --
+must reproduce them to float64 rounding (1e-12 relative to the array maximum; integer results exactly).  Where
+/root/reference is present (the build container) the reference source is also re-run live against the fixtures, so a
+stale fixture or a changed reference cannot go unnoticed.  a1 (interpax.interp2d) is not part of this pin: the cube
+fixture keeps every particle on a node of the SSP grid.
+"""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import rubix_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def stages():
+    d = np.load(os.path.join(GOLDEN, "ref_numpy_stages.npz"))
+    return {k: d[k] for k in d.files}
+
+
+@pytest.fixture(scope="module")
+def cube():
+    d = np.load(os.path.join(GOLDEN, "ref_numpy_cube.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def _close(a, b, tol=TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300), np.abs(a - b).max() / np.abs(b).max()
+
+
+def test_a0_spaxel_ids_and_mask_exact(stages):
+    for tag in ("26", "27"):
+        e = stages["in_edges" + tag]
+        assert np.array_equal(orc.square_spaxel_assignment(stages["in_coords"], e), stages["out_pixel" + tag])
+        assert np.array_equal(orc.mask_particles_outside_aperture(stages["in_coords"], e), stages["out_mask" + tag])
+    # the fixture does exercise the edges: ids on both borders, masked particles, both mask values on edge points
+    assert stages["out_pixel26"].min() == 0 and stages["out_pixel26"].max() == 624
+    assert 0 < stages["out_mask26"].sum() < len(stages["out_mask26"])
+
+
+def test_a3_a4_doppler_and_resample(stages, bc03, muse_wave):
+    lam_z = orc.cosmological_doppler_shift(0.1, bc03["wavelength"].astype(np.float64), dtype=np.float64)
+    shifted = orc.velocity_doppler_shift(lam_z, stages["in_vel"], "z", dtype=np.float64)
+    _close(shifted, stages["out_shifted"], 1e-15)
+    wave = muse_wave.astype(np.float64)
+    res = orc.resample_spectra(stages["in_rows"], shifted, wave)
+    _close(res, stages["out_resampled"])
+    # the zero spectrum stays exactly zero (0 / 0 -> nan_to_num -> 0), the constant one is flux conserving
+    assert np.abs(stages["out_resampled"][3]).max() == 0.0 and np.abs(res[3]).max() == 0.0
+    assert np.all(np.isfinite(res))
+
+
+def test_a5_cube_drops_out_of_range_ids(stages):
+    c = orc.calculate_cube(stages["out_resampled"], stages["out_cube_ids"], 3)
+    assert np.array_equal(c, stages["out_cube"])          # same float64 adds in the same (particle) order
+    flat = c.reshape(9, -1)
+    assert np.abs(flat[7]).max() > 0 and np.abs(flat[5]).max() == 0 and np.abs(flat[6]).max() == 0
+    # ids 9 and 12 (beyond the 3 x 3 cube, as the 27-edge grid produces them) are dropped: the total is the in-range sum
+    keep = stages["out_cube_ids"] < 9
+    assert np.isclose(c.sum(), stages["out_resampled"][keep].sum(), rtol=1e-12)
+
+
+def test_a6_psf_kernels_and_convolution(stages):
+    for name, (a, b, s) in {"psf55": (5, 5, 0.6), "psf46": (4, 6, 1.3), "psf33": (3, 3, 2.0)}.items():
+        k = orc.gaussian_kernel_2d(a, b, s, dtype=np.float64)
+        _close(k, stages["out_" + name], 1e-15)
+        _close(orc.apply_psf(stages["in_cube_small"], k), stages["out_" + name + "_applied"])
+    # asymmetric taps and an even-sized kernel: orientation and the 'same' alignment
+    _close(orc.apply_psf(stages["in_cube_small"], stages["out_psf_skew"]), stages["out_psf_skew_applied"])
+
+
+def test_a7_lsf_kernel_and_convolution(stages):
+    _close(orc.lsf_kernel(0.5, 1.25, dtype=np.float64), stages["out_lsf_kernel"], 1e-15)
+    _close(orc.lsf_kernel(3.0, 1.25, dtype=np.float64), stages["out_lsf_kernel_wide"], 1e-15)
+    _close(orc.apply_lsf(stages["in_lsf_cube"], 0.5, 1.25), stages["out_lsf_applied"])
+    _close(orc.apply_lsf(stages["in_lsf_cube"], 3.0, 1.25), stages["out_lsf_applied_wide"])
+
+
+def test_rotate_galaxy_and_s2n(stages):
+    I = orc.moment_of_inertia_tensor(stages["in_gal_pos"], stages["in_gal_mass"], 4.0)
+    _close(I, stages["out_inertia"])
+    _close(orc.euler_rotation_matrix(20.0, -35.0, 70.0), stages["out_euler"], 1e-15)
+    # eigh's eigenvector signs are LAPACK's in both runs here (numpy): compare without the sign normalisation
+    p, v, _ = orc.rotate_galaxy(stages["in_gal_pos"], stages["in_gal_vel"], stages["in_gal_mass"], 4.0, 20.0, -35.0,
+                                70.0, normalise_signs=False)
+    _close(p, stages["out_gal_pos_rot"], 1e-11)
+    _close(v, stages["out_gal_vel_rot"], 1e-11)
+    nc = stages["in_noise_cube"].copy()
+    _close(orc.calculate_S2N(nc, 50.0), stages["out_s2n"])
+    nc[2, 3] = 0.0
+    assert np.array_equal(orc.calculate_S2N(nc, 50.0), stages["out_s2n_with_dark_spaxel"])   # all zero: NaN median
+    assert np.abs(stages["out_s2n_with_dark_spaxel"]).max() == 0.0
+
+
+def thin(name, c):
+    """The form the cube fixture is stored in (tools/make_ref_golden.py: thin): every 4th channel of every spaxel, all
+    channels summed over the spaxels, all spaxels summed over the channels."""
+    c = np.asarray(c, dtype=np.float64)
+    return {name + "_every4th": c[:, :, ::4], name + "_spectrum": c.sum(axis=(0, 1)), name + "_image": c.sum(axis=2)}
+
+
+def cube_matches(name, c, fixture, tol):
+    for k, v in thin(name, c).items():
+        _close(v, fixture["out_" + k], tol)
+
+
+@pytest.mark.parametrize("method", ["linear", "cubic"])
+def test_whole_path_on_grid_nodes(cube, bc03, muse_wave, method):
+    """filter -> assign -> lookup -> scale -> Doppler -> resample -> cube -> PSF -> LSF: the reference's functions gave
+    ref_numpy_cube.npz; both forms of the oracle (numpy and C, float64) reproduce it.  On grid nodes the lookup is the
+    template row for either ssp.method, so the cubic run checks that the cubic patch is exact at its nodes as well."""
+    x = {k[3:]: v for k, v in cube.items() if k.startswith("in_")}
+    assert np.array_equal(orc.square_spaxel_assignment(x["coords"], x["edges"]), cube["out_pixel"])
+    assert np.array_equal(orc.mask_particles_outside_aperture(x["coords"], x["edges"]), cube["out_mask"])
+    assert 0 < cube["out_mask"].sum() < len(cube["out_mask"])
+    args = (x["coords"], x["velocity"], x["mass"], x["metallicity"], x["age"], x["edges"], 7, bc03["metallicity"],
+            bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1)
+    py, idx = orc.particles_to_cube(*args, method=method, dtype=np.float64)
+    assert np.array_equal(idx, cube["out_pixel"])
+    # the node lookup itself rounds at 1e-16 relative (weights 1 and 0 times float32 rows); 1e-11 covers the cubic
+    # patch's derivative terms cancelling at a node
+    cube_matches("cube", py, cube, 1e-11)
+    cc = c_oracle.particles_to_cube(*args, method=method, dtype=np.float64, n_threads=4)
+    cube_matches("cube", cc, cube, 1e-11)
+    conv = orc.apply_lsf(orc.apply_psf(py, orc.gaussian_kernel_2d(5, 5, 0.6, dtype=np.float64)), 0.5, 1.25)
+    cube_matches("cube_psf_lsf", conv, cube, 1e-11)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "
+                                                                       "container")
+def test_fixtures_are_what_the_reference_source_gives_now():
+    """Re-run the reference's files through tools/refshim.py (in a process of its own: the stand-in modules named jax,
+    jaxtyping, beartype must not leak into this one) and compare with the committed fixtures bit for bit."""
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_ref_golden.py"), "--check"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "identical" in res.stdout

@@ -1,0 +1,194 @@
+"""Golden vectors from the REFERENCE'S OWN SOURCE, executed on numpy through tools/refshim.py.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tools/make_ref_golden.py
+
+The reference functions below are loaded unchanged from /root/reference and called with float64 arrays (seeded inputs,
+committed with the outputs), so the vectors are what the reference's formulas MEAN, free of float32 rounding order.
+``tests/test_oracle_vs_reference_source.py`` holds the oracle (its float64 mode, the one every GPU parity test compares
+against) to them, and re-runs the reference source live whenever /root/reference is present.
+
+Outputs: tests/golden/ref_numpy_stages.npz, tests/golden/ref_numpy_cube.npz.
+Not covered: a1 (interpax.interp2d is not installable and is not stood in for) -- the cube fixture puts every particle
+ON a node of the SSP grid, where the reference's own tests pin the lookup to the template row
+(tests/test_core_ssp.py:158-173), so a2 - a7 are exercised end to end without it.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import refshim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def reference_modules():
+    m = {"ifu": refshim.load("rubix/spectra/ifu.py"), "tel": refshim.load("rubix/telescope/utils.py")}
+    refshim.load("rubix/telescope/psf/kernels.py")
+    m["kern"] = sys.modules["rubix.telescope.psf.kernels"]
+    m["psf"] = refshim.load("rubix/telescope/psf/psf.py")
+    m["lsf"] = refshim.load("rubix/telescope/lsf/lsf.py")
+    m["align"] = refshim.load("rubix/galaxy/alignment.py")
+    m["noise"] = refshim.load("rubix/telescope/noise/noise.py")
+    return m
+
+
+def stage_inputs():
+    """Seeded inputs of the per-stage vectors (float64 unless integer work)."""
+    rng = np.random.default_rng(42)
+    tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    wave = np.load(os.path.join(OUT, "muse_wave.npy")).astype(np.float64)
+    # a0: float32 edges as get_spatial_bin_edges hands them over (26 and 27 of them), coords on / next to edges
+    half = np.float32(4.7619)
+    e26 = (-half + np.float32(2 * half / 25) * np.arange(26, dtype=np.float32)).astype(np.float32)
+    e27 = (-half + np.float32(2 * half / 25) * np.arange(27, dtype=np.float32)).astype(np.float32)
+    c = rng.normal(0, 2.5, (3000, 3)).astype(np.float32)
+    c[:26, 0] = e26
+    c[26:52, 1] = e26
+    c[52:78, 0] = np.nextafter(e26, np.float32(np.inf))
+    c[78:104, 0] = np.nextafter(e26, np.float32(-np.inf))
+    c[104:110] = np.float32([[-9, 0, 0], [9, 0, 0], [0, -9, 0], [0, 9, 0], [4.7619, 4.7619, 0], [-4.7619, -4.7619, 0]])
+    # a3 / a4: twelve template rows at z = 0.1 with velocities up to +-900 km/s, a zero spectrum, a constant one
+    lam_ssp = tpl["wavelength"].astype(np.float64)
+    rows = tpl["flux"].reshape(-1, lam_ssp.size)[rng.integers(0, 6 * 221, 12)].astype(np.float64)
+    rows[3] = 0.0
+    rows[7] = 1.0
+    vel = rng.normal(0, 300, (12, 3))
+    vel[0] = [0.0, 0.0, 0.0]
+    vel[1, 2], vel[2, 2] = 900.0, -900.0
+    return dict(edges26=e26, edges27=e27, coords=c, lam_ssp=lam_ssp, wave=wave, rows=rows, vel=vel,
+                cube_small=rng.random((9, 7, 40)), psf_odd=None, lsf_cube=rng.random((3, 4, 300)),
+                gal_pos=rng.normal(0, 3, (500, 3)), gal_vel=rng.normal(0, 100, (500, 3)),
+                gal_mass=rng.uniform(0.5, 1.5, 500), noise_cube=rng.random((6, 5, 30)))
+
+
+def run_stages(m, x):
+    """Every per-stage vector, from the reference's functions."""
+    ifu, tel, kern, psf, lsf, align, noise = (m[k] for k in ("ifu", "tel", "kern", "psf", "lsf", "align", "noise"))
+    o = {}
+    for tag in ("26", "27"):
+        e = x["edges" + tag]
+        o["pixel" + tag] = np.asarray(tel.square_spaxel_assignment(x["coords"], e)).astype(np.int32)
+        o["mask" + tag] = np.asarray(tel.mask_particles_outside_aperture(x["coords"], e)).astype(bool)
+    lam_z = ifu.cosmological_doppler_shift(0.1, x["lam_ssp"])
+    o["lam_z"] = lam_z
+    shifted = ifu.velocity_doppler_shift(lam_z, x["vel"], "z")
+    o["shifted"] = shifted
+    o["diff"] = ifu.calculate_diff(x["wave"])
+    o["resampled"] = np.stack([ifu.resample_spectrum(x["rows"][k], shifted[k], x["wave"]) for k in range(12)])
+    ids = np.array([0, 3, 3, 8, 1, 9, 7, 2, 0, 3, 4, 12])      # 9, 12: beyond the 3 x 3 cube -> dropped
+    o["cube_ids"] = ids
+    o["cube"] = ifu.calculate_cube(o["resampled"], ids, 3)
+    for name, (a, b, s) in {"psf55": (5, 5, 0.6), "psf46": (4, 6, 1.3), "psf33": (3, 3, 2.0)}.items():
+        k = kern.gaussian_kernel_2d(a, b, s)
+        o[name] = k
+        o[name + "_applied"] = psf.apply_psf(x["cube_small"], k)
+    skew = np.arange(1.0, 16.0).reshape(3, 5) / 120.0        # asymmetric taps: pins the orientation of the convolution
+    o["psf_skew"] = skew
+    o["psf_skew_applied"] = psf.apply_psf(x["cube_small"], skew)
+    o["lsf_kernel"] = lsf._get_kernel(0.5, 1.25, factor=12)
+    o["lsf_kernel_wide"] = lsf._get_kernel(3.0, 1.25, factor=12)
+    o["lsf_applied"] = lsf.apply_lsf(x["lsf_cube"], 0.5, 1.25)
+    o["lsf_applied_wide"] = lsf.apply_lsf(x["lsf_cube"], 3.0, 1.25)
+    o["inertia"] = align.moment_of_inertia_tensor(x["gal_pos"], x["gal_mass"], 4.0)
+    o["euler"] = align.euler_rotation_matrix(20.0, -35.0, 70.0)
+    p, v = align.rotate_galaxy(x["gal_pos"], x["gal_vel"], x["gal_mass"], 4.0, 20.0, -35.0, 70.0)
+    o["gal_pos_rot"], o["gal_vel_rot"] = p, v
+    nc = x["noise_cube"].copy()
+    o["s2n"] = noise.calculate_S2N(nc, 50.0)
+    nc[2, 3] = 0.0                                            # a flux-less spaxel: the NaN-propagating median
+    o["s2n_with_dark_spaxel"] = noise.calculate_S2N(nc, 50.0)
+    return {k: np.asarray(v) for k, v in o.items()}
+
+
+def cube_inputs(n=1500, S=7):
+    """Particles ON nodes of the SSP grid (float32 values, as the CUDA path receives them) on a 7 x 7 spaxel grid."""
+    rng = np.random.default_rng(4242)
+    tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    half = np.float32(4.7619)
+    edges = (-half + np.float32(2 * half / S) * np.arange(S + 1, dtype=np.float32)).astype(np.float32)
+    iz, ia = rng.integers(0, 6, n), rng.integers(0, 221, n)
+    coords = rng.normal(0, 2.5, (n, 3)).astype(np.float32)       # some fall outside the aperture
+    vel = rng.normal(0, 200, (n, 3)).astype(np.float32)
+    mass = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    # keep only particles without a Doppler-shifted knot within 0.01 A of a band edge: there the in-range mask of
+    # rubix/spectra/ifu.py:241-244 flips with the rounding of lam * d, float32 and float64 evaluations of the reference
+    # disagree, and the vector could pin nothing for a float32 implementation (tests/helpers.py: well_conditioned)
+    wave = np.load(os.path.join(OUT, "muse_wave.npy")).astype(np.float64)
+    lam = 1.1 * tpl["wavelength"].astype(np.float64)[None, :] * np.exp(vel[:, 2].astype(np.float64) / 299792.458)[:, None]
+    keep = np.minimum(np.abs(lam - wave[0]).min(1), np.abs(lam - wave[-1]).min(1)) > 1e-2
+    iz, ia, coords, vel, mass = iz[keep], ia[keep], coords[keep], vel[keep], mass[keep]
+    return dict(edges=edges, node_z=iz, node_age=ia, coords=coords, velocity=vel, mass=mass,
+                metallicity=tpl["metallicity"][iz], age=tpl["age"][ia])
+
+
+def run_cube(m, x, S=7):
+    """filter_particles -> spaxel_assignment -> (node lookup) -> scale -> Doppler -> resample -> cube -> PSF -> LSF with
+    the reference's functions, float64 arithmetic on the float32 input values."""
+    ifu, tel, kern, psf, lsf = (m[k] for k in ("ifu", "tel", "kern", "psf", "lsf"))
+    tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    wave = np.load(os.path.join(OUT, "muse_wave.npy")).astype(np.float64)
+    mask = np.asarray(tel.mask_particles_outside_aperture(x["coords"], x["edges"]))
+    mass = np.where(mask, x["mass"].astype(np.float64), 0.0)     # rubix/core/telescope.py:155-174
+    pix = np.asarray(tel.square_spaxel_assignment(x["coords"], x["edges"]))
+    spectra = tpl["flux"].astype(np.float64)[x["node_z"], x["node_age"]]     # a1 at a node = the template row
+    spectra = spectra * mass[:, None]                            # rubix/core/ifu.py:152-154
+    lam_z = ifu.cosmological_doppler_shift(0.1, tpl["wavelength"].astype(np.float64))
+    shifted = ifu.velocity_doppler_shift(lam_z, x["velocity"].astype(np.float64), "z")
+    res = np.stack([ifu.resample_spectrum(spectra[k], shifted[k], wave) for k in range(len(mass))])
+    cube = ifu.calculate_cube(res, pix, S)
+    conv = lsf.apply_lsf(psf.apply_psf(cube, kern.gaussian_kernel_2d(5, 5, 0.6)), 0.5, 1.25)
+    # the cubes are 49 x 3721 doubles (1.5 MB each): the fixture keeps every 4th channel of every spaxel, and all 3721
+    # channels summed over the spaxels (thin() below), so that every voxel still enters a compared number
+    return {"pixel": pix.astype(np.int32), "mask": mask, **thin("cube", cube), **thin("cube_psf_lsf", conv)}
+
+
+def thin(name, cube):
+    cube = np.asarray(cube, dtype=np.float64)
+    return {name + "_every4th": cube[:, :, ::4].copy(), name + "_spectrum": cube.sum(axis=(0, 1)),
+            name + "_image": cube.sum(axis=2)}
+
+
+def check():
+    """Re-run the reference source and compare with the committed fixtures bit for bit (exit status 1 on a mismatch)."""
+    m = reference_modules()
+    st = np.load(os.path.join(OUT, "ref_numpy_stages.npz"))
+    cu = np.load(os.path.join(OUT, "ref_numpy_cube.npz"))
+    bad = []
+    x = stage_inputs()
+    for k, v in run_stages(m, x).items():
+        if "out_" + k in st.files and not np.array_equal(np.asarray(v), st["out_" + k], equal_nan=True):
+            bad.append(k)
+    xc = cube_inputs()
+    bad += [k for k, v in xc.items() if not np.array_equal(v, cu["in_" + k])]
+    bad += [k for k, v in run_cube(m, xc).items() if not np.array_equal(v, cu["out_" + k])]
+    print("reference source vs committed fixtures:", "identical" if not bad else f"MISMATCH in {bad}")
+    return 1 if bad else 0
+
+
+def main():
+    if "--check" in sys.argv:
+        sys.exit(check())
+    m = reference_modules()
+    x = stage_inputs()
+    x.pop("psf_odd")
+    o = run_stages(m, x)
+    np.savez_compressed(os.path.join(OUT, "ref_numpy_stages.npz"), **{"in_" + k: v for k, v in x.items()
+                                                                      if k not in ("lam_ssp", "wave")},
+                        **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")})
+    xc = cube_inputs()
+    oc = run_cube(m, xc)
+    np.savez_compressed(os.path.join(OUT, "ref_numpy_cube.npz"), **{"in_" + k: v for k, v in xc.items()},
+                        **{"out_" + k: v for k, v in oc.items()})
+    for f in ("ref_numpy_stages.npz", "ref_numpy_cube.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
