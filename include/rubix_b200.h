@@ -98,6 +98,20 @@ int rbx_filter_particles(const float *d_coords, int64_t n, const float *d_edges,
 int rbx_filter_and_assign(const float *d_coords, int64_t n, const float *d_edges, int n_edges, float *d_mass,
                           float *d_metallicity, float *d_age, int32_t *d_pixel, uint8_t *d_mask, void *stream);
 
+/* Stable device radix sort of particles by spaxel id (SURVEY 8b minimum set; the grouping step that stands in for
+ * the scatter of jax.ops.segment_sum, rubix/spectra/ifu.py:286-287) -- the sort the cube build runs internally
+ * (csrc/sort.cu: one kernel per 8-bit pass, decoupled look-back), for a plain id array.
+ *   d_pixel   (n,) int32 from rbx_spaxel_assign / rbx_filter_and_assign.  Ids outside [0, num_segments) -- the ones
+ *             segment_sum drops, -1 of rbx_filter_and_assign included -- count as num_segments and sort to the end.
+ *   d_order   (n,) int32: the permutation, bit for bit numpy.argsort(clamped ids, kind="stable").
+ *   d_sorted  (n,) int32 or NULL: the clamped ids in sorted order (d_pixel[d_order] where that is in range).
+ *   d_offsets (num_segments + 1,) int32 or NULL: d_offsets[s] = first sorted position with id >= s, so segment s is
+ *             [d_offsets[s], d_offsets[s+1]) and the dropped particles are [d_offsets[num_segments], n).
+ * Integer work, bit-exact and bit-reproducible.  n <= 2^30. */
+size_t rbx_sort_by_spaxel_workspace_bytes(int64_t n, int num_segments);
+int rbx_sort_by_spaxel(const int32_t *d_pixel, int64_t n, int num_segments, int32_t *d_order, int32_t *d_sorted,
+                       int32_t *d_offsets, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage calls: one per reference stage, materialising the same intermediates as the reference.
  * Used by the stepwise (notebook) path and for stage-level parity.
@@ -118,6 +132,13 @@ int rbx_doppler_resample(const rbx_plan *plan, const float *d_spectra, const flo
  * d_cube (or passes zero_first = 1). */
 int rbx_segment_sum(const float *d_spectra, const int32_t *d_pixel, int64_t n, int W,
                     int num_segments, float *d_cube, int zero_first, void *stream);
+
+/* a5, bit-reproducible: d_order / d_offsets from rbx_sort_by_spaxel; d_cube (num_segments, W) is OVERWRITTEN with
+ * the float32 sums formed one particle after the other in particle order inside every segment -- the sum
+ * jax.ops.segment_sum forms on the CPU backend, so the result is bit-identical to a sequential
+ * float32 scatter-add of the same spectra.  No atomics; empty segments give 0. */
+int rbx_segment_sum_sorted(const float *d_spectra, const int32_t *d_order, const int32_t *d_offsets, int W,
+                           int num_segments, float *d_cube, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused a1..a5: particles -> cube without materialising (n, L) or (n, W).

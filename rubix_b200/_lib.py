@@ -36,6 +36,7 @@ EXPORTED = [
     "rbx_reduce_cube", "rbx_allreduce_cube", "rbx_reduce_scatter_cube", "rbx_allgather_cube", "rbx_allreduce_f64",
     "rbx_rotate_moments", "rbx_rotate_apply",
     "rbx_build_cube_cell_layout", "rbx_build_cube_host",
+    "rbx_sort_by_spaxel", "rbx_sort_by_spaxel_workspace_bytes", "rbx_segment_sum_sorted",
 ]
 
 RBX_OK = 0
@@ -116,6 +117,8 @@ def lib() -> C.CDLL:
     sigs["rbx_pipeline_host_packed"] = [vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, i32, i32, vp, i32, i32,
                                         vp, vp]
     sigs["rbx_build_cube_host"] = [vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, vp]
+    sigs["rbx_sort_by_spaxel"] = [vp, i64, i32, vp, vp, vp, vp, sz, vp]
+    sigs["rbx_segment_sum_sorted"] = [vp, vp, vp, i32, i32, vp, vp]
     sigs["rbx_comm_unique_id"] = [vp]
     sigs["rbx_comm_init"] = [C.POINTER(vp), vp, i32, i32]
     sigs["rbx_comm_destroy"] = [vp]
@@ -135,6 +138,8 @@ def lib() -> C.CDLL:
     L.rbx_build_cube_dusty_workspace_bytes.restype = sz
     L.rbx_apply_noise_workspace_bytes.argtypes = [i32, i32]
     L.rbx_apply_noise_workspace_bytes.restype = sz
+    L.rbx_sort_by_spaxel_workspace_bytes.argtypes = [i64, i32]
+    L.rbx_sort_by_spaxel_workspace_bytes.restype = sz
     L.rbx_rotate_galaxy_workspace_bytes.argtypes = []
     L.rbx_rotate_galaxy_workspace_bytes.restype = sz
     for name, args in sigs.items():

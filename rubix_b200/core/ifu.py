@@ -235,7 +235,9 @@ def get_calculate_datacube(config: dict) -> Callable:
                                       st.age.reshape(-1), pix, num_spaxels)
         else:
             spec = ops.dev(st.spectra)
-            cube = ops.segment_sum(spec.reshape(-1, spec.shape[-1]), pix, num_spaxels * num_spaxels)
+            # b200.deterministic: the staged sum in the reference's CPU order (sorted runs, no atomics), bit-reproducible
+            det = isinstance(config.get("b200"), dict) and bool(config["b200"].get("deterministic"))
+            cube = ops.segment_sum(spec.reshape(-1, spec.shape[-1]), pix, num_spaxels * num_spaxels, deterministic=det)
             cube = cube.reshape(num_spaxels, num_spaxels, spec.shape[-1])
         if isinstance(config.get("b200"), dict) and config["b200"].get("distributed"):
             from ..parallel import allreduce_cube

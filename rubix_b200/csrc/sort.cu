@@ -208,4 +208,105 @@ int radix_sort_pairs(const SortPlan &sp, uint32_t *keys_a, uint32_t *vals_a, uin
   return RBX_OK;
 }
 
+// ---- stand-alone form (rbx_sort_by_spaxel): keys and digit histograms from the spaxel ids ------------------------
+// Inside the cube build prep_kernel writes the keys and their digit histograms; here a small kernel does it for a
+// plain array of spaxel ids.  Ids outside [0, nseg) -- the ones segment_sum drops -- become the key nseg: they sort
+// behind every segment.
+__global__ void __launch_bounds__(256)
+spaxel_keys_kernel(const int32_t *__restrict__ pixel, int n, int nseg, uint32_t *__restrict__ keys,
+                   uint32_t *__restrict__ state, SortPlan sp, size_t per_pass) {
+  __shared__ uint32_t s_hist[kSortMaxPasses][256];
+  for (int q = threadIdx.x; q < kSortMaxPasses * 256; q += blockDim.x) (&s_hist[0][0])[q] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = (uint32_t)pixel[i];           // a negative id is a huge unsigned one
+    const uint32_t k = p < (uint32_t)nseg ? p : (uint32_t)nseg;
+    keys[i] = k;
+#pragma unroll
+    for (int s = 0; s < kSortMaxPasses; ++s)
+      if (s < sp.npass) atomicAdd(&s_hist[s][(k >> sp.shift[s]) & ((1u << sp.bits[s]) - 1u)], 1u);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < sp.npass * 256; q += blockDim.x) {
+    const uint32_t v = (&s_hist[0][0])[q];
+    if (v) atomicAdd(state + (size_t)(q >> 8) * per_pass + (q & 255), v);
+  }
+}
+
+// offsets[s] = first position of the sorted keys with key >= s, s = 0 .. nseg (searchsorted 'left'): every run
+// boundary fills the entries of the (possibly empty) segments it steps over.
+__global__ void segment_offsets_kernel(const uint32_t *__restrict__ sorted, int n, int nseg,
+                                       int32_t *__restrict__ offsets) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)sorted[i];
+    const int prev = i > 0 ? (int)sorted[i - 1] : -1;
+    for (int s = prev + 1; s <= k; ++s) offsets[s] = (int32_t)i;
+    if (i == n - 1)
+      for (int s = k + 1; s <= nseg; ++s) offsets[s] = n;
+  }
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int spaxel_end_bit(int nseg) {
+  int b = 1;
+  while (b < 31 && (1u << b) <= (uint32_t)nseg) ++b;   // bits of the largest key, nseg
+  return b;
+}
+
 }  // namespace rbx
+
+using namespace rbx;
+
+extern "C" size_t rbx_sort_by_spaxel_workspace_bytes(int64_t n, int num_segments) {
+  if (n <= 0 || num_segments <= 0) return 256;
+  const SortPlan sp = make_sort_plan(n, spaxel_end_bit(num_segments));
+  return align256(sizeof(uint32_t) * sort_state_words(sp)) + 3 * align256(sizeof(uint32_t) * (size_t)n) + 256;
+}
+
+extern "C" int rbx_sort_by_spaxel(const int32_t *d_pixel, int64_t n, int num_segments, int32_t *d_order,
+                                  int32_t *d_sorted, int32_t *d_offsets, void *d_workspace, size_t workspace_bytes,
+                                  void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RBX_REQUIRE(n >= 0 && n <= (int64_t(1) << 30), "rbx_sort_by_spaxel: n outside [0, 2^30]");
+  RBX_REQUIRE(num_segments >= 1 && num_segments < (1 << 30), "rbx_sort_by_spaxel: num_segments outside [1, 2^30)");
+  if (n == 0) {
+    if (d_offsets) RBX_CUDA_OK(cudaMemsetAsync(d_offsets, 0, sizeof(int32_t) * ((size_t)num_segments + 1), stream));
+    return RBX_OK;
+  }
+  RBX_REQUIRE(d_pixel && d_order, "rbx_sort_by_spaxel: null pointer");
+  RBX_REQUIRE(d_workspace, "rbx_sort_by_spaxel: null workspace");
+  if (workspace_bytes < rbx_sort_by_spaxel_workspace_bytes(n, num_segments)) {
+    set_error("rbx_sort_by_spaxel: workspace too small (see rbx_sort_by_spaxel_workspace_bytes)");
+    return RBX_ERR_WORKSPACE_TOO_SMALL;
+  }
+  const SortPlan sp = make_sort_plan(n, spaxel_end_bit(num_segments));
+  const size_t state_bytes = align256(sizeof(uint32_t) * sort_state_words(sp));
+  const size_t arr_bytes = align256(sizeof(uint32_t) * (size_t)n);
+  char *ws = (char *)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+  uint32_t *state = (uint32_t *)ws;
+  uint32_t *w0 = (uint32_t *)(ws + state_bytes), *w1 = (uint32_t *)(ws + state_bytes + arr_bytes),
+           *w2 = (uint32_t *)(ws + state_bytes + 2 * arr_bytes);
+  // pass p writes the (b) pair when p is even and the (a) pair when it is odd: the pair the LAST pass writes is
+  // the caller's output arrays, the other pair lives in the workspace
+  uint32_t *out_keys = d_sorted ? (uint32_t *)d_sorted : w2, *out_vals = (uint32_t *)d_order;
+  const bool last_is_b = (sp.npass & 1) != 0;
+  uint32_t *keys_a = last_is_b ? w0 : out_keys, *vals_a = last_is_b ? w1 : out_vals;
+  uint32_t *keys_b = last_is_b ? out_keys : w0, *vals_b = last_is_b ? out_vals : w1;
+  RBX_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * sort_state_words(sp), stream));
+  const int blocks = (int)std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), 148 * 8);
+  spaxel_keys_kernel<<<blocks, 256, 0, stream>>>(d_pixel, (int)n, num_segments, keys_a, state, sp,
+                                                 ((size_t)sp.ntiles + 2) * 256);
+  count_launch();
+  RBX_LAUNCH_OK();
+  uint32_t *ks = nullptr, *vs = nullptr;
+  const int rc = radix_sort_pairs(sp, keys_a, vals_a, keys_b, vals_b, n, state, &ks, &vs, stream);
+  if (rc != RBX_OK) return rc;
+  RBX_REQUIRE(ks == out_keys && vs == out_vals, "rbx_sort_by_spaxel: internal buffer order");
+  if (d_offsets) {
+    segment_offsets_kernel<<<blocks * 4, 256, 0, stream>>>(ks, (int)n, num_segments, d_offsets);
+    count_launch();
+    RBX_LAUNCH_OK();
+  }
+  return RBX_OK;
+}

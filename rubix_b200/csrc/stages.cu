@@ -150,6 +150,23 @@ __global__ void segment_sum_kernel(const float *__restrict__ spec, const int32_t
   }
 }
 
+// a5, bit-reproducible form: the particles of a spaxel are added ONE AFTER THE OTHER in particle order (the order of
+// the stable sort's run), a thread per channel -- the float32 sum the reference's CPU segment_sum forms (SURVEY 8a a5:
+// "order = particle order on CPU"), with no atomics.
+__global__ void __launch_bounds__(128)
+segment_sum_sorted_kernel(const float *__restrict__ spec, const int32_t *__restrict__ order,
+                          const int32_t *__restrict__ offsets, int W, int nseg, float *__restrict__ cube) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+    const int lo = offsets[s], hi = offsets[s + 1];
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = lo; i < hi; ++i) acc += spec[(size_t)order[i] * W + w];
+    cube[(size_t)s * W + w] = acc;
+  }
+}
+
 static int grid_for(int64_t n, int per_block) {
   int64_t b = (n + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -240,6 +257,17 @@ extern "C" int rbx_segment_sum(const float *d_spectra, const int32_t *d_pixel, i
   if (n == 0) return RBX_OK;
   RBX_REQUIRE(d_spectra && d_pixel && n > 0, "rbx_segment_sum: null pointer");
   segment_sum_kernel<<<grid_for(n, 1), 256, 0, (cudaStream_t)stream>>>(d_spectra, d_pixel, n, W, nseg, d_cube);
+  count_launch();
+  RBX_LAUNCH_OK();
+  return RBX_OK;
+}
+
+extern "C" int rbx_segment_sum_sorted(const float *d_spectra, const int32_t *d_order, const int32_t *d_offsets,
+                                      int W, int nseg, float *d_cube, void *stream) {
+  RBX_REQUIRE(d_cube && W > 0 && nseg > 0, "rbx_segment_sum_sorted: bad argument");
+  RBX_REQUIRE(d_spectra && d_order && d_offsets, "rbx_segment_sum_sorted: null pointer");
+  const dim3 grid((unsigned)((W + 127) / 128), (unsigned)std::min(nseg, 32768));
+  segment_sum_sorted_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_spectra, d_order, d_offsets, W, nseg, d_cube);
   count_launch();
   RBX_LAUNCH_OK();
   return RBX_OK;

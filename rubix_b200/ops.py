@@ -123,6 +123,24 @@ def filter_and_assign(coords, edges, mass=None, metallicity=None, age=None) -> t
     return pixel
 
 
+def sort_by_spaxel(pixel, num_segments: int, with_sorted: bool = True, with_offsets: bool = True):
+    """Stable device radix sort of particles by spaxel id (``rbx_sort_by_spaxel``): returns
+    ``(order, sorted_ids, offsets)`` -- ``order`` is numpy's stable argsort of the ids with every id outside
+    ``[0, num_segments)`` counted as ``num_segments`` (the particles segment_sum drops, rubix/spectra/ifu.py:286,
+    sort to the end), ``offsets[s]`` the first sorted position with id >= s (``num_segments + 1`` entries)."""
+    pixel = dev(pixel, torch.int32)
+    if pixel.ndim != 1:
+        raise ValueError(f"pixel must have shape (n,), got {tuple(pixel.shape)}")
+    n, S2 = pixel.numel(), int(num_segments)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    srt = torch.empty(n, dtype=torch.int32, device="cuda") if with_sorted else None
+    off = torch.empty(S2 + 1, dtype=torch.int32, device="cuda") if with_offsets else None
+    nbytes = int(_lib.lib().rbx_sort_by_spaxel_workspace_bytes(n, S2))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().rbx_sort_by_spaxel(_p(pixel), n, S2, _p(order), _p(srt), _p(off), _p(ws), nbytes, _stream()))
+    return order, srt, off
+
+
 def euler_rotation_matrix(alpha: float, beta: float, gamma: float) -> np.ndarray:
     """rubix/galaxy/alignment.py:164-209: R = R_z R_y R_x (degrees), float32."""
     a, b, g = np.deg2rad([alpha, beta, gamma])
@@ -324,12 +342,21 @@ def doppler_resample(plan: Plan, spectra, velocity) -> torch.Tensor:
     return out
 
 
-def segment_sum(spectra, pixel, num_segments: int) -> torch.Tensor:
+def segment_sum(spectra, pixel, num_segments: int, deterministic: bool = False) -> torch.Tensor:
+    """rubix/spectra/ifu.py:286: ``segment_sum`` of the staged spectra.  The default adds with float atomics (any
+    order, like the reference on a GPU backend); ``deterministic=True`` sorts the particles by spaxel
+    (``rbx_sort_by_spaxel``) and adds every spaxel's run one particle after the other in particle order
+    (``rbx_segment_sum_sorted``): bit-reproducible, and the float32 sum the reference forms on the CPU backend."""
     spectra, pixel = dev(spectra), dev(pixel, torch.int32).reshape(-1)
     n, W = spectra.shape
     if pixel.numel() != n:
         raise ValueError("pixel must have one entry per spectrum")
     cube = torch.empty((num_segments, W), dtype=torch.float32, device="cuda")
+    if deterministic:
+        order, _, off = sort_by_spaxel(pixel, num_segments, with_sorted=False)
+        _lib.check(_lib.lib().rbx_segment_sum_sorted(_p(spectra), _p(order), _p(off), W, num_segments, _p(cube),
+                                                     _stream()))
+        return cube
     _lib.check(_lib.lib().rbx_segment_sum(_p(spectra), _p(pixel), n, W, num_segments, _p(cube), 1, _stream()))
     return cube
 

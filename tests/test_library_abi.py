@@ -41,6 +41,13 @@ def test_argument_validation_without_device(lib):
     assert lib.rbx_spaxel_assign(None, 5, None, 1, None, None, None) != 0
     assert lib.rbx_convolve_lsf(None, None, 1, 1, None, 1, 0, None) != 0
     assert lib.rbx_build_cube_workspace_bytes(None, 10, 25) == 0
+    # rbx_sort_by_spaxel: sizes checked first, the workspace query needs no device
+    assert lib.rbx_sort_by_spaxel(None, -1, 625, None, None, None, None, 0, None) != 0
+    assert lib.rbx_sort_by_spaxel(None, 10, 0, None, None, None, None, 0, None) != 0
+    assert lib.rbx_sort_by_spaxel(None, 10, 625, None, None, None, None, 0, None) != 0
+    assert b"null pointer" in lib.rbx_last_error()
+    ws = lib.rbx_sort_by_spaxel_workspace_bytes(10**6, 625)
+    assert 3 * 4 * 10**6 <= ws <= 4 * 4 * 10**6        # three n-word arrays + the tile states of two passes
     h = C.c_void_p()
     rc = lib.rbx_plan_create(C.byref(h), None, 2, None, 2, None, 2, None, None, 1, 0.1, 0, 2, None)
     assert rc == -1  # RBX_ERR_INVALID_ARGUMENT
