@@ -142,3 +142,32 @@ def test_whole_path_against_the_reference_source_cube(ops, cube, bc03, muse_wave
     staged = ops.segment_sum(res, ops.spaxel_assign(coords, x["edges"]), 49, deterministic=True)
     for suffix, v in _thin(staged.cpu().numpy().reshape(7, 7, -1)).items():
         _within(v, cube["out_cube" + suffix], 5e-6, f"{method} staged cube{suffix}")
+
+
+@pytest.mark.parametrize("model", ["Cardelli89", "Gordon23"])
+def test_dusty_variant_against_the_reference_source(ops, model):
+    """rbx_dust_av + rbx_apply_extinction against apply_spaxel_extinction of rubix/spectra/dust/dust_extinction.py run
+    from the reference's source (tests/golden/ref_numpy_dust.npz): spaxels with 0 / 1 / 2 gas cells, stars in front of
+    and behind all gas.  A_V is recovered from the reference's extinction factor at the channel where A(lambda)/A(V)
+    is largest; it reaches 6.6 mag here, so the factor 10^(-0.4 a A_V) amplifies a relative A_V error of 1e-5 to
+    1e-4 of the factor: the product is compared at 3e-4 of the largest spectrum value, A_V itself at 2e-5."""
+    from rubix_b200 import dust as hdust
+    d = np.load(os.path.join(GOLDEN, "ref_numpy_dust.npz"))
+    x = {k[3:]: d[k] for k in d.files if k.startswith("in_")}
+    S, area = int(x["S"]), float(x["spaxel_area"])
+    dtg = hdust.dust_to_gas_parameters("broken power law fit", "Z")             # rubix_config.yml:145-150
+    av = ops.dust_av(x["gas_coords"], x["gas_pixel"], x["gas_mass"], x["gas_metals"], x["star_coords"], x["star_pixel"],
+                     S, dtg, hdust.extinction_constant(3.5), area)
+    axav = hdust.extinction_curve(model, x["wave"], 3.1)
+    key = "cardelli89_axav" if model == "Cardelli89" else "gordon23_axav"
+    k = int(np.argmax(d["out_" + key]))
+    av_ref = -2.5 * np.log10(d[f"out_{model}_factor"][:, k]) / d["out_" + key][k]
+    got = av.cpu().numpy().astype(np.float64)
+    assert av_ref.max() > 1.0 and (av_ref[x["star_pixel"] == 10] == 0).all()
+    assert np.abs(got - av_ref).max() <= 2e-5 * av_ref.max(), np.abs(got - av_ref).max() / av_ref.max()
+    assert (got[x["star_pixel"] == 10] == 0).all()
+    out = ops.apply_extinction(x["spectra"].astype(np.float32), av, axav).cpu().numpy()
+    _within(out, d[f"out_{model}_spectra"], 3e-4, f"dusty spectra {model}")
+    # with the reference's A_V the factor kernel itself is exact to float32 rounding
+    out2 = ops.apply_extinction(x["spectra"].astype(np.float32), av_ref.astype(np.float32), axav).cpu().numpy()
+    _within(out2, d[f"out_{model}_spectra"], 2e-5, f"dusty spectra {model}, reference A_V")

@@ -150,3 +150,71 @@ def test_fixtures_are_what_the_reference_source_gives_now():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "identical" in res.stdout
+
+
+# ---- the dusty variant: rubix/spectra/dust/*.py executed through the same stand-ins -------------------
+@pytest.fixture(scope="module")
+def dust():
+    d = np.load(os.path.join(GOLDEN, "ref_numpy_dust.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def test_dust_curves_and_ratios(dust):
+    mu = dust["in_wave"].astype(np.float64) / 1e4
+    _close(orc.cardelli89(mu, 3.1), dust["out_cardelli89_axav"])
+    _close(orc.cardelli89(mu, 4.5), dust["out_cardelli89_axav_rv45"])
+    _close(orc.gordon23(mu, 3.1), dust["out_gordon23_axav"])
+    _close(orc.gordon23(mu, 2.5), dust["out_gordon23_axav_rv25"])
+    log_oh = np.linspace(7.0, 9.5, 26)
+    for model in ("power law slope free", "broken power law fit"):
+        for xco in ("MW", "Z"):
+            _close(orc.calculate_dust_to_gas_ratio(log_oh, model, xco), dust[f"out_dtg_{model.split()[0]}_{xco}"])
+    _close(orc.calculate_extinction(dust["in_gas_mass"].astype(np.float64), 3.5), dust["out_cell_extinction"])
+
+
+@pytest.mark.parametrize("model", ["Cardelli89", "Gordon23"])
+def test_apply_spaxel_extinction(dust, model):
+    """apply_spaxel_extinction end to end: lexsort by (pixel, z), the 1e30 push of foreign gas cells, cumulative column,
+    jnp.interp(left="extrapolate"), masks, undo-sort, extinction factor -- spaxels with 0 / 1 / 2 gas cells, stars in
+    front of and behind all gas included.  The oracle pushes with a float32 1e30 (x64 is off in the reference), the
+    vectors with a float64 one: the pushed cells carry the value 0 at a distance of 1e30, so this moves A_V by less than
+    1e-25 relative."""
+    x = {k[3:]: v for k, v in dust.items() if k.startswith("in_")}
+    cfg = {"extinction_model": model, "Rv": 3.1, "dust_grain_density": 3.5,
+           "dust_to_gas_model": "broken power law fit", "Xco": "Z"}          # rubix_config.yml:145-150
+    args = (x["wave"], x["gas_coords"][:, 2], x["gas_pixel"], x["gas_mass"], x["gas_metals"], x["star_coords"][:, 2],
+            x["star_pixel"], int(x["S"]), float(x["spaxel_area"]), cfg)
+    factor, av = orc.apply_spaxel_extinction(np.ones_like(x["spectra"]), *args)
+    _close(factor, dust[f"out_{model}_factor"], 1e-11)
+    out, _ = orc.apply_spaxel_extinction(x["spectra"], *args)
+    _close(out, dust[f"out_{model}_spectra"], 1e-11)
+    # the vector does contain the cases it claims: extinguished and untouched stars (spaxel 10 has no gas), a star
+    # behind all the gas of its spaxel (the whole column) and one in front of it (the reference gives it the FIRST
+    # cell's extinction, not 0: the interpolation runs between the pushed-away cells at -1e30 |z| and the first cell)
+    f = dust[f"out_{model}_factor"]
+    assert f.min() < 0.5 and np.isclose(f.max(), 1.0) and (f <= 1.0 + 1e-12).all()
+    in2 = x["star_pixel"] == 2
+    assert av[1] == av[in2].max() and av[0] == av[in2].min() and 0 < av[0] < 0.1 * av[1]
+    assert (av[x["star_pixel"] == 10] == 0).all() and (x["star_pixel"] == 10).any()
+
+
+def test_product_host_side_dust_tables_match_the_reference_source(dust):
+    """rubix_b200/dust.py (product code, evaluated on the host once per configuration, float32): the extinction curves,
+    the dust-to-gas fit parameters and the A_V constant against the reference-source vectors."""
+    from rubix_b200 import dust as hdust
+    wave = dust["in_wave"]
+    for model, key, rv in (("Cardelli89", "cardelli89_axav", 3.1), ("Cardelli89", "cardelli89_axav_rv45", 4.5),
+                           ("Gordon23", "gordon23_axav", 3.1), ("Gordon23", "gordon23_axav_rv25", 2.5)):
+        c = hdust.extinction_curve(model, wave, rv)
+        assert c.dtype == np.float32
+        _close(c, dust["out_" + key], 2e-6)
+    log_oh = np.linspace(7.0, 9.5, 26)
+    for model in ("power law slope free", "broken power law fit"):
+        for xco in ("MW", "Z"):
+            ah, bh, al, bl, xt = (float(v) for v in hdust.dust_to_gas_parameters(model, xco))
+            a, b = np.where(log_oh > xt, ah, al), np.where(log_oh > xt, bh, bl)
+            ref = dust[f"out_dtg_{model.split()[0]}_{xco}"]
+            got = 1.0 / 10.0 ** (a + b * (8.69 - log_oh))
+            assert np.abs(got / ref - 1).max() <= 1e-6        # float32 table entries
+    k = hdust.extinction_constant(3.5)
+    _close(k * dust["in_gas_mass"].astype(np.float64), dust["out_cell_extinction"], 1e-12)

@@ -9,7 +9,8 @@ committed with the outputs), so the vectors are what the reference's formulas ME
 ``tests/test_oracle_vs_reference_source.py`` holds the oracle (its float64 mode, the one every GPU parity test compares
 against) to them, and re-runs the reference source live whenever /root/reference is present.
 
-Outputs: tests/golden/ref_numpy_stages.npz, tests/golden/ref_numpy_cube.npz.
+Outputs: tests/golden/ref_numpy_stages.npz, ref_numpy_cube.npz, ref_numpy_dust.npz (the dusty variant: extinction curves,
+dust-to-gas ratios, cell extinction and apply_spaxel_extinction of rubix/spectra/dust/).
 Not covered: a1 (interpax.interp2d is not installable and is not stood in for) -- the cube fixture puts every particle
 ON a node of the SSP grid, where the reference's own tests pin the lookup to the template row
 (tests/test_core_ssp.py:158-173), so a2 - a7 are exercised end to end without it.
@@ -149,6 +150,63 @@ def run_cube(m, x, S=7):
     return {"pixel": pix.astype(np.int32), "mask": mask, **thin("cube", cube), **thin("cube_psf_lsf", conv)}
 
 
+def dust_inputs():
+    """Gas cells and stars on 12 spaxels: crowded spaxels, spaxels with 0 / 1 / 2 gas cells, stars in front of and
+    behind all the gas of their spaxel, a spaxel with gas and no stars.  float32 values (the CUDA path's inputs)."""
+    rng = np.random.default_rng(77)
+    S, ng, ns, W = 12, 700, 260, 24
+    gp = rng.integers(0, 8, ng)                     # spaxels 0 .. 7 crowded
+    gp[:1] = 8                                      # spaxel 8: one gas cell
+    gp[1:3] = 9                                     # spaxel 9: two gas cells; 10: none; 11: gas but no stars
+    gp[3:9] = 11
+    sp = rng.integers(0, 11, ns)
+    gz = rng.normal(0, 1.0, ng).astype(np.float32)
+    sz = rng.normal(0, 1.6, ns).astype(np.float32)
+    sz[:4] = [-30.0, 30.0, -29.0, 31.0]             # in front of / behind everything
+    sp[:4] = [2, 2, 8, 9]
+    gas_coords = np.concatenate([rng.normal(0, 1, (ng, 2)).astype(np.float32), gz[:, None]], axis=1)
+    star_coords = np.concatenate([rng.normal(0, 1, (ns, 2)).astype(np.float32), sz[:, None]], axis=1)
+    metals = rng.uniform(0.001, 0.05, (ng, 9)).astype(np.float32)
+    metals[:, 0] = rng.uniform(0.70, 0.76, ng).astype(np.float32)            # hydrogen
+    metals[:, 4] = (10 ** rng.uniform(-4.2, -2.0, ng)).astype(np.float32)    # oxygen: 12 + log(O/H) from 7.6 to 9.8
+    return dict(S=np.int64(S), gas_coords=gas_coords, gas_pixel=gp.astype(np.int32),
+                gas_mass=rng.uniform(1e4, 1e6, ng).astype(np.float32), gas_metals=metals, star_coords=star_coords,
+                star_pixel=sp.astype(np.int32), spectra=rng.uniform(0.5, 2.0, (ns, W)),
+                wave=np.linspace(3600.0, 9900.0, W).astype(np.float32), spaxel_area=np.float64(0.145))
+
+
+def run_dust(x):
+    """apply_spaxel_extinction (rubix/spectra/dust/dust_extinction.py:169-358) and its helpers, for both extinction
+    curves, on a stand-in RubixData carrying exactly the fields the function reads."""
+    from types import SimpleNamespace as NS
+    for f in ("helpers", "generic_models", "dust_baseclasses", "extinction_models"):
+        refshim.load(f"rubix/spectra/dust/{f}.py")
+    de = refshim.load("rubix/spectra/dust/dust_extinction.py")
+    em = sys.modules["rubix.spectra.dust.extinction_models"]
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    o = {}
+    mu = f64(x["wave"]) / 1e4
+    o["cardelli89_axav"] = em.Cardelli89(Rv=3.1)(mu)
+    o["cardelli89_axav_rv45"] = em.Cardelli89(Rv=4.5)(mu)
+    o["gordon23_axav"] = em.Gordon23(Rv=3.1)(mu)
+    o["gordon23_axav_rv25"] = em.Gordon23(Rv=2.5)(mu)
+    log_oh = np.linspace(7.0, 9.5, 26)
+    for model in ("power law slope free", "broken power law fit"):
+        for xco in ("MW", "Z"):
+            o[f"dtg_{model.split()[0]}_{xco}"] = de.calculate_dust_to_gas_ratio(log_oh, model, xco)
+    o["cell_extinction"] = de.calculate_extinction(f64(x["gas_mass"]), 3.5)
+    for model in ("Cardelli89", "Gordon23"):
+        for spectra, tag in ((np.ones_like(x["spectra"]), "factor"), (x["spectra"], "spectra")):
+            rd = NS(gas=NS(coords=f64(x["gas_coords"])[None], pixel_assignment=x["gas_pixel"][None],
+                           metals=f64(x["gas_metals"])[None], mass=f64(x["gas_mass"])[None]),
+                    stars=NS(coords=f64(x["star_coords"])[None], pixel_assignment=x["star_pixel"][None],
+                             mass=np.ones((1, len(x["star_pixel"]))), spectra=spectra[None]))
+            cfg = {"ssp": {"dust": {"extinction_model": model, "Rv": 3.1, "dust_grain_density": 3.5}}}
+            o[f"{model}_{tag}"] = np.asarray(de.apply_spaxel_extinction(cfg, rd, f64(x["wave"]), int(x["S"]),
+                                                                        f64(x["spaxel_area"])))[0]
+    return {k: np.asarray(v) for k, v in o.items()}
+
+
 def thin(name, cube):
     cube = np.asarray(cube, dtype=np.float64)
     return {name + "_every4th": cube[:, :, ::4].copy(), name + "_spectrum": cube.sum(axis=(0, 1)),
@@ -168,6 +226,10 @@ def check():
     xc = cube_inputs()
     bad += [k for k, v in xc.items() if not np.array_equal(v, cu["in_" + k])]
     bad += [k for k, v in run_cube(m, xc).items() if not np.array_equal(v, cu["out_" + k])]
+    du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
+    xd = dust_inputs()
+    bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
+    bad += [k for k, v in run_dust(xd).items() if not np.array_equal(v, du["out_" + k])]
     print("reference source vs committed fixtures:", "identical" if not bad else f"MISMATCH in {bad}")
     return 1 if bad else 0
 
@@ -186,7 +248,10 @@ def main():
     oc = run_cube(m, xc)
     np.savez_compressed(os.path.join(OUT, "ref_numpy_cube.npz"), **{"in_" + k: v for k, v in xc.items()},
                         **{"out_" + k: v for k, v in oc.items()})
-    for f in ("ref_numpy_stages.npz", "ref_numpy_cube.npz"):
+    xd = dust_inputs()
+    np.savez_compressed(os.path.join(OUT, "ref_numpy_dust.npz"), **{"in_" + k: v for k, v in xd.items()},
+                        **{"out_" + k: v for k, v in run_dust(xd).items()})
+    for f in ("ref_numpy_stages.npz", "ref_numpy_cube.npz", "ref_numpy_dust.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
 

@@ -83,6 +83,53 @@ def _segment_sum(data, segment_ids, num_segments):
     return out
 
 
+def _interp(x, xp, fp, left=None, right=None, period=None):
+    """jnp.interp.  Without "extrapolate" it is numpy's; with it, the formula of jax's implementation (the documented
+    behaviour: linear continuation of the first / last segment) -- numpy has no such option."""
+    if period is not None:
+        raise NotImplementedError("periodic interp is not used on the path")
+    if left != "extrapolate" and right != "extrapolate":
+        return np.interp(x, xp, fp, left=left, right=right)
+    x, xp, fp = np.asarray(x), np.asarray(xp), np.asarray(fp)
+    i = np.clip(np.searchsorted(xp, x, side="right"), 1, len(xp) - 1)
+    df, dx, delta = fp[i] - fp[i - 1], xp[i] - xp[i - 1], x - xp[i - 1]
+    dx0 = np.abs(dx) <= np.spacing(np.finfo(xp.dtype).eps)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        f = np.where(dx0, fp[i - 1], fp[i - 1] + (delta / np.where(dx0, 1, dx)) * df)
+    if left != "extrapolate":
+        f = np.where(x < xp[0], fp[0] if left is None else left, f)
+    if right != "extrapolate":
+        f = np.where(x > xp[-1], fp[-1] if right is None else right, f)
+    return f
+
+
+def _scan(f, init, xs):
+    carry, ys = init, []
+    for x in xs:
+        carry, y = f(carry, x)
+        ys.append(y)
+    return carry, (None if all(y is None for y in ys) else np.stack(ys))
+
+
+def _sort_key_val(keys, values):
+    order = np.argsort(keys, kind="stable")           # lax.sort_key_val is a stable sort by key
+    return np.asarray(keys)[order], np.asarray(values)[order]
+
+
+class _EqxModule:
+    """equinox.Module, as far as the extinction models need it: subclasses are dataclasses."""
+
+    def __init_subclass__(cls, **kw):
+        import dataclasses
+        super().__init_subclass__(**kw)
+        dataclasses.dataclass(cls)
+
+
+def _eqx_field(converter=None, static=False, default=None, **kw):
+    import dataclasses
+    return dataclasses.field(default=default)
+
+
 class _Rotation:
     """jax.scipy.spatial.transform.Rotation, the part alignment.py uses (scipy's has the same conventions)."""
 
@@ -133,14 +180,18 @@ def install():
     jnp.zeros = lambda *a, **k: np.zeros(*a, **k).view(_Arr)
     jnp.array = lambda *a, **k: np.array(*a, **k)
     jnp.ndarray = np.ndarray
+    jnp.interp = _interp
     sig = _module("jax.scipy.signal", convolve=scipy.signal.convolve, convolve2d=scipy.signal.convolve2d)
     tr = _module("jax.scipy.spatial.transform", Rotation=_Rotation)
     sp = _module("jax.scipy.spatial", transform=tr)
     jsp = _module("jax.scipy", signal=sig, spatial=sp)
     ops = _module("jax.ops", segment_sum=_segment_sum)
     rnd = _module("jax.random")
-    _module("jax", numpy=jnp, scipy=jsp, ops=ops, random=rnd, vmap=_vmap, jit=lambda f, **k: f, Array=np.ndarray,
-            _rbx_shim=True)
+    lax = _module("jax.lax", scan=_scan, sort_key_val=_sort_key_val,
+                  cond=lambda pred, t, f, operand=None: t(operand) if pred else f(operand))
+    _module("jax", numpy=jnp, scipy=jsp, ops=ops, random=rnd, lax=lax, vmap=_vmap, jit=lambda f, **k: f,
+            Array=np.ndarray, _rbx_shim=True)
+    _module("equinox", Module=_EqxModule, AbstractVar=_Subscriptable, field=_eqx_field, filter_jit=lambda c: c)
     ident = lambda *a, **k: (a[0] if a and callable(a[0]) and not k else (lambda f: f))
     names = {k: _Subscriptable for k in ("Array", "Float", "Int", "Bool", "PyTree", "Shaped", "Num")}
     _module("jaxtyping", jaxtyped=lambda *a, **k: (lambda f: f), **names)
@@ -149,7 +200,11 @@ def install():
     _module("rubix", config=cfg, __path__=[])
     _module("rubix.cosmology", __path__=[])
     _module("rubix.cosmology.base", BaseCosmology=object)
-    for pkg in ("rubix.spectra", "rubix.telescope", "rubix.telescope.psf", "rubix.telescope.lsf",
+    import logging
+    _module("rubix.core", __path__=[])
+    _module("rubix.core.data", RubixData=object)
+    _module("rubix.logger", get_logger=lambda *a, **k: logging.getLogger("rubix-refshim"))
+    for pkg in ("rubix.spectra", "rubix.spectra.dust", "rubix.telescope", "rubix.telescope.psf", "rubix.telescope.lsf",
                 "rubix.telescope.noise", "rubix.galaxy"):
         _module(pkg, __path__=[])
     _installed = True
