@@ -218,3 +218,24 @@ def test_product_host_side_dust_tables_match_the_reference_source(dust):
             assert np.abs(got / ref - 1).max() <= 1e-6        # float32 table entries
     k = hdust.extinction_constant(3.5)
     _close(k * dust["in_gas_mass"].astype(np.float64), dust["out_cell_extinction"], 1e-12)
+
+
+def test_product_host_side_cosmology_and_bin_edges(stages):
+    """rubix_b200/cosmology.py and telescope.calculate_spatial_bin_edges (product host code, once per configuration)
+    against rubix/cosmology/base.py + rubix/telescope/utils.py:30-37 run from source in float32.  Distances and the
+    angular scale agree bit for bit; the edges come from numpy's float64 arange in the stand-in and from a float32
+    arange here (as jnp.arange gives with x64 off): same number of edges, values within one float32 ulp."""
+    from rubix_b200.cosmology import PLANCK15
+    from rubix_b200.telescope import calculate_spatial_bin_edges
+    zs = stages["cosmo_z"]
+    assert np.array_equal(np.array([PLANCK15.angular_scale(float(z)) for z in zs]), stages["cosmo_angular_scale"])
+    assert np.array_equal(np.array([PLANCK15.comoving_distance_to_z(float(z)) for z in zs]), stages["cosmo_comoving"])
+    assert np.array_equal(np.array([PLANCK15.luminosity_distance_to_z(float(z)) for z in zs]),
+                          stages["cosmo_luminosity"])
+    assert stages["cosmo_angular_scale"].dtype == np.float32
+    for tag, fov, nb, z in (("muse", 5.0, 25, 0.1), ("fov30", 30.0, 150, 0.1), ("z03", 5.0, 25, 0.3)):
+        e, size = calculate_spatial_bin_edges(fov, nb, z, PLANCK15)
+        ref = stages["cosmo_edges_" + tag]
+        assert e.dtype == np.float32 and len(e) == len(ref) and len(e) in (nb + 1, nb + 2)
+        assert float(size) == float(stages["cosmo_size_" + tag])
+        assert np.abs(e.astype(np.float64) - ref).max() <= 1.2e-7 * np.abs(ref).max()

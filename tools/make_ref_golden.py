@@ -150,6 +150,34 @@ def run_cube(m, x, S=7):
     return {"pixel": pix.astype(np.int32), "mask": mask, **thin("cube", cube), **thin("cube_psf_lsf", conv)}
 
 
+def run_cosmology():
+    """rubix/cosmology/base.py + utils.py and calculate_spatial_bin_edges (rubix/telescope/utils.py:30-37) in float32:
+    the class holds float32 parameters, and with x64 off ``jnp.linspace`` of Python floats is float32 too (the stand-in
+    is switched to that for this function).  Both sides are numpy here, so this pins the LOGIC (256-point trapezoid by
+    scan, constants, the arange that yields 26 or 27 edges), not XLA's float32 pow / exp roundings."""
+    import jax.numpy as jnp      # the stand-in installed by refshim
+    refshim.load("rubix/cosmology/utils.py")
+    sys.modules.pop("rubix.cosmology.base", None)
+    keep = jnp.linspace
+    jnp.linspace = lambda *a, **k: np.linspace(*a, **k).astype(np.float32)
+    try:
+        base = refshim.load("rubix/cosmology/base.py")
+        sys.modules.pop("rubix.telescope.utils", None)
+        tel = refshim.load("rubix/telescope/utils.py")          # re-bound to the real BaseCosmology
+        c = base.BaseCosmology(0.3075, -1.0, 0.0, 0.6774)       # PLANCK15, rubix/cosmology/__init__.py:3
+        zs = np.array([0.01, 0.05, 0.1, 0.3, 1.0])
+        o = {"z": zs, "angular_scale": np.array([c.angular_scale(float(z)) for z in zs]),
+             "comoving": np.array([c.comoving_distance_to_z(float(z)) for z in zs]),
+             "luminosity": np.array([c.luminosity_distance_to_z(float(z)) for z in zs])}
+        for tag, fov, nb in (("muse", 5.0, 25), ("fov30", 30.0, 150), ("z03", 5.0, 25)):
+            # spatial_bins as a Python int: numpy would promote float32 / np.int64 to float64, jax (x64 off) keeps float32
+            e, size = tel.calculate_spatial_bin_edges(fov, int(nb), 0.3 if tag == "z03" else 0.1, c)
+            o["edges_" + tag], o["size_" + tag] = np.asarray(e), np.asarray(size)
+    finally:
+        jnp.linspace = keep
+    return o
+
+
 def dust_inputs():
     """Gas cells and stars on 12 spaxels: crowded spaxels, spaxels with 0 / 1 / 2 gas cells, stars in front of and
     behind all the gas of their spaxel, a spaxel with gas and no stars.  float32 values (the CUDA path's inputs)."""
@@ -226,6 +254,7 @@ def check():
     xc = cube_inputs()
     bad += [k for k, v in xc.items() if not np.array_equal(v, cu["in_" + k])]
     bad += [k for k, v in run_cube(m, xc).items() if not np.array_equal(v, cu["out_" + k])]
+    bad += [k for k, v in run_cosmology().items() if not np.array_equal(v, st["cosmo_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -243,7 +272,8 @@ def main():
     o = run_stages(m, x)
     np.savez_compressed(os.path.join(OUT, "ref_numpy_stages.npz"), **{"in_" + k: v for k, v in x.items()
                                                                       if k not in ("lam_ssp", "wave")},
-                        **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")})
+                        **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")},
+                        **{"cosmo_" + k: v for k, v in run_cosmology().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     np.savez_compressed(os.path.join(OUT, "ref_numpy_cube.npz"), **{"in_" + k: v for k, v in xc.items()},

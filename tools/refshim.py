@@ -105,7 +105,7 @@ def _interp(x, xp, fp, left=None, right=None, period=None):
 
 def _scan(f, init, xs):
     carry, ys = init, []
-    for x in xs:
+    for x in (zip(*xs) if isinstance(xs, tuple) else xs):     # a tuple of arrays is scanned element-wise
         carry, y = f(carry, x)
         ys.append(y)
     return carry, (None if all(y is None for y in ys) else np.stack(ys))
@@ -187,7 +187,7 @@ def install():
     jsp = _module("jax.scipy", signal=sig, spatial=sp)
     ops = _module("jax.ops", segment_sum=_segment_sum)
     rnd = _module("jax.random")
-    lax = _module("jax.lax", scan=_scan, sort_key_val=_sort_key_val,
+    lax = _module("jax.lax", scan=_scan, sort_key_val=_sort_key_val, exp=np.exp,
                   cond=lambda pred, t, f, operand=None: t(operand) if pred else f(operand))
     _module("jax", numpy=jnp, scipy=jsp, ops=ops, random=rnd, lax=lax, vmap=_vmap, jit=lambda f, **k: f,
             Array=np.ndarray, _rbx_shim=True)
