@@ -171,3 +171,47 @@ def test_dusty_variant_against_the_reference_source(ops, model):
     # with the reference's A_V the factor kernel itself is exact to float32 rounding
     out2 = ops.apply_extinction(x["spectra"].astype(np.float32), av_ref.astype(np.float32), axav).cpu().numpy()
     _within(out2, d[f"out_{model}_spectra"], 2e-5, f"dusty spectra {model}, reference A_V")
+
+
+def test_factory_closures_against_the_reference_closures(ops, stages):
+    """The drop-in boundary: the closures of rubix/core/{psf,lsf,rotation}.py, run from the reference's source on a
+    stand-in RubixData, against the mirror's closures (staged and fused mode) on the same data."""
+    import itertools
+    from rubix_b200 import core
+    cube = stages["in_lsf_cube"].astype(np.float32)
+    for fused in (False, True):
+        cfg = {"telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6},
+                             "lsf": {"sigma": 0.5}}, "b200": {"fused": fused}}
+        rd = core.RubixData()
+        rd.stars.datacube = ops.dev(cube)
+        f_psf, f_lsf = core.get_convolve_psf(cfg), core.get_convolve_lsf(cfg)
+        assert (f_psf.__name__, f_lsf.__name__) == ("convolve_psf", "convolve_lsf")
+        rd = f_psf(rd)
+        _within(np.asarray(rd.stars.datacube.cpu() if hasattr(rd.stars.datacube, "cpu") else rd.stars.datacube),
+                stages["boundary_psf_closure"], 2e-6, f"convolve_psf closure fused={fused}")
+        rd = f_lsf(rd)
+        _within(rd.stars.datacube.cpu().numpy(), stages["boundary_psf_lsf_closures"], 2e-6,
+                f"convolve_psf + convolve_lsf closures fused={fused}")
+    # rotate_galaxy: eigh's eigenvector signs are backend-dependent in the reference itself (LAPACK in the vector, the
+    # largest-component-positive convention on the device), so the closure must reproduce the vector for ONE of the
+    # eight sign choices of the principal axes: (p R D) E with D = diag(+-1), p R recovered from the vector by E^T
+    cfg = {"galaxy": {"dist_z": 0.1, "rotation": {"alpha": 20.0, "beta": -35.0, "gamma": 70.0}},
+           "data": {"args": {"particle_type": ["stars"]}}}
+    rd = core.make_rubix_data(stages["in_gal_pos"], stages["in_gal_vel"], stages["in_gal_mass"],
+                              np.zeros(500, np.float32), np.zeros(500, np.float32))
+    rd.galaxy.halfmassrad_stars = 4.0
+    f_rot = core.get_galaxy_rotation(cfg)
+    assert f_rot.__name__ == "rotate_galaxy"
+    rd = f_rot(rd)
+    E = stages["out_euler"]
+    best = np.inf
+    for signs in itertools.product((1.0, -1.0), repeat=3):
+        D = np.array(signs)
+        err = 0.0
+        for got, key in ((rd.stars.coords, "boundary_rotation_closure_coords"),
+                         (rd.stars.velocity, "boundary_rotation_closure_velocity")):
+            ref = ((stages[key] @ E.T) * D) @ E
+            err = max(err, np.abs(got.cpu().numpy().astype(np.float64) - ref).max() / np.abs(ref).max())
+        best = min(best, err)
+    print(f"[rotate_galaxy closure] best sign choice: {best:.3e}")
+    assert best <= 1e-5

@@ -239,3 +239,26 @@ def test_product_host_side_cosmology_and_bin_edges(stages):
         assert e.dtype == np.float32 and len(e) == len(ref) and len(e) in (nb + 1, nb + 2)
         assert float(size) == float(stages["cosmo_size_" + tag])
         assert np.abs(e.astype(np.float64) - ref).max() <= 1.2e-7 * np.abs(ref).max()
+
+
+def test_mirror_factories_behave_like_the_reference_factories(stages):
+    """The drop-in boundary: rubix/core/{psf,lsf,noise,rotation,cosmology}.py were run from source on a
+    table of malformed and valid configurations (tools/make_ref_golden.py: BOUNDARY_CASES); the mirror's factories must
+    raise the same exception type with the same message, or return a closure of the same __name__."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_ref_golden import BOUNDARY_CASES, outcome
+    from rubix_b200 import core
+    from rubix_b200.cosmology import get_cosmology
+    ours = {"get_convolve_psf": core.get_convolve_psf, "get_convolve_lsf": core.get_convolve_lsf,
+            "get_apply_noise": core.get_apply_noise, "get_galaxy_rotation": core.get_galaxy_rotation,
+            "get_cosmology": get_cosmology}
+    ref = json.loads(str(stages["boundary_outcomes_json"]))
+    assert set(ref) == set(ours) and sum(len(v) for v in ref.values()) == 23
+    for name, cases in BOUNDARY_CASES.items():
+        for cfg, want in zip(cases, ref[name]):
+            got = outcome(ours[name], cfg)
+            if want[0] == "ok" and name == "get_cosmology":
+                assert got[0] == "ok", (name, cfg, got)      # an object, not a closure: the class name is the mirror's own
+            else:
+                assert got == want, (name, cfg, got, want)

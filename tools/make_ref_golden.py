@@ -178,6 +178,90 @@ def run_cosmology():
     return o
 
 
+# malformed / valid configurations handed to the reference's factories and to the mirror's (tests compare the outcome)
+BOUNDARY_CASES = {
+    "get_convolve_psf": [
+        {"telescope": {"name": "MUSE"}},
+        {"telescope": {"name": "MUSE", "psf": {}}},
+        {"telescope": {"name": "MUSE", "psf": {"name": "gaussian"}}},
+        {"telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5}}},
+        {"telescope": {"name": "MUSE", "psf": {"name": "moffat", "size": 5, "sigma": 0.6}}},
+        {"telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6}}},
+    ],
+    "get_convolve_lsf": [
+        {"telescope": {"name": "MUSE"}},
+        {"telescope": {"name": "MUSE", "lsf": {}}},
+        {"telescope": {"name": "MUSE", "lsf": {"sigma": 0.5}}},
+    ],
+    "get_apply_noise": [
+        {"telescope": {"name": "MUSE"}},
+        {"telescope": {"name": "MUSE", "noise": {}}},
+        {"telescope": {"name": "MUSE", "noise": {"signal_to_noise": 10}}},
+        {"telescope": {"name": "MUSE", "noise": {"signal_to_noise": 10, "noise_distribution": "normal"}}},
+    ],
+    "get_galaxy_rotation": [
+        {"galaxy": {"dist_z": 0.1}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"type": "sideways"}}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"alpha": 1.0}}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"alpha": 1.0, "beta": 2.0}}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"type": "face-on"}}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"type": "edge-on"}}},
+        {"galaxy": {"dist_z": 0.1, "rotation": {"alpha": 20.0, "beta": -35.0, "gamma": 70.0}}},
+    ],
+    "get_cosmology": [
+        {"cosmology": {"name": "WMAP9"}},
+        {"cosmology": {"name": "planck15"}},
+        {"cosmology": {"name": "CUSTOM", "args": {"Om0": 0.3, "w0": -1.0, "wa": 0.0, "h": 0.7}}},
+    ],
+}
+
+
+def outcome(factory, cfg):
+    """What a factory call gives: ("error", type name, message) or ("ok", the returned object's __name__ / type)."""
+    try:
+        f = factory(cfg)
+    except Exception as e:   # noqa: BLE001
+        return ["error", type(e).__name__, str(e)]
+    return ["ok", getattr(f, "__name__", type(f).__name__)]
+
+
+def run_boundary(x):
+    """The reference's own factories (rubix/core/{psf,lsf,noise,rotation,cosmology}.py): outcomes for BOUNDARY_CASES
+    and what their closures do to a stand-in RubixData (only the attributes the closures touch)."""
+    import json
+    from types import SimpleNamespace as NS
+    refshim.load("rubix/telescope/psf/kernels.py")
+    refshim.load("rubix/telescope/psf/psf.py")
+    refshim.load("rubix/telescope/lsf/lsf.py")
+    refshim.load("rubix/telescope/noise/noise.py")
+    refshim.load("rubix/galaxy/alignment.py")
+    refshim.load("rubix/cosmology/utils.py")
+    sys.modules.pop("rubix.cosmology.base", None)
+    base = refshim.load("rubix/cosmology/base.py")
+    cosmo_pkg = sys.modules["rubix.cosmology"]
+    cosmo_pkg.RubixCosmology = base.BaseCosmology                      # rubix/cosmology/__init__.py:1-3
+    cosmo_pkg.PLANCK15 = base.BaseCosmology(0.3075, -1.0, 0.0, 0.6774)
+    # get_telescope needs the telescope factory (yaml + equinox classes); the LSF factory reads one attribute of it
+    sys.modules["rubix.core.telescope"] = type(sys)("rubix.core.telescope")
+    sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(wave_res=1.25)   # telescopes.yaml: MUSE
+    core = {k: refshim.load(f"rubix/core/{k}.py") for k in ("psf", "lsf", "noise", "rotation", "cosmology")}
+    fac = {"get_convolve_psf": core["psf"].get_convolve_psf, "get_convolve_lsf": core["lsf"].get_convolve_lsf,
+           "get_apply_noise": core["noise"].get_apply_noise, "get_galaxy_rotation": core["rotation"].get_galaxy_rotation,
+           "get_cosmology": core["cosmology"].get_cosmology}
+    table = {name: [outcome(fac[name], cfg) for cfg in cases] for name, cases in BOUNDARY_CASES.items()}
+    o = {"outcomes_json": np.array(json.dumps(table))}
+    cube = x["lsf_cube"]
+    rd = NS(stars=NS(datacube=cube.copy()))
+    o["psf_closure"] = fac["get_convolve_psf"](BOUNDARY_CASES["get_convolve_psf"][-1])(rd).stars.datacube
+    o["psf_lsf_closures"] = fac["get_convolve_lsf"](BOUNDARY_CASES["get_convolve_lsf"][-1])(rd).stars.datacube
+    cfg = dict(BOUNDARY_CASES["get_galaxy_rotation"][-1], data={"args": {"particle_type": ["stars"]}})
+    rd = NS(stars=NS(coords=x["gal_pos"].copy(), velocity=x["gal_vel"].copy(), mass=x["gal_mass"].copy()),
+            galaxy=NS(halfmassrad_stars=4.0))
+    rd = fac["get_galaxy_rotation"](cfg)(rd)
+    o["rotation_closure_coords"], o["rotation_closure_velocity"] = rd.stars.coords, rd.stars.velocity
+    return {k: np.asarray(v) for k, v in o.items()}
+
+
 def dust_inputs():
     """Gas cells and stars on 12 spaxels: crowded spaxels, spaxels with 0 / 1 / 2 gas cells, stars in front of and
     behind all the gas of their spaxel, a spaxel with gas and no stars.  float32 values (the CUDA path's inputs)."""
@@ -255,6 +339,7 @@ def check():
     bad += [k for k, v in xc.items() if not np.array_equal(v, cu["in_" + k])]
     bad += [k for k, v in run_cube(m, xc).items() if not np.array_equal(v, cu["out_" + k])]
     bad += [k for k, v in run_cosmology().items() if not np.array_equal(v, st["cosmo_" + k])]
+    bad += [k for k, v in run_boundary(x).items() if not np.array_equal(v, st["boundary_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -273,7 +358,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "ref_numpy_stages.npz"), **{"in_" + k: v for k, v in x.items()
                                                                       if k not in ("lam_ssp", "wave")},
                         **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")},
-                        **{"cosmo_" + k: v for k, v in run_cosmology().items()})
+                        **{"cosmo_" + k: v for k, v in run_cosmology().items()},
+                        **{"boundary_" + k: v for k, v in run_boundary(x).items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     np.savez_compressed(os.path.join(OUT, "ref_numpy_cube.npz"), **{"in_" + k: v for k, v in xc.items()},
