@@ -161,3 +161,58 @@ def test_two_rank_dusty_variant_shards_stars_and_replicates_gas(tmp_path, bc03):
     assert av.max() > 0.1 and ref.max() > 0
     assert np.array_equal(got["av"], av)                       # per-star A_V does not depend on the star sharding
     assert np.abs(got["cube"] - ref).max() <= 1e-12 * ref.max()
+
+
+def _reference_vector_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import c_oracle
+        from oracle import rubix_oracle as orc
+        from rubix_b200 import parallel, synthetic
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        tpl = np.load(os.path.join(root, "rubix_b200", "templates", "bc03lr_f32.npz"))
+        fx = np.load(os.path.join(root, "tests", "golden", "ref_numpy_cube.npz"))
+        data = {k: fx["in_" + k] for k in ("coords", "velocity", "mass", "metallicity", "age")}
+        wave = synthetic.muse_wave()
+        mine = parallel.shard_particles(data, rank, world)
+        cube = c_oracle.particles_to_cube(mine["coords"], mine["velocity"], mine["mass"], mine["metallicity"],
+                                          mine["age"], fx["in_edges"], 7, tpl["metallicity"], tpl["age"],
+                                          tpl["wavelength"], tpl["flux"], wave, 0.1, method="linear", dtype=np.float64,
+                                          n_threads=1)
+        W = len(wave)
+        packed = torch.from_numpy(parallel.slab_pack(cube.reshape(49, W), world, 12))
+        t = torch.from_numpy(np.ascontiguousarray(cube))
+        parallel.allreduce_cube(t)
+        dist.all_reduce(packed)
+        pk = orc.gaussian_kernel_2d(5, 5, 0.6, dtype=np.float64)   # the vector is float64 throughout
+        own = packed[rank].numpy().reshape(7, 7, -1)
+        own = parallel.slab_interior(orc.apply_lsf(orc.apply_psf(own, pk), 0.5, 1.25), W, rank, world, 12)
+        parts = [None] * world
+        dist.all_gather_object(parts, (rank, own, len(mine["mass"])))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "refvec.npz"), cube=t.numpy(), counts=np.array([p[2] for p in parts]),
+                     conv=np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=2))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_reproduce_the_reference_closures_over_two_devices(tmp_path):
+    """The reference-source vector tests/golden/ref_numpy_cube.npz holds the cube rubix/core/ifu.py's own closures give
+    with the particles reshaped to TWO devices (pmap + jnp.sum(axis=0)).  Two gloo ranks, sharded by
+    parallel.shard_particles (the same contiguous ceil(n / 2) split), reduced with parallel.allreduce_cube, PSF + LSF
+    per wavelength slab of the slab-major exchange: the same cube."""
+    world = 2
+    mp.spawn(_reference_vector_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "refvec.npz")
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_numpy_cube.npz"))
+    n = len(fx["in_mass"])
+    assert list(got["counts"]) == [-(-n // 2), n - -(-n // 2)] and fx["out_core_closures_spectra_shape"][1] == -(-n // 2)
+    for name, c in (("cube", got["cube"]), ("cube_psf_lsf", got["conv"])):
+        for suffix, v in (("_every4th", c[:, :, ::4]), ("_spectrum", c.sum(axis=(0, 1))), ("_image", c.sum(axis=2))):
+            ref = fx["out_" + name + suffix]
+            assert np.abs(v - ref).max() <= 1e-11 * np.abs(ref).max(), (name, suffix)
+    for suffix, v in (("_spectrum", got["cube"].sum(axis=(0, 1))), ("_image", got["cube"].sum(axis=2))):
+        ref = fx["out_cube_via_core_closures" + suffix]
+        assert np.abs(v - ref).max() <= 1e-11 * np.abs(ref).max()

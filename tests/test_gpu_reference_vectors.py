@@ -108,7 +108,7 @@ def _thin(c):
 
 @pytest.mark.parametrize("method", ["linear", "cubic"])
 def test_whole_path_against_the_reference_source_cube(ops, cube, bc03, muse_wave, method):
-    """1492 particles on nodes of the SSP grid (where the reference's tests pin the lookup to the template row, for
+    """About 1500 particles on nodes of the SSP grid (where the reference's tests pin the lookup to the template row, for
     either ssp.method), 7 x 7 spaxels: device call, host call and the staged kernels against the cube the reference's
     functions gave.  The fixture holds every 4th channel of every spaxel plus the spaxel-summed spectrum and the
     channel-summed image (tools/make_ref_golden.py: thin)."""

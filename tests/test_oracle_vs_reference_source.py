@@ -262,3 +262,25 @@ def test_mirror_factories_behave_like_the_reference_factories(stages):
                 assert got[0] == "ok", (name, cfg, got)      # an object, not a closure: the class name is the mirror's own
             else:
                 assert got == want, (name, cfg, got, want)
+
+
+def test_device_axis_sum_of_the_reference_closures(cube, bc03, muse_wave):
+    """rubix/core/ifu.py's own closures (scale_spectrum_by_mass -> doppler_shift_and_resampling -> calculate_datacube)
+    were run from source on the particles padded and reshaped to TWO devices (rubix/core/data.py:447-487; pmap +
+    jnp.sum(axis=0), rubix/core/ifu.py:324-333).  Their cube equals the direct evaluation, and the oracle's partial
+    cubes of the same two contiguous shards add up to it: the contract of the multi-GPU path."""
+    n_in = len(cube["in_mass"])
+    assert tuple(cube["out_core_closures_spectra_shape"]) == (2, -(-n_in // 2), 3721)     # zero-padded to 2 x ceil(n / 2)
+    for k in ("_spectrum", "_image"):
+        _close(cube["out_cube_via_core_closures" + k], cube["out_cube" + k], 1e-13)
+    x = {k[3:]: v for k, v in cube.items() if k.startswith("in_")}
+    n = len(x["mass"])
+    per = -(-n // 2)
+    total = 0.0
+    for r in range(2):
+        sl = slice(r * per, min(n, (r + 1) * per))
+        total = total + c_oracle.particles_to_cube(x["coords"][sl], x["velocity"][sl], x["mass"][sl], x["metallicity"][sl],
+                                                   x["age"][sl], x["edges"], 7, bc03["metallicity"], bc03["age"],
+                                                   bc03["wavelength"], bc03["flux"], muse_wave, 0.1, method="linear",
+                                                   dtype=np.float64, n_threads=2)
+    cube_matches("cube", total, cube, 1e-11)

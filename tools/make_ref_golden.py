@@ -262,6 +262,46 @@ def run_boundary(x):
     return {k: np.asarray(v) for k, v in o.items()}
 
 
+def run_core_closures(xc, S=7, n_dev=2):
+    """The closures of rubix/core/ifu.py -- scale_spectrum_by_mass, doppler_shift_and_resampling, calculate_datacube --
+    run from source on a stand-in RubixData with a DEVICE AXIS of two: the particles are padded and reshaped to
+    (2, P, ...) as rubix/core/data.py:447-487 does, pmap runs the per-device cube, jnp.sum(axis=0) adds them
+    (rubix/core/ifu.py:324-333: the reduction the multi-GPU path does with one NCCL collective).  get_telescope and
+    get_ssp are stood in by objects holding the three attributes the closures read; the lookup (a1, interpax) is
+    replaced by the template rows of the node particles, as in run_cube."""
+    from types import SimpleNamespace as NS
+    tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    wave = np.load(os.path.join(OUT, "muse_wave.npy")).astype(np.float64)
+    tel = refshim.load("rubix/telescope/utils.py")
+    refshim.load("rubix/spectra/ifu.py")
+    sys.modules["rubix.core.telescope"] = type(sys)("rubix.core.telescope")
+    sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(wave_seq=wave, sbin=np.int64(S), wave_res=1.25)
+    ssp = type(sys)("rubix.core.ssp")
+    ssp.get_ssp = lambda config: NS(wavelength=tpl["wavelength"].astype(np.float64))
+    ssp.get_lookup_interpolation = ssp.get_lookup_interpolation_pmap = ssp.get_lookup_interpolation_vmap = None
+    sys.modules["rubix.core.ssp"] = ssp
+    sys.modules.pop("rubix.core.ifu", None)
+    ifu = refshim.load("rubix/core/ifu.py")
+    cfg = {"galaxy": {"dist_z": 0.1}, "telescope": {"name": "MUSE"}}
+    mask = np.asarray(tel.mask_particles_outside_aperture(xc["coords"], xc["edges"]))
+    n = len(mask)
+    per = -(-n // n_dev)
+
+    def shard(a):                                   # rubix/core/data.py:471-482: zero padding, then (n_dev, per, ...)
+        a = np.asarray(a)
+        pad = np.zeros((per * n_dev - n,) + a.shape[1:], dtype=a.dtype)
+        return np.concatenate([a, pad]).reshape((n_dev, per) + a.shape[1:])
+
+    rows = tpl["flux"].astype(np.float64)[xc["node_z"], xc["node_age"]]
+    rd = NS(stars=NS(spectra=shard(rows), mass=shard(np.where(mask, xc["mass"].astype(np.float64), 0.0)),
+                     velocity=shard(xc["velocity"].astype(np.float64)),
+                     pixel_assignment=shard(np.asarray(tel.square_spaxel_assignment(xc["coords"], xc["edges"])))),
+            gas=NS(spectra=None, velocity=None))
+    for get in (ifu.get_scale_spectrum_by_mass, ifu.get_doppler_shift_and_resampling, ifu.get_calculate_datacube):
+        rd = get(cfg)(rd)
+    return np.asarray(rd.stars.datacube), tuple(rd.stars.spectra.shape)
+
+
 def dust_inputs():
     """Gas cells and stars on 12 spaxels: crowded spaxels, spaxels with 0 / 1 / 2 gas cells, stars in front of and
     behind all the gas of their spaxel, a spaxel with gas and no stars.  float32 values (the CUDA path's inputs)."""
@@ -338,6 +378,8 @@ def check():
     xc = cube_inputs()
     bad += [k for k, v in xc.items() if not np.array_equal(v, cu["in_" + k])]
     bad += [k for k, v in run_cube(m, xc).items() if not np.array_equal(v, cu["out_" + k])]
+    bad += [k for k, v in thin("cube_via_core_closures", run_core_closures(xc)[0]).items()
+            if not k.endswith("every4th") and not np.array_equal(v, cu["out_" + k])]
     bad += [k for k, v in run_cosmology().items() if not np.array_equal(v, st["cosmo_" + k])]
     bad += [k for k, v in run_boundary(x).items() if not np.array_equal(v, st["boundary_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
@@ -362,6 +404,9 @@ def main():
                         **{"boundary_" + k: v for k, v in run_boundary(x).items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
+    via, shape = run_core_closures(xc)
+    oc.update({k: v for k, v in thin("cube_via_core_closures", via).items() if not k.endswith("every4th")})
+    oc["core_closures_spectra_shape"] = np.array(shape)
     np.savez_compressed(os.path.join(OUT, "ref_numpy_cube.npz"), **{"in_" + k: v for k, v in xc.items()},
                         **{"out_" + k: v for k, v in oc.items()})
     xd = dust_inputs()

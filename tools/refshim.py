@@ -73,6 +73,14 @@ def _vmap(fn, in_axes=0, out_axes=0):
     return mapped
 
 
+def _pmap(fn):
+    """jax.pmap as a loop over the leading (device) axis of every positional and keyword argument."""
+    def mapped(*args, **kw):
+        n = len(args[0]) if args else len(next(iter(kw.values())))
+        return np.stack([fn(*[a[i] for a in args], **{k: v[i] for k, v in kw.items()}) for i in range(n)])
+    return mapped
+
+
 def _segment_sum(data, segment_ids, num_segments):
     data, ids = np.asarray(data), np.asarray(segment_ids)
     out = np.zeros((num_segments,) + data.shape[1:], dtype=data.dtype)
@@ -189,8 +197,10 @@ def install():
     rnd = _module("jax.random")
     lax = _module("jax.lax", scan=_scan, sort_key_val=_sort_key_val, exp=np.exp,
                   cond=lambda pred, t, f, operand=None: t(operand) if pred else f(operand))
-    _module("jax", numpy=jnp, scipy=jsp, ops=ops, random=rnd, lax=lax, vmap=_vmap, jit=lambda f, **k: f,
-            Array=np.ndarray, _rbx_shim=True)
+    import functools
+    tree = _module("jax.tree_util", Partial=functools.partial)
+    _module("jax", numpy=jnp, scipy=jsp, ops=ops, random=rnd, lax=lax, tree_util=tree, vmap=_vmap, pmap=_pmap,
+            jit=lambda f, **k: f, Array=np.ndarray, _rbx_shim=True)
     _module("equinox", Module=_EqxModule, AbstractVar=_Subscriptable, field=_eqx_field, filter_jit=lambda c: c)
     ident = lambda *a, **k: (a[0] if a and callable(a[0]) and not k else (lambda f: f))
     names = {k: _Subscriptable for k in ("Array", "Float", "Int", "Bool", "PyTree", "Shaped", "Num")}
@@ -202,7 +212,7 @@ def install():
     _module("rubix.cosmology.base", BaseCosmology=object)
     import logging
     _module("rubix.core", __path__=[])
-    _module("rubix.core.data", RubixData=object)
+    _module("rubix.core.data", RubixData=object, StarsData=object, GasData=object)
     _module("rubix.logger", get_logger=lambda *a, **k: logging.getLogger("rubix-refshim"))
     for pkg in ("rubix.spectra", "rubix.spectra.dust", "rubix.telescope", "rubix.telescope.psf", "rubix.telescope.lsf",
                 "rubix.telescope.noise", "rubix.galaxy"):
