@@ -8,7 +8,8 @@
  * are materialised for every particle, then scatter-added), so that it can be timed as "the
  * reference's algorithm on host cores".  Compiled twice: REAL=float (rbxo32_*) mirrors the JAX
  * float32 arithmetic, REAL=double (rbxo64_*) evaluates the same formulas in double on the same
- * float32 inputs.  Validated against oracle/rubix_oracle.py (numpy) in tests/test_oracle_c.py.
+ * float32 inputs.  Validated against oracle/rubix_oracle.py (numpy) in tests/test_oracle_c.py and against the
+ * cube the reference's own source files give (tests/golden/ref_numpy_cube.npz, tests/test_oracle_vs_reference_source.py).
  *
  * interp2d is interpax.interp2d (PyPI, unpinned by the reference): off-node values are
  * "parity unpinned" -- see the header of rubix_oracle.py.

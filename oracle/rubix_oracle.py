@@ -16,11 +16,19 @@ PARITY PINS
 -----------
 * Checked against every known-answer test the reference holds for this path
   (tests/test_oracle_golden.py lists them with file:line).
+* Checked against OUTPUTS OF THE REFERENCE'S OWN SOURCE run here: tools/refshim.py executes the reference files for a0,
+  a2 - a7, rotate_galaxy, calculate_S2N, the dust modules, the cosmology and the rubix.core factories of the path
+  unchanged with numpy standing in for jax.numpy (float64); the vectors are committed as
+  tests/golden/ref_numpy_{stages,cube,dust}.npz with their generator tools/make_ref_golden.py, and
+  tests/test_oracle_vs_reference_source.py holds this file's float64 mode (and the C form) to them at 1e-11
+  (integer results exactly).  That pins the LOGIC of everything but a1 to the reference's code; it is not jax
+  arithmetic (numpy's rounding order, numpy's double-precision ``interp``).
 * ``interp2d`` is NOT in the reference tree: it is ``interpax.interp2d`` (PyPI ``interpax``,
   unpinned in the reference's pyproject.toml:38, no lock file).  Its published algorithm is restated
   in :func:`interp2d` below.  The reference's tests pin it only at grid nodes and out-of-grid
   (tests/test_core_ssp.py:95-181, tests/test_ssp_grid.py:653-698).  **Off-node interpolated values:
-  parity unpinned** (no golden vector exists in the reference and interpax cannot be run here).
+  parity unpinned against interpax** (no golden vector exists in the reference and interpax cannot be run here);
+  tests/test_interp2d_scipy.py pins them to two independent scipy implementations of the published algorithm.
 """
 
 from __future__ import annotations
