@@ -284,3 +284,43 @@ def test_device_axis_sum_of_the_reference_closures(cube, bc03, muse_wave):
                                                    bc03["wavelength"], bc03["flux"], muse_wave, 0.1, method="linear",
                                                    dtype=np.float64, n_threads=2)
     cube_matches("cube", total, cube, 1e-11)
+
+
+def test_mirror_telescope_factory_matches_the_reference_factory(stages):
+    """rubix_b200/telescope.py (product host code) against rubix/telescope/{apertures,base,factory}.py run from source:
+    all 15 telescopes of telescopes.yaml -- sbin, the aperture mask bit for bit (square, circular and hexagonal),
+    wave_seq / wave_edges lengths and end points, the error for an unknown name."""
+    import json
+    from rubix_b200.telescope import TelescopeFactory
+    meta = json.loads(str(stages["telescope_meta_json"]))
+    unknown = meta.pop("__unknown__")
+    assert len(meta) == 15 and {m["aperture_sum"] < m["n_aperture"] for m in meta.values()} == {True, False}
+    f = TelescopeFactory()
+    assert set(f.telescopes_config) == set(meta)
+    exact = 0
+    for name, m in meta.items():
+        t = f.create_telescope(name)
+        assert int(t.sbin) == m["sbin"] and t.pixel_type == m["pixel_type"], name
+        region = np.asarray(t.aperture_region)
+        assert region.size == m["n_aperture"] and float(region.sum()) == m["aperture_sum"], name
+        assert np.array_equal(np.packbits(region > 0), stages["telescope_aperture_" + name]), name
+        ws, we = np.asarray(t.wave_seq), np.asarray(t.wave_edges)
+        # arange lengths are ceil((stop - start) / step): the vector evaluates that on float64 grids, the mirror on the
+        # float32 values jax holds with x64 off (MUSE: 3721.0 exactly against 3721.0004 -> 3721 or 3722 edges), so a
+        # length may differ by one where the quotient is an integer up to rounding; the first element never does
+        assert abs(ws.size - m["n_wave"]) <= 1 and abs(we.size - m["n_edges"]) <= 1, (name, ws.size, we.size, m)
+        exact += (ws.size == m["n_wave"]) + (we.size == m["n_edges"])
+        for got, want in ((ws[0], m["wave_first"]), (we[0], m["edge_first"])):
+            assert abs(float(got) - want) <= 2e-7 * abs(want) + 1e-12, name      # float32 grid here, float64 in the vector
+        # last elements: numpy's float32 arange (what jnp.arange evaluates with x64 off) accumulates the rounding of
+        # its float32 step over the grid (0.1 A over the 878 channels of NIRSpec G140M), the float64 vector does not: only a
+        # loose 2e-5 is asserted; the MUSE grid, the one on the path, is pinned bit-exactly by tests/golden/muse_wave.npy
+        if ws.size == m["n_wave"]:
+            assert abs(float(ws[-1]) - m["wave_last"]) <= 2e-5 * m["wave_last"], name
+        if we.size == m["n_edges"]:
+            assert abs(float(we[-1]) - m["edge_last"]) <= 2e-5 * m["edge_last"], name
+        assert (float(t.fov), float(t.spatial_res), float(t.wave_res)) == (m["fov"], m["spatial_res"], m["wave_res"])
+    assert exact >= 24, exact            # of 30 lengths, the ones that do not sit on an integer quotient
+    with pytest.raises(Exception) as e:
+        f.create_telescope("HST")
+    assert [type(e.value).__name__, str(e.value)] == unknown

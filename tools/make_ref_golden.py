@@ -302,6 +302,43 @@ def run_core_closures(xc, S=7, n_dev=2):
     return np.asarray(rd.stars.datacube), tuple(rd.stars.spectra.shape)
 
 
+def run_telescopes():
+    """rubix/telescope/{apertures,base,factory}.py from source: every telescope of telescopes.yaml through
+    TelescopeFactory.create_telescope -- sbin, aperture mask (square / circular / hexagonal), length and end points of
+    wave_seq and wave_edges.  The wave grids are numpy float64 aranges here (float32 in jax, x64 off): lengths and end
+    points are compared, the MUSE grid itself is pinned bit-exactly by tests/golden/muse_wave.npy."""
+    import json
+    import warnings
+    import yaml
+    mod = type(sys)("rubix.utils")
+    mod.read_yaml = lambda path: yaml.safe_load(open(path))
+    sys.modules["rubix.utils"] = mod
+    sys.modules.pop("rubix.telescope.utils", None)
+    refshim.load("rubix/telescope/utils.py")
+    refshim.load("rubix/telescope/apertures.py")
+    refshim.load("rubix/telescope/base.py")
+    fac = refshim.load("rubix/telescope/factory.py")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f = fac.TelescopeFactory()
+    o, meta = {}, {}
+    for name in f.telescopes_config:
+        t = f.create_telescope(name)
+        o["aperture_" + name] = np.packbits(np.asarray(t.aperture_region) > 0)
+        ws, we = np.asarray(t.wave_seq), np.asarray(t.wave_edges)
+        meta[name] = {"sbin": int(t.sbin), "n_aperture": int(np.asarray(t.aperture_region).size),
+                      "aperture_sum": float(np.asarray(t.aperture_region).sum()), "pixel_type": str(t.pixel_type),
+                      "n_wave": int(ws.size), "wave_first": float(ws[0]), "wave_last": float(ws[-1]),
+                      "n_edges": int(we.size), "edge_first": float(we[0]), "edge_last": float(we[-1]),
+                      "fov": float(t.fov), "spatial_res": float(t.spatial_res), "wave_res": float(t.wave_res)}
+    try:
+        f.create_telescope("HST")
+    except Exception as e:   # noqa: BLE001
+        meta["__unknown__"] = [type(e).__name__, str(e)]
+    o["meta_json"] = np.array(json.dumps(meta))
+    return o
+
+
 def dust_inputs():
     """Gas cells and stars on 12 spaxels: crowded spaxels, spaxels with 0 / 1 / 2 gas cells, stars in front of and
     behind all the gas of their spaxel, a spaxel with gas and no stars.  float32 values (the CUDA path's inputs)."""
@@ -382,6 +419,7 @@ def check():
             if not k.endswith("every4th") and not np.array_equal(v, cu["out_" + k])]
     bad += [k for k, v in run_cosmology().items() if not np.array_equal(v, st["cosmo_" + k])]
     bad += [k for k, v in run_boundary(x).items() if not np.array_equal(v, st["boundary_" + k])]
+    bad += [k for k, v in run_telescopes().items() if not np.array_equal(v, st["telescope_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -401,7 +439,8 @@ def main():
                                                                       if k not in ("lam_ssp", "wave")},
                         **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")},
                         **{"cosmo_" + k: v for k, v in run_cosmology().items()},
-                        **{"boundary_" + k: v for k, v in run_boundary(x).items()})
+                        **{"boundary_" + k: v for k, v in run_boundary(x).items()},
+                        **{"telescope_" + k: v for k, v in run_telescopes().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     via, shape = run_core_closures(xc)
