@@ -186,14 +186,16 @@ def get_doppler_shift_and_resampling(config: dict) -> Callable:
 DUSTY_CHUNK = 1 << 20
 
 
-def _dusty_cube(plan, st, mass, pix, num_spaxels: int, extinction):
+def _dusty_cube(plan, st, mass, pix, num_spaxels: int, extinction, impl=None):
     """calc_dusty_ifu with deferred spectra: SSP lookup and mass scaling per chunk of particles, then
-    resampling + extinction + per-spaxel sum in one kernel (rbx_build_cube_dusty)."""
+    resampling + extinction + per-spaxel sum in one kernel (rbx_build_cube_dusty).  ``impl``
+    (``config["b200"]["dusty_impl"]``, else ``RBX_DUSTY_IMPL``): "binned" (default: through the knot-based cube
+    kernel, no cube atomics) or "onepass"."""
     from .. import ops
     av, axav = extinction
     met, age, vel = st.metallicity.reshape(-1), st.age.reshape(-1), st.velocity.reshape(-1, 3)
     n = met.numel()
-    if os.environ.get("RBX_DUSTY_IMPL", "binned") == "binned":
+    if (impl or os.environ.get("RBX_DUSTY_IMPL", "binned")) == "binned":
         cube = ops.build_cube_dusty_binned(plan, vel, mass, met, age, pix, num_spaxels, av, axav)
         if cube is not None:
             return cube
@@ -229,7 +231,8 @@ def get_calculate_datacube(config: dict) -> Callable:
             plan = get_plan(config)
             mass = st.mass.reshape(-1) if d.scaled else __import__("torch").ones_like(st.metallicity.reshape(-1))
             if d.extinction is not None:
-                cube = _dusty_cube(plan, st, mass, pix, num_spaxels, d.extinction)
+                b200 = config.get("b200") if isinstance(config.get("b200"), dict) else {}
+                cube = _dusty_cube(plan, st, mass, pix, num_spaxels, d.extinction, impl=b200.get("dusty_impl"))
             else:
                 cube = ops.build_cube(plan, st.velocity.reshape(-1, 3), mass, st.metallicity.reshape(-1),
                                       st.age.reshape(-1), pix, num_spaxels)
