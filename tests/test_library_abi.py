@@ -86,3 +86,19 @@ def test_slab_geometry_and_comm_argument_checks(lib):
     assert lib.rbx_reduce_scatter_cube(None, None, None, 0, None) != 0
     assert lib.rbx_comm_init(None, None, 0, 1) != 0
     assert lib.rbx_build_cube_status(None, 0, 25, None, None, None, None) != 0
+
+
+def test_plain_c_client_compiles_links_and_gets_error_codes(lib, tmp_path):
+    """The boundary is a C ABI: tests/abi/abi_client.c includes the header as C99 (-Wall -Wextra -Werror -pedantic),
+    links librubix_b200.so and checks versions, geometry helpers, the option table and argument validation."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi", "abi_client.c"), "-o", exe, "-L", libdir, "-lrubix_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "abi_client: ok" in res.stdout, res.stdout + res.stderr
