@@ -208,6 +208,17 @@ BOUNDARY_CASES = {
         {"galaxy": {"dist_z": 0.1, "rotation": {"type": "edge-on"}}},
         {"galaxy": {"dist_z": 0.1, "rotation": {"alpha": 20.0, "beta": -35.0, "gamma": 70.0}}},
     ],
+    "get_ssp": [
+        {},
+        {"ssp": {}},
+        {"ssp": {"template": {}}},
+    ],
+    # the interpolation method the lookup is built with (rubix/core/ssp.py:57-62: "cubic" when ssp.method is absent)
+    "ssp_method": [
+        {"ssp": {"template": {"name": "BruzualCharlot2003"}}},
+        {"ssp": {"template": {"name": "BruzualCharlot2003"}, "method": "linear"}},
+        {"ssp": {"template": {"name": "BruzualCharlot2003"}, "method": "cubic"}},
+    ],
     "get_cosmology": [
         {"cosmology": {"name": "WMAP9"}},
         {"cosmology": {"name": "planck15"}},
@@ -222,7 +233,7 @@ def outcome(factory, cfg):
         f = factory(cfg)
     except Exception as e:   # noqa: BLE001
         return ["error", type(e).__name__, str(e)]
-    return ["ok", getattr(f, "__name__", type(f).__name__)]
+    return ["ok", f if isinstance(f, str) else getattr(f, "__name__", type(f).__name__)]
 
 
 def run_boundary(x):
@@ -244,10 +255,19 @@ def run_boundary(x):
     # get_telescope needs the telescope factory (yaml + equinox classes); the LSF factory reads one attribute of it
     sys.modules["rubix.core.telescope"] = type(sys)("rubix.core.telescope")
     sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(wave_res=1.25)   # telescopes.yaml: MUSE
-    core = {k: refshim.load(f"rubix/core/{k}.py") for k in ("psf", "lsf", "noise", "rotation", "cosmology")}
+    # get_ssp_template reads the HDF5 template (h5py): stood in by an object whose lookup factory hands back the
+    # interpolation method it was asked for
+    for pkg in ("rubix.spectra.ssp",):
+        sys.modules.setdefault(pkg, type(sys)(pkg)).__path__ = []
+    fmod = type(sys)("rubix.spectra.ssp.factory")
+    fmod.get_ssp_template = lambda name: NS(get_lookup_interpolation=lambda method: method)
+    sys.modules["rubix.spectra.ssp.factory"] = fmod
+    sys.modules.pop("rubix.core.ssp", None)
+    core = {k: refshim.load(f"rubix/core/{k}.py") for k in ("psf", "lsf", "noise", "rotation", "cosmology", "ssp")}
     fac = {"get_convolve_psf": core["psf"].get_convolve_psf, "get_convolve_lsf": core["lsf"].get_convolve_lsf,
            "get_apply_noise": core["noise"].get_apply_noise, "get_galaxy_rotation": core["rotation"].get_galaxy_rotation,
-           "get_cosmology": core["cosmology"].get_cosmology}
+           "get_cosmology": core["cosmology"].get_cosmology, "get_ssp": core["ssp"].get_ssp,
+           "ssp_method": core["ssp"].get_lookup_interpolation}
     table = {name: [outcome(fac[name], cfg) for cfg in cases] for name, cases in BOUNDARY_CASES.items()}
     o = {"outcomes_json": np.array(json.dumps(table))}
     cube = x["lsf_cube"]
