@@ -37,3 +37,32 @@ def cube_close(out, ref, tag="", rtol_max=5e-6):
     # north star: rtol 1e-5 per voxel relative to the cube's total flux
     assert err <= 1e-5 * tot, f"{tag}: north-star tolerance violated"
     assert err <= rtol_max * mx, f"{tag}: max error {err:.3e} > {rtol_max} * {mx:.3e}"
+
+
+def build_c_host(tmp_path):
+    """Compile tests/abi/c_host_pipeline.c (plain C99, only include/rubix_b200.h) against the in-tree library."""
+    import os
+    import subprocess
+    from rubix_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_host_pipeline")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "abi", "c_host_pipeline.c"), "-o", exe, "-L", libdir, "-lrubix_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def write_c_host_inputs(d, tpl, wave, particles, edges, S, psf, lsf, method):
+    """The raw arrays c_host_pipeline reads (float32 / int32, C order)."""
+    import os
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+    n = len(particles["mass"])
+    dims = np.array([len(tpl["metallicity"]), len(tpl["age"]), len(tpl["wavelength"]), len(wave), n, len(edges), S,
+                     psf.shape[0], psf.shape[1], len(lsf), {"linear": 0, "cubic": 1}[method]], dtype=np.int32)
+    dims.tofile(os.path.join(d, "dims.i32"))
+    for name, a in (("metallicity", tpl["metallicity"]), ("age", tpl["age"]), ("wavelength", tpl["wavelength"]),
+                    ("flux", tpl["flux"]), ("wave", wave), ("coords", particles["coords"]),
+                    ("velocity", particles["velocity"]), ("mass", particles["mass"]), ("met", particles["metallicity"]),
+                    ("age_p", particles["age"]), ("edges", edges), ("psf", psf), ("lsf", lsf)):
+        f32(a).tofile(os.path.join(d, name + ".f32"))

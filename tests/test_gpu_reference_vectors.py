@@ -215,3 +215,24 @@ def test_factory_closures_against_the_reference_closures(ops, stages):
         best = min(best, err)
     print(f"[rotate_galaxy closure] best sign choice: {best:.3e}")
     assert best <= 1e-5
+
+
+def test_c_host_runs_the_whole_path(ops, cube, bc03, muse_wave, tmp_path):
+    """A plain C host (tests/abi/c_host_pipeline.c: only include/rubix_b200.h, host buffers, no Python in the process)
+    runs plan creation + rbx_pipeline_host on the particles of the reference-source cube vector: its cube is bit-identical
+    to the ctypes call and meets the vector like every other entry point."""
+    import subprocess
+    from oracle import rubix_oracle as orc
+    from helpers import build_c_host, write_c_host_inputs
+    x = {k[3:]: v for k, v in cube.items() if k.startswith("in_")}
+    pk, lk = orc.gaussian_kernel_2d(5, 5, 0.6), orc.lsf_kernel(0.5, 1.25)
+    exe = build_c_host(tmp_path)
+    write_c_host_inputs(str(tmp_path), bc03, muse_wave, x, x["edges"], 7, pk, lk, "cubic")
+    res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    got = np.fromfile(tmp_path / "cube.f32", dtype=np.float32).reshape(7, 7, -1)
+    for suffix, v in _thin(got).items():
+        _within(v, cube["out_cube_psf_lsf" + suffix], 5e-6, f"C host cube_psf_lsf{suffix}")
+    plan = ops.Plan(bc03["metallicity"], bc03["age"], bc03["wavelength"], bc03["flux"], muse_wave, 0.1, method="cubic")
+    same = ops.pipeline_host(plan, x["coords"], x["velocity"], x["mass"], x["metallicity"], x["age"], x["edges"], 7, pk, lk)
+    assert np.array_equal(got, same)

@@ -102,3 +102,28 @@ def test_plain_c_client_compiles_links_and_gets_error_codes(lib, tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0 and "abi_client: ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_c_host_of_the_whole_path_fails_loudly_without_a_device(lib, tmp_path, bc03, muse_wave):
+    """tests/abi/c_host_pipeline.c drives rbx_plan_create + rbx_pipeline_host from C with host buffers only.  Without a
+    GPU it must stop with the library's error (no CPU fallback); on a GPU box tests/test_gpu_reference_vectors.py
+    compares its cube with the reference-source vector."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from helpers import build_c_host, write_c_host_inputs
+    from rubix_b200 import synthetic
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a device is present: the GPU test runs the C host")
+    except ImportError:
+        pass
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = build_c_host(tmp_path)
+    write_c_host_inputs(str(tmp_path), bc03, muse_wave, synthetic.bench_g(100), synthetic.spatial_edges(5), 5,
+                        np.full((3, 3), 1 / 9, np.float32), np.ones(1, np.float32), "linear")
+    res = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 1 and "rbx_plan_create" in res.stderr, res.stdout + res.stderr
+    assert not (tmp_path / "cube.f32").exists()
