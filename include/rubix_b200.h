@@ -136,7 +136,8 @@ int rbx_segment_sum(const float *d_spectra, const int32_t *d_pixel, int64_t n, i
 /* a5, bit-reproducible: d_order / d_offsets from rbx_sort_by_spaxel; d_cube (num_segments, W) is OVERWRITTEN with
  * the float32 sums formed one particle after the other in particle order inside every segment -- the sum
  * jax.ops.segment_sum forms on the CPU backend, so the result is bit-identical to a sequential
- * float32 scatter-add of the same spectra.  No atomics; empty segments give 0. */
+ * float32 scatter-add of the same spectra.  No atomics; empty segments give 0 (d_spectra / d_order may be NULL when
+ * every segment is empty). */
 int rbx_segment_sum_sorted(const float *d_spectra, const int32_t *d_order, const int32_t *d_offsets, int W,
                            int num_segments, float *d_cube, void *stream);
 

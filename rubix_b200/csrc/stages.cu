@@ -265,7 +265,8 @@ extern "C" int rbx_segment_sum(const float *d_spectra, const int32_t *d_pixel, i
 extern "C" int rbx_segment_sum_sorted(const float *d_spectra, const int32_t *d_order, const int32_t *d_offsets,
                                       int W, int nseg, float *d_cube, void *stream) {
   RBX_REQUIRE(d_cube && W > 0 && nseg > 0, "rbx_segment_sum_sorted: bad argument");
-  RBX_REQUIRE(d_spectra && d_order && d_offsets, "rbx_segment_sum_sorted: null pointer");
+  // d_spectra / d_order may be NULL for an empty particle set (all offsets equal: nothing is dereferenced)
+  RBX_REQUIRE(d_offsets, "rbx_segment_sum_sorted: null offsets");
   const dim3 grid((unsigned)((W + 127) / 128), (unsigned)std::min(nseg, 32768));
   segment_sum_sorted_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_spectra, d_order, d_offsets, W, nseg, d_cube);
   count_launch();

@@ -351,6 +351,8 @@ def segment_sum(spectra, pixel, num_segments: int, deterministic: bool = False) 
     n, W = spectra.shape
     if pixel.numel() != n:
         raise ValueError("pixel must have one entry per spectrum")
+    if n == 0:                                   # an empty galaxy: nothing to launch
+        return torch.zeros((num_segments, W), dtype=torch.float32, device="cuda")
     cube = torch.empty((num_segments, W), dtype=torch.float32, device="cuda")
     if deterministic:
         order, _, off = sort_by_spaxel(pixel, num_segments, with_sorted=False)

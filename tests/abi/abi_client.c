@@ -30,6 +30,7 @@ int main(void) {
   CHECK(strstr(rbx_last_error(), "null plan") != NULL);
   CHECK(rbx_sort_by_spaxel(NULL, 10, 0, NULL, NULL, NULL, NULL, 0, NULL) == RBX_ERR_INVALID_ARGUMENT);
   CHECK(rbx_segment_sum_sorted(NULL, NULL, NULL, 0, 0, NULL, NULL) == RBX_ERR_INVALID_ARGUMENT);
+  CHECK(rbx_segment_sum_sorted(NULL, NULL, NULL, 10, 5, (float *)&w, NULL) == RBX_ERR_INVALID_ARGUMENT);
   CHECK(rbx_reduce_cube(NULL, NULL, NULL, 0, 0, NULL) != RBX_OK);
   CHECK(rbx_build_cube_workspace_bytes(NULL, 10, 25) == 0);
   {
