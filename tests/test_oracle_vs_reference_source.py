@@ -325,3 +325,32 @@ def test_mirror_telescope_factory_matches_the_reference_factory(stages):
     with pytest.raises(Exception) as e:
         f.create_telescope("HST")
     assert [type(e.value).__name__, str(e.value)] == unknown
+
+
+def test_pipeline_order_matches_the_reference_machinery(stages, tng_subset):
+    """rubix/pipeline/linear_pipeline.py, run from source on the reference's pipeline_config.yml with recorders in place
+    of the twelve stage functions, gives the node order and the call order of calc_ifu and calc_dusty_ifu;
+    RubixPipeline.assemble() of the mirror must produce closures of exactly those names in exactly that order."""
+    import copy
+    import json
+    from rubix_b200 import core
+    ref = json.loads(str(stages["pipeline_json"]))
+    assert set(ref) == {"calc_ifu", "calc_dusty_ifu"}
+    cfg0 = {
+        "pipeline": {"name": "calc_ifu"},
+        "logger": {"log_level": "WARNING", "log_file_path": None,
+                   "format": "%(asctime)s - %(name)s - %(levelname)s - %(message)s"},
+        "telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6}, "lsf": {"sigma": 0.5},
+                      "noise": {"signal_to_noise": 50.0, "noise_distribution": "normal"}},
+        "cosmology": {"name": "PLANCK15"},
+        "galaxy": {"dist_z": 0.1, "rotation": {"alpha": 20.0, "beta": -35.0, "gamma": 70.0}},
+        "ssp": {"template": {"name": "BruzualCharlot2003"},
+                "dust": {"extinction_model": "Cardelli89", "Rv": 3.1, "dust_grain_density": 3.5}},
+        "data": {"args": {"particle_type": ["stars"]}},
+    }
+    for name, want in ref.items():
+        assert want["nodes"] == want["called"] and len(want["nodes"]) == (11 if name == "calc_ifu" else 12)
+        cfg = copy.deepcopy(cfg0)
+        cfg["pipeline"]["name"] = name
+        pipe = core.RubixPipeline(cfg, data=core.make_rubix_data(**tng_subset, device=False))
+        assert [fn.__name__ for fn in pipe.assemble()] == want["called"], name

@@ -322,6 +322,37 @@ def run_core_closures(xc, S=7, n_dev=2):
     return np.asarray(rd.stars.datacube), tuple(rd.stars.spectra.shape)
 
 
+def run_pipeline_orders():
+    """rubix/pipeline/{transformer,abstract_pipeline,linear_pipeline}.py from source on the reference's own
+    rubix/config/pipeline_config.yml: for every pipeline defined there, the node order LinearTransformerPipeline assembles
+    from the depends_on chain, and the order in which its composed expression calls the twelve functions
+    rubix/core/pipeline.py:105-133 registers (stood in by recorders of the same names)."""
+    import json
+    import yaml
+    for pkg in ("rubix.pipeline",):
+        sys.modules.setdefault(pkg, type(sys)(pkg)).__path__ = []
+    sys.modules["jax"].make_jaxpr = lambda f, **k: f
+    refshim.load("rubix/pipeline/transformer.py")
+    sys.modules["rubix.pipeline"].abstract_pipeline = refshim.load("rubix/pipeline/abstract_pipeline.py")
+    lin = refshim.load("rubix/pipeline/linear_pipeline.py")
+    cfgs = yaml.safe_load(open(os.path.join(refshim.REF, "rubix", "config", "pipeline_config.yml")))
+    names = ["rotate_galaxy", "filter_particles", "spaxel_assignment", "calculate_spectra", "reshape_data",
+             "scale_spectrum_by_mass", "doppler_shift_and_resampling", "calculate_extinction", "calculate_datacube",
+             "convolve_psf", "convolve_lsf", "apply_noise"]
+
+    def recorder(name):
+        def fn(trace):
+            return trace + [name]
+        fn.__name__ = name
+        return fn
+
+    out = {}
+    for pname, cfg in cfgs.items():
+        pipe = lin.LinearTransformerPipeline(cfg, [recorder(n) for n in names])
+        out[pname] = {"nodes": list(pipe._names), "called": pipe.expression([])}
+    return {"json": np.array(json.dumps(out))}
+
+
 def run_telescopes():
     """rubix/telescope/{apertures,base,factory}.py from source: every telescope of telescopes.yaml through
     TelescopeFactory.create_telescope -- sbin, aperture mask (square / circular / hexagonal), length and end points of
@@ -440,6 +471,7 @@ def check():
     bad += [k for k, v in run_cosmology().items() if not np.array_equal(v, st["cosmo_" + k])]
     bad += [k for k, v in run_boundary(x).items() if not np.array_equal(v, st["boundary_" + k])]
     bad += [k for k, v in run_telescopes().items() if not np.array_equal(v, st["telescope_" + k])]
+    bad += [k for k, v in run_pipeline_orders().items() if not np.array_equal(v, st["pipeline_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -460,7 +492,8 @@ def main():
                         **{"out_" + k: v for k, v in o.items() if k not in ("diff", "lam_z")},
                         **{"cosmo_" + k: v for k, v in run_cosmology().items()},
                         **{"boundary_" + k: v for k, v in run_boundary(x).items()},
-                        **{"telescope_" + k: v for k, v in run_telescopes().items()})
+                        **{"telescope_" + k: v for k, v in run_telescopes().items()},
+                        **{"pipeline_" + k: v for k, v in run_pipeline_orders().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     via, shape = run_core_closures(xc)
