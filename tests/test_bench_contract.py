@@ -41,3 +41,22 @@ def test_product_arm_needs_a_gpu():
     r = _run("--steps", "1", "--warmup", "3", "--particles", "1000", "--no-cpu")
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is the checker: no file of the product (rubix_b200/, Python or CUDA / C++) may import, link or name
+    it; in bench.py it appears only inside the CPU legs (cpu_arm) and the parity object."""
+    import re
+    hits = []
+    for base, _, files in os.walk(os.path.join(ROOT, "rubix_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", "Makefile")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                if re.search(r"\boracle\b|librubix_oracle|rbxo(32|64)_", text):
+                    hits.append(os.path.join(base, f))
+    assert hits == [], hits
+    # the shipped library does not link the checker either
+    so = os.path.join(ROOT, "rubix_b200", "librubix_b200.so")
+    if os.path.exists(so):
+        out = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+        assert "oracle" not in out
