@@ -80,3 +80,33 @@ def test_cube_from_cells_equals_the_reference_cube(bc03, muse_wave):
     got = particles_to_cube_knots(spec, knots, pix, 9, t)
     assert np.isfinite(got).all()
     assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_channel_unit_knot_positions_are_at_least_as_accurate_as_the_reference_float32(bc03, muse_wave):
+    """The kernels place a knot with ONE float32 FMA in channel units, u' = a eps + b (a = lam_z / delta,
+    b = (lam_z - t0) / delta - 1/2 rounded once from double in plan.cu, eps = expm1(v / c) in the particle record;
+    DESIGN.md section 5, 'channel units').  Emulated here with numpy -- the FMA as a float64 product (exact for two
+    float32 factors) and sum, rounded once to float32 -- and compared, in units of channels, with the exact position of
+    the same float32 inputs and with what the reference's own float32 arithmetic gives (lam_z * exp(v / c),
+    rubix/spectra/ifu.py:190): the claim is an error below 3e-4 channels, no worse than the reference's."""
+    f = np.float32
+    lam_z = (f(1.1) * bc03["wavelength"]).astype(f)                     # rubix/spectra/ifu.py:80 in float32
+    t0, delta = float(muse_wave[0]), 1.25
+    band = (lam_z > 4500) & (lam_z < 9500)
+    lz = lam_z[band].astype(np.float64)
+    a = (lz / delta).astype(f)
+    b = ((lz - t0) / delta - 0.5).astype(f)
+    rng = np.random.default_rng(2)
+    v = np.concatenate([rng.normal(0, 300, 4000), rng.uniform(-1000, 1000, 1000)]).astype(f)
+    c = 299792.458
+    eps = np.expm1(v.astype(np.float64) / c).astype(f)                  # expm1f: correctly rounded to within an ulp
+    u_kernel = (a.astype(np.float64)[None, :] * eps.astype(np.float64)[:, None] + b.astype(np.float64)[None, :]).astype(f)
+    u_exact = (lz[None, :] * np.exp(v.astype(np.float64) / c)[:, None] - t0) / delta - 0.5
+    d32 = np.exp((v / f(c)).astype(f)).astype(f)                        # the reference: exp(v / c) in float32 ...
+    x32 = (lam_z[band][None, :] * d32[:, None]).astype(f)               # ... times lam_z in float32
+    u_ref32 = (x32.astype(np.float64) - t0) / delta - 0.5
+    err_kernel = np.abs(u_kernel.astype(np.float64) - u_exact).max()
+    err_ref32 = np.abs(u_ref32 - u_exact).max()
+    print(f"knot position error in channels: kernel form {err_kernel:.2e}, reference float32 form {err_ref32:.2e}")
+    assert err_kernel <= 3e-4
+    assert err_kernel <= err_ref32
