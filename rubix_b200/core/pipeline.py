@@ -90,30 +90,56 @@ def prepare_input(config: dict) -> RubixData:
     types = config["data"]["args"]["particle_type"] if "data" in config else ["stars"]
     raw = load_rubix_galaxy(path, types)
     st = raw["particle_data"].get("stars")
-    if st is None:
+    gas = raw["particle_data"].get("gas")
+    if st is None and gas is None:
         raise ValueError("Neither stars nor gas coordinates are available.")
     center = raw["subhalo_center"].astype(np.float32)
-    coords = st["coords"]
-    if np.any(center < coords.min(0)) or np.any(center > coords.max(0)):
-        raise ValueError("Center is not within the bounds of the galaxy")
-    logger.info("Centering stars particles")
-    arrays = dict(coords=(coords - center).astype(np.float32), velocity=st["velocity"], mass=st["mass"],
-                  metallicity=st["metallicity"], age=st["age"])
+
+    def centred(part):
+        """rubix/galaxy/alignment.py:14-64 (center_particles): the centre must lie inside the particles' bounding box;
+        coordinates relative to it, velocities relative to the median velocity of the particles within 10 kpc."""
+        coords = np.ascontiguousarray(part["coords"], dtype=np.float32)
+        vel = np.ascontiguousarray(part["velocity"], dtype=np.float32)
+        if np.any(center < coords.min(0)) or np.any(center > coords.max(0)):
+            raise ValueError("Center is not within the bounds of the galaxy")
+        near = np.linalg.norm(coords - center, axis=1) < 10
+        central_velocity = np.median(vel[near], axis=0).astype(np.float32)
+        return (coords - center).astype(np.float32), (vel - central_velocity).astype(np.float32)
+
     sub = config.get("data", {}).get("subset", {})
+    idx = None
     if sub.get("use_subset"):
-        np.random.seed(42)  # rubix/core/data.py:565
-        idx = np.random.choice(np.arange(len(arrays["coords"])), size=sub["subset_size"], replace=False)
-        arrays = {k: v[idx] for k, v in arrays.items()}
-        logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for stars")
-    rd = make_rubix_data(**arrays, device=False)
-    gas = raw["particle_data"].get("gas")
-    if gas is not None:   # rubix/core/data.py:541-600: every stored attribute, centred coordinates
+        # rubix/core/data.py:562-580: seed 42, indices drawn from the STAR count (the gas count only when there are no
+        # stars) and applied to every particle type
+        np.random.seed(42)
+        count = len(st["coords"]) if st is not None else len(gas["coords"])
+        idx = np.random.choice(np.arange(count), size=sub["subset_size"], replace=False)
+    rd = RubixData()
+    if st is not None:
+        logger.info("Centering stars particles")
+        coords, velocity = centred(st)
+        arrays = dict(coords=coords, velocity=velocity, mass=st["mass"], metallicity=st["metallicity"], age=st["age"])
+        if idx is not None:
+            arrays = {k: v[idx] for k, v in arrays.items()}
+            logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for stars")
+        rd = make_rubix_data(**arrays, device=False)
+    if gas is not None:   # rubix/core/data.py:541-600: every stored attribute, centred coordinates and velocities
         logger.info("Centering gas particles")
+        gcoords, gvel = centred(gas) if "velocity" in gas else (None, None)
         for k, v in gas.items():
-            v = (v - center).astype(np.float32) if k == "coords" else np.ascontiguousarray(v, dtype=np.float32)
-            if sub.get("use_subset"):   # the reference draws the indices from the STAR count for gas too
+            if k == "coords" and gcoords is not None:
+                v = gcoords
+            elif k == "coords":
+                v = (np.asarray(v, dtype=np.float32) - center).astype(np.float32)
+            elif k == "velocity":
+                v = gvel
+            else:
+                v = np.ascontiguousarray(v, dtype=np.float32)
+            if idx is not None:
                 v = v[idx]
             setattr(rd.gas, k, v)
+        if idx is not None:
+            logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for gas")
     rd.galaxy.redshift = raw["redshift"]
     rd.galaxy.center = center
     rd.galaxy.halfmassrad_stars = raw["subhalo_halfmassrad_stars"]

@@ -354,3 +354,39 @@ def test_pipeline_order_matches_the_reference_machinery(stages, tng_subset):
         cfg["pipeline"]["name"] = name
         pipe = core.RubixPipeline(cfg, data=core.make_rubix_data(**tng_subset, device=False))
         assert [fn.__name__ for fn in pipe.assemble()] == want["called"], name
+
+
+def test_prepare_input_centres_like_the_reference(stages, monkeypatch, tmp_path):
+    """prepare_input (product host code) against center_particles of rubix/galaxy/alignment.py run from source: the
+    coordinates relative to the subhalo centre AND the velocities relative to the median velocity of the particles
+    within 10 kpc, for stars and for gas (each with its own median), the bounds error, and a gas-only galaxy
+    (rubix/core/data.py:566-575 falls back to the gas count)."""
+    from rubix_b200.core import pipeline as pl
+    f32 = np.float32
+    centre = stages["out_centre"]
+    stars = dict(coords=(stages["in_gal_pos"] + centre).astype(f32),
+                 velocity=(stages["in_gal_vel"] + f32([120.0, -40.0, 15.0])).astype(f32),
+                 mass=np.ones(500, f32), metallicity=np.full(500, 0.01, f32), age=np.full(500, 6.0, f32))
+    gas = dict(coords=(stages["in_gal_pos"] * 4.0 + centre).astype(f32), velocity=stars["velocity"].copy(),
+               mass=np.arange(500, dtype=f32))
+    raw = {"particle_data": {"stars": stars, "gas": gas}, "redshift": 0.1, "subhalo_center": centre,
+           "subhalo_halfmassrad_stars": 2.0}
+    monkeypatch.setattr(pl, "load_rubix_galaxy", lambda path, types: raw)
+    cfg = {"output_path": str(tmp_path), "data": {"args": {"particle_type": ["stars", "gas"]}}}
+    rd = pl.prepare_input(cfg)
+    for part, key in ((rd.stars, "stars"), (rd.gas, "gas")):
+        assert np.array_equal(np.asarray(part.coords), stages[f"out_centre_{key}_coords"]), key
+        assert np.array_equal(np.asarray(part.velocity), stages[f"out_centre_{key}_velocity"]), key
+    assert not np.array_equal(stages["out_centre_stars_velocity"], stages["out_centre_gas_velocity"])   # own medians
+    # gas only
+    raw["particle_data"] = {"gas": gas}
+    cfg["data"]["subset"] = {"use_subset": True, "subset_size": 40}
+    rd = pl.prepare_input(cfg)
+    np.random.seed(42)
+    idx = np.random.choice(np.arange(500), size=40, replace=False)
+    assert np.array_equal(np.asarray(rd.gas.coords), stages["out_centre_gas_coords"][idx]) and rd.stars.coords is None
+    # the centre outside the particles' bounding box
+    raw["particle_data"] = {"stars": dict(stars, coords=(stages["in_gal_pos"].astype(f32) + f32(100.0)))}
+    with pytest.raises(ValueError) as e:
+        pl.prepare_input({"output_path": str(tmp_path), "data": {"args": {"particle_type": ["stars"]}}})
+    assert f"{type(e.value).__name__}: {e.value}" == str(stages["out_centre_error"])
