@@ -92,7 +92,8 @@ def test_fused_and_staged_factories_agree_with_oracle(core, bc03, muse_wave, tng
             assert isinstance(rd.stars.spectra, DeferredSpectra) and rd.stars.spectra.shape == (1, len(d["mass"]), 3721)
         cubes[fused] = rd.stars.datacube.cpu().numpy()
     ref, nb = _oracle_cube(cfg, d, bc03, muse_wave, method)
-    # with 27 float32 edges (nb = 26) ids >= 625 are dropped on both sides, like segment_sum does
+    # the edge count follows float32 rounding (26 edges, nb = 25, for MUSE at z = 0.1; a configuration that rounds to
+    # 27 edges would give nb = 26 and ids >= 625, which both sides drop like segment_sum does)
     _cube_close(cubes[True], ref, f"factory fused {method} (nb={nb})")
     _cube_close(cubes[True], cubes[False].astype(np.float64), f"factory fused vs staged {method}", rtol_max=1e-5)
 
