@@ -390,3 +390,22 @@ def test_prepare_input_centres_like_the_reference(stages, monkeypatch, tmp_path)
     with pytest.raises(ValueError) as e:
         pl.prepare_input({"output_path": str(tmp_path), "data": {"args": {"particle_type": ["stars"]}}})
     assert f"{type(e.value).__name__}: {e.value}" == str(stages["out_centre_error"])
+
+
+def test_product_host_side_taps_and_euler_matrix(stages):
+    """What the mirror's factories hand to the GPU -- the PSF / LSF taps (rubix_b200/telescope.py, float32) and the Euler
+    matrix of rotate_galaxy (rubix_b200/ops.py, host numpy) -- against the reference's functions run from source."""
+    from rubix_b200 import telescope as tel
+    for name, (m, n, s) in {"psf55": (5, 5, 0.6), "psf46": (4, 6, 1.3), "psf33": (3, 3, 2.0)}.items():
+        k = tel.get_psf_kernel("gaussian", m, n, sigma=s)
+        assert k.dtype == np.float32 and k.shape == (m, n)
+        _close(k, stages["out_" + name], 3e-7)
+    _close(tel.lsf_kernel(0.5, 1.25), stages["out_lsf_kernel"], 3e-7)
+    _close(tel.lsf_kernel(3.0, 1.25), stages["out_lsf_kernel_wide"], 3e-7)
+    with pytest.raises(ValueError, match="Unknown PSF kernel name: moffat"):
+        tel.get_psf_kernel("moffat", 5, 5, sigma=0.6)
+    try:
+        from rubix_b200.ops import euler_rotation_matrix
+    except Exception as e:   # torch missing: nothing to check on this box
+        pytest.skip(str(e))
+    _close(euler_rotation_matrix(20.0, -35.0, 70.0), stages["out_euler"], 1e-7)
