@@ -409,3 +409,17 @@ def test_product_host_side_taps_and_euler_matrix(stages):
     except Exception as e:   # torch missing: nothing to check on this box
         pytest.skip(str(e))
     _close(euler_rotation_matrix(20.0, -35.0, 70.0), stages["out_euler"], 1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "
+                                                                       "container")
+def test_differential_fuzz_of_the_oracle_against_the_reference_source():
+    """tools/fuzz_oracle_vs_reference.py: seeded random and degenerate inputs (bands that miss the spectrum, zero and
+    negative spectra, particles on edges, empty spaxels, nobody inside the half-mass radius, kernels as large as the
+    image, stars exactly at gas cells) through the reference's source and the oracle -- no disagreement beyond float64
+    rounding.  (The script detects a 1e-9 relative perturbation of the interpolation and a strict-instead-of-inclusive
+    aperture mask: checked by mutation when it was written.)"""
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_oracle_vs_reference.py"), "60", "3"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "oracle == reference source everywhere" in res.stdout, res.stdout + res.stderr[-2000:]
