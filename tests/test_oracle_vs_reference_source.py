@@ -253,9 +253,9 @@ def test_mirror_factories_behave_like_the_reference_factories(stages):
     from rubix_b200.core.ssp import get_method
     ours = {"get_ssp": core.get_ssp, "ssp_method": get_method, "get_convolve_psf": core.get_convolve_psf, "get_convolve_lsf": core.get_convolve_lsf,
             "get_apply_noise": core.get_apply_noise, "get_galaxy_rotation": core.get_galaxy_rotation,
-            "get_cosmology": get_cosmology}
+            "get_cosmology": get_cosmology, "get_extinction": core.get_extinction}
     ref = json.loads(str(stages["boundary_outcomes_json"]))
-    assert set(ref) == set(ours) and sum(len(v) for v in ref.values()) == 29
+    assert set(ref) == set(ours) and sum(len(v) for v in ref.values()) == 32
     for name, cases in BOUNDARY_CASES.items():
         for cfg, want in zip(cases, ref[name]):
             got = outcome(ours[name], cfg)

@@ -238,6 +238,15 @@ BOUNDARY_CASES = {
         {"ssp": {"template": {"name": "BruzualCharlot2003"}, "method": "linear"}},
         {"ssp": {"template": {"name": "BruzualCharlot2003"}, "method": "cubic"}},
     ],
+    "get_extinction": [
+        {"ssp": {"template": {"name": "BruzualCharlot2003"}}, "telescope": {"name": "MUSE"}, "galaxy": {"dist_z": 0.1},
+         "cosmology": {"name": "PLANCK15"}},
+        {"ssp": {"template": {"name": "BruzualCharlot2003"}, "dust": {}}, "telescope": {"name": "MUSE"},
+         "galaxy": {"dist_z": 0.1}, "cosmology": {"name": "PLANCK15"}},
+        {"ssp": {"template": {"name": "BruzualCharlot2003"},
+                 "dust": {"extinction_model": "Cardelli89", "Rv": 3.1, "dust_grain_density": 3.5}},
+         "telescope": {"name": "MUSE"}, "galaxy": {"dist_z": 0.1}, "cosmology": {"name": "PLANCK15"}},
+    ],
     "get_cosmology": [
         {"cosmology": {"name": "WMAP9"}},
         {"cosmology": {"name": "planck15"}},
@@ -273,7 +282,8 @@ def run_boundary(x):
     cosmo_pkg.PLANCK15 = base.BaseCosmology(0.3075, -1.0, 0.0, 0.6774)
     # get_telescope needs the telescope factory (yaml + equinox classes); the LSF factory reads one attribute of it
     sys.modules["rubix.core.telescope"] = type(sys)("rubix.core.telescope")
-    sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(wave_res=1.25)   # telescopes.yaml: MUSE
+    sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(     # telescopes.yaml: MUSE
+        wave_res=1.25, sbin=np.int64(25), fov=5.0, wave_seq=np.arange(4700.15, 9351.4, 1.25))
     # get_ssp_template reads the HDF5 template (h5py): stood in by an object whose lookup factory hands back the
     # interpolation method it was asked for
     for pkg in ("rubix.spectra.ssp",):
@@ -282,11 +292,14 @@ def run_boundary(x):
     fmod.get_ssp_template = lambda name: NS(get_lookup_interpolation=lambda method: method)
     sys.modules["rubix.spectra.ssp.factory"] = fmod
     sys.modules.pop("rubix.core.ssp", None)
-    core = {k: refshim.load(f"rubix/core/{k}.py") for k in ("psf", "lsf", "noise", "rotation", "cosmology", "ssp")}
+    for f in ("helpers", "generic_models", "dust_baseclasses", "extinction_models", "dust_extinction"):
+        refshim.load(f"rubix/spectra/dust/{f}.py")
+    sys.modules.pop("rubix.core.dust", None)
+    core = {k: refshim.load(f"rubix/core/{k}.py") for k in ("psf", "lsf", "noise", "rotation", "cosmology", "ssp", "dust")}
     fac = {"get_convolve_psf": core["psf"].get_convolve_psf, "get_convolve_lsf": core["lsf"].get_convolve_lsf,
            "get_apply_noise": core["noise"].get_apply_noise, "get_galaxy_rotation": core["rotation"].get_galaxy_rotation,
            "get_cosmology": core["cosmology"].get_cosmology, "get_ssp": core["ssp"].get_ssp,
-           "ssp_method": core["ssp"].get_lookup_interpolation}
+           "ssp_method": core["ssp"].get_lookup_interpolation, "get_extinction": core["dust"].get_extinction}
     table = {name: [outcome(fac[name], cfg) for cfg in cases] for name, cases in BOUNDARY_CASES.items()}
     o = {"outcomes_json": np.array(json.dumps(table))}
     cube = x["lsf_cube"]
