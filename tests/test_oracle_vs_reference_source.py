@@ -423,3 +423,22 @@ def test_differential_fuzz_of_the_oracle_against_the_reference_source():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_oracle_vs_reference.py"), "60", "3"],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "oracle == reference source everywhere" in res.stdout, res.stdout + res.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "
+                                                                       "container")
+def test_import_swap_through_the_reference_pipeline_machinery():
+    """INTEGRATION.md section 1, executed: the mirror's twelve closures registered with the reference's own
+    LinearTransformerPipeline (run from source; registration by __name__, bound_transformer's deepcopy, depends_on
+    ordering, expression composition) for calc_ifu and calc_dusty_ifu.  Without a GPU the composed expression stops at
+    its first stage with the library's no-CPU-fallback error."""
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "import_swap_check.py")], capture_output=True,
+                         text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout + res.stderr[-2000:]
+    out = res.stdout
+    assert "calc_ifu assembled: rotate_galaxy -> filter_particles -> spaxel_assignment -> reshape_data -> " \
+           "calculate_spectra -> scale_spectrum_by_mass -> doppler_shift_and_resampling -> calculate_datacube -> " \
+           "convolve_psf -> convolve_lsf -> apply_noise" in out
+    assert "doppler_shift_and_resampling -> calculate_extinction -> calculate_datacube" in out
+    assert out.count("there is no CPU fallback") == 2
