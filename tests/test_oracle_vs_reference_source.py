@@ -442,3 +442,21 @@ def test_import_swap_through_the_reference_pipeline_machinery():
            "convolve_psf -> convolve_lsf -> apply_noise" in out
     assert "doppler_shift_and_resampling -> calculate_extinction -> calculate_datacube" in out
     assert out.count("there is no CPU fallback") == 2
+
+
+def test_data_classes_and_reshape_array_match_the_reference(stages):
+    """a8: the types crossing the boundary.  Attribute names of Galaxy / StarsData / GasData / RubixData and
+    reshape_array (zero padding to n_dev x ceil(n / n_dev), rubix/core/data.py:447-487) from the reference's source
+    against rubix_b200/core/data.py."""
+    import json
+    from rubix_b200.core import data as ours
+    names = json.loads(str(stages["data_names_json"]))
+    for cls, want in names.items():
+        obj = getattr(ours, cls)()
+        got = sorted(a for a in dir(obj) if not a.startswith("_") and not callable(getattr(obj, a)))
+        assert got == want, (cls, sorted(set(want) - set(got)), sorted(set(got) - set(want)))
+    assert "pixel_assignment" in names["StarsData"] and "metals" in names["GasData"]
+    a1, a2 = np.arange(1.0, 8.0), np.arange(1.0, 15.0).reshape(7, 2)
+    for n_dev in (2, 3):
+        assert np.array_equal(ours.reshape_array(a1, n_dev).numpy(), stages[f"data_reshape1d_{n_dev}"])
+        assert np.array_equal(ours.reshape_array(a2, n_dev).numpy(), stages[f"data_reshape2d_{n_dev}"])

@@ -385,6 +385,39 @@ def run_pipeline_orders():
     return {"json": np.array(json.dumps(out))}
 
 
+def run_data_classes():
+    """rubix/core/data.py from source: the attribute names of Galaxy / StarsData / GasData / RubixData (a8, the types that
+    cross the boundary) and reshape_array for a device count of two and three (zero padding, 1-D and 2-D)."""
+    import json
+    import types
+    sys.modules["jax.tree_util"].register_pytree_node_class = lambda c=None: (c if c is not None else (lambda k: k))
+    g = types.ModuleType("rubix.galaxy")
+    g.IllustrisAPI, g.get_input_handler, g.__path__ = object, (lambda *a, **k: None), []
+    sys.modules["rubix.galaxy"] = g
+    refshim.load("rubix/galaxy/alignment.py")
+    u = sys.modules.get("rubix.utils") or types.ModuleType("rubix.utils")
+    u.load_galaxy_data = lambda *a, **k: None
+    if not hasattr(u, "read_yaml"):
+        u.read_yaml = lambda path: None
+    sys.modules["rubix.utils"] = u
+    sys.modules.pop("rubix.core.data", None)
+    data = refshim.load("rubix/core/data.py")
+    names = {}
+    for cls in ("Galaxy", "StarsData", "GasData", "RubixData"):
+        obj = getattr(data, cls)()
+        names[cls] = sorted(a for a in dir(obj) if not a.startswith("_") and not callable(getattr(obj, a)))
+    o = {"names_json": np.array(json.dumps(names))}
+    a1, a2 = np.arange(1.0, 8.0), np.arange(1.0, 15.0).reshape(7, 2)
+    for n_dev in (2, 3):
+        sys.modules["jax"].device_count = lambda n=n_dev: n
+        o[f"reshape1d_{n_dev}"], o[f"reshape2d_{n_dev}"] = data.reshape_array(a1), data.reshape_array(a2)
+    sys.modules.pop("rubix.core.data", None)          # other runs register their own stand-in for this module
+    sys.modules["rubix.core.data"] = types.ModuleType("rubix.core.data")
+    sys.modules["rubix.core.data"].RubixData = sys.modules["rubix.core.data"].StarsData = object
+    sys.modules["rubix.core.data"].GasData = object
+    return o
+
+
 def run_telescopes():
     """rubix/telescope/{apertures,base,factory}.py from source: every telescope of telescopes.yaml through
     TelescopeFactory.create_telescope -- sbin, aperture mask (square / circular / hexagonal), length and end points of
@@ -505,6 +538,7 @@ def check():
     bad += [k for k, v in run_boundary(x).items() if not np.array_equal(v, st["boundary_" + k])]
     bad += [k for k, v in run_telescopes().items() if not np.array_equal(v, st["telescope_" + k])]
     bad += [k for k, v in run_pipeline_orders().items() if not np.array_equal(v, st["pipeline_" + k])]
+    bad += [k for k, v in run_data_classes().items() if not np.array_equal(v, st["data_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -526,7 +560,8 @@ def main():
                         **{"cosmo_" + k: v for k, v in run_cosmology().items()},
                         **{"boundary_" + k: v for k, v in run_boundary(x).items()},
                         **{"telescope_" + k: v for k, v in run_telescopes().items()},
-                        **{"pipeline_" + k: v for k, v in run_pipeline_orders().items()})
+                        **{"pipeline_" + k: v for k, v in run_pipeline_orders().items()},
+                        **{"data_" + k: v for k, v in run_data_classes().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     via, shape = run_core_closures(xc)
