@@ -107,39 +107,29 @@ def prepare_input(config: dict) -> RubixData:
         return (coords - center).astype(np.float32), (vel - central_velocity).astype(np.float32)
 
     sub = config.get("data", {}).get("subset", {})
-    idx = None
-    if sub.get("use_subset"):
-        # rubix/core/data.py:562-580: seed 42, indices drawn from the STAR count (the gas count only when there are no
-        # stars) and applied to every particle type
-        np.random.seed(42)
-        count = len(st["coords"]) if st is not None else len(gas["coords"])
-        idx = np.random.choice(np.arange(count), size=sub["subset_size"], replace=False)
     rd = RubixData()
-    if st is not None:
-        logger.info("Centering stars particles")
-        coords, velocity = centred(st)
-        arrays = dict(coords=coords, velocity=velocity, mass=st["mass"], metallicity=st["metallicity"], age=st["age"])
-        if idx is not None:
-            arrays = {k: v[idx] for k, v in arrays.items()}
-            logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for stars")
-        rd = make_rubix_data(**arrays, device=False)
-    if gas is not None:   # rubix/core/data.py:541-600: every stored attribute, centred coordinates and velocities
-        logger.info("Centering gas particles")
-        gcoords, gvel = centred(gas) if "velocity" in gas else (None, None)
-        for k, v in gas.items():
-            if k == "coords" and gcoords is not None:
-                v = gcoords
-            elif k == "coords":
-                v = (np.asarray(v, dtype=np.float32) - center).astype(np.float32)
-            elif k == "velocity":
-                v = gvel
-            else:
-                v = np.ascontiguousarray(v, dtype=np.float32)
-            if idx is not None:
-                v = v[idx]
-            setattr(rd.gas, k, v)
-        if idx is not None:
-            logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} for gas")
+    # rubix/core/data.py:528-600: the particle types in the order the config names them; each is centred on ALL its
+    # particles and then, with data.subset.use_subset, cut down to seed-42 indices drawn from the CURRENT length of the
+    # star arrays (the gas arrays when no stars are loaded) -- so gas that follows subsetted stars gets a permutation of
+    # its first subset_size cells.  Reproduced, not fixed.
+    for part_type in types:
+        part = {"stars": st, "gas": gas}.get(part_type)
+        if part is None:
+            continue
+        logger.info(f"Centering {part_type} particles")
+        coords, velocity = centred(part)
+        target = getattr(rd, part_type)
+        for k, v in part.items():
+            v = coords if k == "coords" else velocity if k == "velocity" else np.ascontiguousarray(v, dtype=np.float32)
+            setattr(target, k, v)
+        if sub.get("use_subset"):
+            np.random.seed(42)  # rubix/core/data.py:565
+            count = len(rd.stars.coords) if rd.stars.coords is not None else len(rd.gas.coords)
+            idx = np.random.choice(np.arange(count), size=sub["subset_size"], replace=False)
+            for k in part:
+                setattr(target, k, getattr(target, k)[idx])
+            logger.warning(f"The Subset value is set in config. Using only subset of size {sub['subset_size']} "
+                           f"for {part_type}")
     rd.galaxy.redshift = raw["redshift"]
     rd.galaxy.center = center
     rd.galaxy.halfmassrad_stars = raw["subhalo_halfmassrad_stars"]

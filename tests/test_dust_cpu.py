@@ -210,7 +210,9 @@ def test_unknown_extinction_model_message():
 
 def test_prepare_input_loads_and_centres_gas(monkeypatch, tmp_path):
     """rubix/core/data.py:541-600: every stored gas attribute is loaded, coordinates are centred on the subhalo
-    centre, and the subset indices are drawn from the STAR count (seed 42) for gas too."""
+    centre, and with a subset the gas indices are drawn (seed 42) from the length the STAR arrays have at that point --
+    already cut to subset_size -- so the gas keeps a permutation of its first subset_size cells (the reference's own
+    prepare_input run from source gives exactly this: tests/test_oracle_vs_reference_source.py)."""
     from rubix_b200.core import pipeline as pl
     rng = np.random.default_rng(0)
     ns, ng = 50, 80
@@ -232,7 +234,10 @@ def test_prepare_input_loads_and_centres_gas(monkeypatch, tmp_path):
     rd = pl.prepare_input(cfg)
     np.random.seed(42)
     idx = np.random.choice(np.arange(ns), size=20, replace=False)
-    assert len(rd.stars.mass) == 20 and np.array_equal(rd.gas.mass, gas["mass"][idx])
+    assert len(rd.stars.mass) == 20 and np.array_equal(rd.stars.coords, (stars["coords"] - 10.0)[idx])
+    np.random.seed(42)
+    perm = np.random.choice(np.arange(20), size=20, replace=False)
+    assert np.array_equal(rd.gas.mass, gas["mass"][perm])
 
 
 # ---- the reference's class interface (tests/test_dust_classes.py:112-166) ---------------------------------------

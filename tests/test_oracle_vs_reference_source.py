@@ -460,3 +460,35 @@ def test_data_classes_and_reshape_array_match_the_reference(stages):
     for n_dev in (2, 3):
         assert np.array_equal(ours.reshape_array(a1, n_dev).numpy(), stages[f"data_reshape1d_{n_dev}"])
         assert np.array_equal(ours.reshape_array(a2, n_dev).numpy(), stages[f"data_reshape2d_{n_dev}"])
+
+
+def test_prepare_input_against_the_reference_prepare_input(stages, monkeypatch, tmp_path):
+    """rubix/core/data.py:491-603 (prepare_input) run from source with its HDF5 reader stood in, against the mirror's
+    prepare_input on the same arrays: every particle attribute bit for bit -- stars + gas, with the seed-42 subset
+    (indices from the star count for gas too), and a gas-only galaxy with a subset (indices from the gas count)."""
+    from rubix_b200.core import pipeline as pl
+    f32 = np.float32
+    centre = f32([3.0, -2.0, 1.0])
+    stars = dict(coords=(stages["in_gal_pos"] + centre).astype(f32),
+                 velocity=(stages["in_gal_vel"] + f32([120.0, -40.0, 15.0])).astype(f32),
+                 mass=np.linspace(0.5, 1.5, 500).astype(f32), metallicity=np.full(500, 0.01, f32),
+                 age=np.linspace(5.0, 10.0, 500).astype(f32))
+    gas = dict(coords=(stages["in_gal_pos"] * 4.0 + centre).astype(f32), velocity=stars["velocity"][::-1].copy(),
+               mass=np.arange(500, dtype=f32), metals=np.arange(4500, dtype=f32).reshape(500, 9))
+    compared = 0
+    for tag, types_, subset in (("both", ["stars", "gas"], None), ("both_subset", ["stars", "gas"], 40),
+                                ("gas_only_subset", ["gas"], 25)):
+        raw = {"redshift": 0.1, "subhalo_center": centre, "subhalo_halfmassrad_stars": 2.0,
+               "particle_data": {k: dict(v) for k, v in (("stars", stars), ("gas", gas)) if k in types_}}
+        monkeypatch.setattr(pl, "load_rubix_galaxy", lambda path, types, raw=raw: raw)
+        cfg = {"output_path": str(tmp_path), "data": {"args": {"particle_type": types_}}}
+        if subset:
+            cfg["data"]["subset"] = {"use_subset": True, "subset_size": subset}
+        rd = pl.prepare_input(cfg)
+        for part in types_:
+            for k in raw["particle_data"][part]:
+                want = stages[f"data_prepare_{tag}_{part}_{k}"]
+                got = np.asarray(getattr(getattr(rd, part), k))
+                assert got.shape == want.shape and np.array_equal(got, want), (tag, part, k)
+                compared += 1
+    assert compared == 22

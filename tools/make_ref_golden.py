@@ -411,6 +411,29 @@ def run_data_classes():
     for n_dev in (2, 3):
         sys.modules["jax"].device_count = lambda n=n_dev: n
         o[f"reshape1d_{n_dev}"], o[f"reshape2d_{n_dev}"] = data.reshape_array(a1), data.reshape_array(a2)
+    # prepare_input (rubix/core/data.py:491-603) itself, its HDF5 reader stood in by a function returning arrays
+    f32 = np.float32
+    x = stage_inputs()
+    centre = f32([3.0, -2.0, 1.0])
+    stars = dict(coords=(x["gal_pos"] + centre).astype(f32), velocity=(x["gal_vel"] + f32([120.0, -40.0, 15.0])).astype(f32),
+                 mass=np.linspace(0.5, 1.5, 500).astype(f32), metallicity=np.full(500, 0.01, f32),
+                 age=np.linspace(5.0, 10.0, 500).astype(f32))
+    gas = dict(coords=(x["gal_pos"] * 4.0 + centre).astype(f32), velocity=stars["velocity"][::-1].copy(),
+               mass=np.arange(500, dtype=f32), metals=np.arange(4500, dtype=f32).reshape(500, 9))
+    units = {"galaxy": {"redshift": "", "center": "kpc", "halfmassrad_stars": "kpc"},
+             "stars": {k: "u" for k in stars}, "gas": {k: "u" for k in gas}}
+    for tag, types_, subset in (("both", ["stars", "gas"], None), ("both_subset", ["stars", "gas"], 40),
+                                ("gas_only_subset", ["gas"], 25)):
+        raw = {"redshift": 0.1, "subhalo_center": centre, "subhalo_halfmassrad_stars": 2.0,
+               "particle_data": {k: dict(v) for k, v in (("stars", stars), ("gas", gas)) if k in types_}}
+        data.load_galaxy_data = lambda path, raw=raw: (raw, units)
+        cfg = {"output_path": "/nonexistent", "data": {"args": {"particle_type": types_}}}
+        if subset:
+            cfg["data"]["subset"] = {"use_subset": True, "subset_size": subset}
+        rd = data.prepare_input(cfg)
+        for part in types_:
+            for k in raw["particle_data"][part]:
+                o[f"prepare_{tag}_{part}_{k}"] = np.asarray(getattr(getattr(rd, part), k))
     sys.modules.pop("rubix.core.data", None)          # other runs register their own stand-in for this module
     sys.modules["rubix.core.data"] = types.ModuleType("rubix.core.data")
     sys.modules["rubix.core.data"].RubixData = sys.modules["rubix.core.data"].StarsData = object
