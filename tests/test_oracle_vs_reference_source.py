@@ -492,3 +492,23 @@ def test_prepare_input_against_the_reference_prepare_input(stages, monkeypatch, 
                 assert got.shape == want.shape and np.array_equal(got, want), (tag, part, k)
                 compared += 1
     assert compared == 22
+
+
+def test_configuration_data_is_the_reference_configuration(stages):
+    """rubix_b200/config.py and telescope.TELESCOPES hold the reference's configuration as Python data: equal to the
+    reference's own pipeline_config.yml, telescopes.yaml and the parts of rubix_config.yml the path reads."""
+    import json
+    from rubix_b200 import config as C
+    from rubix_b200 import telescope as T
+    ref = json.loads(str(stages["config_json"]))
+    assert C.PIPELINES == ref["pipelines"]
+    assert T.TELESCOPES == ref["telescopes"]
+    assert C.IFU == ref["ifu"] and C.DUST == ref["dust"]
+    for k, v in C.CONSTANTS.items():
+        assert float(v) == float(ref["constants"][k]), k           # the YAML holds some of them as strings ('3.828e33')
+    assert float(ref["constants"]["SPEED_OF_LIGHT"]) == 299792.458
+    bc03 = ref["bc03"]
+    ours = C.SSP["templates"]["BruzualCharlot2003"]
+    assert ours["file_name"] == bc03["file_name"] and ours["format"].lower() == bc03["format"].lower()
+    for field, info in bc03["fields"].items():
+        assert ours["fields"][field]["name"] == info["name"] and ours["fields"][field]["in_log"] == info["in_log"]

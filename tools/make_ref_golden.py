@@ -385,6 +385,19 @@ def run_pipeline_orders():
     return {"json": np.array(json.dumps(out))}
 
 
+def run_config_data():
+    """The reference's configuration files as data: pipeline_config.yml, telescopes.yaml and the parts of rubix_config.yml
+    the path reads (constants, ifu.doppler, ssp.dust, the BC03 template entry)."""
+    import json
+    import yaml
+    rd = lambda *p: yaml.safe_load(open(os.path.join(refshim.REF, "rubix", *p)))
+    cfg = rd("config", "rubix_config.yml")
+    out = {"pipelines": rd("config", "pipeline_config.yml"), "telescopes": rd("telescope", "telescopes.yaml"),
+           "constants": cfg["constants"], "ifu": cfg["ifu"], "dust": cfg["ssp"]["dust"],
+           "bc03": cfg["ssp"]["templates"]["BruzualCharlot2003"]}
+    return {"json": np.array(json.dumps(out, sort_keys=True))}
+
+
 def run_data_classes():
     """rubix/core/data.py from source: the attribute names of Galaxy / StarsData / GasData / RubixData (a8, the types that
     cross the boundary) and reshape_array for a device count of two and three (zero padding, 1-D and 2-D)."""
@@ -562,6 +575,7 @@ def check():
     bad += [k for k, v in run_telescopes().items() if not np.array_equal(v, st["telescope_" + k])]
     bad += [k for k, v in run_pipeline_orders().items() if not np.array_equal(v, st["pipeline_" + k])]
     bad += [k for k, v in run_data_classes().items() if not np.array_equal(v, st["data_" + k])]
+    bad += [k for k, v in run_config_data().items() if not np.array_equal(v, st["config_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -584,7 +598,8 @@ def main():
                         **{"boundary_" + k: v for k, v in run_boundary(x).items()},
                         **{"telescope_" + k: v for k, v in run_telescopes().items()},
                         **{"pipeline_" + k: v for k, v in run_pipeline_orders().items()},
-                        **{"data_" + k: v for k, v in run_data_classes().items()})
+                        **{"data_" + k: v for k, v in run_data_classes().items()},
+                        **{"config_" + k: v for k, v in run_config_data().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     via, shape = run_core_closures(xc)
