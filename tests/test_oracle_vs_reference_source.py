@@ -512,3 +512,18 @@ def test_configuration_data_is_the_reference_configuration(stages):
     assert ours["file_name"] == bc03["file_name"] and ours["format"].lower() == bc03["format"].lower()
     for field, info in bc03["fields"].items():
         assert ours["fields"][field]["name"] == info["name"] and ours["fields"][field]["in_log"] == info["in_log"]
+
+
+def test_apply_noise_arithmetic(stages, monkeypatch):
+    """get_apply_noise's closure (rubix/core/noise.py:63-78 -> calculate_noise_cube) run from source with jax.random
+    stood in by a fixed array of normals: the oracle's apply_noise fed the same normals gives the same cube, with and
+    without a flux-less spaxel (which switches the noise off everywhere: the NaN-propagating median).  The random stream
+    itself (threefry, erfinv) is pinned elsewhere (tests/test_oracle_golden.py) or unpinned."""
+    normals = stages["boundary_noise_normals"]
+    monkeypatch.setattr(orc, "sample_noise", lambda n, distribution="normal", key=(0, 0): normals.reshape(-1)[:n])
+    nc = stages["in_noise_cube"].copy()
+    _close(orc.apply_noise(nc, 10, "normal"), stages["boundary_noise_closure"])
+    assert np.abs(stages["boundary_noise_closure"] - nc).max() > 0
+    nc[2, 3] = 0.0
+    out = orc.apply_noise(nc, 10, "normal")
+    assert np.array_equal(out, stages["boundary_noise_closure_dark_spaxel"]) and np.array_equal(out, nc)

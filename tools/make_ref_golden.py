@@ -306,6 +306,21 @@ def run_boundary(x):
     rd = NS(stars=NS(datacube=cube.copy()))
     o["psf_closure"] = fac["get_convolve_psf"](BOUNDARY_CASES["get_convolve_psf"][-1])(rd).stars.datacube
     o["psf_lsf_closures"] = fac["get_convolve_lsf"](BOUNDARY_CASES["get_convolve_lsf"][-1])(rd).stars.datacube
+    # apply_noise: the random numbers come from jax.random (threefry, not available here), so the stand-in hands out a
+    # fixed array of standard normals, stored with the result: what is pinned is the ARITHMETIC around them
+    # (rubix/core/noise.py:63-78, rubix/telescope/noise/noise.py:81-115), for a cube with and without a dark spaxel
+    rnd = sys.modules["jax.random"]
+    normals = np.random.default_rng(123).standard_normal(x["noise_cube"].shape)
+    rnd.PRNGKey = lambda seed: ("key", seed)
+    rnd.normal = lambda key, shape: normals.reshape(shape)
+    rnd.uniform = lambda key, shape: (normals.reshape(shape) % 1.0)
+    o["noise_normals"] = normals
+    for tag, dark in (("noise_closure", False), ("noise_closure_dark_spaxel", True)):
+        nc = x["noise_cube"].copy()
+        if dark:
+            nc[2, 3] = 0.0
+        with np.errstate(all="ignore"):
+            o[tag] = fac["get_apply_noise"](BOUNDARY_CASES["get_apply_noise"][-1])(NS(stars=NS(datacube=nc))).stars.datacube
     cfg = dict(BOUNDARY_CASES["get_galaxy_rotation"][-1], data={"args": {"particle_type": ["stars"]}})
     rd = NS(stars=NS(coords=x["gal_pos"].copy(), velocity=x["gal_vel"].copy(), mass=x["gal_mass"].copy()),
             galaxy=NS(halfmassrad_stars=4.0))
