@@ -527,3 +527,29 @@ def test_apply_noise_arithmetic(stages, monkeypatch):
     nc[2, 3] = 0.0
     out = orc.apply_noise(nc, 10, "normal")
     assert np.array_equal(out, stages["boundary_noise_closure_dark_spaxel"]) and np.array_equal(out, nc)
+
+
+def test_store_fits_against_the_reference_store_fits(stages, tmp_path):
+    """store_fits (rubix/core/fits.py:13-101) run from source with astropy.io.fits stood in by recorders, against the
+    mirror writing a real file with the numpy-only FITS writer and reading it back: same file name, the same keywords
+    with the same values in the same order in both headers (FITS upper-cases DIST_z), the same (wavelength, y, x)
+    array."""
+    import json
+    from types import SimpleNamespace as NS
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_ref_golden import FITS_CONFIG
+    from rubix_b200 import fitslite
+    from rubix_b200.core.fits import store_fits
+    ref = json.loads(str(stages["fits_json"]))
+    cube = np.arange(2 * 3 * 5, dtype=np.float32).reshape(2, 3, 5)
+    name = store_fits(FITS_CONFIG, NS(stars=NS(datacube=cube), gas=NS(datacube=None)), str(tmp_path) + "/out_")
+    assert os.path.basename(name) == ref["filename"]
+    (primary, none), (hdr, data) = fitslite.read_fits(name)
+    assert none is None and np.array_equal(data, stages["fits_image"]) and data.shape == (5, 3, 2)
+    structural = {"SIMPLE", "BITPIX", "NAXIS", "NAXIS1", "NAXIS2", "NAXIS3", "EXTEND", "XTENSION", "PCOUNT", "GCOUNT"}
+    for got, want in ((primary, ref["primary"]), (hdr, ref["image_header"])):
+        want = [(k.upper(), v) for k, v in want if k != "SIMPLE"]
+        got_items = [(k, v) for k, v in got.items() if k not in structural]
+        assert [k for k, _ in got_items] == [k for k, _ in want]
+        for (k, a), (_, b) in zip(got_items, want):
+            assert a == b or (isinstance(b, float) and abs(a - b) <= 1e-15 * abs(b)), (k, a, b)

@@ -413,6 +413,64 @@ def run_config_data():
     return {"json": np.array(json.dumps(out, sort_keys=True))}
 
 
+FITS_CONFIG = {
+    "pipeline": {"name": "calc_ifu"}, "galaxy": {"dist_z": 0.1, "rotation": {"type": "edge-on"}},
+    "simulation": {"name": "IllustrisTNG"}, "cosmology": {"name": "PLANCK15"},
+    "data": {"args": {"snapshot": 99, "particle_type": ["stars"]}, "load_galaxy_args": {"id": 14},
+             "subset": {"use_subset": True, "subset_size": 1000}},
+    "ssp": {"template": {"name": "BruzualCharlot2003"}},
+    "telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6}, "lsf": {"sigma": 0.5},
+                  "noise": {"signal_to_noise": 10, "noise_distribution": "normal"}},
+}
+
+
+def run_store_fits():
+    """store_fits (rubix/core/fits.py:13-101) from source with astropy.io.fits stood in by recorders: the two headers
+    (keywords, values, order), the array handed to the IMAGE extension and the output file name."""
+    import json
+    import types
+    from types import SimpleNamespace as NS
+    rec = {}
+
+    class Header(dict):
+        pass
+
+    class HDUList(list):
+        def writeto(self, name, overwrite=False):
+            rec["filename"] = name
+
+    fits = types.ModuleType("astropy.io.fits")
+    fits.Header = Header
+    fits.PrimaryHDU = lambda header=None: rec.setdefault("primary", header)
+    fits.ImageHDU = lambda data, header=None: rec.update(image=np.asarray(data), image_header=header)
+    fits.HDUList = HDUList
+    for name, mod in (("astropy", types.ModuleType("astropy")), ("astropy.io", types.ModuleType("astropy.io")),
+                      ("astropy.io.fits", fits), ("matplotlib", types.ModuleType("matplotlib")),
+                      ("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot")),
+                      ("matplotlib.colors", types.ModuleType("matplotlib.colors")),
+                      ("mpdaf", types.ModuleType("mpdaf")), ("mpdaf.obj", types.ModuleType("mpdaf.obj"))):
+        sys.modules[name] = mod
+    sys.modules["astropy.io"].fits = fits
+    sys.modules["matplotlib.colors"].LogNorm = object
+    sys.modules["mpdaf.obj"].Cube = object
+    sys.modules["rubix.core.telescope"] = types.ModuleType("rubix.core.telescope")
+    sys.modules["rubix.core.telescope"].get_telescope = lambda config: NS(spatial_res=0.2, wave_res=1.25,
+                                                                          wave_range=[4700.15, 9351.4])
+    sys.modules.pop("rubix.core.fits", None)
+    mod = refshim.load("rubix/core/fits.py")
+    cube = np.arange(2 * 3 * 5, dtype=np.float32).reshape(2, 3, 5)
+    import tempfile
+    d = tempfile.mkdtemp()
+    mod.store_fits(FITS_CONFIG, NS(stars=NS(datacube=cube)), d + "/out_")
+    for m in ("astropy", "astropy.io", "astropy.io.fits", "matplotlib", "matplotlib.pyplot", "matplotlib.colors", "mpdaf",
+              "mpdaf.obj"):
+        sys.modules.pop(m, None)
+    return {"json": np.array(json.dumps({"primary": list(rec["primary"].items()),
+                                         "image_header": list(rec["image_header"].items()),
+                                         "filename": os.path.basename(rec["filename"])})),
+            "image": rec["image"]}
+
+
 def run_data_classes():
     """rubix/core/data.py from source: the attribute names of Galaxy / StarsData / GasData / RubixData (a8, the types that
     cross the boundary) and reshape_array for a device count of two and three (zero padding, 1-D and 2-D)."""
@@ -591,6 +649,7 @@ def check():
     bad += [k for k, v in run_pipeline_orders().items() if not np.array_equal(v, st["pipeline_" + k])]
     bad += [k for k, v in run_data_classes().items() if not np.array_equal(v, st["data_" + k])]
     bad += [k for k, v in run_config_data().items() if not np.array_equal(v, st["config_" + k])]
+    bad += [k for k, v in run_store_fits().items() if not np.array_equal(v, st["fits_" + k])]
     du = np.load(os.path.join(OUT, "ref_numpy_dust.npz"))
     xd = dust_inputs()
     bad += [k for k, v in xd.items() if not np.array_equal(v, du["in_" + k])]
@@ -614,7 +673,8 @@ def main():
                         **{"telescope_" + k: v for k, v in run_telescopes().items()},
                         **{"pipeline_" + k: v for k, v in run_pipeline_orders().items()},
                         **{"data_" + k: v for k, v in run_data_classes().items()},
-                        **{"config_" + k: v for k, v in run_config_data().items()})
+                        **{"config_" + k: v for k, v in run_config_data().items()},
+                        **{"fits_" + k: v for k, v in run_store_fits().items()})
     xc = cube_inputs()
     oc = run_cube(m, xc)
     via, shape = run_core_closures(xc)
