@@ -165,6 +165,13 @@ class RubixPipeline:
     def _get_pipeline_functions(self) -> list:
         self.logger.info("Setting up the pipeline...")
         c = self.user_config
+        if isinstance(c.get("b200"), dict) and c["b200"].get("strict"):
+            # exactly rubix/core/pipeline.py:105-133: all twelve factories, unconditionally -- a configuration without
+            # galaxy.rotation, ssp.dust or telescope.noise raises the factory's ValueError, as it does in the reference
+            return [get_galaxy_rotation(c), get_filter_particles(c), get_spaxel_assignment(c), get_calculate_spectra(c),
+                    get_reshape_data(c), get_scale_spectrum_by_mass(c), get_doppler_shift_and_resampling(c),
+                    get_extinction(c), get_calculate_datacube(c), get_convolve_psf(c), get_convolve_lsf(c),
+                    get_apply_noise(c)] + self.extra_functions
         rot = [get_galaxy_rotation(c)] if "rotation" in c.get("galaxy", {}) else []
         noise = [get_apply_noise(c)] if "noise" in c.get("telescope", {}) else []
         dusty = [get_extinction(c)] if self.user_config["pipeline"]["name"] == "calc_dusty_ifu" else []

@@ -230,3 +230,31 @@ def test_hexagonal_aperture_matches_the_reference_loop():
     tel = TelescopeFactory({"HEX": dict(fov=5.0, spatial_res=0.2, wave_range=[4700.15, 9351.4], wave_res=1.25,
                                          lsf_fwhm=2.51, aperture_type="hexagonal", pixel_type="square")}).create_telescope("HEX")
     assert np.array_equal(np.asarray(tel.aperture_region), ref(25))
+
+
+def test_rubix_pipeline_strict_mode_validates_like_the_reference(tng_subset):
+    """config["b200"]["strict"]: all twelve factories are called unconditionally, as rubix/core/pipeline.py:105-133 does,
+    so a configuration without galaxy.rotation / ssp.dust / telescope.noise raises the factory's own error (by default the
+    mirror skips those stages with a warning)."""
+    import copy
+    from rubix_b200 import core
+    base = {
+        "pipeline": {"name": "calc_ifu"}, "cosmology": {"name": "PLANCK15"}, "galaxy": {"dist_z": 0.1},
+        "telescope": {"name": "MUSE", "psf": {"name": "gaussian", "size": 5, "sigma": 0.6}, "lsf": {"sigma": 0.5}},
+        "ssp": {"template": {"name": "BruzualCharlot2003"}}, "data": {"args": {"particle_type": ["stars"]}},
+    }
+    rd = core.make_rubix_data(**tng_subset, device=False)
+    assert len(core.RubixPipeline(copy.deepcopy(base), data=rd).assemble()) == 9            # relaxed: three stages skipped
+    strict = copy.deepcopy(base)
+    strict["b200"] = {"strict": True}
+    with pytest.raises(ValueError, match="Rotation information not provided in galaxy config"):
+        core.RubixPipeline(strict, data=rd).assemble()
+    strict["galaxy"]["rotation"] = {"type": "face-on"}
+    with pytest.raises(ValueError, match="Dust configuration not found in config file."):
+        core.RubixPipeline(strict, data=rd).assemble()
+    strict["ssp"]["dust"] = {"extinction_model": "Cardelli89", "Rv": 3.1, "dust_grain_density": 3.5}
+    with pytest.raises(ValueError, match="Noise information not provided in telescope config"):
+        core.RubixPipeline(strict, data=rd).assemble()
+    strict["telescope"]["noise"] = {"signal_to_noise": 10, "noise_distribution": "normal"}
+    names = [fn.__name__ for fn in core.RubixPipeline(strict, data=rd).assemble()]
+    assert len(names) == 11 and names[0] == "rotate_galaxy" and names[-1] == "apply_noise"   # calc_ifu has no dust node
