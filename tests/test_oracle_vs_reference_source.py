@@ -553,3 +553,20 @@ def test_store_fits_against_the_reference_store_fits(stages, tmp_path):
         assert [k for k, _ in got_items] == [k for k, _ in want]
         for (k, a), (_, b) in zip(got_items, want):
             assert a == b or (isinstance(b, float) and abs(a - b) <= 1e-15 * abs(b)), (k, a, b)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "
+                                                                       "container")
+def test_shipped_template_is_the_reference_template():
+    """rubix_b200/templates/bc03lr_f32.npz against the reference's BC03lr.h5 (read without h5py by rubix_b200/h5lite.py):
+    every dataset cast to float32 as rubix/spectra/ssp/grid.py:323-331 does; and, as a check of the reader that does not
+    go through its own parsing of the data layout, the bytes of every array it returns occur verbatim in the file."""
+    from rubix_b200.h5lite import H5File
+    path = "/root/reference/rubix/spectra/ssp/templates/BC03lr.h5"
+    raw = open(path, "rb").read()
+    tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    with H5File(path) as f:
+        for k, shape in (("age", (221,)), ("metallicity", (6,)), ("wavelength", (842,)), ("flux", (6, 221, 842))):
+            a = f[k].read()
+            assert a.shape == shape and np.ascontiguousarray(a).tobytes() in raw, k
+            assert tpl[k].dtype == np.float32 and np.array_equal(tpl[k], a.astype(np.float32)), k
