@@ -570,3 +570,14 @@ def test_shipped_template_is_the_reference_template():
             a = f[k].read()
             assert a.shape == shape and np.ascontiguousarray(a).tobytes() in raw, k
             assert tpl[k].dtype == np.float32 and np.array_equal(tpl[k], a.astype(np.float32)), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "
+                                                                       "container")
+def test_data_fixtures_are_what_the_reference_files_give_now():
+    """tools/make_golden.py --check: the SSP template, muse_wave.npy and tng50_subset.npz regenerated from the reference's
+    own data files (BC03lr.h5, notebooks/data/dummy_datacube.h5, tests/output/rubix_galaxy.h5) equal the committed ones."""
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_golden.py"), "--check"], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "identical" in res.stdout, res.stdout + res.stderr[-2000:]

@@ -33,11 +33,20 @@ KPC_IN_KM = 3.0856775814913673e16
 
 
 def main():
+    global OUT
+    check = "--check" in sys.argv
+    committed = OUT
+    if check:   # regenerate into a scratch directory and compare array by array with the committed fixtures
+        import tempfile
+        OUT = tempfile.mkdtemp()
+        os.makedirs(os.path.join(OUT, "templates"), exist_ok=True)
     os.makedirs(OUT, exist_ok=True)
 
     with H5File(f"{REF}/rubix/spectra/ssp/templates/BC03lr.h5") as f:
         tpl = {k: f[k].read().astype(np.float32) for k in ("age", "metallicity", "wavelength", "flux")}
-    np.savez_compressed(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"), **tpl)
+    tpl_path = (os.path.join(OUT, "templates", "bc03lr_f32.npz") if check
+                else os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+    np.savez_compressed(tpl_path, **tpl)
 
     with H5File(f"{REF}/notebooks/data/dummy_datacube.h5") as f:
         np.save(os.path.join(OUT, "muse_wave.npy"), f["wave"].read())
@@ -61,8 +70,21 @@ def main():
         "age": stars["age"].astype(np.float32)[idx],
     }
     np.savez_compressed(os.path.join(OUT, "tng50_subset.npz"), **sub)
+    if check:
+        bad = []
+        pairs = [(tpl_path, os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz")),
+                 (os.path.join(OUT, "tng50_subset.npz"), os.path.join(committed, "tng50_subset.npz"))]
+        for new, old in pairs:
+            a, b = np.load(new), np.load(old)
+            bad += [f"{os.path.basename(old)}:{k}" for k in set(a.files) | set(b.files)
+                    if k not in a.files or k not in b.files or not np.array_equal(a[k], b[k])]
+        if not np.array_equal(np.load(os.path.join(OUT, "muse_wave.npy")), np.load(os.path.join(committed, "muse_wave.npy"))):
+            bad.append("muse_wave.npy")
+        print("reference data files vs committed fixtures:", "identical" if not bad else f"MISMATCH in {bad}")
+        sys.exit(1 if bad else 0)
     for fn in sorted(os.listdir(OUT)):
-        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+        if not os.path.isdir(os.path.join(OUT, fn)):
+            print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
 
 if __name__ == "__main__":
