@@ -581,3 +581,21 @@ def test_data_fixtures_are_what_the_reference_files_give_now():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_golden.py"), "--check"], capture_output=True,
                          text=True, timeout=600)
     assert res.returncode == 0 and "identical" in res.stdout, res.stdout + res.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/tests/output/rubix_galaxy.h5"), reason="the reference tree only "
+                    "exists in the build container")
+def test_prepare_input_on_the_reference_galaxy_file_gives_the_tng_fixture(tng_subset):
+    """prepare_input on the reference's own tests/output/rubix_galaxy.h5 (read by rubix_b200/h5lite.py) with the seed-42
+    subset of 4096 stars: the particles of tests/golden/tng50_subset.npz bit for bit (the fixture holds the velocities
+    converted from the file's kpc/s to km/s)."""
+    from rubix_b200.core.pipeline import prepare_input
+    cfg = {"output_path": "/root/reference/tests/output",
+           "data": {"args": {"particle_type": ["stars"]}, "subset": {"use_subset": True, "subset_size": 4096}},
+           "logger": {"log_level": "ERROR", "log_file_path": None, "format": "%(message)s"}}
+    rd = prepare_input(cfg)
+    for k in ("coords", "mass", "metallicity", "age"):
+        assert np.array_equal(np.asarray(getattr(rd.stars, k)), tng_subset[k]), k
+    kms = (np.asarray(rd.stars.velocity).astype(np.float64) * 3.0856775814913673e16).astype(np.float32)
+    assert np.array_equal(kms, tng_subset["velocity"])
+    assert rd.galaxy.halfmassrad_stars is not None and float(rd.galaxy.redshift) >= 0
