@@ -22,7 +22,10 @@ PARITY PINS
   tests/golden/ref_numpy_{stages,cube,dust}.npz with their generator tools/make_ref_golden.py, and
   tests/test_oracle_vs_reference_source.py holds this file's float64 mode (and the C form) to them at 1e-11
   (integer results exactly).  That pins the LOGIC of everything but a1 to the reference's code; it is not jax
-  arithmetic (numpy's rounding order, numpy's double-precision ``interp``).
+  arithmetic (numpy's rounding order, numpy's double-precision ``interp``).  tools/fuzz_oracle_vs_reference.py adds
+  random and degenerate inputs (600 cases per function agree) and checks the OPERATION ORDER of the float32 mode: with
+  numpy float32 arithmetic on both sides (``jnp.interp`` by jax's formula in the input dtype) the Doppler shifts,
+  ``resample_spectrum`` and ``calculate_cube`` agree with the reference's source bit for bit.
 * ``interp2d`` is NOT in the reference tree: it is ``interpax.interp2d`` (PyPI ``interpax``,
   unpinned in the reference's pyproject.toml:38, no lock file).  Its published algorithm is restated
   in :func:`interp2d` below.  The reference's tests pin it only at grid nodes and out-of-grid

@@ -423,6 +423,8 @@ def test_differential_fuzz_of_the_oracle_against_the_reference_source():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_oracle_vs_reference.py"), "60", "3"],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "oracle == reference source everywhere" in res.stdout, res.stdout + res.stderr[-2000:]
+    # and the float32 mode follows the reference's operation order: bit-identical in numpy float32 arithmetic
+    assert "oracle float32 mode == reference source in float32, bit for bit" in res.stdout, res.stdout
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/rubix"), reason="the reference tree only exists in the build "

@@ -154,12 +154,67 @@ def fuzz(cases, seed):
     return bad
 
 
+def float32_order(cases, seed):
+    """The oracle's float32 mode claims the reference's OPERATION ORDER.  With numpy's float32 arithmetic on both sides
+    -- the reference's source expressions evaluated as written, ``jnp.interp`` stood in by jax's own formula in the
+    input dtype -- the cosmological and velocity Doppler shifts, resample_spectrum and calculate_cube must then agree
+    BIT FOR BIT (what XLA fuses or contracts on top of that order cannot be known here)."""
+    import jax.numpy as jnp      # the stand-in
+
+    def interp_in_dtype(x, xp, fp, left=None, right=None, period=None):
+        x, xp, fp = np.asarray(x), np.asarray(xp), np.asarray(fp)
+        i = np.clip(np.searchsorted(xp, x, side="right"), 1, len(xp) - 1)
+        df, dx, delta = fp[i] - fp[i - 1], xp[i] - xp[i - 1], x - xp[i - 1]
+        dx0 = np.abs(dx) <= np.spacing(np.finfo(xp.dtype).eps)
+        with np.errstate(all="ignore"):
+            f = np.where(dx0, fp[i - 1], fp[i - 1] + (delta / np.where(dx0, 1, dx)) * df)
+        f = np.where(x < xp[0], fp[0], f)
+        return np.where(x > xp[-1], fp[-1], f)
+
+    keep = jnp.interp
+    jnp.interp = interp_in_dtype
+    try:
+        sys.modules.pop("rubix.spectra.ifu", None)
+        ifu = refshim.load("rubix/spectra/ifu.py")
+        tpl = np.load(os.path.join(ROOT, "rubix_b200", "templates", "bc03lr_f32.npz"))
+        wave = np.load(os.path.join(ROOT, "tests", "golden", "muse_wave.npy"))
+        rng = np.random.default_rng(seed)
+        f = np.float32
+        bad = []
+        lam_z = ifu.cosmological_doppler_shift(0.1, tpl["wavelength"])
+        if lam_z.dtype != f or not np.array_equal(lam_z, orc.cosmological_doppler_shift(0.1, tpl["wavelength"])):
+            bad.append(("cosmological_doppler_shift", 0))
+        vel = rng.normal(0, 300, (cases, 3)).astype(f)
+        sh, so = ifu.velocity_doppler_shift(lam_z, vel, "z"), orc.velocity_doppler_shift(lam_z, vel, "z")
+        if sh.dtype != f or not np.array_equal(sh, so):
+            bad.append(("velocity_doppler_shift", 0))
+        rows = tpl["flux"].reshape(-1, 842)[rng.integers(0, 1326, cases)] * rng.uniform(0.5, 1.5, cases).astype(f)[:, None]
+        res = []
+        for k in range(cases):
+            with np.errstate(all="ignore"):
+                a, b = ifu.resample_spectrum(rows[k], sh[k], wave), orc.resample_spectrum(rows[k], so[k], wave)
+            res.append(a)
+            if a.dtype != f or not np.array_equal(a, b):
+                bad.append(("resample_spectrum", k))
+        ids = rng.integers(0, 30, cases)
+        if not np.array_equal(ifu.calculate_cube(np.stack(res), ids, 5), orc.calculate_cube(np.stack(res), ids, 5)):
+            bad.append(("calculate_cube", 0))
+    finally:
+        jnp.interp = keep
+        sys.modules.pop("rubix.spectra.ifu", None)
+    return bad
+
+
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         bad = fuzz(cases, seed)
+        bad32 = float32_order(min(cases, 200), seed)
+    print(f"float32 operation order, {min(cases, 200)} particles: " +
+          ("oracle float32 mode == reference source in float32, bit for bit" if not bad32 else f"differs: {bad32[:10]}"))
+    bad = bad + bad32
     names = sorted({b[0] for b in bad})
     print(f"fuzz: {cases} cases per function, seed {seed}: " +
           ("oracle == reference source everywhere" if not bad else f"{len(bad)} disagreement(s) in {names}: {bad[:12]}"))
