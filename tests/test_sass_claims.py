@@ -88,3 +88,30 @@ def test_psf_lsf_march_kernel_uses_tma_bulk_copies(sass):
         assert count(c, r"^UBLKCP") >= 2 and count(c, r"^SYNCS") >= 1, name   # cp.async.bulk + mbarrier waits
         assert count(c, r"^RED") == 0 and count(c, r"^ATOM") == 0, name
     assert any(count(c, r"^FFMA2") > 0 for c in march.values())              # column pairs through FFMA2
+
+
+def test_register_budgets_behind_the_occupancy_claims():
+    """cuobjdump -res-usage: the defaults of the linear cube kernel (two warps per cell array, 12 warps per SM) need
+    <= 168 registers and no stack (65536 / (12 x 32) = 170); prep_kernel <= 64 (four 256-thread blocks per SM);
+    radix_pass_kernel <= 80 (three blocks per SM, its launch bound)."""
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.SO_PATH], capture_output=True, text=True, timeout=300).stdout
+    usage, name = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+)", line)
+        if m and name:
+            usage[name] = tuple(int(v) for v in m.groups())
+    pick = lambda frag: {k: v for k, v in usage.items() if frag in k}
+    linear_pairs = pick("fused_cube_warp_kernelILi0ELb1ELi384E")            # method linear, pairs, 384-cell arrays
+    assert len(linear_pairs) == 2                                           # channel-order and transposed cell layout
+    for name, (reg, stack, _) in linear_pairs.items():
+        assert reg <= 168 and stack == 0, (name, reg, stack)
+    (reg, _, _), = pick("rbx11prep_kernel").values()
+    assert reg <= 64
+    (reg, _, shared), = pick("rbx17radix_pass_kernel").values()
+    assert reg <= 80 and shared <= 48 * 1024
